@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — BoomerAMG-PCG solve throughput (MDOF/s) on B200, BASELINE.json's metric.
+
+    python bench.py --gpus 1 --steps K --warmup W            # hb200 arm (this repository)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path
+
+A "step" is one complete AMG-PCG solve (x0 = 0, b = ones, tol 1e-8, two-norm stopping, V(1,1)
+l1-Jacobi, HMIS + ext+i hierarchy from the reference's own BoomerAMGSetup) of
+`ij -27pt -n 256 256 256 -solver 1 -rlx 18` (BASELINE.json configs[1]); with N GPUs each rank
+owns one 256^3 brick (weak scaling, `-P` process grid as ij lays it out).
+value = global rows / solve time / 1e6.  The hierarchy setup (reference, CPU) and its upload
+are timed separately and reported in `config`, never inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hb200", choices=["hb200", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="brick edge per GPU")
+    ap.add_argument("--problem", default="27pt", choices=["27pt", "laplacian", "vardifconv"])
+    ap.add_argument("--solver", default="pcg", choices=["pcg", "gmres"])
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--cpu-iters", type=int, default=3, help="iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spmv-only", action="store_true", help="configs[4]: SpMV bandwidth line")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(args, rank, world):
+    from oracle import refbridge as rb
+    mpi = world > 1
+    rb.load(mpi=mpi)
+    P = PGRID[world]
+    n = args.n
+    gn = (n * P[0], n * P[1], n * P[2])
+    t0 = time.time()
+    pb = rb.Problem(args.problem, gn, P=P, mpi=mpi)
+    gen_s = time.time() - t0
+    setup_s = pb.setup_amg(relax_type=18)
+    return rb, pb, gn, gen_s, setup_s
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle/_ref = unmodified hypre 3.1.0,
+    OpenMP, all host cores), same config / metric.  Each step is a bounded sample: `cpu_iters`
+    PCG iterations of the same 256^3 solve, extrapolated to the full iteration count by the
+    per-iteration cost (an AMG-PCG iteration costs the same every time)."""
+    rank, world, local = dist_env()
+    if world > 1 and rank != 0:
+        return
+    from oracle import refbridge as rb
+    rb.load(mpi=False)
+    n = args.n
+    t0 = time.time()
+    pb = rb.Problem(args.problem, (n, n, n))
+    setup_s = pb.setup_amg(relax_type=18)
+    cores = rb.num_threads()
+    its_full = None
+    # full iteration count: known by parity for the default config, else measured once
+    if args.n <= 128:
+        full = pb.pcg(precond="amg", tol=args.tol, max_iter=100, two_norm=1)
+        its_full = full["iterations"]
+    k = args.cpu_iters
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = pb.pcg(precond="amg", tol=args.tol, max_iter=k, two_norm=1)
+        if s >= args.warmup:
+            times.append(r["seconds"])
+    t_k = float(np.mean(times))
+    if its_full is None:
+        its_full = int(os.environ.get("HB200_REF_ITERS", "16"))
+    t_full = t_k * (its_full + 1) / (k + 1)
+    rows = pb.global_rows
+    val = rows / t_full / 1e6
+    line = {
+        "impl": "reference", "metric": "amg_pcg_solve_mdof_per_s", "value": val, "unit": "MDOF/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ij -{args.problem} -n {n} {n} {n} -solver 1 -rlx 18 (BoomerAMG-PCG, "
+                               "HMIS + ext+i, l1-Jacobi V(1,1)), reference CPU build (OpenMP)",
+                   "rows": rows, "setup_s": setup_s, "iterations_assumed": its_full},
+        "cpu_baseline": {"value": val, "unit": "MDOF/s", "cores": cores, "kind": "reference",
+                         "sample": f"{k} PCG iterations of the same solve per step "
+                                   f"({t_k:.3f} s), scaled by ({its_full}+1)/({k}+1) to the full solve"},
+        "e2e": {"value": val, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hb200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    import hypre_b200 as hb
+    from hypre_b200._lib import lib, check
+    hb.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = [hb.comm_get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        hb.comm_init(rank, world, uid[0])
+        if args.halo == "peer":
+            check(lib.hb200_set_halo_mode(1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        hb.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- hierarchy from the reference's own setup (CPU), uploaded once: timed separately
+    rb, pb, gn, gen_s, setup_s = build_problem(args, rank, world)
+    t0 = time.time()
+    mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), use_graph=not args.no_graph)
+    hb.sync()
+    upload_s = time.time() - t0
+    A = mats[0][0]
+    nloc = A.num_rows
+    rows = pb.global_rows
+    nnz0 = A.num_nonzeros
+    b_host = torch.from_numpy(np.array(pb.b)).pin_memory()
+    x_host = torch.zeros(nloc, dtype=torch.float64).pin_memory()
+    b = b_host.cuda()
+    x = torch.zeros(nloc, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.ExternalStream(lib.hb200_compute_stream())
+
+    if args.solver == "pcg":
+        solver = hb.ParCSRPCG(tol=args.tol, max_iter=100, two_norm=1, logging=1)
+    else:
+        solver = hb.ParCSRGMRES(tol=args.tol, max_iter=100, k_dim=5, logging=1)
+    solver.set_precond(amg)
+
+    def step_dev():
+        check(lib.hb200_vec_set(x.data_ptr(), 0.0, nloc))
+        return solver.solve(A, b, x)
+
+    def step_host():
+        x_host.zero_()
+        return solver.solve(A, b_host.numpy(), x_host.numpy())
+
+    for _ in range(args.warmup):
+        res = step_dev()
+    its = res.num_iterations if args.warmup else None
+
+    # ---- timed region: K solves, device-resident inputs
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        res = step_dev()
+        launches += int(res.kernel_launches)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    its = res.num_iterations
+    relres = res.rel_residual_norm
+    value = rows / (ms * 1e-3) / 1e6
+
+    # ---- e2e: same solve through the host-buffer entry point (H2D b, x0; D2H x inside)
+    for _ in range(min(2, args.warmup)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel: fine-level CSR SpMV (stream kernel), timed alone
+    peak, peak_src = peaks()
+    xs = torch.randn(A.num_cols, dtype=torch.float64, device="cuda")
+    ys = torch.empty(nloc, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(3):
+        check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+    hb.sync()
+    reps = 20
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(reps):
+        check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+    s1.record(stream)
+    hb.sync()
+    spmv_ms = s0.elapsed_time(s1) / reps
+    spmv_bytes = 12.0 * nnz0 + 4.0 * nloc + 8.0 * A.num_cols + 8.0 * nloc
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "spmv_stream<EPI_AXPBY> on A_0 (y = A x)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "ms_per_launch": spmv_ms,
+                "bytes_per_launch": spmv_bytes, "bytes_per_nnz": spmv_bytes / max(nnz0, 1),
+                "traffic": None}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own solve, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        k = args.cpu_iters
+        r = pb.pcg(precond="amg", tol=args.tol, max_iter=k, two_norm=1)
+        t_full = r["seconds"] * (its + 1) / (k + 1)
+        cpu = {"value": rows / t_full / 1e6, "unit": "MDOF/s", "cores": rb.num_threads(),
+               "kind": "reference",
+               "sample": f"{k} PCG iterations of the same solve on the host cores ({r['seconds']:.3f} s), "
+                         f"scaled by ({its}+1)/({k}+1) to the full {its}-iteration solve"}
+
+    if rank == 0:
+        n = args.n
+        line = {
+            "metric": "amg_pcg_solve_mdof_per_s", "value": value, "unit": "MDOF/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"ij -{args.problem} -n {gn[0]} {gn[1]} {gn[2]} -P {PGRID[world][0]} "
+                            f"{PGRID[world][1]} {PGRID[world][2]} -solver {1 if args.solver == 'pcg' else 3} "
+                            "-rlx 18 (BoomerAMG-PCG, HMIS + ext+i, l1-Jacobi V(1,1)); hierarchy from the "
+                            "reference's BoomerAMGSetup, uploaded once (not timed)",
+                "rows": rows, "rows_per_gpu": nloc, "nnz_A0_per_gpu": nnz0, "levels": pb.num_levels,
+                "iterations": its, "final_rel_res": relres, "tol": args.tol,
+                "cache": "inputs larger than L2 (A_0 alone is %.1f GB)" % (12.0 * nnz0 / 1e9),
+                "setup_s_reference_cpu": setup_s, "generate_s": gen_s, "upload_s": upload_s,
+                "cuda_graph_vcycle": (not args.no_graph) and world == 1, "halo": args.halo if world > 1 else None,
+                "timing": "CUDA events on the hb200 compute stream, max over ranks",
+            },
+            "e2e": {"value": rows / (e2e_ms * 1e-3) / 1e6, "unit": "MDOF/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 16 * nloc, "d2h_bytes_per_step": 8 * nloc,
+                    "api": "hb200_pcg_solve_host (host b, x; the call behind HYPRE_PCGSolve)"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

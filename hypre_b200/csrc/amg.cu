@@ -1,0 +1,496 @@
+// amg.cu — device-resident BoomerAMG hierarchy and the multigrid cycle.
+//
+// Reference: hypre_BoomerAMGCycle (src/parcsr_ls/par_cycle.c:23-889; level-counter state
+// machine :225-243, 694-865), hypre_BoomerAMGSolve (src/parcsr_ls/par_amg_solve.c:22-424),
+// hypre_ParAMGData (src/parcsr_ls/par_amg.h:18-310).
+//
+// Differences from the reference that do not change results:
+//  * work vectors are per-level arenas (F, U, U_alt, Vtemp) instead of fine-sized temporaries
+//    that are logically resized per level (par_cycle.c:307-311);
+//  * Jacobi-type sweeps are out of place (one fused SpMV pass); U[l] ping-pongs between two
+//    buffers and at level 0 the starting buffer is chosen so that the last sweep lands in the
+//    caller's vector (no copy back);
+//  * hypre_ParVectorSetZeros(U[l+1]) (par_cycle.c:742) only sets the all-zeros flag: the first
+//    sweep on the coarse level is the SpMV-free element-wise form (par_relax.c:1221-1228), so
+//    the memset would be dead traffic;
+//  * restriction uses a stored transpose of P (deterministic row-parallel SpMV).
+#include "hb_internal.cuh"
+#include "relax.cuh"
+#include <math.h>
+
+struct hb200_amg_level {
+   hb200_parcsr *A = nullptr, *P = nullptr;
+   int     n = 0;
+   double *l1 = nullptr;
+   int    *cf = nullptr;
+   double  relax_weight = 1.0, omega = 1.0;
+   double *F = nullptr, *U = nullptr, *Ualt = nullptr, *Vtemp = nullptr;
+   double *cheby_ds = nullptr;
+   std::vector<double> cheby_coefs;
+   int     cheby_order_set = 0;
+   double *cheby_work = nullptr;   // 4*n, allocated on demand
+   // run-time state
+   double *u_cur = nullptr;
+   bool    u_zero = false;
+};
+
+struct hb200_amg {
+   int num_levels = 0;
+   std::vector<hb200_amg_level> lev;
+   int num_grid_sweeps[4] = {1, 1, 1, 1};
+   int grid_relax_type[4] = {18, 18, 18, 9};
+   int relax_order = 0, cycle_type = 1, fcycle = 0;
+   int cheby_order = 2, cheby_scale = 1, cheby_variant = 0;
+   int user_relax_type = -1;
+   double tol = 0.0;
+   int min_iter = 0, max_iter = 1, converge_type = 0;
+   hb::GEData ge;
+   bool has_ge = false;
+   bool use_graph = false;
+   // graph cache: one executable graph per (f, u, zero flag) the cycle has been called with
+   struct GraphEntry {
+      const double *f; double *u; int zero;
+      cudaGraphExec_t exec; long long launches;
+   };
+   std::vector<GraphEntry> graphs;
+   long long cycles_run = 0;
+};
+
+namespace hb {
+
+static int level_alloc(hb200_amg_level &L, bool level0)
+{
+   const size_t n = (size_t) (L.n ? L.n : 1);
+   if (!level0) {
+      if (!L.F) HB_CUDA(cudaMalloc(&L.F, sizeof(double) * n));
+      if (!L.U) { HB_CUDA(cudaMalloc(&L.U, sizeof(double) * n)); HB_CUDA(cudaMemset(L.U, 0, sizeof(double) * n)); }
+   }
+   if (!L.Ualt) { HB_CUDA(cudaMalloc(&L.Ualt, sizeof(double) * n)); HB_CUDA(cudaMemset(L.Ualt, 0, sizeof(double) * n)); }
+   if (!L.Vtemp) HB_CUDA(cudaMalloc(&L.Vtemp, sizeof(double) * n));
+   return 0;
+}
+
+// number of out-of-place (buffer-swapping) sweeps level 0 will see in one cycle
+static int level0_swaps(const hb200_amg *amg, bool zero_guess)
+{
+   auto sweeps_for = [&](int cycle_param, int relax_type, int nsweep, bool zero) {
+      int swaps = 0;
+      if (!relax_is_jacobi(relax_type)) return 0;
+      for (int j = 0; j < nsweep; j++) {
+         const int npts = (amg->relax_order == 1 && cycle_param < 3) ? 2 : 1;
+         for (int q = 0; q < npts; q++) {
+            const int rp = npts == 2 ? 1 : 0;   // only whether it is non-zero matters
+            const bool form7 = (relax_type == 7) || (relax_type == 18 && rp == 0);
+            if (zero && form7) { zero = false; continue; }   // element-wise, writes in place
+            zero = false;
+            swaps++;
+         }
+      }
+      return swaps;
+   };
+   if (amg->num_levels == 1) {
+      int rt = amg->user_relax_type == -1 ? 6 : amg->user_relax_type;
+      return sweeps_for(3 /* relax_points forced 0 */, rt, amg->num_grid_sweeps[0], zero_guess);
+   }
+   int s = sweeps_for(1, amg->grid_relax_type[1], amg->num_grid_sweeps[1], zero_guess);
+   s += sweeps_for(2, amg->grid_relax_type[2], amg->num_grid_sweeps[2], false);
+   return s;
+}
+
+static int do_relax(hb200_amg *amg, int level, int relax_type, int relax_order, int cycle_param,
+                    bool force_no_cf)
+{
+   hb200_amg_level &L = amg->lev[level];
+   Ctx &c = ctx();
+   const double *f = L.F;
+   if (relax_type == 9 || relax_type == 19) {
+      HB_REQUIRE(amg->has_ge, HB200_ERROR_GENERIC, "coarse relax type 9 but no GE data was set");
+      HB_CHECK(ge_solve(amg->ge, f, L.u_cur));
+      L.u_zero = false;
+      return 0;
+   }
+   if (relax_type == 16) {
+      HB_REQUIRE(!L.cheby_coefs.empty(), HB200_ERROR_GENERIC, "Chebyshev relaxation but no coefficients set");
+      if (!L.cheby_work) HB_CUDA(cudaMalloc(&L.cheby_work, sizeof(double) * 4 * (size_t) (L.n ? L.n : 1)));
+      if (L.u_zero) HB_CHECK(vec_set(L.u_cur, 0.0, (size_t) L.n, c.s_comp));
+      const size_t n = (size_t) (L.n ? L.n : 1);
+      HB_CHECK(cheby_solve(L.A, f, L.cheby_ds, L.cheby_coefs.data(), amg->cheby_order,
+                           amg->cheby_scale, L.u_cur, L.cheby_work, L.cheby_work + n,
+                           L.cheby_work + 2 * n, L.cheby_work + 3 * n));
+      L.u_zero = false;
+      return 0;
+   }
+   // hypre_BoomerAMGRelaxIF (par_relax_interface.c:19-65)
+   int pts[2] = {0, 0};
+   int npts = 1;
+   if (!force_no_cf && relax_order == 1 && cycle_param < 3) {
+      npts = 2;
+      pts[0] = cycle_param < 2 ? 1 : -1;
+      pts[1] = -pts[0];
+   }
+   for (int q = 0; q < npts; q++) {
+      if (relax_is_jacobi(relax_type)) {
+         double *other = (L.u_cur == L.Ualt) ? L.U : L.Ualt;
+         bool shortcut = false;
+         const bool form7 = (relax_type == 7) || (relax_type == 18 && pts[q] == 0);
+         if (L.u_zero && form7) {
+            // element-wise zero-guess sweep writes straight into the current buffer
+            HB_CHECK(relax_jacobi_oop(L.A, f, L.cf, relax_type, pts[q], L.relax_weight, L.l1,
+                                      nullptr, L.u_cur, true, &shortcut));
+         } else {
+            HB_CHECK(relax_jacobi_oop(L.A, f, L.cf, relax_type, pts[q], L.relax_weight, L.l1,
+                                      L.u_cur, other, L.u_zero, &shortcut));
+            L.u_cur = other;
+         }
+      } else if (relax_is_gs(relax_type)) {
+         if (L.u_zero) HB_CHECK(vec_set(L.u_cur, 0.0, (size_t) L.n, c.s_comp));
+         HB_CHECK(relax_hybrid_gs(L.A, f, L.cf, relax_type, pts[q], L.relax_weight, L.omega, L.l1,
+                                  L.u_cur, L.Vtemp));
+      } else {
+         return set_error(HB200_ERROR_ARG, "relax type %d is not on the B200 path", relax_type);
+      }
+      L.u_zero = false;   // par_relax.c:170
+   }
+   return 0;
+}
+
+static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zeros)
+{
+   Ctx &c = ctx();
+   const int nl = amg->num_levels;
+   hb200_amg_level &L0 = amg->lev[0];
+   // level-0 aliases (par_amg_solve.c:108-110)
+   L0.F = (double *) f_dev;
+   L0.U = u_dev;
+   const int swaps = level0_swaps(amg, u_all_zeros);
+   if (u_all_zeros && (swaps & 1)) L0.u_cur = L0.Ualt; else L0.u_cur = u_dev;
+   L0.u_zero = u_all_zeros;
+   if (u_all_zeros && L0.u_cur != u_dev) {
+      // nothing to initialise: the first sweep overwrites the buffer (zero flag)
+   }
+   for (int l = 1; l < nl; l++) { amg->lev[l].u_cur = amg->lev[l].U; amg->lev[l].u_zero = false; }
+
+   // ---- the reference's cycling state machine (par_cycle.c:225-243, 300-865) ----
+   std::vector<int> lev_counter(nl);
+   lev_counter[0] = 1;
+   for (int k = 1; k < nl; k++) lev_counter[k] = amg->fcycle ? 1 : amg->cycle_type;
+   int fcycle_lev = nl - 2;
+   int level = 0, cycle_param = 1;
+   bool not_finished = true;
+   while (not_finished) {
+      int num_sweep, relax_type;
+      bool one_level = false;
+      if (nl > 1) {
+         num_sweep = amg->num_grid_sweeps[cycle_param];
+         relax_type = amg->grid_relax_type[cycle_param];
+      } else {
+         num_sweep = amg->num_grid_sweeps[0];
+         relax_type = amg->user_relax_type == -1 ? 6 : amg->user_relax_type;
+         one_level = true;
+      }
+      for (int j = 0; j < num_sweep; j++) {
+         HB_CHECK(do_relax(amg, level, relax_type, amg->relax_order, cycle_param, one_level));
+      }
+      --lev_counter[level];
+      if (lev_counter[level] >= 0 && level != nl - 1) {
+         // go down: residual + restriction (par_cycle.c:742-790)
+         hb200_amg_level &Lf = amg->lev[level];
+         hb200_amg_level &Lc = amg->lev[level + 1];
+         Lc.u_cur = Lc.U;
+         Lc.u_zero = true;                     // hypre_ParVectorSetZeros(U_array[coarse])
+         if (Lf.u_zero) {
+            // r = f - A*0 : no relaxation happened on this level (num_sweeps == 0)
+            HB_CHECK(vec_copy(Lf.F, Lf.Vtemp, (size_t) Lf.n, c.s_comp));
+         } else {
+            HB_CHECK(parcsr_matvec(Lf.A, -1.0, Lf.u_cur, 1.0, Lf.F, Lf.Vtemp));
+         }
+         HB_CHECK(parcsr_matvecT(Lf.P, 1.0, Lf.Vtemp, 0.0, Lc.F));
+         ++level;
+         lev_counter[level] = lev_counter[level] > amg->cycle_type ? lev_counter[level] : amg->cycle_type;
+         cycle_param = (level == nl - 1) ? 3 : 1;
+      } else if (level != 0) {
+         // go up: interpolation u_f += P u_c (par_cycle.c:815-843)
+         hb200_amg_level &Lf = amg->lev[level - 1];
+         hb200_amg_level &Lc = amg->lev[level];
+         if (Lc.u_zero) HB_CHECK(vec_set(Lc.u_cur, 0.0, (size_t) Lc.n, c.s_comp));
+         if (Lf.u_zero) { HB_CHECK(vec_set(Lf.u_cur, 0.0, (size_t) Lf.n, c.s_comp)); }
+         HB_CHECK(parcsr_matvec(Lf.P, 1.0, Lc.u_cur, 1.0, Lf.u_cur, Lf.u_cur));
+         Lf.u_zero = false;
+         --level;
+         cycle_param = 2;
+         if (amg->fcycle && fcycle_lev == level) {
+            lev_counter[level] = lev_counter[level] > 1 ? lev_counter[level] : 1;
+            fcycle_lev--;
+         }
+      } else {
+         not_finished = false;
+      }
+   }
+   if (L0.u_zero) {
+      // no sweep touched u (all sweep counts 0 and one level): materialise the zeros
+      HB_CHECK(vec_set(L0.u_cur, 0.0, (size_t) L0.n, c.s_comp));
+      L0.u_zero = false;
+   }
+   if (L0.u_cur != u_dev) {
+      HB_CHECK(vec_copy(L0.u_cur, u_dev, (size_t) L0.n, c.s_comp));
+      L0.u_cur = u_dev;
+   }
+   return 0;
+}
+
+int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zeros)
+{
+   Ctx &c = ctx();
+   if (!amg->use_graph || c.nranks > 1) {
+      return cycle_body(amg, f_dev, u_dev, u_all_zeros);
+   }
+   // CUDA-graph path: the topology of a cycle is fixed by the hierarchy, so capture once per
+   // (f, u, zero flag) and replay; removes the launch latency of the ~60 small coarse-level
+   // kernels.
+   for (auto &g : amg->graphs) {
+      if (g.f == f_dev && g.u == u_dev && g.zero == (int) u_all_zeros) {
+         HB_CUDA(cudaGraphLaunch(g.exec, c.s_comp));
+         c.launches += g.launches;
+         return 0;
+      }
+   }
+   // the first cycle of a hierarchy runs eagerly: it builds the lazily allocated scratch
+   // (Chebyshev work vectors, GS wavefront schedules), which cannot happen under capture
+   if (amg->cycles_run++ == 0) return cycle_body(amg, f_dev, u_dev, u_all_zeros);
+   for (int l = 0; l + 1 < amg->num_levels; l++) HB_CHECK(parcsr_ensure_T(amg->lev[l].P));
+   if (amg->graphs.size() >= 8) {
+      cudaGraphExecDestroy(amg->graphs.front().exec);
+      amg->graphs.erase(amg->graphs.begin());
+   }
+   const long long before = c.launches;
+   cudaGraph_t graph = nullptr;
+   HB_CUDA(cudaStreamBeginCapture(c.s_comp, cudaStreamCaptureModeThreadLocal));
+   c.capturing = true;
+   int f = cycle_body(amg, f_dev, u_dev, u_all_zeros);
+   c.capturing = false;
+   cudaError_t e = cudaStreamEndCapture(c.s_comp, &graph);
+   if (f) { if (graph) cudaGraphDestroy(graph); return f; }
+   if (e != cudaSuccess) return set_error(HB200_ERROR_GENERIC, "graph capture failed: %s", cudaGetErrorString(e));
+   hb200_amg::GraphEntry ge;
+   ge.f = f_dev; ge.u = u_dev; ge.zero = (int) u_all_zeros;
+   ge.launches = c.launches - before;
+   c.launches = before;
+   e = cudaGraphInstantiate(&ge.exec, graph, 0);
+   cudaGraphDestroy(graph);
+   if (e != cudaSuccess) return set_error(HB200_ERROR_GENERIC, "graph instantiate failed: %s", cudaGetErrorString(e));
+   amg->graphs.push_back(ge);
+   HB_CUDA(cudaGraphLaunch(ge.exec, c.s_comp));
+   c.launches += ge.launches;
+   return 0;
+}
+
+int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
+              int *num_iterations, double *rel_resid_norm)
+{
+   // hypre_BoomerAMGSolve (par_amg_solve.c:22-424) without the printing
+   Ctx &c = ctx();
+   (void) A;
+   hb200_amg_level &L0 = amg->lev[0];
+   const size_t n = (size_t) L0.n;
+   const double tol = amg->tol;
+   double resid_nrm = 1.0, resid_nrm_init = 0.0, rhs_norm = 0.0, relative_resid = 1.0;
+   const int S = kScalarSlots - 4;
+   int flag = 0;
+   if (tol > 0.0) {
+      // Vtemp = f ; Vtemp = A u - f ; ||Vtemp||   (:170-182)
+      if (u_all_zeros) { HB_CHECK(vec_set(u, 0.0, n, c.s_comp)); u_all_zeros = false; }
+      HB_CHECK(parcsr_matvec(L0.A, 1.0, u, -1.0, f, L0.Vtemp));
+      HB_CHECK(vec_dot2_dev(L0.Vtemp, L0.Vtemp, f, f, n, S, S + 1, c.s_comp));
+      HB_CHECK(scalars_allreduce(S, 2, c.s_comp));
+      double v[2];
+      HB_CHECK(scalars_fetch(S, 2, v, c.s_comp));
+      resid_nrm = sqrt(v[0]);
+      if (resid_nrm != 0.0 && !(resid_nrm / resid_nrm == resid_nrm / resid_nrm)) {
+         return set_error(HB200_ERROR_GENERIC, "hb200_amg_solve: INFs and/or NaNs detected in input");
+      }
+      resid_nrm_init = resid_nrm;
+      if (amg->converge_type == 0) {
+         rhs_norm = sqrt(v[1]);
+         relative_resid = rhs_norm != 0.0 ? resid_nrm_init / rhs_norm : resid_nrm_init;
+      } else {
+         relative_resid = 1.0;
+      }
+   }
+   int cycle_count = 0;
+   while ((relative_resid >= tol || cycle_count < amg->min_iter) && cycle_count < amg->max_iter) {
+      HB_CHECK(amg_cycle(amg, f, u, u_all_zeros));
+      u_all_zeros = false;
+      if (tol > 0.0) {
+         HB_CHECK(parcsr_matvec(L0.A, 1.0, u, -1.0, f, L0.Vtemp));
+         HB_CHECK(vec_dot_dev(L0.Vtemp, L0.Vtemp, n, S, c.s_comp));
+         HB_CHECK(scalars_allreduce(S, 1, c.s_comp));
+         double v;
+         HB_CHECK(scalars_fetch(S, 1, &v, c.s_comp));
+         resid_nrm = sqrt(v);
+         if (amg->converge_type == 0) relative_resid = rhs_norm != 0.0 ? resid_nrm / rhs_norm : resid_nrm;
+         else                          relative_resid = resid_nrm / resid_nrm_init;
+      }
+      ++cycle_count;
+   }
+   if (cycle_count == amg->max_iter && tol > 0.0) flag |= HB200_ERROR_CONV;
+   if (num_iterations) *num_iterations = cycle_count;
+   if (rel_resid_norm) *rel_resid_norm = relative_resid;
+   return flag;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb200_amg_create(hb200_amg **out, int num_levels)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(out && num_levels >= 1, HB200_ERROR_ARG, "bad arguments");
+   hb200_amg *a = new hb200_amg();
+   a->num_levels = num_levels;
+   a->lev.resize(num_levels);
+   *out = a;
+   return 0;
+}
+
+int hb200_amg_destroy(hb200_amg *amg)
+{
+   if (!amg) return 0;
+   cudaDeviceSynchronize();
+   for (int l = 0; l < amg->num_levels; l++) {
+      hb200_amg_level &L = amg->lev[l];
+      if (L.l1) cudaFree(L.l1);
+      if (L.cf) cudaFree(L.cf);
+      if (l > 0) { if (L.F) cudaFree(L.F); if (L.U) cudaFree(L.U); }
+      if (L.Ualt) cudaFree(L.Ualt);
+      if (L.Vtemp) cudaFree(L.Vtemp);
+      if (L.cheby_ds) cudaFree(L.cheby_ds);
+      if (L.cheby_work) cudaFree(L.cheby_work);
+   }
+   if (amg->ge.d_LfT) cudaFree(amg->ge.d_LfT);
+   if (amg->ge.d_UT) cudaFree(amg->ge.d_UT);
+   if (amg->ge.d_Udiag) cudaFree(amg->ge.d_Udiag);
+   if (amg->ge.d_b) cudaFree(amg->ge.d_b);
+   for (auto &g : amg->graphs) cudaGraphExecDestroy(g.exec);
+   delete amg;
+   return 0;
+}
+
+int hb200_amg_set_level(hb200_amg *amg, int level, hb200_parcsr *A, hb200_parcsr *P,
+                        const double *l1_norms, const int *cf_marker, double relax_weight,
+                        double omega)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && A && level >= 0 && level < amg->num_levels, HB200_ERROR_ARG, "bad arguments");
+   HB_REQUIRE(P != nullptr || level == amg->num_levels - 1, HB200_ERROR_ARG, "P missing on a non-coarsest level");
+   hb200_amg_level &L = amg->lev[level];
+   L.A = A; L.P = P; L.n = A->num_rows;
+   L.relax_weight = relax_weight; L.omega = omega;
+   const size_t n = (size_t) (L.n ? L.n : 1);
+   if (l1_norms) {
+      if (!L.l1) HB_CUDA(cudaMalloc(&L.l1, sizeof(double) * n));
+      HB_CUDA(cudaMemcpy(L.l1, l1_norms, sizeof(double) * (size_t) L.n, cudaMemcpyHostToDevice));
+   }
+   if (cf_marker) {
+      if (!L.cf) HB_CUDA(cudaMalloc(&L.cf, sizeof(int) * n));
+      HB_CUDA(cudaMemcpy(L.cf, cf_marker, sizeof(int) * (size_t) L.n, cudaMemcpyHostToDevice));
+   }
+   HB_CHECK(level_alloc(L, level == 0));
+   if (P) HB_CHECK(parcsr_ensure_T(P));
+   return 0;
+}
+
+int hb200_amg_set_level_cheby(hb200_amg *amg, int level, const double *ds, const double *coefs, int order)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && coefs && level >= 0 && level < amg->num_levels, HB200_ERROR_ARG, "bad arguments");
+   hb200_amg_level &L = amg->lev[level];
+   HB_REQUIRE(L.A != nullptr, HB200_ERROR_ARG, "set_level must precede set_level_cheby");
+   L.cheby_coefs.assign(coefs, coefs + order + 1);
+   L.cheby_order_set = order;
+   if (ds) {
+      if (!L.cheby_ds) HB_CUDA(cudaMalloc(&L.cheby_ds, sizeof(double) * (size_t) (L.n ? L.n : 1)));
+      HB_CUDA(cudaMemcpy(L.cheby_ds, ds, sizeof(double) * (size_t) L.n, cudaMemcpyHostToDevice));
+   }
+   return 0;
+}
+
+int hb200_amg_set_cycle(hb200_amg *amg, const int *num_grid_sweeps4, const int *grid_relax_type4,
+                        int relax_order, int cycle_type, int fcycle, int cheby_order,
+                        int cheby_scale, int cheby_variant, int user_relax_type)
+{
+   HB_REQUIRE(amg && num_grid_sweeps4 && grid_relax_type4, HB200_ERROR_ARG, "bad arguments");
+   for (int k = 0; k < 4; k++) {
+      amg->num_grid_sweeps[k] = num_grid_sweeps4[k];
+      amg->grid_relax_type[k] = grid_relax_type4[k];
+   }
+   amg->relax_order = relax_order; amg->cycle_type = cycle_type; amg->fcycle = fcycle;
+   amg->cheby_order = cheby_order; amg->cheby_scale = cheby_scale; amg->cheby_variant = cheby_variant;
+   amg->user_relax_type = user_relax_type;
+   return 0;
+}
+
+int hb200_amg_set_solve(hb200_amg *amg, double tol, int min_iter, int max_iter, int converge_type)
+{
+   HB_REQUIRE(amg != nullptr, HB200_ERROR_ARG, "null amg");
+   amg->tol = tol; amg->min_iter = min_iter; amg->max_iter = max_iter; amg->converge_type = converge_type;
+   return 0;
+}
+
+int hb200_amg_set_coarse_ge(hb200_amg *amg, const double *A_mat, int n, int first_row, int num_local)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && A_mat && n >= 1 && first_row >= 0 && num_local >= 0 && first_row + num_local <= n,
+              HB200_ERROR_ARG, "bad arguments");
+   std::vector<double> LfT, UT, Ud;
+   HB_CHECK(ge_factor_host(A_mat, n, LfT, UT, Ud));
+   GEData &g = amg->ge;
+   g.n = n; g.first_row = first_row; g.num_local = num_local;
+   const size_t nn = (size_t) n * n;
+   HB_CUDA(cudaMalloc(&g.d_LfT, sizeof(double) * nn));
+   HB_CUDA(cudaMalloc(&g.d_UT, sizeof(double) * nn));
+   HB_CUDA(cudaMalloc(&g.d_Udiag, sizeof(double) * n));
+   HB_CUDA(cudaMalloc(&g.d_b, sizeof(double) * n));
+   HB_CUDA(cudaMemcpy(g.d_LfT, LfT.data(), sizeof(double) * nn, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMemcpy(g.d_UT, UT.data(), sizeof(double) * nn, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMemcpy(g.d_Udiag, Ud.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+   amg->has_ge = true;
+   return 0;
+}
+
+int hb200_amg_set_use_graph(hb200_amg *amg, int enable)
+{
+   HB_REQUIRE(amg != nullptr, HB200_ERROR_ARG, "null amg");
+   amg->use_graph = enable != 0;
+   return 0;
+}
+
+int hb200_amg_cycle(hb200_amg *amg, const double *f, double *u, int u_all_zeros)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && f && u, HB200_ERROR_ARG, "null argument");
+   for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
+   return amg_cycle(amg, f, u, u_all_zeros != 0);
+}
+
+int hb200_amg_solve(hb200_amg *amg, const double *f, double *u, int u_all_zeros, int *num_iterations,
+                    double *rel_resid_norm)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && f && u, HB200_ERROR_ARG, "null argument");
+   for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
+   return amg_solve(amg, amg->lev[0].A, f, u, u_all_zeros != 0, num_iterations, rel_resid_norm);
+}
+
+int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n)
+{
+   HB_REQUIRE(amg && dev && level >= 0 && level < amg->num_levels, HB200_ERROR_ARG, "bad arguments");
+   hb200_amg_level &L = amg->lev[level];
+   *dev = which == 0 ? L.F : L.u_cur;
+   if (n) *n = L.n;
+   return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// hb_internal.cuh — shared declarations of libhb200 (not part of the C-ABI).
+//
+// One process = one GPU = one Ctx: a compute stream, a comm stream, an optional NCCL
+// communicator, and small pinned/device scratch used by the deterministic reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/hb200.h"
+
+#ifdef HB200_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+int set_error(int flag, const char *fmt, ...);
+
+#define HB_CUDA(call)                                                                    \
+   do {                                                                                  \
+      cudaError_t e_ = (call);                                                           \
+      if (e_ != cudaSuccess)                                                             \
+         return hb::set_error(HB200_ERROR_GENERIC, "CUDA error %s at %s:%d: %s", #call,  \
+                              __FILE__, __LINE__, cudaGetErrorString(e_));               \
+   } while (0)
+
+#define HB_CHECK(expr)                                                                   \
+   do {                                                                                  \
+      int f_ = (expr);                                                                   \
+      if (f_) return f_;                                                                 \
+   } while (0)
+
+#define HB_REQUIRE(cond, flag, msg)                                                      \
+   do {                                                                                  \
+      if (!(cond)) return hb::set_error((flag), "%s (%s:%d)", (msg), __FILE__, __LINE__);\
+   } while (0)
+
+#ifdef HB200_WITH_NCCL
+#define HB_NCCL(call)                                                                    \
+   do {                                                                                  \
+      ncclResult_t r_ = (call);                                                          \
+      if (r_ != ncclSuccess)                                                             \
+         return hb::set_error(HB200_ERROR_GENERIC, "NCCL error %s at %s:%d: %s", #call,  \
+                              __FILE__, __LINE__, ncclGetErrorString(r_));               \
+   } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+constexpr int kNumSMs        = 148;     // B200
+constexpr int kRedBlocksMax  = 1184;    // 148 * 8 partials for two-stage reductions
+constexpr int kScalarSlots   = 128;     // device scalar slots (dot results, alpha, beta ...)
+
+struct Ctx {
+   bool          ready = false;
+   int           device = 0;
+   cudaStream_t  s_comp = nullptr;   // all kernels
+   cudaStream_t  s_comm = nullptr;   // halo pack / NCCL / peer puts
+   cudaEvent_t   ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+   int           rank = 0, nranks = 1;
+#ifdef HB200_WITH_NCCL
+   ncclComm_t    nccl = nullptr;
+#endif
+   int           halo_mode = 0;
+   // reduction scratch
+   double       *d_partials = nullptr;   // kRedBlocksMax * 4 doubles
+   unsigned int *d_counter  = nullptr;   // last-block-done tickets (one per slot)
+   double       *d_scalars  = nullptr;   // kScalarSlots doubles
+   double       *h_scalars  = nullptr;   // pinned mirror
+   long long     launches = 0;
+   bool          capturing = false;      // inside CUDA graph capture
+   // persistent workspace (Krylov work vectors): stable addresses across solves keep the
+   // captured V-cycle graphs valid and take cudaMalloc out of the solve
+   void         *ws_ptr[16] = {nullptr};
+   size_t        ws_bytes[16] = {0};
+};
+int ws_get(int slot, size_t bytes, double **out);
+Ctx &ctx();
+int  require_ready();
+
+#define HB_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
+   do {                                                                                  \
+      kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+      hb::ctx().launches++;                                                              \
+   } while (0)
+
+#define HB_LAUNCH_CHECK()                                                                \
+   do {                                                                                  \
+      cudaError_t e_ = cudaPeekAtLastError();                                            \
+      if (e_ != cudaSuccess)                                                             \
+         return hb::set_error(HB200_ERROR_GENERIC, "kernel launch failed at %s:%d: %s",  \
+                              __FILE__, __LINE__, cudaGetErrorString(e_));               \
+   } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device CSR block
+// ---------------------------------------------------------------------------------------
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2 };
+
+struct DCsr {
+   int        nrows = 0, ncols = 0;
+   long long  nnz = 0;
+   int       *i = nullptr;        // nrows+1
+   int       *j = nullptr;        // nnz
+   double    *a = nullptr;        // nnz
+   // list of rows with at least one entry (hypre_CSRMatrixRownnz, csr_matrix.c:381-397);
+   // built for every block, used when it is sparse in rows (offd blocks)
+   int       *rownnz = nullptr;
+   int        num_rownnz = 0;
+   // nnz-balanced partition for the stream kernel: blk_row[b] .. blk_row[b+1]
+   int       *blk_row = nullptr;
+   int        nblks = 0;
+   int        kind = SPMV_STREAM;
+   int        lanes = 1;          // lanes per row (vector kernel: K; stream kernel: phase-2 L)
+   int        max_row_nnz = 0;
+   double     avg_row_nnz = 0.0;
+};
+
+int  dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha);
+int  dcsr_free(DCsr &M);
+void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
+int  dcsr_build_partition(DCsr &M, const int *hi);
+// host-side transpose (stable: entries of each output row in ascending source-row order,
+// the order hypre_CSRMatrixMatvecTHost accumulates in, csr_matvec.c:1095-1110)
+void host_csr_transpose(int nrows, int ncols, const int *ai, const int *aj, const double *aa,
+                        std::vector<int> &ti, std::vector<int> &tj, std::vector<double> &ta);
+
+// ---------------------------------------------------------------------------------------
+// SpMV epilogues.  One struct, a compile-time kind: keeps the template count small.
+// ---------------------------------------------------------------------------------------
+enum EpiKind {
+   EPI_AXPBY = 0,     // y = beta*b + alpha*sum            (beta == 0: b not read)
+   EPI_ACC,           // y += alpha*sum                    (offd pass of EPI_AXPBY)
+   EPI_JACOBI7,       // y = u + (w*f - w*sum)/d  [marked]  (par_relax.c:1216-1244)
+   EPI_JACOBI7_ACC,   // y -= (w*sum)/d           [marked]  (offd pass)
+   EPI_JACOBI_CORE,   // y = (1-w*skip)*u + w*(f - sum)/d, only if d != 0 [marked] (par_relax.c:258-295)
+   EPI_JACOBI_CORE_ACC,
+   EPI_CHEBY_SCALED_R,// r = ds*(f - sum); y(orig_u)=u; u = r*c   (par_cheby_solve.c:284-305)
+   EPI_CHEBY_STEP,    // u = mult*r + ds*sum                       (par_cheby_solve.c:324-331)
+   EPI_CHEBY_LAST     // u = orig_u + ds*(mult*r + ds*sum)         (last step fused with :338-341)
+};
+
+struct EpiArgs {
+   double        alpha = 1.0, beta = 0.0, w = 1.0;
+   const double *b = nullptr;      // AXPBY: b;  JACOBI: f
+   const double *u = nullptr;      // JACOBI: old u
+   const double *d = nullptr;      // JACOBI: l1 norms or NULL (use diagonal)
+   const int    *cf = nullptr;     // CF marker or NULL
+   int           relax_points = 0;
+   int           skip_diag = 0;
+   double       *y = nullptr;      // output
+   double       *y2 = nullptr;     // second output (Chebyshev)
+   const double *r = nullptr;      // Chebyshev r
+   // optional fused dot: partial[block] = sum_rows y[row]*dotw[row] (deterministic 2-stage)
+   const double *dotw = nullptr;
+   int           dot_slot = -1;
+};
+
+// y-type epilogue launchers (kernels_spmv.cu).  rows_list: optional compressed row list.
+int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
+                bool use_rownnz, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// BLAS-1 (kernels_blas1.cu).  Scalars live in ctx().d_scalars[slot]; dots are two-stage,
+// last-block-reduces, fixed order => bitwise reproducible run to run.
+// ---------------------------------------------------------------------------------------
+int vec_set(double *y, double v, size_t n, cudaStream_t st);
+int vec_copy(const double *x, double *y, size_t n, cudaStream_t st);
+int vec_scale(double a, double *y, size_t n, cudaStream_t st);
+int vec_axpy(double a, const double *x, double *y, size_t n, cudaStream_t st);
+int vec_axpby_out(double a, const double *x, double b, const double *y, double *z, size_t n, cudaStream_t st);
+int vec_divpy(const double *x, const double *b, double *y, const int *marker, int mval, size_t n, cudaStream_t st);
+int vec_scale_div(double w, const double *f, const double *d, double *u, const int *marker, int mval,
+                  const double *u_old, size_t n, cudaStream_t st);   // u = (w*f)/d (zero-guess Jacobi)
+int vec_diag_scale(const double *diag, const double *x, double *y, size_t n, cudaStream_t st);
+// dot into device slot (local part only)
+int vec_dot_dev(const double *x, const double *y, size_t n, int slot, cudaStream_t st);
+// two dots at once: slot0 = <x,y>, slot1 = <z,z2>
+int vec_dot2_dev(const double *x, const double *y, const double *z, const double *z2, size_t n,
+                 int slot0, int slot1, cudaStream_t st);
+// finalize a fused dot whose per-block partials were written by another kernel
+int dot_finalize(int nblocks, int slot, cudaStream_t st);
+// allreduce (sum) of `count` consecutive device scalar slots over all ranks (NCCL); no-op for 1 rank
+int scalars_allreduce(int slot, int count, cudaStream_t st);
+// copy `count` slots to pinned host and wait
+int scalars_fetch(int slot, int count, double *out, cudaStream_t st);
+
+// PCG fused updates (krylov.cu uses them)
+//   x += alpha*p; r -= alpha*s; slot_rr = <r,r>   with alpha = S[slot_gamma]/S[slot_sdotp]
+int pcg_update_xr(const double *p, const double *s, double *x, double *r, size_t n,
+                  int slot_gamma, int slot_sdotp, int slot_rr, int slot_flag, int skip_break,
+                  cudaStream_t st);
+//   p = s + beta*p with beta = S[slot_num]/S[slot_den]
+int pcg_update_p(const double *s, double *p, size_t n, int slot_num, int slot_den, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// ParCSR
+// ---------------------------------------------------------------------------------------
+struct CommPkgD {
+   int num_sends = 0, num_recvs = 0;
+   std::vector<int> send_procs, send_map_starts, send_map_elmts, recv_procs, recv_vec_starts;
+   int    *d_send_map_elmts = nullptr;
+   double *d_send_buf = nullptr;      // send_map_starts[num_sends]
+   double *d_recv_buf = nullptr;      // = x_ext, num_cols_offd
+   // MatvecT unpack: CSR-of-E grouping send entries by target row (deterministic)
+   int    *d_unpack_rows = nullptr, *d_unpack_ptr = nullptr, *d_unpack_idx = nullptr;
+   int     n_unpack_rows = 0;
+   // peer-put halo (mode 1)
+   std::vector<double *> peer_recv_ptr;   // per send i: remote address to write segment into
+   std::vector<void *>   peer_mapped;     // IPC-opened bases
+   unsigned long long   *d_flags = nullptr;          // local arrival flags, one per recv
+   std::vector<unsigned long long *> peer_flag_ptr;  // per send i: remote flag address
+   unsigned long long    epoch = 0;
+   double **d_peer_dst = nullptr;                    // device copies for the put kernel
+   unsigned long long **d_peer_flag = nullptr;
+   int    *d_send_seg = nullptr;                     // segment id of each send entry
+   bool    peer_ready = false;
+};
+
+}  // namespace hb
+
+struct hb200_parcsr {
+   int      num_rows = 0, num_cols = 0, num_cols_offd = 0;
+   int64_t  first_row = 0, first_col = 0, global_rows = 0, global_cols = 0;
+   hb::DCsr diag, offd;
+   bool     has_T = false;
+   hb::DCsr diagT, offdT;            // built lazily for MatvecT (restriction)
+   std::vector<int64_t> col_map_offd;
+   int64_t *d_col_map_offd = nullptr;
+   hb::CommPkgD pkg;
+   double  *d_ytmp = nullptr;        // MatvecT: offd^T x (num_cols_offd)
+   double  *d_diaginv = nullptr;     // lazily built for DIAGSCALE precond
+   // kept host copies of the CSR (needed to build transposes / level schedules lazily)
+   std::vector<int> h_diag_i, h_diag_j, h_offd_i, h_offd_j;
+   std::vector<double> h_diag_a, h_offd_a;
+   bool     keep_host = true;
+   // level schedule of the diag block for hybrid Gauss-Seidel (relax.cu), built lazily
+   void    *gs_sched = nullptr;
+};
+
+namespace hb {
+int parcsr_ensure_T(hb200_parcsr *A);
+int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp);   // pack + exchange on s_comm
+int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp);                     // make s_comp wait
+int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,
+                  double *y, const double *dotw = nullptr, int dot_slot = -1);
+int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y);
+int gs_sched_free(void *p);
+}  // namespace hb

@@ -1,0 +1,420 @@
+// kernels_spmv.cu — CSR SpMV kernels for sm_100a with fused epilogues.
+//
+// Replaces the hot loop of hypre_CSRMatrixMatvecOutOfPlaceHost (src/seq_mv/csr_matvec.c:683-
+// 845) and its device twins (cuSPARSE CSR_ALG2 / hypreGPUKernel_CSRMatvecShuffle,
+// src/seq_mv/csr_spmv_device.c:149-262).  Two kernels, chosen per matrix (per AMG level):
+//
+//  * spmv_stream  — nnz-balanced ("merge-style"): a CTA owns a contiguous run of rows
+//    holding <= CAP nonzeros (partition built once at upload).  Phase 1 streams col_ind /
+//    values with 128-bit loads (int4 + 2x double2 per thread, perfectly coalesced, aligned
+//    down to a 4-entry boundary), gathers x through the read-only L1 path and parks the
+//    products in shared memory.  Phase 2 sums each row from shared memory with L lanes per
+//    row (L = 1: one thread adds the products in CSR order with separate mul/add — exactly
+//    the operation order of the reference's sequential loop, so the result is bit-identical
+//    to the 1-thread CPU reference) and applies the epilogue.
+//  * spmv_vector  — K lanes per row, warp-shuffle reduction; used for offd blocks through the
+//    compressed non-empty-row list (hypre_CSRMatrixRownnz) and as a cross-check kernel.
+//
+// HBM traffic model: 12 B/nnz (4 B index + 8 B value) + 4 B/row row pointer +
+// the epilogue's vectors; x is gathered through L1/L2 (a 27-point row block touches 9 short
+// x segments, reuse factor ~27).
+#include "hb_internal.cuh"
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum, double diag)
+{
+   if (EPI == EPI_AXPBY) {
+      // reference: y = (beta/alpha)*b; y += sum; y *= alpha  ==  beta*b + alpha*sum
+      // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
+      double v;
+      if (ea.beta == 0.0) { v = ea.alpha * sum; }
+      else                { v = ea.beta * ea.b[row] + ea.alpha * sum; }
+      ea.y[row] = v;
+   }
+   else if (EPI == EPI_ACC) {
+      ea.y[row] += ea.alpha * sum;
+   }
+   else if (EPI == EPI_JACOBI7) {
+      // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
+      const double uo = ea.u[row];
+      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
+         const double vt = (ea.w == 1.0) ? (ea.b[row] - sum) : (ea.w * ea.b[row] - ea.w * sum);
+         ea.y[row] = uo + vt / ea.d[row];
+      } else {
+         ea.y[row] = uo;
+      }
+   }
+   else if (EPI == EPI_JACOBI7_ACC) {
+      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
+         ea.y[row] -= (ea.w * sum) / ea.d[row];
+      }
+   }
+   else if (EPI == EPI_JACOBI_CORE) {
+      // hypre_BoomerAMGRelaxWeightedJacobi_core (par_relax.c:258-295)
+      const double uo = ea.u[row];
+      const double di = ea.d ? ea.d[row] : diag;
+      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
+         const double res = ea.b[row] - sum;
+         if (ea.skip_diag) { ea.y[row] = uo * (1.0 - ea.w) + ea.w * res / di; }
+         else              { ea.y[row] = uo + ea.w * res / di; }
+      } else {
+         ea.y[row] = uo;
+      }
+   }
+   else if (EPI == EPI_JACOBI_CORE_ACC) {
+      const double di = ea.d ? ea.d[row] : diag;
+      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
+         ea.y[row] -= ea.w * sum / di;
+      }
+   }
+}
+
+template <int EPI>
+__device__ __forceinline__ constexpr bool epi_needs_diag()
+{
+   return EPI == EPI_JACOBI_CORE || EPI == EPI_JACOBI_CORE_ACC;
+}
+
+// ---------------------------------------------------------------------------------------
+// stream kernel
+// ---------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+
+template <int EPI, int L, int CAP>
+__global__ void __launch_bounds__(kStreamThreads)
+spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind,
+            const double *__restrict__ val, const double *__restrict__ x,
+            const int *__restrict__ blk_row, EpiArgs ea)
+{
+   __shared__ double prod[CAP + 4];
+   const int tid = threadIdx.x;
+   const int r0  = blk_row[blockIdx.x];
+   const int r1  = blk_row[blockIdx.x + 1];
+   const int p0  = rowptr[r0];
+   const int p1  = rowptr[r1];
+   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+
+   if (p1 - p0 + 3 > CAP) {
+      // a single row longer than the shared-memory window: whole CTA on one row
+      double s = 0.0;
+      for (int p = p0 + skip + tid; p < p1; p += kStreamThreads) {
+         s += val[p] * __ldg(x + colind[p]);
+      }
+      __shared__ double red[kStreamThreads / 32];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if ((tid & 31) == 0) red[tid >> 5] = s;
+      __syncthreads();
+      if (tid == 0) {
+         double t = 0.0;
+#pragma unroll
+         for (int w = 0; w < kStreamThreads / 32; w++) t += red[w];
+         epi_apply<EPI>(ea, r0, t, epi_needs_diag<EPI>() ? val[p0] : 0.0);
+      }
+      return;
+   }
+
+   // ---- phase 1: coalesced 128-bit streaming of (col, val), gather x, products -> smem
+   const int base = p0 & ~3;
+   for (int q = base + 4 * tid; q < p1; q += 4 * kStreamThreads) {
+      const int4    c  = *reinterpret_cast<const int4 *>(colind + q);
+      const double2 v0 = *reinterpret_cast<const double2 *>(val + q);
+      const double2 v1 = *reinterpret_cast<const double2 *>(val + q + 2);
+      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y);
+      const double x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      double *dst = prod + (q - base);
+      // separate multiply (rounded) then ordered adds in phase 2 == the reference's
+      // tempx += A_data[jj] * x_data[A_j[jj]] without FMA contraction
+      dst[0] = __dmul_rn(v0.x, x0);
+      dst[1] = __dmul_rn(v0.y, x1);
+      dst[2] = __dmul_rn(v1.x, x2);
+      dst[3] = __dmul_rn(v1.y, x3);
+   }
+   __syncthreads();
+
+   // ---- phase 2: L lanes per row
+   const int nrows = r1 - r0;
+   if (L == 1) {
+      for (int r = tid; r < nrows; r += kStreamThreads) {
+         const int row = r0 + r;
+         const int a = rowptr[row] - base, b = rowptr[row + 1] - base;
+         double s = 0.0;
+         for (int k = a + skip; k < b; k++) s = __dadd_rn(s, prod[k]);
+         epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
+      }
+   } else {
+      const int lane = tid % L;
+      const int grp  = tid / L;
+      constexpr int NG = kStreamThreads / L;
+      // all lanes of a warp run the same trip count so that the shuffles stay converged
+      const int trips = (nrows + NG - 1) / NG;
+      for (int t = 0; t < trips; t++) {
+         const int r = grp + t * NG;
+         double s = 0.0;
+         int row = r0 + r;
+         int a = 0;
+         if (r < nrows) {
+            a = rowptr[row] - base;
+            const int b = rowptr[row + 1] - base;
+            for (int k = a + skip + lane; k < b; k += L) s += prod[k];
+         }
+#pragma unroll
+         for (int o = L / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, L);
+         if (r < nrows && lane == 0) {
+            epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
+         }
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------------------
+// vector kernel: K lanes per row, optional compressed row list
+// ---------------------------------------------------------------------------------------
+constexpr int kVecThreads = 256;
+
+template <int EPI, int K>
+__global__ void __launch_bounds__(kVecThreads)
+spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ rowptr,
+            const int *__restrict__ colind, const double *__restrict__ val,
+            const double *__restrict__ x, EpiArgs ea)
+{
+   const int gtid = blockIdx.x * kVecThreads + threadIdx.x;
+   const int idx  = gtid / K;
+   const int lane = threadIdx.x % K;
+   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+   double s = 0.0;
+   int row = 0, p0 = 0;
+   const bool active = idx < nlist;
+   if (active) {
+      row = rowlist ? rowlist[idx] : idx;
+      p0 = rowptr[row];
+      const int p1 = rowptr[row + 1];
+      for (int p = p0 + skip + lane; p < p1; p += K) {
+         s += val[p] * __ldg(x + colind[p]);
+      }
+   }
+#pragma unroll
+   for (int o = K / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, K);
+   if (active && lane == 0) {
+      epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[p0] : 0.0);
+   }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+constexpr int kStreamCap = 2048;
+
+template <int EPI, int L>
+static int launch_stream_L(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   HB_LAUNCH((spmv_stream<EPI, L, kStreamCap>), M.nblks, kStreamThreads, 0, st, M.i, M.j, M.a, x,
+             M.blk_row, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+template <int EPI>
+static int launch_stream(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   switch (M.lanes) {
+      case 1:  return launch_stream_L<EPI, 1>(M, x, ea, st);
+      case 2:  return launch_stream_L<EPI, 2>(M, x, ea, st);
+      case 4:  return launch_stream_L<EPI, 4>(M, x, ea, st);
+      case 8:  return launch_stream_L<EPI, 8>(M, x, ea, st);
+      case 16: return launch_stream_L<EPI, 16>(M, x, ea, st);
+      default: return launch_stream_L<EPI, 32>(M, x, ea, st);
+   }
+}
+
+template <int EPI, int K>
+static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
+                           cudaStream_t st)
+{
+   const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
+   const long long threads = (long long) nlist * K;
+   const int grid = (int) ((threads + kVecThreads - 1) / kVecThreads);
+   HB_LAUNCH((spmv_vector<EPI, K>), grid, kVecThreads, 0, st, nlist,
+             use_rownnz ? M.rownnz : (const int *) nullptr, M.i, M.j, M.a, x, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+template <int EPI>
+static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
+                         int lanes, cudaStream_t st)
+{
+   switch (lanes) {
+      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, use_rownnz, st);
+      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, use_rownnz, st);
+      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, use_rownnz, st);
+      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, use_rownnz, st);
+      case 16: return launch_vector_K<EPI, 16>(M, x, ea, use_rownnz, st);
+      default: return launch_vector_K<EPI, 32>(M, x, ea, use_rownnz, st);
+   }
+}
+
+static int vector_lanes_for(double avg)
+{
+   // same breakpoints as the reference's own kernel (csr_spmv_device.c:302-308), extended down
+   if (avg >= 64) return 32;
+   if (avg >= 32) return 16;
+   if (avg >= 16) return 8;
+   if (avg >= 6)  return 4;
+   if (avg >= 3)  return 2;
+   return 1;
+}
+
+template <int EPI>
+static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
+                         cudaStream_t st)
+{
+   const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
+   if (nlist == 0) return 0;
+   if (!use_rownnz && M.kind == SPMV_STREAM && M.nblks > 0) {
+      return launch_stream<EPI>(M, x, ea, st);
+   }
+   int lanes = (M.kind == SPMV_VECTOR && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
+   if (lanes == 0) {
+      const double avg = use_rownnz ? (double) M.nnz / (double) (M.num_rownnz ? M.num_rownnz : 1)
+                                    : M.avg_row_nnz;
+      lanes = vector_lanes_for(avg);
+   }
+   return launch_vector<EPI>(M, x, ea, use_rownnz, lanes, st);
+}
+
+int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, bool use_rownnz,
+                cudaStream_t st)
+{
+   switch (epi_kind) {
+      case EPI_AXPBY:           return spmv_dispatch<EPI_AXPBY>(M, x, ea, use_rownnz, st);
+      case EPI_ACC:             return spmv_dispatch<EPI_ACC>(M, x, ea, use_rownnz, st);
+      case EPI_JACOBI7:         return spmv_dispatch<EPI_JACOBI7>(M, x, ea, use_rownnz, st);
+      case EPI_JACOBI7_ACC:     return spmv_dispatch<EPI_JACOBI7_ACC>(M, x, ea, use_rownnz, st);
+      case EPI_JACOBI_CORE:     return spmv_dispatch<EPI_JACOBI_CORE>(M, x, ea, use_rownnz, st);
+      case EPI_JACOBI_CORE_ACC: return spmv_dispatch<EPI_JACOBI_CORE_ACC>(M, x, ea, use_rownnz, st);
+      default: return set_error(HB200_ERROR_ARG, "spmv_launch: unknown epilogue %d", epi_kind);
+   }
+}
+
+// ---------------------------------------------------------------------------------------
+// DCsr management
+// ---------------------------------------------------------------------------------------
+int dcsr_build_partition(DCsr &M, const int *hi)
+{
+   // greedy nnz-balanced partition: consecutive rows with (nnz + 3) <= kStreamCap and at most
+   // kStreamThreads * 4 rows; a row that alone exceeds the window gets its own block.
+   std::vector<int> blk;
+   blk.reserve((size_t) (M.nnz / (kStreamCap / 2)) + 16);
+   const int n = M.nrows;
+   const int max_rows = kStreamThreads * 4;
+   int r = 0;
+   blk.push_back(0);
+   while (r < n) {
+      const int p0 = hi[r];
+      int e = r + 1;
+      // grow while the window fits
+      while (e < n && (hi[e + 1] - p0 + 3) <= kStreamCap && (e - r) < max_rows) e++;
+      blk.push_back(e);
+      r = e;
+   }
+   M.nblks = (int) blk.size() - 1;
+   if (M.blk_row) { cudaFree(M.blk_row); M.blk_row = nullptr; }
+   if (M.nblks > 0) {
+      HB_CUDA(cudaMalloc(&M.blk_row, sizeof(int) * blk.size()));
+      HB_CUDA(cudaMemcpy(M.blk_row, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice));
+   }
+   return 0;
+}
+
+void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
+{
+   if (kind == SPMV_AUTO) kind = SPMV_STREAM;
+   M.kind = kind;
+   if (lanes > 0) { M.lanes = lanes; return; }
+   if (kind == SPMV_STREAM) {
+      // phase-2 lanes per row: keep the per-thread serial chain short on the dense coarse levels
+      const double a = M.avg_row_nnz;
+      M.lanes = a <= 40 ? 1 : a <= 80 ? 2 : a <= 160 ? 4 : a <= 320 ? 8 : 16;
+   } else {
+      M.lanes = vector_lanes_for(M.avg_row_nnz);
+   }
+}
+
+int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha)
+{
+   M.nrows = nrows;
+   M.ncols = ncols;
+   M.nnz = nrows > 0 ? hi[nrows] : 0;
+   const size_t nnz_pad = (size_t) M.nnz + 8;   // the stream kernel reads up to 3 entries past the end
+   HB_CUDA(cudaMalloc(&M.i, sizeof(int) * ((size_t) nrows + 1)));
+   HB_CUDA(cudaMalloc(&M.j, sizeof(int) * nnz_pad));
+   HB_CUDA(cudaMalloc(&M.a, sizeof(double) * nnz_pad));
+   HB_CUDA(cudaMemset(M.j, 0, sizeof(int) * nnz_pad));
+   HB_CUDA(cudaMemset(M.a, 0, sizeof(double) * nnz_pad));
+   if (nrows > 0) {
+      HB_CUDA(cudaMemcpy(M.i, hi, sizeof(int) * ((size_t) nrows + 1), cudaMemcpyHostToDevice));
+   } else {
+      int z = 0;
+      HB_CUDA(cudaMemcpy(M.i, &z, sizeof(int), cudaMemcpyHostToDevice));
+   }
+   if (M.nnz > 0) {
+      HB_CUDA(cudaMemcpy(M.j, hj, sizeof(int) * (size_t) M.nnz, cudaMemcpyHostToDevice));
+      HB_CUDA(cudaMemcpy(M.a, ha, sizeof(double) * (size_t) M.nnz, cudaMemcpyHostToDevice));
+   }
+   // non-empty row list + row statistics
+   std::vector<int> rn;
+   int mx = 0;
+   for (int r = 0; r < nrows; r++) {
+      const int len = hi[r + 1] - hi[r];
+      if (len > 0) rn.push_back(r);
+      if (len > mx) mx = len;
+   }
+   M.max_row_nnz = mx;
+   M.avg_row_nnz = nrows > 0 ? (double) M.nnz / (double) nrows : 0.0;
+   M.num_rownnz = (int) rn.size();
+   if (M.num_rownnz > 0) {
+      HB_CUDA(cudaMalloc(&M.rownnz, sizeof(int) * rn.size()));
+      HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
+   }
+   dcsr_choose_kernel(M, SPMV_AUTO, 0);
+   if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
+   return 0;
+}
+
+int dcsr_free(DCsr &M)
+{
+   if (M.i) cudaFree(M.i);
+   if (M.j) cudaFree(M.j);
+   if (M.a) cudaFree(M.a);
+   if (M.rownnz) cudaFree(M.rownnz);
+   if (M.blk_row) cudaFree(M.blk_row);
+   M = DCsr();
+   return 0;
+}
+
+void host_csr_transpose(int nrows, int ncols, const int *ai, const int *aj, const double *aa,
+                        std::vector<int> &ti, std::vector<int> &tj, std::vector<double> &ta)
+{
+   const int nnz = nrows > 0 ? ai[nrows] : 0;
+   ti.assign((size_t) ncols + 1, 0);
+   tj.resize(nnz);
+   ta.resize(nnz);
+   for (int p = 0; p < nnz; p++) ti[aj[p] + 1]++;
+   for (int c = 0; c < ncols; c++) ti[c + 1] += ti[c];
+   std::vector<int> next(ti.begin(), ti.end() - 1);
+   for (int r = 0; r < nrows; r++) {
+      for (int p = ai[r]; p < ai[r + 1]; p++) {
+         const int q = next[aj[p]]++;
+         tj[q] = r;
+         ta[q] = aa[p];
+      }
+   }
+}
+
+}  // namespace hb

@@ -1,0 +1,394 @@
+// parcsr.cu — device-resident hypre_ParCSRMatrix (diag + offd CSR, col_map_offd, CommPkg),
+// the halo exchange, and the ParCSR matvec / transposed matvec.
+//
+// Reference: hypre_ParCSRMatrixMatvecOutOfPlaceHost (src/parcsr_mv/par_csr_matvec.c:21-232),
+// hypre_ParCSRMatrixMatvecTHost (:288-514), hypre_ParCSRCommHandleCreate_v2 / Destroy
+// (src/parcsr_mv/par_csr_communication.c:358-723).
+//
+// Data flow of y = alpha*A*x + beta*b on one rank (same ordering as the reference, :170-217):
+//   comm stream : pack x[send_map_elmts] -> send_buf ; grouped ncclSend/ncclRecv -> x_ext
+//   comp stream : diag block SpMV (all rows, epilogue y = beta*b + alpha*sum)   [overlapped]
+//   comp stream : wait(halo) ; offd block SpMV over the non-empty-row list, y += alpha*sum
+#include "hb_internal.cuh"
+#include <algorithm>
+#include <numeric>
+#include <string.h>
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------
+// halo kernels
+// ---------------------------------------------------------------------------------------
+__global__ void pack_kernel(int n, const int *__restrict__ map, const double *__restrict__ x,
+                            double *__restrict__ buf)
+{
+   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < n) buf[k] = x[map[k]];
+}
+
+// y[rows[t]] += buf[idx[ptr[t]]] + buf[idx[ptr[t]+1]] + ...  in ascending send-entry order:
+// the order of the reference's sequential loop (par_csr_matvec.c:491-496)
+__global__ void unpack_add_kernel(int nrows, const int *__restrict__ rows,
+                                  const int *__restrict__ ptr, const int *__restrict__ idx,
+                                  const double *__restrict__ buf, double *__restrict__ y)
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t < nrows) {
+      double v = y[rows[t]];
+      for (int q = ptr[t]; q < ptr[t + 1]; q++) v = __dadd_rn(v, buf[idx[q]]);
+      y[rows[t]] = v;
+   }
+}
+
+static int exchange(hb200_parcsr *A, bool forward, cudaStream_t st)
+{
+   // forward (job 1): send send_buf segments to send_procs, receive x_ext segments from
+   // recv_procs.  reverse (job 2): roles swapped (par_csr_communication.c:381-410).
+   Ctx &c = ctx();
+   CommPkgD &pk = A->pkg;
+   if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
+#ifdef HB200_WITH_NCCL
+   HB_REQUIRE(c.nccl != nullptr, HB200_ERROR_GENERIC,
+              "matrix has off-processor couplings but hb200_comm_init was not called");
+   HB_NCCL(ncclGroupStart());
+   for (int i = 0; i < pk.num_recvs; i++) {
+      const int cnt = pk.recv_vec_starts[i + 1] - pk.recv_vec_starts[i];
+      double *p = (forward ? pk.d_recv_buf : A->d_ytmp) + pk.recv_vec_starts[i];
+      if (forward) HB_NCCL(ncclRecv(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
+      else         HB_NCCL(ncclSend(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
+   }
+   for (int i = 0; i < pk.num_sends; i++) {
+      const int cnt = pk.send_map_starts[i + 1] - pk.send_map_starts[i];
+      double *p = pk.d_send_buf + pk.send_map_starts[i];
+      if (forward) HB_NCCL(ncclSend(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
+      else         HB_NCCL(ncclRecv(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
+   }
+   HB_NCCL(ncclGroupEnd());
+   return 0;
+#else
+   (void) forward; (void) st; (void) c;
+   return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL");
+#endif
+}
+
+int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp)
+{
+   Ctx &c = ctx();
+   CommPkgD &pk = A->pkg;
+   if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
+   HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
+   HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+   const int nsend = pk.num_sends ? pk.send_map_starts[pk.num_sends] : 0;
+   if (nsend > 0) {
+      HB_LAUNCH(pack_kernel, (nsend + 255) / 256, 256, 0, c.s_comm, nsend, pk.d_send_map_elmts, x,
+                pk.d_send_buf);
+      HB_LAUNCH_CHECK();
+   }
+   return exchange(A, true, c.s_comm);
+}
+
+int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
+{
+   Ctx &c = ctx();
+   CommPkgD &pk = A->pkg;
+   if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
+   HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+   HB_CUDA(cudaStreamWaitEvent(st_comp, c.ev_b, 0));
+   return 0;
+}
+
+int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,
+                  double *y, const double *dotw, int dot_slot)
+{
+   (void) dotw; (void) dot_slot;
+   Ctx &c = ctx();
+   if (alpha == 0.0) {
+      // csr_matvec.c:92-105: y = beta*b
+      if (beta == 0.0) return vec_set(y, 0.0, A->num_rows, c.s_comp);
+      return vec_axpby_out(beta, b, 0.0, b, y, A->num_rows, c.s_comp);
+   }
+   HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
+   EpiArgs ea;
+   ea.alpha = alpha; ea.beta = beta; ea.b = b; ea.y = y;
+   HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
+   if (A->num_cols_offd > 0) {
+      HB_CHECK(parcsr_halo_end(A, c.s_comp));
+      EpiArgs eo;
+      eo.alpha = alpha; eo.y = y;
+      HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_ACC, eo, true, c.s_comp));
+   } else {
+      HB_CHECK(parcsr_halo_end(A, c.s_comp));
+   }
+   return 0;
+}
+
+// download a device CSR block to the host (used to build transposes / schedules lazily)
+static int dcsr_download(const DCsr &M, std::vector<int> &hi, std::vector<int> &hj,
+                         std::vector<double> &ha)
+{
+   hi.resize((size_t) M.nrows + 1);
+   hj.resize((size_t) M.nnz);
+   ha.resize((size_t) M.nnz);
+   HB_CUDA(cudaMemcpy(hi.data(), M.i, sizeof(int) * hi.size(), cudaMemcpyDeviceToHost));
+   if (M.nnz) {
+      HB_CUDA(cudaMemcpy(hj.data(), M.j, sizeof(int) * hj.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(ha.data(), M.a, sizeof(double) * ha.size(), cudaMemcpyDeviceToHost));
+   }
+   return 0;
+}
+
+int parcsr_ensure_T(hb200_parcsr *A)
+{
+   if (A->has_T) return 0;
+   // stored transposes, as the reference does under keepTranspose (par_csr_matvec.c:298-299,
+   // 430-468): restriction stays a row-parallel, atomics-free, deterministic SpMV
+   std::vector<int> hi, hj, ti, tj;
+   std::vector<double> ha, ta;
+   HB_CHECK(dcsr_download(A->diag, hi, hj, ha));
+   host_csr_transpose(A->diag.nrows, A->diag.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
+   HB_CHECK(dcsr_upload(A->diagT, A->diag.ncols, A->diag.nrows, ti.data(), tj.data(), ta.data()));
+   if (A->num_cols_offd > 0) {
+      HB_CHECK(dcsr_download(A->offd, hi, hj, ha));
+      host_csr_transpose(A->offd.nrows, A->offd.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
+      HB_CHECK(dcsr_upload(A->offdT, A->offd.ncols, A->offd.nrows, ti.data(), tj.data(), ta.data()));
+      HB_CUDA(cudaMalloc(&A->d_ytmp, sizeof(double) * (size_t) A->num_cols_offd));
+   }
+   A->has_T = true;
+   return 0;
+}
+
+int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y)
+{
+   Ctx &c = ctx();
+   HB_CHECK(parcsr_ensure_T(A));
+   CommPkgD &pk = A->pkg;
+   const bool comm = (pk.num_sends || pk.num_recvs);
+   if (A->num_cols_offd > 0) {
+      // y_tmp = alpha * offd^T x  (par_csr_matvec.c:402-420)
+      EpiArgs eo;
+      eo.alpha = alpha; eo.beta = 0.0; eo.y = A->d_ytmp;
+      HB_CHECK(spmv_launch(A->offdT, x, EPI_AXPBY, eo, false, c.s_comp));
+   }
+   if (comm) {
+      HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
+      HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+      HB_CHECK(exchange(A, false, c.s_comm));
+   }
+   // y = alpha * diag^T x + beta * y   (overlapped with the reverse exchange)
+   EpiArgs ed;
+   ed.alpha = alpha; ed.beta = beta; ed.b = y; ed.y = y;
+   HB_CHECK(spmv_launch(A->diagT, x, EPI_AXPBY, ed, false, c.s_comp));
+   if (A->diagT.nrows == 0) { /* nothing local */ }
+   if (comm) {
+      HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+      HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
+      if (pk.n_unpack_rows > 0) {
+         HB_LAUNCH(unpack_add_kernel, (pk.n_unpack_rows + 255) / 256, 256, 0, c.s_comp,
+                   pk.n_unpack_rows, pk.d_unpack_rows, pk.d_unpack_ptr, pk.d_unpack_idx,
+                   pk.d_send_buf, y);
+         HB_LAUNCH_CHECK();
+      }
+   }
+   return 0;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb200_parcsr_create(hb200_parcsr **Aout, int num_rows, int num_cols, int num_cols_offd,
+                        const int *diag_i, const int *diag_j, const double *diag_data,
+                        const int *offd_i, const int *offd_j, const double *offd_data,
+                        const int64_t *col_map_offd, int64_t first_row_index,
+                        int64_t first_col_diag, int64_t global_num_rows, int64_t global_num_cols,
+                        int num_sends, const int *send_procs, const int *send_map_starts,
+                        const int *send_map_elmts, int num_recvs, const int *recv_procs,
+                        const int *recv_vec_starts)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(Aout != nullptr, HB200_ERROR_ARG, "null output handle");
+   HB_REQUIRE(num_rows >= 0 && num_cols >= 0 && num_cols_offd >= 0, HB200_ERROR_ARG, "negative size");
+   HB_REQUIRE(num_rows == 0 || diag_i != nullptr, HB200_ERROR_ARG, "diag_i is NULL");
+   HB_REQUIRE(num_cols_offd == 0 || (offd_i && col_map_offd), HB200_ERROR_ARG,
+              "offd block given without offd_i / col_map_offd");
+   hb200_parcsr *A = new hb200_parcsr();
+   A->num_rows = num_rows;
+   A->num_cols = num_cols;
+   A->num_cols_offd = num_cols_offd;
+   A->first_row = first_row_index;
+   A->first_col = first_col_diag;
+   A->global_rows = global_num_rows;
+   A->global_cols = global_num_cols;
+   int zero = 0;
+   int f = dcsr_upload(A->diag, num_rows, num_cols, num_rows ? diag_i : &zero, diag_j, diag_data);
+   if (f) { delete A; return f; }
+   if (num_cols_offd > 0) {
+      f = dcsr_upload(A->offd, num_rows, num_cols_offd, offd_i, offd_j, offd_data);
+      if (f) { hb200_parcsr_destroy(A); return f; }
+      // offd blocks always go through the vector kernel over the non-empty-row list
+      dcsr_choose_kernel(A->offd, SPMV_VECTOR, 0);
+      A->col_map_offd.assign(col_map_offd, col_map_offd + num_cols_offd);
+      HB_CUDA(cudaMalloc(&A->d_col_map_offd, sizeof(int64_t) * (size_t) num_cols_offd));
+      HB_CUDA(cudaMemcpy(A->d_col_map_offd, col_map_offd, sizeof(int64_t) * (size_t) num_cols_offd,
+                         cudaMemcpyHostToDevice));
+   }
+   CommPkgD &pk = A->pkg;
+   pk.num_sends = num_sends;
+   pk.num_recvs = num_recvs;
+   if (num_sends > 0) {
+      pk.send_procs.assign(send_procs, send_procs + num_sends);
+      pk.send_map_starts.assign(send_map_starts, send_map_starts + num_sends + 1);
+      const int ns = pk.send_map_starts[num_sends];
+      pk.send_map_elmts.assign(send_map_elmts, send_map_elmts + ns);
+      if (ns > 0) {
+         HB_CUDA(cudaMalloc(&pk.d_send_map_elmts, sizeof(int) * (size_t) ns));
+         HB_CUDA(cudaMemcpy(pk.d_send_map_elmts, send_map_elmts, sizeof(int) * (size_t) ns,
+                            cudaMemcpyHostToDevice));
+         HB_CUDA(cudaMalloc(&pk.d_send_buf, sizeof(double) * (size_t) ns));
+         // deterministic MatvecT unpack plan: group send entries by target row, stable
+         std::vector<int> order(ns);
+         std::iota(order.begin(), order.end(), 0);
+         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return pk.send_map_elmts[a] < pk.send_map_elmts[b];
+         });
+         std::vector<int> rows, ptr;
+         for (int q = 0; q < ns; q++) {
+            const int r = pk.send_map_elmts[order[q]];
+            if (rows.empty() || rows.back() != r) { rows.push_back(r); ptr.push_back(q); }
+         }
+         ptr.push_back(ns);
+         pk.n_unpack_rows = (int) rows.size();
+         HB_CUDA(cudaMalloc(&pk.d_unpack_rows, sizeof(int) * rows.size()));
+         HB_CUDA(cudaMalloc(&pk.d_unpack_ptr, sizeof(int) * ptr.size()));
+         HB_CUDA(cudaMalloc(&pk.d_unpack_idx, sizeof(int) * order.size()));
+         HB_CUDA(cudaMemcpy(pk.d_unpack_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
+         HB_CUDA(cudaMemcpy(pk.d_unpack_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+         HB_CUDA(cudaMemcpy(pk.d_unpack_idx, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+      }
+   } else {
+      pk.send_map_starts.assign(1, 0);
+   }
+   if (num_recvs > 0) {
+      pk.recv_procs.assign(recv_procs, recv_procs + num_recvs);
+      pk.recv_vec_starts.assign(recv_vec_starts, recv_vec_starts + num_recvs + 1);
+   } else {
+      pk.recv_vec_starts.assign(1, 0);
+   }
+   if (num_cols_offd > 0) {
+      HB_CUDA(cudaMalloc(&pk.d_recv_buf, sizeof(double) * (size_t) num_cols_offd));
+      HB_CUDA(cudaMemset(pk.d_recv_buf, 0, sizeof(double) * (size_t) num_cols_offd));
+   }
+   *Aout = A;
+   return 0;
+}
+
+int hb200_parcsr_destroy(hb200_parcsr *A)
+{
+   if (!A) return 0;
+   cudaDeviceSynchronize();
+   dcsr_free(A->diag);
+   dcsr_free(A->offd);
+   dcsr_free(A->diagT);
+   dcsr_free(A->offdT);
+   CommPkgD &pk = A->pkg;
+   if (A->d_col_map_offd) cudaFree(A->d_col_map_offd);
+   if (pk.d_send_map_elmts) cudaFree(pk.d_send_map_elmts);
+   if (pk.d_send_buf) cudaFree(pk.d_send_buf);
+   if (pk.d_recv_buf) cudaFree(pk.d_recv_buf);
+   if (pk.d_unpack_rows) cudaFree(pk.d_unpack_rows);
+   if (pk.d_unpack_ptr) cudaFree(pk.d_unpack_ptr);
+   if (pk.d_unpack_idx) cudaFree(pk.d_unpack_idx);
+   if (A->d_ytmp) cudaFree(A->d_ytmp);
+   if (A->d_diaginv) cudaFree(A->d_diaginv);
+   if (A->gs_sched) gs_sched_free(A->gs_sched);
+   delete A;
+   return 0;
+}
+
+int hb200_parcsr_num_rows(const hb200_parcsr *A) { return A ? A->num_rows : -1; }
+int hb200_parcsr_num_cols(const hb200_parcsr *A) { return A ? A->num_cols : -1; }
+long long hb200_parcsr_num_nonzeros(const hb200_parcsr *A)
+{
+   return A ? A->diag.nnz + A->offd.nnz : -1;
+}
+
+int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, int *offd_i,
+                               int *offd_j, int64_t *col_map_offd, int *send_map_starts,
+                               int *send_map_elmts, int *recv_vec_starts, int *send_procs,
+                               int *recv_procs)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
+   HB_CUDA(cudaDeviceSynchronize());
+   if (diag_i) HB_CUDA(cudaMemcpy(diag_i, A->diag.i, sizeof(int) * ((size_t) A->num_rows + 1), cudaMemcpyDeviceToHost));
+   if (diag_j && A->diag.nnz) HB_CUDA(cudaMemcpy(diag_j, A->diag.j, sizeof(int) * (size_t) A->diag.nnz, cudaMemcpyDeviceToHost));
+   if (A->num_cols_offd > 0) {
+      if (offd_i) HB_CUDA(cudaMemcpy(offd_i, A->offd.i, sizeof(int) * ((size_t) A->num_rows + 1), cudaMemcpyDeviceToHost));
+      if (offd_j && A->offd.nnz) HB_CUDA(cudaMemcpy(offd_j, A->offd.j, sizeof(int) * (size_t) A->offd.nnz, cudaMemcpyDeviceToHost));
+      if (col_map_offd) HB_CUDA(cudaMemcpy(col_map_offd, A->d_col_map_offd, sizeof(int64_t) * (size_t) A->num_cols_offd, cudaMemcpyDeviceToHost));
+   }
+   const CommPkgD &pk = A->pkg;
+   if (send_map_starts) memcpy(send_map_starts, pk.send_map_starts.data(), sizeof(int) * pk.send_map_starts.size());
+   if (recv_vec_starts) memcpy(recv_vec_starts, pk.recv_vec_starts.data(), sizeof(int) * pk.recv_vec_starts.size());
+   if (send_procs && pk.num_sends) memcpy(send_procs, pk.send_procs.data(), sizeof(int) * pk.num_sends);
+   if (recv_procs && pk.num_recvs) memcpy(recv_procs, pk.recv_procs.data(), sizeof(int) * pk.num_recvs);
+   if (send_map_elmts && pk.d_send_map_elmts) {
+      HB_CUDA(cudaMemcpy(send_map_elmts, pk.d_send_map_elmts, sizeof(int) * pk.send_map_elmts.size(), cudaMemcpyDeviceToHost));
+   }
+   return 0;
+}
+
+int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
+{
+   HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
+   HB_REQUIRE(kind >= 0 && kind <= 2, HB200_ERROR_ARG, "kind must be 0, 1 or 2");
+   HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
+              HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
+   dcsr_choose_kernel(A->diag, kind, lanes_per_row);
+   if (A->has_T) dcsr_choose_kernel(A->diagT, kind, lanes_per_row);
+   return 0;
+}
+
+int hb200_parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta,
+                        const double *b, double *y)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A && x && y && (b || beta == 0.0), HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(x != y, HB200_ERROR_ARG, "x must not alias y");
+   return parcsr_matvec(A, alpha, x, beta, b, y);
+}
+
+int hb200_parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A && x && y, HB200_ERROR_ARG, "null argument");
+   return parcsr_matvecT(A, alpha, x, beta, y);
+}
+
+int hb200_parcsr_matvec_host(hb200_parcsr *A, double alpha, const double *x_host, double beta,
+                             double *y_host)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A && x_host && y_host, HB200_ERROR_ARG, "null argument");
+   Ctx &c = ctx();
+   double *dx = nullptr, *dy = nullptr;
+   HB_CUDA(cudaMalloc(&dx, sizeof(double) * (size_t) (A->num_cols ? A->num_cols : 1)));
+   HB_CUDA(cudaMalloc(&dy, sizeof(double) * (size_t) (A->num_rows ? A->num_rows : 1)));
+   HB_CUDA(cudaMemcpyAsync(dx, x_host, sizeof(double) * (size_t) A->num_cols, cudaMemcpyHostToDevice, c.s_comp));
+   if (beta != 0.0) {
+      HB_CUDA(cudaMemcpyAsync(dy, y_host, sizeof(double) * (size_t) A->num_rows, cudaMemcpyHostToDevice, c.s_comp));
+   }
+   int f = parcsr_matvec(A, alpha, dx, beta, dy, dy);
+   if (!f) {
+      cudaError_t e = cudaMemcpyAsync(y_host, dy, sizeof(double) * (size_t) A->num_rows, cudaMemcpyDeviceToHost, c.s_comp);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c.s_comp);
+      if (e != cudaSuccess) f = set_error(HB200_ERROR_GENERIC, "matvec_host copy back: %s", cudaGetErrorString(e));
+   }
+   cudaFree(dx);
+   cudaFree(dy);
+   return f;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+/*
+ * hb200.h — C-ABI of libhb200.so: the B200-native (sm_100a CUDA + NCCL) BoomerAMG
+ * *solve phase* inside PCG/GMRES.
+ *
+ * This is the drop-in boundary for ONE hot path of hypre 3.1.0 (paths below are relative
+ * to the reference tree, /root/reference): plain pointers and sizes, no hypre types, no
+ * torch types.  Each entry point names the reference interface it replaces.  The
+ * reference-side binding (the C shim that overrides hypre's own symbols and forwards to
+ * these calls) is hypre_b200/csrc/hypre_shim.c; INTEGRATION.md shows how a maintainer
+ * links it.
+ *
+ * Conventions (mirroring the reference):
+ *   - HYPRE_Int  = int32 (src/utilities/HYPRE_utilities.h:83-84); HYPRE_BigInt is passed
+ *     as int64 here (the shim widens it when the reference is built without MIXEDINT).
+ *   - HYPRE_Real = HYPRE_Complex = double (HYPRE_utilities.h:130,156).  All arithmetic fp64.
+ *   - Every function returns an int error flag with hypre's bit meaning
+ *     (src/utilities/HYPRE_utilities.h:273-277): 0 ok, 1 generic (incl. CUDA/NCCL
+ *     failure), 2 memory, 4 argument, 256 convergence.  hb200_last_error() has the text.
+ *   - "dev" pointers are device (HBM) pointers owned by the caller (hb200_malloc or any
+ *     CUDA allocation, e.g. a torch tensor's data_ptr()); "host" pointers are host memory.
+ *   - One process drives one GPU (src/utilities/device_utils.c:2764 hypre_bind_device_id);
+ *     all ranks of a job call collectively, exactly like the MPI reference.
+ *   - There is NO CPU fallback: every entry point fails with flag 1 when no sm_100 device
+ *     or no CUDA runtime is usable.
+ */
+#ifndef HB200_H
+#define HB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB200_ERROR_GENERIC 1
+#define HB200_ERROR_MEMORY  2
+#define HB200_ERROR_ARG     4
+#define HB200_ERROR_CONV    256
+
+typedef struct hb200_parcsr hb200_parcsr;   /* device-resident hypre_ParCSRMatrix + CommPkg */
+typedef struct hb200_amg    hb200_amg;      /* device-resident hypre_ParAMGData (solve part) */
+
+/* ------------------------------------------------------------------------------------ */
+/* runtime                                                                                */
+/* ------------------------------------------------------------------------------------ */
+
+/* Binds this process to `device`, creates the compute + comm streams.  Replaces
+ * hypre_bind_device_id / HYPRE_Init device part (src/utilities/general.c HYPRE_Init). */
+int hb200_init(int device);
+int hb200_finalize(void);
+const char *hb200_last_error(void);
+const char *hb200_version(void);
+
+/* Multi-GPU: one NCCL communicator over all ranks replaces the MPI communicator of
+ * hypre_ParCSRMatrixComm for the solve phase (src/utilities/mpistubs.c:940+ hot-path
+ * wrappers Isend/Irecv/Waitall/Allreduce/Allgatherv).  Rank 0 calls get_unique_id, the
+ * host program broadcasts the 128 bytes by any means (torch.distributed, MPI, a file),
+ * then every rank calls comm_init. */
+int hb200_comm_get_unique_id(void *id128);
+int hb200_comm_init(int rank, int nranks, const void *id128);
+int hb200_comm_rank(void);
+int hb200_comm_size(void);
+int hb200_comm_barrier(void);
+/* halo transport: 0 = NCCL send/recv (default), 1 = direct NVLink peer stores into
+ * IPC-mapped receive buffers (pack+put fused in one kernel). */
+int hb200_set_halo_mode(int mode);
+
+/* device memory + transfers (hypre_TAlloc/hypre_TMemcpy, src/utilities/memory.c:956-990) */
+int hb200_malloc(void **dev, size_t bytes);
+int hb200_free(void *dev);
+int hb200_memcpy_h2d(void *dev, const void *host, size_t bytes);
+int hb200_memcpy_d2h(void *host, const void *dev, size_t bytes);
+int hb200_memcpy_d2d(void *dst, const void *src, size_t bytes);
+int hb200_sync(void);                 /* hypre_SyncComputeStream */
+void *hb200_compute_stream(void);     /* cudaStream_t, for callers that time with events */
+/* launch counter: number of kernels launched by this library since the last reset */
+long long hb200_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------ */
+/* (a1,a2) ParCSR matrix + CommPkg                                                        */
+/* ------------------------------------------------------------------------------------ */
+
+/* Uploads one hypre_ParCSRMatrix (src/parcsr_mv/par_csr_matrix.h:27-92): diag and offd
+ * hypre_CSRMatrix blocks (src/seq_mv/csr_matrix.h:33-62; local / compressed column
+ * indices, first entry of every diag row = diagonal element as the reference's relaxation
+ * assumes, par_relax.c:274), col_map_offd, the row/col ownership, and its
+ * hypre_ParCSRCommPkg (src/parcsr_mv/par_csr_communication.h:51-75) by value.
+ * All array arguments are HOST pointers and are copied; they may be freed on return.
+ * For 1 rank pass num_cols_offd = 0, num_sends = num_recvs = 0 and NULL arrays. */
+int hb200_parcsr_create(hb200_parcsr **A,
+                        int num_rows, int num_cols, int num_cols_offd,
+                        const int *diag_i, const int *diag_j, const double *diag_data,
+                        const int *offd_i, const int *offd_j, const double *offd_data,
+                        const int64_t *col_map_offd,
+                        int64_t first_row_index, int64_t first_col_diag,
+                        int64_t global_num_rows, int64_t global_num_cols,
+                        int num_sends, const int *send_procs, const int *send_map_starts,
+                        const int *send_map_elmts,
+                        int num_recvs, const int *recv_procs, const int *recv_vec_starts);
+int hb200_parcsr_destroy(hb200_parcsr *A);
+int hb200_parcsr_num_rows(const hb200_parcsr *A);
+int hb200_parcsr_num_cols(const hb200_parcsr *A);
+long long hb200_parcsr_num_nonzeros(const hb200_parcsr *A);   /* local diag+offd */
+/* Device -> host round trip of the integer maps (bit-exact parity check).
+ * Any output pointer may be NULL.  Sizes are those given at creation. */
+int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
+                               int *offd_i, int *offd_j, int64_t *col_map_offd,
+                               int *send_map_starts, int *send_map_elmts,
+                               int *recv_vec_starts, int *send_procs, int *recv_procs);
+/* Selects the SpMV kernel for this matrix: 0 = auto from nnz/row (default),
+ * 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced stream (merge-style). */
+int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
+
+/* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):
+ *   y = alpha*A*x + beta*b, halo exchange (job 1) overlapped with the diag block.
+ * x: num_cols doubles, b,y: num_rows doubles (dev).  y may alias b, must not alias x. */
+int hb200_parcsr_matvec(hb200_parcsr *A, double alpha, const double *x_dev,
+                        double beta, const double *b_dev, double *y_dev);
+/* (a4) hypre_ParCSRMatrixMatvecT (par_csr_matvec.c:523-546): y = alpha*A^T*x + beta*y,
+ * reverse halo (job 2) + deterministic scatter-add into y[send_map_elmts]. */
+int hb200_parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x_dev,
+                         double beta, double *y_dev);
+/* HYPRE_ParCSRMatrixMatvec with HOST vectors (src/parcsr_mv/HYPRE_parcsr_matrix.c:385):
+ * copies x (and y when beta != 0) to the device, runs the kernel, copies y back. */
+int hb200_parcsr_matvec_host(hb200_parcsr *A, double alpha, const double *x_host,
+                             double beta, double *y_host);
+
+/* ------------------------------------------------------------------------------------ */
+/* (a14) ParVector BLAS-1 (src/parcsr_mv/par_vector.c:416-627, src/seq_mv/vector.c)        */
+/* ------------------------------------------------------------------------------------ */
+int hb200_vec_set(double *y_dev, double value, size_t n);        /* SetConstantValues/SetZeros */
+int hb200_vec_copy(const double *x_dev, double *y_dev, size_t n);  /* hypre_ParVectorCopy       */
+int hb200_vec_scale(double alpha, double *y_dev, size_t n);      /* hypre_ParVectorScale        */
+int hb200_vec_axpy(double alpha, const double *x_dev, double *y_dev, size_t n); /* ...Axpy      */
+/* hypre_ParVectorInnerProd: local dot + allreduce(SUM) over all ranks (par_vector.c:600-627) */
+int hb200_vec_inner_prod(const double *x_dev, const double *y_dev, size_t n, double *result);
+/* hypre_ParVectorPointwiseDivpy[Marked]: y += x ./ b (vector.c:1083-1296); marker may be NULL */
+int hb200_vec_pointwise_divpy(const double *x_dev, const double *b_dev, double *y_dev,
+                              const int *marker_dev, int marker_val, size_t n);
+
+/* ------------------------------------------------------------------------------------ */
+/* (a9-a13) relaxation                                                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* hypre_BoomerAMGRelax (src/parcsr_ls/par_relax.c:23-173), same argument meaning.
+ * relax_type: 0 weighted Jacobi, 7 Jacobi (matvec form), 18 l1-Jacobi,
+ *             3/4/6 hybrid GS fwd/bwd/symmetric, 8/13/14/88/89 l1 hybrid GS variants.
+ * cf_marker_dev / relax_points: CF ordering (par_relax.c:262); NULL / 0 = all points.
+ * l1_norms_dev: required for 8/13/14/18/88/89.  vtemp_dev: num_rows doubles of scratch.
+ * u_all_zeros: hypre_ParVectorAllZeros(u) (par_vector.h:40-41): legalises the SpMV-free
+ * first Jacobi sweep (par_relax.c:1221-1228). */
+int hb200_relax(hb200_parcsr *A, const double *f_dev, const int *cf_marker_dev,
+                int relax_type, int relax_points, double relax_weight, double omega,
+                const double *l1_norms_dev, double *u_dev, int u_all_zeros,
+                double *vtemp_dev);
+/* hypre_BoomerAMGRelaxIF (src/parcsr_ls/par_relax_interface.c:19-65): C/F ordered sweeps. */
+int hb200_relax_if(hb200_parcsr *A, const double *f_dev, const int *cf_marker_dev,
+                   int relax_type, int relax_order, int cycle_param, double relax_weight,
+                   double omega, const double *l1_norms_dev, double *u_dev, int u_all_zeros,
+                   double *vtemp_dev);
+/* hypre_ParCSRRelax_Cheby_Solve (src/parcsr_ls/par_cheby_solve.c:352-390):
+ * u += p(A) r, coefs[order+1] on the host, ds = D^{-1/2} (dev) when scale != 0. */
+int hb200_cheby_solve(hb200_parcsr *A, const double *f_dev, const double *ds_dev,
+                      const double *coefs_host, int order, int scale, int variant,
+                      double *u_dev);
+
+/* ------------------------------------------------------------------------------------ */
+/* (a7,a8) BoomerAMG hierarchy + cycle                                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* Mirror of the solve-time part of hypre_ParAMGData (src/parcsr_ls/par_amg.h:18-310). */
+int hb200_amg_create(hb200_amg **amg, int num_levels);
+int hb200_amg_destroy(hb200_amg *amg);   /* does NOT destroy the level matrices */
+/* level l: A_array[l]; P_array[l] (NULL on the coarsest level; R = P^T is applied through
+ * a transpose built at upload, par_amg_setup.c:831); l1_norms[l] / cf_marker[l] are HOST
+ * arrays of A's num_rows entries or NULL.  relax_weight[l], omega[l] (par_amg.h:66-67). */
+int hb200_amg_set_level(hb200_amg *amg, int level, hb200_parcsr *A, hb200_parcsr *P,
+                        const double *l1_norms_host, const int *cf_marker_host,
+                        double relax_weight, double omega);
+/* Chebyshev data of level l: ds (num_rows, host, may be NULL when scale == 0), coefs[order+1] */
+int hb200_amg_set_level_cheby(hb200_amg *amg, int level, const double *ds_host,
+                              const double *coefs_host, int order);
+/* cycle parameters: num_grid_sweeps[4], grid_relax_type[4] (index = cycle_param: 1 down,
+ * 2 up, 3 coarse; par_cycle.c:317-342), relax_order, cycle_type (1 V, 2 W), fcycle,
+ * cheby_order/scale/variant, user_relax_type for 1-level hierarchies (par_cycle.c:349-356) */
+int hb200_amg_set_cycle(hb200_amg *amg, const int *num_grid_sweeps4,
+                        const int *grid_relax_type4, int relax_order, int cycle_type,
+                        int fcycle, int cheby_order, int cheby_scale, int cheby_variant,
+                        int user_relax_type);
+/* solver parameters of hypre_BoomerAMGSolve (par_amg_solve.c:22): tol, min/max_iter,
+ * converge_type.  As a preconditioner ij sets tol = 0, max_iter = 1 (ij.c:320,324). */
+int hb200_amg_set_solve(hb200_amg *amg, double tol, int min_iter, int max_iter,
+                        int converge_type);
+/* coarsest-level direct solve, relax types 9/99 (src/parcsr_ls/par_gauss_elim.c:457):
+ * A_mat is the dense n x n matrix exactly as hypre_GaussElimSetup stores it (row-major,
+ * global n = coarsest global rows), first_row = this rank's first coarse row. */
+int hb200_amg_set_coarse_ge(hb200_amg *amg, const double *A_mat_host, int n, int first_row,
+                            int num_local_rows);
+/* Capture the whole V-cycle in a CUDA graph (launch-latency bound coarse levels). */
+int hb200_amg_set_use_graph(hb200_amg *amg, int enable);
+/* hypre_BoomerAMGCycle (par_cycle.c:23): one cycle on F_array[0]=f, U_array[0]=u (dev).
+ * u_all_zeros as in hb200_relax. */
+int hb200_amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, int u_all_zeros);
+/* hypre_BoomerAMGSolve (par_amg_solve.c:22-424): cycles until tol / max_iter; outputs
+ * may be NULL. */
+int hb200_amg_solve(hb200_amg *amg, const double *f_dev, double *u_dev, int u_all_zeros,
+                    int *num_iterations, double *rel_resid_norm);
+/* per-level device vectors after a cycle, for parity tests: which = 0 F_array, 1 U_array */
+int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n);
+
+/* ------------------------------------------------------------------------------------ */
+/* (a15,a16) Krylov drivers                                                               */
+/* ------------------------------------------------------------------------------------ */
+
+#define HB200_PRECOND_NONE      0
+#define HB200_PRECOND_AMG       1   /* HYPRE_BoomerAMGSolve */
+#define HB200_PRECOND_DIAGSCALE 2   /* HYPRE_ParCSRDiagScale (HYPRE_parcsr_pcg.c) */
+
+/* Fields = the user-settable part of hypre_PCGData (src/krylov/pcg.h:104-149) */
+typedef struct {
+   double tol, a_tol, atolf, cf_tol, rtol;
+   int    max_iter, two_norm, rel_change, recompute_residual, recompute_residual_p;
+   int    stop_crit, skip_break, flex, hybrid;
+   int    logging;        /* > 0: fill norms[] / rel_norms[] (pcg.c:774-778) */
+   int    print_level;    /* > 1: rank 0 prints the reference's iteration table */
+} hb200_pcg_params;
+
+typedef struct {
+   int    num_iterations;
+   int    converged;
+   double rel_residual_norm;
+   int    error_flag;           /* hypre error bits raised inside the solve */
+   double solve_ms;             /* device time of the solve (CUDA events) */
+   long long kernel_launches;   /* hb200 kernels launched during the solve */
+} hb200_krylov_result;
+
+void hb200_pcg_default_params(hb200_pcg_params *p);   /* hypre_PCGCreate defaults, pcg.c:52-110 */
+/* hypre_PCGSolve (src/krylov/pcg.c:313-1016) with the ParCSR function table of
+ * HYPRE_ParCSRPCGCreate (src/parcsr_ls/HYPRE_parcsr_pcg.c:15-38).  b, x dev pointers;
+ * norms/rel_norms host arrays of max_iter+1 entries or NULL. */
+int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                    const hb200_pcg_params *params, const double *b_dev, double *x_dev,
+                    double *norms, double *rel_norms, hb200_krylov_result *result);
+/* Same call with HOST b and x (what HYPRE_PCGSolve sees in a CPU-memory application):
+ * H2D of b and x0, solve, D2H of x, all inside. */
+int hb200_pcg_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                         const hb200_pcg_params *params, const double *b_host,
+                         double *x_host, double *norms, double *rel_norms,
+                         hb200_krylov_result *result);
+
+/* user-settable part of hypre_GMRESData (src/krylov/gmres.h:74-114) */
+typedef struct {
+   double tol, a_tol, cf_tol;
+   int    k_dim, min_iter, max_iter, rel_change, skip_real_r_check, stop_crit, hybrid;
+   int    logging, print_level;
+} hb200_gmres_params;
+
+void hb200_gmres_default_params(hb200_gmres_params *p);   /* hypre_GMRESCreate, gmres.c:52-110 */
+/* hypre_GMRESSolve (src/krylov/gmres.c:294-1100), ParCSR table of HYPRE_ParCSRGMRESCreate
+ * (src/parcsr_ls/HYPRE_parcsr_gmres.c:15-46). */
+int hb200_gmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                      const hb200_gmres_params *params, const double *b_dev, double *x_dev,
+                      double *norms, hb200_krylov_result *result);
+int hb200_gmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                           const hb200_gmres_params *params, const double *b_host,
+                           double *x_host, double *norms, hb200_krylov_result *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HB200_H */

@@ -79,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(out)
     if jobs or not os.path.exists(LIB):
         link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                "-l:libnccl.so.2", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+                "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         run(link)
     return LIB
 

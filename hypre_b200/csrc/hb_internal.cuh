@@ -11,7 +11,7 @@
 #include "../../include/hb200.h"
 
 #ifdef HB200_WITH_NCCL
-#include <nccl.h>
+#include "nccl_dyn.cuh"
 #endif
 
 namespace hb {
@@ -46,7 +46,7 @@ int set_error(int flag, const char *fmt, ...);
       ncclResult_t r_ = (call);                                                          \
       if (r_ != ncclSuccess)                                                             \
          return hb::set_error(HB200_ERROR_GENERIC, "NCCL error %s at %s:%d: %s", #call,  \
-                              __FILE__, __LINE__, ncclGetErrorString(r_));               \
+                              __FILE__, __LINE__, hb::nccl_api().GetErrorString(r_));    \
    } while (0)
 #endif
 
@@ -101,7 +101,7 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3 };
 
 struct DCsr {
    int        nrows = 0, ncols = 0;

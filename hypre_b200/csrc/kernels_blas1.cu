@@ -249,7 +249,7 @@ int scalars_allreduce(int slot, int count, cudaStream_t st)
    Ctx &c = ctx();
    if (c.nranks <= 1) return 0;
 #ifdef HB200_WITH_NCCL
-   HB_NCCL(ncclAllReduce(c.d_scalars + slot, c.d_scalars + slot, count, ncclDouble, ncclSum, c.nccl, st));
+   HB_NCCL(nccl_api().AllReduce(c.d_scalars + slot, c.d_scalars + slot, count, ncclDouble, ncclSum, c.nccl, st));
    return 0;
 #else
    return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL but nranks > 1");

@@ -173,6 +173,94 @@ spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind,
 }
 
 // ---------------------------------------------------------------------------------------
+// stream kernel, lane-consecutive variant: lane l of a warp takes nonzero p+l, so the x gathers
+// of one load instruction fall on neighbouring columns (a 27-point row is 9 runs of 3
+// consecutive columns) and coalesce into few L1 sectors; col_ind / values are read with
+// scalar but perfectly coalesced loads, UNROLL of them in flight per thread.
+// ---------------------------------------------------------------------------------------
+template <int EPI, int L, int CAP, int NT>
+__global__ void __launch_bounds__(NT)
+spmv_stream_lc(const int *__restrict__ rowptr, const int *__restrict__ colind,
+               const double *__restrict__ val, const double *__restrict__ x,
+               const int *__restrict__ blk_row, EpiArgs ea)
+{
+   __shared__ double prod[CAP];
+   const int tid = threadIdx.x;
+   const int r0  = blk_row[blockIdx.x];
+   const int r1  = blk_row[blockIdx.x + 1];
+   const int p0  = rowptr[r0];
+   const int p1  = rowptr[r1];
+   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+   const int nnzb = p1 - p0;
+
+   if (nnzb > CAP) {
+      double s = 0.0;
+      for (int p = p0 + skip + tid; p < p1; p += NT) s += val[p] * __ldg(x + colind[p]);
+      __shared__ double red[NT / 32];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if ((tid & 31) == 0) red[tid >> 5] = s;
+      __syncthreads();
+      if (tid == 0) {
+         double t = 0.0;
+#pragma unroll
+         for (int w = 0; w < NT / 32; w++) t += red[w];
+         epi_apply<EPI>(ea, r0, t, epi_needs_diag<EPI>() ? val[p0] : 0.0);
+      }
+      return;
+   }
+
+   // ---- phase 1
+   constexpr int U = 4;
+   int k = tid;
+   for (; k + (U - 1) * NT < nnzb; k += U * NT) {
+      int c[U];
+      double v[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c[u] = colind[p0 + k + u * NT];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = val[p0 + k + u * NT];
+#pragma unroll
+      for (int u = 0; u < U; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) prod[k + u * NT] = __dmul_rn(v[u], xv[u]);
+   }
+   for (; k < nnzb; k += NT) prod[k] = __dmul_rn(val[p0 + k], __ldg(x + colind[p0 + k]));
+   __syncthreads();
+
+   // ---- phase 2
+   const int nrows = r1 - r0;
+   if (L == 1) {
+      for (int r = tid; r < nrows; r += NT) {
+         const int row = r0 + r;
+         const int a = rowptr[row] - p0, b = rowptr[row + 1] - p0;
+         double s = 0.0;
+         for (int q = a + skip; q < b; q++) s = __dadd_rn(s, prod[q]);
+         epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
+      }
+   } else {
+      const int lane = tid % L;
+      const int grp  = tid / L;
+      constexpr int NG = NT / L;
+      const int trips = (nrows + NG - 1) / NG;
+      for (int t = 0; t < trips; t++) {
+         const int r = grp + t * NG;
+         double s = 0.0;
+         const int row = r0 + r;
+         if (r < nrows) {
+            const int a = rowptr[row] - p0, b = rowptr[row + 1] - p0;
+            for (int q = a + skip + lane; q < b; q += L) s += prod[q];
+         }
+#pragma unroll
+         for (int o = L / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, L);
+         if (r < nrows && lane == 0) {
+            epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
+         }
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------------------
 // vector kernel: K lanes per row, optional compressed row list
 // ---------------------------------------------------------------------------------------
 constexpr int kVecThreads = 256;
@@ -213,8 +301,13 @@ constexpr int kStreamCap = 2048;
 template <int EPI, int L>
 static int launch_stream_L(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
-   HB_LAUNCH((spmv_stream<EPI, L, kStreamCap>), M.nblks, kStreamThreads, 0, st, M.i, M.j, M.a, x,
-             M.blk_row, ea);
+   if (M.kind == SPMV_STREAM_V4) {
+      HB_LAUNCH((spmv_stream<EPI, L, kStreamCap>), M.nblks, kStreamThreads, 0, st, M.i, M.j, M.a, x,
+                M.blk_row, ea);
+   } else {
+      HB_LAUNCH((spmv_stream_lc<EPI, L, kStreamCap, kStreamThreads>), M.nblks, kStreamThreads, 0, st,
+                M.i, M.j, M.a, x, M.blk_row, ea);
+   }
    HB_LAUNCH_CHECK();
    return 0;
 }
@@ -276,7 +369,7 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
-   if (!use_rownnz && M.kind == SPMV_STREAM && M.nblks > 0) {
+   if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
    }
    int lanes = (M.kind == SPMV_VECTOR && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
@@ -337,7 +430,7 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
    if (kind == SPMV_AUTO) kind = SPMV_STREAM;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
-   if (kind == SPMV_STREAM) {
+   if (kind == SPMV_STREAM || kind == SPMV_STREAM_V4) {
       // phase-2 lanes per row: keep the per-thread serial chain short on the dense coarse levels
       const double a = M.avg_row_nnz;
       M.lanes = a <= 40 ? 1 : a <= 80 ? 2 : a <= 160 ? 4 : a <= 320 ? 8 : 16;

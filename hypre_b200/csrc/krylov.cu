@@ -557,7 +557,7 @@ static int gmres_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_
          rs[i - 1] = cc[i - 1] * rs[i - 1];
          hh[i - 1][i - 1] = ss[i - 1] * hh[i][i - 1] + cc[i - 1] * hh[i - 1][i - 1];
          r_norm = fabs(rs[i]);
-         if (P->print_level > 0 || log) {
+         if (P->print_level > 0) {   // gmres.c:662-664: norms[iter] is only kept when printing
             if (norms) norms[iter] = r_norm;
             if (!my_id && P->print_level > 1 && norms) {
                if (b_norm > 0.0) printf("% 5d    %e    %f   %e\n", iter, norms[iter], norms[iter] / norms[iter - 1], norms[iter] / b_norm);

@@ -50,20 +50,20 @@ static int exchange(hb200_parcsr *A, bool forward, cudaStream_t st)
 #ifdef HB200_WITH_NCCL
    HB_REQUIRE(c.nccl != nullptr, HB200_ERROR_GENERIC,
               "matrix has off-processor couplings but hb200_comm_init was not called");
-   HB_NCCL(ncclGroupStart());
+   HB_NCCL(nccl_api().GroupStart());
    for (int i = 0; i < pk.num_recvs; i++) {
       const int cnt = pk.recv_vec_starts[i + 1] - pk.recv_vec_starts[i];
       double *p = (forward ? pk.d_recv_buf : A->d_ytmp) + pk.recv_vec_starts[i];
-      if (forward) HB_NCCL(ncclRecv(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
-      else         HB_NCCL(ncclSend(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
+      if (forward) HB_NCCL(nccl_api().Recv(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
+      else         HB_NCCL(nccl_api().Send(p, cnt, ncclDouble, pk.recv_procs[i], c.nccl, st));
    }
    for (int i = 0; i < pk.num_sends; i++) {
       const int cnt = pk.send_map_starts[i + 1] - pk.send_map_starts[i];
       double *p = pk.d_send_buf + pk.send_map_starts[i];
-      if (forward) HB_NCCL(ncclSend(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
-      else         HB_NCCL(ncclRecv(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
+      if (forward) HB_NCCL(nccl_api().Send(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
+      else         HB_NCCL(nccl_api().Recv(p, cnt, ncclDouble, pk.send_procs[i], c.nccl, st));
    }
-   HB_NCCL(ncclGroupEnd());
+   HB_NCCL(nccl_api().GroupEnd());
    return 0;
 #else
    (void) forward; (void) st; (void) c;
@@ -343,7 +343,7 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, 
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
 {
    HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
-   HB_REQUIRE(kind >= 0 && kind <= 2, HB200_ERROR_ARG, "kind must be 0, 1 or 2");
+   HB_REQUIRE(kind >= 0 && kind <= 3, HB200_ERROR_ARG, "kind must be 0..3");
    HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
               HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
    dcsr_choose_kernel(A->diag, kind, lanes_per_row);

@@ -242,7 +242,7 @@ int ge_solve(const GEData &ge, const double *f_local, double *u_local)
                 ge.num_local, f_local, ge.d_b);
       HB_LAUNCH_CHECK();
 #ifdef HB200_WITH_NCCL
-      HB_NCCL(ncclAllReduce(ge.d_b, ge.d_b, ge.n, ncclDouble, ncclSum, c.nccl, c.s_comp));
+      HB_NCCL(nccl_api().AllReduce(ge.d_b, ge.d_b, ge.n, ncclDouble, ncclSum, c.nccl, c.s_comp));
 #endif
       if (ge.num_local == 0) return 0;   // par_gauss_elim.c:600-617: ranks without rows leave
    } else {

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
+#include <dlfcn.h>
 
 namespace hb {
 
@@ -34,6 +35,37 @@ int require_ready()
    }
    return 0;
 }
+
+#ifdef HB200_WITH_NCCL
+static NcclApi g_nccl;
+NcclApi &nccl_api() { return g_nccl; }
+
+int nccl_load()
+{
+   if (g_nccl.loaded) return 0;
+   // RTLD_NOLOAD first: reuse whatever NCCL the process already has (e.g. PyTorch's)
+   void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+   if (!h) return set_error(HB200_ERROR_GENERIC, "cannot load libnccl.so.2: %s", dlerror());
+#define HB_SYM(field, name)                                                              \
+   *(void **) (&g_nccl.field) = dlsym(h, name);                                          \
+   if (!g_nccl.field) return set_error(HB200_ERROR_GENERIC, "libnccl lacks %s", name);
+   HB_SYM(GetUniqueId, "ncclGetUniqueId")
+   HB_SYM(CommInitRank, "ncclCommInitRank")
+   HB_SYM(CommDestroy, "ncclCommDestroy")
+   HB_SYM(AllReduce, "ncclAllReduce")
+   HB_SYM(AllGather, "ncclAllGather")
+   HB_SYM(Send, "ncclSend")
+   HB_SYM(Recv, "ncclRecv")
+   HB_SYM(GroupStart, "ncclGroupStart")
+   HB_SYM(GroupEnd, "ncclGroupEnd")
+   HB_SYM(GetErrorString, "ncclGetErrorString")
+#undef HB_SYM
+   g_nccl.loaded = true;
+   return 0;
+}
+#endif
 
 int ws_get(int slot, size_t bytes, double **out)
 {
@@ -104,7 +136,7 @@ int hb200_finalize(void)
    if (!c.ready) return 0;
    cudaDeviceSynchronize();
 #ifdef HB200_WITH_NCCL
-   if (c.nccl) { ncclCommDestroy(c.nccl); c.nccl = nullptr; }
+   if (c.nccl) { nccl_api().CommDestroy(c.nccl); c.nccl = nullptr; }
 #endif
    for (int k = 0; k < 16; k++) if (c.ws_ptr[k]) cudaFree(c.ws_ptr[k]);
    cudaFree(c.d_partials);
@@ -125,8 +157,9 @@ int hb200_comm_get_unique_id(void *id128)
 {
 #ifdef HB200_WITH_NCCL
    HB_REQUIRE(id128 != nullptr, HB200_ERROR_ARG, "null id buffer");
+   HB_CHECK(nccl_load());
    ncclUniqueId id;
-   HB_NCCL(ncclGetUniqueId(&id));
+   HB_NCCL(nccl_api().GetUniqueId(&id));
    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
    memcpy(id128, &id, 128);
    return 0;
@@ -144,9 +177,10 @@ int hb200_comm_init(int rank, int nranks, const void *id128)
    if (nranks == 1) { c.rank = 0; c.nranks = 1; return 0; }
 #ifdef HB200_WITH_NCCL
    HB_REQUIRE(id128 != nullptr, HB200_ERROR_ARG, "null id buffer");
+   HB_CHECK(nccl_load());
    ncclUniqueId id;
    memcpy(&id, id128, 128);
-   HB_NCCL(ncclCommInitRank(&c.nccl, nranks, id, rank));
+   HB_NCCL(nccl_api().CommInitRank(&c.nccl, nranks, id, rank));
    c.rank = rank;
    c.nranks = nranks;
    return 0;

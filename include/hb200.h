@@ -109,7 +109,8 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
                                int *send_map_starts, int *send_map_elmts,
                                int *recv_vec_starts, int *send_procs, int *recv_procs);
 /* Selects the SpMV kernel for this matrix: 0 = auto from nnz/row (default),
- * 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced stream (merge-style). */
+ * 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced stream (merge-style),
+ * 3 = stream with 128-bit index/value loads (kept for comparison). */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):

@@ -1,0 +1,383 @@
+"""GPU parity tests: hb200 CUDA path (through the C-ABI) vs the compiled reference
+(oracle/_ref, the unmodified hypre 3.1.0 CPU build) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): SpMV / relax outputs 1e-12 relative; CommPkg maps and
+col_map_offd bit-exact; iteration counts +-1 (we expect equality); final relative residual to
+the solver tolerance.  Where the CUDA kernel keeps the reference's operation order (stream
+kernel with one lane per row) the result is compared bit-for-bit.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hypre_b200 as h
+    h.init(0)
+    return h
+
+
+@pytest.fixture(scope="module")
+def rb():
+    from oracle import refbridge
+    if not refbridge.available():
+        pytest.fail("oracle/_ref/libref_bridge.so missing: build it with `make -C oracle ref bridge`")
+    refbridge.load()
+    refbridge.set_num_threads(1)   # deterministic reference (GS / MatvecT depend on threads)
+    return refbridge
+
+
+class Case:
+    def __init__(self, rb, hb, kind, n, **amg_kw):
+        self.pb = rb.Problem(kind, n)
+        self.pb.setup_amg(**amg_kw)
+        self.h = self.pb.hierarchy()
+        self.mats, self.amg = hb.amg_from_hierarchy(self.h)
+        self.nl = self.pb.num_levels
+
+
+@pytest.fixture(scope="module")
+def lap7(rb, hb):
+    return Case(rb, hb, "laplacian", (24, 22, 20), relax_type=18)
+
+
+@pytest.fixture(scope="module")
+def lap27(rb, hb):
+    return Case(rb, hb, "27pt", (18, 17, 16), relax_type=18)
+
+
+@pytest.fixture(scope="module")
+def vdc(rb, hb):
+    return Case(rb, hb, "vardifconv", (20, 20, 20), relax_type=18)
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+# ----------------------------------------------------------------------------------------
+# data model round trip
+# ----------------------------------------------------------------------------------------
+def test_maps_roundtrip_bit_exact(lap27):
+    for l, (A, P) in enumerate(lap27.mats):
+        for M, view in ((A, lap27.h["levels"][l]["A"]), (P, lap27.h["levels"][l]["P"])):
+            if M is None:
+                continue
+            ref = view.arrays()
+            got = M.download_maps()
+            assert np.array_equal(got["diag_i"], ref["diag_i"])
+            assert np.array_equal(got["diag_j"], ref["diag_j"])
+            assert np.array_equal(got["send_map_starts"][: M.num_sends + 1],
+                                  ref["send_map_starts"] if ref["send_map_starts"] is not None else np.zeros(1, np.int32))
+
+
+# ----------------------------------------------------------------------------------------
+# SpMV (a3, a5)
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_name", ["lap7", "lap27", "vdc"])
+@pytest.mark.parametrize("ab", [(1.0, 0.0), (-1.0, 1.0), (1.0, 1.0), (-0.7, 0.7), (2.5, -1.5)])
+def test_matvec_all_levels(request, torch, case_name, ab):
+    case = request.getfixturevalue(case_name)
+    alpha, beta = ab
+    rng = np.random.default_rng(1234)
+    for l, (A, P) in enumerate(case.mats):
+        for which, M in ((0, A), (1, P)):
+            if M is None:
+                continue
+            x = rng.standard_normal(M.num_cols)
+            b = rng.standard_normal(M.num_rows)
+            yref = case.pb.matvec(alpha, x, beta, b, level=l, which=which)
+            y = torch.empty(M.num_rows, dtype=torch.float64, device="cuda")
+            M.matvec(alpha, dev(torch, x), beta, y, b=dev(torch, b))
+            err = relerr(y.cpu().numpy(), yref)
+            assert err <= RTOL, (case_name, l, which, alpha, beta, err)
+
+
+def test_matvec_bit_exact_fine_level(lap27, torch):
+    """one lane per row in the stream kernel keeps the reference's summation order"""
+    A = lap27.mats[0][0]
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(A.num_cols)
+    b = rng.standard_normal(A.num_rows)
+    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (1.0, 1.0)):
+        yref = lap27.pb.matvec(alpha, x, beta, b)
+        y = torch.empty(A.num_rows, dtype=torch.float64, device="cuda")
+        A.matvec(alpha, dev(torch, x), beta, y, b=dev(torch, b))
+        assert np.array_equal(y.cpu().numpy(), yref), (alpha, beta)
+
+
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32)])
+def test_matvec_kernel_variants(lap27, torch, kind, lanes):
+    rng = np.random.default_rng(5)
+    for l in (0, 2):
+        if l >= lap27.nl:
+            continue
+        A = lap27.mats[l][0]
+        x = rng.standard_normal(A.num_cols)
+        yref = lap27.pb.matvec(1.0, x, 0.0, None, level=l)
+        A.set_spmv_kernel(kind, lanes)
+        y = torch.empty(A.num_rows, dtype=torch.float64, device="cuda")
+        A.matvec(1.0, dev(torch, x), 0.0, y)
+        A.set_spmv_kernel(0, 0)
+        assert relerr(y.cpu().numpy(), yref) <= RTOL, (l, kind, lanes)
+
+
+def test_matvec_host_entry(lap7):
+    A = lap7.mats[0][0]
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(A.num_cols)
+    y = rng.standard_normal(A.num_rows)
+    yref = lap7.pb.matvec(2.0, x, -1.0, y)
+    A.matvec(2.0, x, -1.0, y)
+    assert relerr(y, yref) <= RTOL
+
+
+@pytest.mark.parametrize("case_name", ["lap7", "lap27"])
+def test_matvecT_restriction(request, torch, case_name):
+    case = request.getfixturevalue(case_name)
+    rng = np.random.default_rng(99)
+    for l, (A, P) in enumerate(case.mats):
+        if P is None:
+            continue
+        x = rng.standard_normal(P.num_rows)
+        y0 = rng.standard_normal(P.num_cols)
+        for alpha, beta in ((1.0, 0.0), (-2.0, 0.5)):
+            yref = case.pb.matvecT(alpha, x, beta, y0, level=l, which=1)
+            y = dev(torch, y0)
+            P.matvecT(alpha, dev(torch, x), beta, y)
+            assert relerr(y.cpu().numpy(), yref) <= RTOL, (case_name, l, alpha, beta)
+
+
+# ----------------------------------------------------------------------------------------
+# BLAS-1 (a14)
+# ----------------------------------------------------------------------------------------
+def test_blas1(lap7, hb, torch):
+    rng = np.random.default_rng(3)
+    n = lap7.mats[0][0].num_rows
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    ref = lap7.pb.inner_prod(x, y)
+    got = hb.inner_prod(dev(torch, x), dev(torch, y))
+    assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)) * 10
+    dy = dev(torch, y)
+    hb.axpy(-0.37, dev(torch, x), dy)
+    assert np.array_equal(dy.cpu().numpy(), y + (-0.37) * x)   # same mul-then-add rounding
+
+
+# ----------------------------------------------------------------------------------------
+# relaxation (a9-a12)
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("relax_type", [0, 7, 18])
+@pytest.mark.parametrize("points", [0, 1, -1])
+@pytest.mark.parametrize("zero", [False, True])
+def test_relax_jacobi(lap27, hb, torch, relax_type, points, zero):
+    rng = np.random.default_rng(21)
+    for l in range(min(lap27.nl - 1, 3)):
+        A = lap27.mats[l][0]
+        L = lap27.h["levels"][l]
+        n = A.num_rows
+        f = rng.standard_normal(n)
+        u = np.zeros(n) if zero else rng.standard_normal(n)
+        for w in (1.0, 0.8):
+            uref = lap27.pb.relax(l, relax_type, f, u, relax_points=points, relax_weight=w,
+                                  u_all_zeros=zero, use_l1=(relax_type != 0))
+            du = dev(torch, u)
+            if zero:
+                du.fill_(123.0)    # the flag, not the memory, says "zero"
+            hb.relax(A, dev(torch, f), du, relax_type, relax_points=points, relax_weight=w,
+                     l1_norms=dev(torch, L["l1_norms"]) if relax_type != 0 else None,
+                     cf_marker=torch.from_numpy(np.ascontiguousarray(L["cf_marker"])).cuda(),
+                     u_all_zeros=zero)
+            err = relerr(du.cpu().numpy(), uref)
+            assert err <= RTOL, (relax_type, points, zero, l, w, err)
+
+
+@pytest.mark.parametrize("relax_type", [3, 4, 6, 8, 13, 14, 88, 89])
+@pytest.mark.parametrize("weights", [(1.0, 1.0), (0.9, 1.1)])
+@pytest.mark.parametrize("points", [0, 1])
+def test_relax_hybrid_gs(lap27, hb, torch, relax_type, weights, points):
+    rng = np.random.default_rng(31)
+    w, om = weights
+    for l in range(min(lap27.nl - 1, 3)):
+        A = lap27.mats[l][0]
+        L = lap27.h["levels"][l]
+        n = A.num_rows
+        f = rng.standard_normal(n)
+        u = rng.standard_normal(n)
+        use_l1 = relax_type in (8, 13, 14, 88, 89)
+        uref = lap27.pb.relax(l, relax_type, f, u, relax_points=points, relax_weight=w, omega=om,
+                              use_l1=use_l1)
+        du = dev(torch, u)
+        hb.relax(A, dev(torch, f), du, relax_type, relax_points=points, relax_weight=w, omega=om,
+                 l1_norms=dev(torch, L["l1_norms"]) if use_l1 else None,
+                 cf_marker=torch.from_numpy(np.ascontiguousarray(L["cf_marker"])).cuda())
+        err = relerr(du.cpu().numpy(), uref)
+        assert err <= 1e-11, (relax_type, weights, points, l, err)
+
+
+def test_chebyshev(rb, hb, torch):
+    for scale in (1, 0):
+        case = Case(rb, hb, "laplacian", (16, 15, 14), relax_type=16, cheby_scale=scale, cheby_order=3)
+        rng = np.random.default_rng(41)
+        for l in range(min(case.nl - 1, 3)):
+            A = case.mats[l][0]
+            L = case.h["levels"][l]
+            f = rng.standard_normal(A.num_rows)
+            u = rng.standard_normal(A.num_rows)
+            uref = case.pb.cheby(l, f, u)
+            du = dev(torch, u)
+            hb.cheby_solve(A, dev(torch, f), du, L["cheby_coefs"], case.h["params"]["cheby_order"],
+                           scale, ds=dev(torch, L["cheby_ds"]) if L["cheby_ds"] is not None else None)
+            assert relerr(du.cpu().numpy(), uref) <= 1e-11, (scale, l)
+
+
+# ----------------------------------------------------------------------------------------
+# cycle (a7, a8, a13)
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_name", ["lap7", "lap27", "vdc"])
+@pytest.mark.parametrize("zero", [True, False])
+def test_vcycle(request, torch, case_name, zero):
+    case = request.getfixturevalue(case_name)
+    rng = np.random.default_rng(51)
+    n = case.mats[0][0].num_rows
+    f = rng.standard_normal(n)
+    u = np.zeros(n) if zero else rng.standard_normal(n)
+    uref = case.pb.amg_solve(f, u, u_all_zeros=zero)
+    du = dev(torch, u)
+    case.amg.cycle(dev(torch, f), du, u_all_zeros=zero)
+    err = relerr(du.cpu().numpy(), uref)
+    assert err <= 1e-11, (case_name, zero, err)
+    # coarse right-hand sides and corrections, level by level
+    for l in range(1, case.nl):
+        for which in (0, 1):
+            ref = case.pb.level_vector(l, which)
+            ptr, m = case.amg.level_vector(l, which)
+            got = torch.empty(m, dtype=torch.float64, device="cuda")
+            from hypre_b200._lib import lib, check
+            check(lib.hb200_memcpy_d2d(got.data_ptr(), ptr, 8 * m))
+            import hypre_b200
+            hypre_b200.sync()
+            assert relerr(got.cpu().numpy(), ref) <= 1e-10, (case_name, l, which)
+
+
+def test_vcycle_graph_replay(lap27, torch):
+    rng = np.random.default_rng(52)
+    n = lap27.mats[0][0].num_rows
+    f = rng.standard_normal(n)
+    uref = lap27.pb.amg_solve(f, np.zeros(n), u_all_zeros=True)
+    lap27.amg.set_use_graph(True)
+    try:
+        df = dev(torch, f)
+        du = torch.zeros(n, dtype=torch.float64, device="cuda")
+        for _ in range(3):   # warm-up call, capture, replay
+            lap27.amg.cycle(df, du, u_all_zeros=True)
+            assert relerr(du.cpu().numpy(), uref) <= 1e-11
+    finally:
+        lap27.amg.set_use_graph(False)
+
+
+@pytest.mark.parametrize("smoother", [dict(relax_type=18, relax_order=1), dict(relax_type=8),
+                                      dict(relax_type=-1), dict(relax_type=18, cycle_type=2),
+                                      dict(relax_type=16), dict(relax_type=18, num_sweeps=2)])
+def test_vcycle_smoother_variants(rb, hb, torch, smoother):
+    case = Case(rb, hb, "laplacian", (14, 13, 12), **smoother)
+    rng = np.random.default_rng(53)
+    n = case.mats[0][0].num_rows
+    f = rng.standard_normal(n)
+    uref = case.pb.amg_solve(f, np.zeros(n), u_all_zeros=True)
+    du = torch.zeros(n, dtype=torch.float64, device="cuda")
+    case.amg.cycle(dev(torch, f), du, u_all_zeros=True)
+    assert relerr(du.cpu().numpy(), uref) <= 1e-10, smoother
+
+
+# ----------------------------------------------------------------------------------------
+# Krylov (a15, a16)
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_name", ["lap7", "lap27"])
+def test_pcg_amg(request, hb, torch, case_name):
+    case = request.getfixturevalue(case_name)
+    ref = case.pb.pcg(precond="amg", tol=1e-8, max_iter=100, two_norm=1)
+    A = case.mats[0][0]
+    pcg = hb.ParCSRPCG(tol=1e-8, max_iter=100, two_norm=1)
+    pcg.set_precond(case.amg)
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    pcg.solve(A, dev(torch, case.pb.b), x)
+    assert pcg.num_iterations == ref["iterations"]
+    k = ref["iterations"]
+    assert relerr(pcg.norms[: k + 1], ref["norms"]) <= 1e-9
+    assert abs(pcg.final_relative_residual_norm - ref["final_rel_res"]) <= 1e-6 * ref["final_rel_res"]
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-9
+    # host-buffer entry point gives the same answer
+    xh = np.zeros(A.num_rows)
+    pcg.solve(A, np.array(case.pb.b), xh)
+    assert np.array_equal(xh, x.cpu().numpy())
+
+
+@pytest.mark.parametrize("opts", [dict(two_norm=0), dict(two_norm=1, flex=1), dict(two_norm=1, rel_change=1),
+                                  dict(two_norm=1, recompute_res=1)])
+def test_pcg_options(lap7, hb, torch, opts):
+    ref = lap7.pb.pcg(precond="amg", tol=1e-8, max_iter=100, **opts)
+    A = lap7.mats[0][0]
+    kw = dict(opts)
+    if "recompute_res" in kw:
+        kw["recompute_residual"] = kw.pop("recompute_res")
+    pcg = hb.ParCSRPCG(tol=1e-8, max_iter=100, **kw)
+    pcg.set_precond(lap7.amg)
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    pcg.solve(A, dev(torch, lap7.pb.b), x)
+    assert abs(pcg.num_iterations - ref["iterations"]) <= 1
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-7
+
+
+def test_pcg_diagscale(lap7, hb, torch):
+    ref = lap7.pb.pcg(precond="diagscale", tol=1e-8, max_iter=500, two_norm=1)
+    A = lap7.mats[0][0]
+    pcg = hb.ParCSRPCG(tol=1e-8, max_iter=500, two_norm=1)
+    pcg.set_precond("diagscale")
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    pcg.solve(A, dev(torch, lap7.pb.b), x)
+    assert abs(pcg.num_iterations - ref["iterations"]) <= 1
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-7
+
+
+def test_gmres_amg_nonsymmetric(vdc, hb, torch):
+    ref = vdc.pb.gmres(precond="amg", tol=1e-8, max_iter=100, k_dim=5)
+    A = vdc.mats[0][0]
+    gm = hb.ParCSRGMRES(tol=1e-8, max_iter=100, k_dim=5)
+    gm.set_precond(vdc.amg)
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    gm.solve(A, dev(torch, vdc.pb.b), x)
+    assert abs(gm.num_iterations - ref["iterations"]) <= 1
+    # the reference keeps norms[iter] only when print_level > 0 (gmres.c:662); norms[0] always
+    assert abs(gm.norms[0] - ref["norms"][0]) <= 1e-12 * ref["norms"][0]
+    assert abs(gm.final_relative_residual_norm - ref["final_rel_res"]) <= 1e-5 * ref["final_rel_res"]
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-7
+
+
+def test_zero_rhs_and_errors(lap7, hb, torch):
+    A = lap7.mats[0][0]
+    pcg = hb.ParCSRPCG(tol=1e-8, max_iter=10, two_norm=1)
+    pcg.set_precond(lap7.amg)
+    x = torch.ones(A.num_rows, dtype=torch.float64, device="cuda")
+    b = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    pcg.solve(A, b, x)            # pcg.c:482-497: x := b
+    assert pcg.num_iterations == 0 and float(x.abs().max()) == 0.0
+    bn = torch.full((A.num_rows,), float("nan"), dtype=torch.float64, device="cuda")
+    with pytest.raises(hb.HB200Error):
+        pcg.solve(A, bn, x)       # pcg.c:426-450

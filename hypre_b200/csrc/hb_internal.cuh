@@ -116,7 +116,7 @@ struct DCsr {
    // nnz-balanced partition for the stream kernel: blk_row[b] .. blk_row[b+1]
    int       *blk_row = nullptr;
    int        nblks = 0;
-   int        kind = SPMV_STREAM;
+   int        kind = SPMV_VECTOR;
    int        lanes = 1;          // lanes per row (vector kernel: K; stream kernel: phase-2 L)
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;

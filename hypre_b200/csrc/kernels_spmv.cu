@@ -354,12 +354,12 @@ static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, bool
 
 static int vector_lanes_for(double avg)
 {
-   // same breakpoints as the reference's own kernel (csr_spmv_device.c:302-308), extended down
-   if (avg >= 64) return 32;
-   if (avg >= 32) return 16;
-   if (avg >= 16) return 8;
-   if (avg >= 6)  return 4;
-   if (avg >= 3)  return 2;
+   // measured on B200 over the levels of 27-pt and 7-pt hierarchies (profiles/r1_level_sweep.md):
+   // the fastest lane count keeps ~6-14 nonzeros per lane
+   if (avg >= 150) return 32;
+   if (avg >= 80)  return 16;
+   if (avg >= 36)  return 8;
+   if (avg >= 10)  return 2;
    return 1;
 }
 
@@ -427,7 +427,9 @@ int dcsr_build_partition(DCsr &M, const int *hi)
 
 void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
 {
-   if (kind == SPMV_AUTO) kind = SPMV_STREAM;
+   // the sub-warp vector kernel beat the shared-memory stream kernel on every level measured
+   // (profiles/r1_level_sweep.md): the stream kernel is L1-wavefront bound by its smem round trip
+   if (kind == SPMV_AUTO) kind = SPMV_VECTOR;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
    if (kind == SPMV_STREAM || kind == SPMV_STREAM_V4) {

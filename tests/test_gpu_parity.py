@@ -113,6 +113,7 @@ def test_matvec_all_levels(request, torch, case_name, ab):
 def test_matvec_bit_exact_fine_level(lap27, torch):
     """one lane per row in the stream kernel keeps the reference's summation order"""
     A = lap27.mats[0][0]
+    A.set_spmv_kernel(2, 1)
     rng = np.random.default_rng(7)
     x = rng.standard_normal(A.num_cols)
     b = rng.standard_normal(A.num_rows)
@@ -121,9 +122,10 @@ def test_matvec_bit_exact_fine_level(lap27, torch):
         y = torch.empty(A.num_rows, dtype=torch.float64, device="cuda")
         A.matvec(alpha, dev(torch, x), beta, y, b=dev(torch, b))
         assert np.array_equal(y.cpu().numpy(), yref), (alpha, beta)
+    A.set_spmv_kernel(0, 0)
 
 
-@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32)])
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8)])
 def test_matvec_kernel_variants(lap27, torch, kind, lanes):
     rng = np.random.default_rng(5)
     for l in (0, 2):

@@ -104,6 +104,8 @@ def build_problem(args, rank, world):
     from oracle import refbridge as rb
     mpi = world > 1
     rb.load(mpi=mpi)
+    if world > 1:
+        rb.set_num_threads(max(1, (os.cpu_count() or world) // world))
     P = PGRID[world]
     n = args.n
     gn = (n * P[0], n * P[1], n * P[2])

@@ -235,7 +235,7 @@ struct hb200_parcsr {
    int64_t *d_col_map_offd = nullptr;
    hb::CommPkgD pkg;
    double  *d_ytmp = nullptr;        // MatvecT: offd^T x (num_cols_offd)
-   double  *d_diaginv = nullptr;     // lazily built for DIAGSCALE precond
+   double  *d_diaginv = nullptr;     // lazily extracted diagonal (DIAGSCALE precond, Jacobi type 0)
    // kept host copies of the CSR (needed to build transposes / level schedules lazily)
    std::vector<int> h_diag_i, h_diag_j, h_offd_i, h_offd_j;
    std::vector<double> h_diag_a, h_offd_a;
@@ -246,6 +246,7 @@ struct hb200_parcsr {
 
 namespace hb {
 int parcsr_ensure_T(hb200_parcsr *A);
+int parcsr_diag(hb200_parcsr *A, const double **diag);   // lazily extracted diagonal of the diag block
 int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp);   // pack + exchange on s_comm
 int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp);                     // make s_comp wait
 int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,

@@ -1,0 +1,591 @@
+/*
+ * hypre_shim.c — the reference-side binding of libhb200: a small C library (libHYPRE_b200.so) that
+ * OVERRIDES the hot-path symbols of hypre 3.1.0 and forwards them to the hb200 C-ABI
+ * (include/hb200.h).  An application (e.g. the unmodified src/test/ij.c) links — or LD_PRELOADs —
+ * this library in front of its libHYPRE and keeps calling HYPRE_IJ* / HYPRE_ParCSR* /
+ * HYPRE_BoomerAMG* / HYPRE_ParCSRPCG* exactly as before:
+ *
+ *   hypre_PCGSolve            (src/krylov/pcg.c:313)            -> hb200_pcg_solve_host
+ *   hypre_GMRESSolve          (src/krylov/gmres.c:294)          -> hb200_gmres_solve_host
+ *   hypre_BoomerAMGSolve      (src/parcsr_ls/par_amg_solve.c:22)-> hb200_amg_solve
+ *   HYPRE_ParCSRMatrixMatvec  (src/parcsr_mv/HYPRE_parcsr_matrix.c:385) -> hb200_parcsr_matvec_host
+ *   HYPRE_ParCSRMatrixMatvecT (:401)                            -> hb200_parcsr_matvecT
+ *   hypre_ParCSRMatrixDestroy / hypre_BoomerAMGDestroy / hypre_BoomerAMGSetup: mirror lifetime
+ *
+ * Everything else (IJ assembly, BoomerAMGSetup, all other solvers) stays the reference's own
+ * code.  The multigrid hierarchy is read out of hypre_ParAMGData after the reference's setup
+ * (SURVEY Appendix B manifest) and uploaded once per setup.
+ *
+ * The generic Krylov drivers also serve struct/sstruct matrices through other function tables;
+ * those calls, and BoomerAMG configurations that are not on the accelerated path (block mode,
+ * Schwarz/ILU/Euclid smoothers, additive cycles, AIR restriction ...), are passed to the
+ * original symbol (dlsym RTLD_NEXT) with a one-time notice — or refused with a hypre error when
+ * HYPRE_B200_STRICT=1.  A missing GPU / CUDA failure is always an error, never a silent CPU run.
+ *
+ * Compiled against the reference headers where they lie (oracle/Makefile target `shim`).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "_hypre_utilities.h"
+#include "HYPRE.h"
+#include "_hypre_parcsr_mv.h"
+#include "_hypre_parcsr_ls.h"
+#include "_hypre_krylov.h"
+
+#include "hb200.h"
+
+/* ---------------------------------------------------------------------------------------------- */
+
+static int g_ready = 0, g_failed = 0, g_verbose = 0, g_strict = 0;
+
+static void *next_sym(const char *name)
+{
+   void *p = dlsym(RTLD_NEXT, name);
+   if (!p)
+   {
+      fprintf(stderr, "[hypre_b200] cannot find the reference's %s behind the shim: %s\n", name, dlerror());
+      abort();
+   }
+   return p;
+}
+
+static void notice_once(int *flag, const char *what)
+{
+   if (!*flag)
+   {
+      *flag = 1;
+      fprintf(stderr, "[hypre_b200] %s: not on the B200 path, running the reference's own code\n", what);
+   }
+}
+
+static int shim_init(MPI_Comm comm)
+{
+   int nprocs = 1, myid = 0, dev = 0;
+   const char *e;
+   if (g_ready) { return 0; }
+   if (g_failed) { return 1; }
+   g_verbose = getenv("HYPRE_B200_VERBOSE") != NULL;
+   g_strict = getenv("HYPRE_B200_STRICT") != NULL && atoi(getenv("HYPRE_B200_STRICT")) != 0;
+   hypre_MPI_Comm_size(comm, &nprocs);
+   hypre_MPI_Comm_rank(comm, &myid);
+   e = getenv("LOCAL_RANK");
+   if (!e) { e = getenv("MINIMPI_RANK"); }
+   dev = e ? atoi(e) : myid;
+   {
+      /* bind round-robin when there are fewer devices than ranks */
+      const char *nd = getenv("HYPRE_B200_NUM_DEVICES");
+      if (nd && atoi(nd) > 0) { dev = dev % atoi(nd); }
+   }
+   if (hb200_init(dev) != 0)
+   {
+      g_failed = 1;
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+      fprintf(stderr, "[hypre_b200] FATAL: %s\n", hb200_last_error());
+      return 1;
+   }
+   if (nprocs > 1)
+   {
+      char id[128];
+      memset(id, 0, sizeof(id));
+      if (myid == 0 && hb200_comm_get_unique_id(id) != 0)
+      {
+         fprintf(stderr, "[hypre_b200] FATAL: %s\n", hb200_last_error());
+         g_failed = 1;
+      }
+      hypre_MPI_Bcast(id, 128, hypre_MPI_BYTE, 0, comm);
+      if (g_failed || hb200_comm_init(myid, nprocs, id) != 0)
+      {
+         g_failed = 1;
+         hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+         fprintf(stderr, "[hypre_b200] FATAL: %s\n", hb200_last_error());
+         return 1;
+      }
+   }
+   g_ready = 1;
+   if (g_verbose && myid == 0) { fprintf(stderr, "[hypre_b200] %s bound, %d rank(s)\n", hb200_version(), nprocs); }
+   return 0;
+}
+
+/* ---- device mirrors ---------------------------------------------------------------------------- */
+
+typedef struct mat_mirror
+{
+   struct mat_mirror  *next;
+   hypre_ParCSRMatrix *A;
+   HYPRE_Complex      *diag_data;   /* identity check: same arrays as at upload time */
+   HYPRE_Int           diag_nnz;
+   hb200_parcsr       *dev;
+} mat_mirror;
+
+typedef struct amg_mirror
+{
+   struct amg_mirror *next;
+   void              *amg_data;
+   hb200_amg         *dev;
+   int                num_levels;
+   hb200_parcsr     **owned;   /* level matrices created for this hierarchy (A_l for l >= 1, P_l) */
+   int                num_owned;
+   hypre_ParCSRMatrix *A0;
+} amg_mirror;
+
+static mat_mirror *g_mats = NULL;
+static amg_mirror *g_amgs = NULL;
+
+static hb200_parcsr *upload_matrix(hypre_ParCSRMatrix *A)
+{
+   hypre_CSRMatrix     *diag = hypre_ParCSRMatrixDiag(A), *offd = hypre_ParCSRMatrixOffd(A);
+   hypre_ParCSRCommPkg *pkg;
+   HYPRE_BigInt        *cmap = hypre_ParCSRMatrixColMapOffd(A);
+   HYPRE_Int            nco = hypre_CSRMatrixNumCols(offd), k;
+   int64_t             *cmap64 = NULL;
+   hb200_parcsr        *dev = NULL;
+   int                  flag;
+   if (!hypre_ParCSRMatrixCommPkg(A)) { hypre_MatvecCommPkgCreate(A); }   /* par_csr_matvec.c:102-106 */
+   pkg = hypre_ParCSRMatrixCommPkg(A);
+   if (nco > 0)
+   {
+      cmap64 = (int64_t *) malloc(sizeof(int64_t) * (size_t) nco);
+      for (k = 0; k < nco; k++) { cmap64[k] = (int64_t) cmap[k]; }
+   }
+   flag = hb200_parcsr_create(&dev, hypre_CSRMatrixNumRows(diag), hypre_CSRMatrixNumCols(diag), nco,
+                              hypre_CSRMatrixI(diag), hypre_CSRMatrixJ(diag), hypre_CSRMatrixData(diag),
+                              hypre_CSRMatrixI(offd), hypre_CSRMatrixJ(offd), hypre_CSRMatrixData(offd), cmap64,
+                              (int64_t) hypre_ParCSRMatrixFirstRowIndex(A), (int64_t) hypre_ParCSRMatrixFirstColDiag(A),
+                              (int64_t) hypre_ParCSRMatrixGlobalNumRows(A), (int64_t) hypre_ParCSRMatrixGlobalNumCols(A),
+                              pkg ? hypre_ParCSRCommPkgNumSends(pkg) : 0, pkg ? hypre_ParCSRCommPkgSendProcs(pkg) : NULL,
+                              pkg ? hypre_ParCSRCommPkgSendMapStarts(pkg) : NULL,
+                              pkg ? hypre_ParCSRCommPkgSendMapElmts(pkg) : NULL,
+                              pkg ? hypre_ParCSRCommPkgNumRecvs(pkg) : 0, pkg ? hypre_ParCSRCommPkgRecvProcs(pkg) : NULL,
+                              pkg ? hypre_ParCSRCommPkgRecvVecStarts(pkg) : NULL);
+   free(cmap64);
+   if (flag)
+   {
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+      return NULL;
+   }
+   return dev;
+}
+
+static hb200_parcsr *mirror_matrix(hypre_ParCSRMatrix *A)
+{
+   mat_mirror *m;
+   hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(A);
+   for (m = g_mats; m; m = m->next)
+   {
+      if (m->A == A)
+      {
+         if (m->diag_data == hypre_CSRMatrixData(diag) && m->diag_nnz == hypre_CSRMatrixNumNonzeros(diag)) { return m->dev; }
+         hb200_parcsr_destroy(m->dev);   /* same address, different matrix: re-upload */
+         m->dev = upload_matrix(A);
+         m->diag_data = hypre_CSRMatrixData(diag);
+         m->diag_nnz = hypre_CSRMatrixNumNonzeros(diag);
+         return m->dev;
+      }
+   }
+   m = (mat_mirror *) calloc(1, sizeof(mat_mirror));
+   m->A = A;
+   m->dev = upload_matrix(A);
+   m->diag_data = hypre_CSRMatrixData(diag);
+   m->diag_nnz = hypre_CSRMatrixNumNonzeros(diag);
+   if (!m->dev) { free(m); return NULL; }
+   m->next = g_mats;
+   g_mats = m;
+   return m->dev;
+}
+
+static void drop_matrix(hypre_ParCSRMatrix *A)
+{
+   mat_mirror **pp = &g_mats;
+   while (*pp)
+   {
+      if ((*pp)->A == A)
+      {
+         mat_mirror *m = *pp;
+         *pp = m->next;
+         hb200_parcsr_destroy(m->dev);
+         free(m);
+         return;
+      }
+      pp = &(*pp)->next;
+   }
+}
+
+static void drop_amg(void *amg_data)
+{
+   amg_mirror **pp = &g_amgs;
+   while (*pp)
+   {
+      if ((*pp)->amg_data == amg_data)
+      {
+         amg_mirror *m = *pp;
+         int k;
+         *pp = m->next;
+         hb200_amg_destroy(m->dev);
+         for (k = 0; k < m->num_owned; k++) { hb200_parcsr_destroy(m->owned[k]); }
+         free(m->owned);
+         free(m);
+         return;
+      }
+      pp = &(*pp)->next;
+   }
+}
+
+static int relax_type_on_path(int t)
+{
+   return t == 0 || t == 7 || t == 18 || t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14 ||
+          t == 88 || t == 89 || t == 16;
+}
+
+/* NULL = hierarchy is on the accelerated path; otherwise the reason it is not */
+static const char *amg_unsupported(hypre_ParAMGData *amg)
+{
+   HYPRE_Int nl = hypre_ParAMGDataNumLevels(amg), k;
+   HYPRE_Int *grt = hypre_ParAMGDataGridRelaxType(amg);
+   if (hypre_ParAMGDataBlockMode(amg)) { return "block-mode BoomerAMG"; }
+   if (hypre_ParAMGDataSmoothNumLevels(amg) > 0) { return "complex smoothers (Schwarz/Pilut/ParaSails/Euclid/ILU/FSAI)"; }
+   if (hypre_ParAMGDataRestriction(amg)) { return "AIR restriction"; }
+   if (hypre_ParAMGDataGridRelaxPoints(amg)) { return "user grid_relax_points"; }
+   if (hypre_ParAMGDataParticipate(amg)) { return "sequential coarse AMG (seq_threshold)"; }
+   if (hypre_ParAMGDataFlexibleNumLevels(amg) > 0) { return "flexible cycle structure"; }
+   if (hypre_ParAMGDataPartialCycleCoarsestLevel(amg) >= 0) { return "partial cycles"; }
+   if ((hypre_ParAMGDataAdditive(amg) >= 0 && hypre_ParAMGDataAdditive(amg) < nl) ||
+       (hypre_ParAMGDataMultAdditive(amg) >= 0 && hypre_ParAMGDataMultAdditive(amg) < nl) ||
+       (hypre_ParAMGDataSimple(amg) >= 0 && hypre_ParAMGDataSimple(amg) < nl)) { return "additive cycles"; }
+   if (nl > 1)
+   {
+      for (k = 1; k <= 2; k++) { if (!relax_type_on_path(grt[k])) { return "relaxation type of the down/up cycle"; } }
+      if (!(grt[3] == 9 || grt[3] == 19 || relax_type_on_path(grt[3]))) { return "coarsest-level solver type"; }
+   }
+   else
+   {
+      HYPRE_Int t = hypre_ParAMGDataUserRelaxType(amg);
+      if (t == -1) { t = 6; }
+      if (!(t == 9 || t == 19 || relax_type_on_path(t))) { return "single-level relaxation type"; }
+   }
+   return NULL;
+}
+
+static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
+{
+   hypre_ParAMGData *amg = (hypre_ParAMGData *) amg_vdata;
+   amg_mirror *m;
+   HYPRE_Int nl, l, coarse_type;
+   hypre_ParCSRMatrix **A_array, **P_array;
+   hypre_Vector **l1, **ds;
+   hypre_IntArray **cf;
+   HYPRE_Real **coefs;
+   for (m = g_amgs; m; m = m->next) { if (m->amg_data == amg_vdata && m->A0 == A0) { return m->dev; } }
+   drop_amg(amg_vdata);
+   nl = hypre_ParAMGDataNumLevels(amg);
+   A_array = hypre_ParAMGDataAArray(amg);
+   P_array = hypre_ParAMGDataPArray(amg);
+   l1 = hypre_ParAMGDataL1Norms(amg);
+   cf = hypre_ParAMGDataCFMarkerArray(amg);
+   ds = hypre_ParAMGDataChebyDS(amg);
+   coefs = hypre_ParAMGDataChebyCoefs(amg);
+   m = (amg_mirror *) calloc(1, sizeof(amg_mirror));
+   m->amg_data = amg_vdata; m->A0 = A0; m->num_levels = nl;
+   m->owned = (hb200_parcsr **) calloc((size_t) (2 * nl + 2), sizeof(hb200_parcsr *));
+   if (hb200_amg_create(&m->dev, nl)) { goto fail; }
+   for (l = 0; l < nl; l++)
+   {
+      /* level 0 is the caller's matrix (par_amg_solve.c:108), mirrored once and shared with the Krylov solver */
+      hb200_parcsr *dA = (l == 0) ? mirror_matrix(A0) : upload_matrix(A_array[l]);
+      hb200_parcsr *dP = NULL;
+      int uses_cheby = 0, k;
+      if (!dA) { goto fail; }
+      if (l > 0) { m->owned[m->num_owned++] = dA; }
+      if (l < nl - 1)
+      {
+         dP = upload_matrix(P_array[l]);
+         if (!dP) { goto fail; }
+         m->owned[m->num_owned++] = dP;
+      }
+      if (hb200_amg_set_level(m->dev, l, dA, dP,
+                              (l1 && l1[l]) ? hypre_VectorData(l1[l]) : NULL,
+                              (cf && cf[l]) ? hypre_IntArrayData(cf[l]) : NULL,
+                              hypre_ParAMGDataRelaxWeight(amg)[l], hypre_ParAMGDataOmega(amg)[l])) { goto fail; }
+      for (k = 1; k <= 3; k++) { if (hypre_ParAMGDataGridRelaxType(amg)[k] == 16) { uses_cheby = 1; } }
+      if (uses_cheby && coefs && coefs[l])
+      {
+         if (hb200_amg_set_level_cheby(m->dev, l, (ds && ds[l]) ? hypre_VectorData(ds[l]) : NULL, coefs[l],
+                                       hypre_ParAMGDataChebyOrder(amg))) { goto fail; }
+      }
+   }
+   if (hb200_amg_set_cycle(m->dev, hypre_ParAMGDataNumGridSweeps(amg), hypre_ParAMGDataGridRelaxType(amg),
+                           hypre_ParAMGDataRelaxOrder(amg), hypre_ParAMGDataCycleType(amg),
+                           hypre_ParAMGDataFCycle(amg), hypre_ParAMGDataChebyOrder(amg),
+                           hypre_ParAMGDataChebyScale(amg), hypre_ParAMGDataChebyVariant(amg),
+                           hypre_ParAMGDataUserRelaxType(amg))) { goto fail; }
+   coarse_type = nl > 1 ? hypre_ParAMGDataGridRelaxType(amg)[3] : hypre_ParAMGDataUserRelaxType(amg);
+   if (coarse_type == 9 || coarse_type == 19)
+   {
+      hypre_ParCSRMatrix *Ac = A_array[nl - 1];
+      HYPRE_Int n = (HYPRE_Int) hypre_ParCSRMatrixGlobalNumRows(Ac);
+      HYPRE_Real *A_mat;
+      HYPRE_Real *zeros = NULL;
+      if (hypre_ParAMGDataGSSetup(amg) == 0) { hypre_GaussElimSetup(amg, nl - 1, coarse_type); }
+      A_mat = hypre_ParAMGDataAMat(amg);
+      if (!A_mat) { zeros = (HYPRE_Real *) calloc((size_t) n * (size_t) n, sizeof(HYPRE_Real)); A_mat = zeros; }
+      if (hb200_amg_set_coarse_ge(m->dev, A_mat, n, (int) hypre_ParCSRMatrixFirstRowIndex(Ac),
+                                  hypre_ParCSRMatrixNumRows(Ac))) { free(zeros); goto fail; }
+      free(zeros);
+   }
+   if (!getenv("HYPRE_B200_NO_GRAPH")) { hb200_amg_set_use_graph(m->dev, 1); }
+   m->next = g_amgs;
+   g_amgs = m;
+   return m->dev;
+fail:
+   hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+   fprintf(stderr, "[hypre_b200] hierarchy upload failed: %s\n", hb200_last_error());
+   if (m->dev) { hb200_amg_destroy(m->dev); }
+   for (l = 0; l < m->num_owned; l++) { hb200_parcsr_destroy(m->owned[l]); }
+   free(m->owned);
+   free(m);
+   return NULL;
+}
+
+/* ---- lifetime hooks ------------------------------------------------------------------------------ */
+
+HYPRE_Int hypre_ParCSRMatrixDestroy(hypre_ParCSRMatrix *matrix)
+{
+   static HYPRE_Int (*orig)(hypre_ParCSRMatrix *) = NULL;
+   if (!orig) { orig = (HYPRE_Int (*)(hypre_ParCSRMatrix *)) next_sym("hypre_ParCSRMatrixDestroy"); }
+   if (matrix) { drop_matrix(matrix); }
+   return orig(matrix);
+}
+
+HYPRE_Int hypre_BoomerAMGDestroy(void *data)
+{
+   static HYPRE_Int (*orig)(void *) = NULL;
+   if (!orig) { orig = (HYPRE_Int (*)(void *)) next_sym("hypre_BoomerAMGDestroy"); }
+   if (data) { drop_amg(data); }
+   return orig(data);
+}
+
+HYPRE_Int hypre_BoomerAMGSetup(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_ParVector *f, hypre_ParVector *u)
+{
+   static HYPRE_Int (*orig)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *) = NULL;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *)) next_sym("hypre_BoomerAMGSetup"); }
+   drop_amg(amg_vdata);   /* a new setup invalidates the uploaded hierarchy */
+   return orig(amg_vdata, A, f, u);   /* the reference's own setup, on the CPU */
+}
+
+/* ---- BoomerAMG solve ------------------------------------------------------------------------------- */
+
+HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_ParVector *f, hypre_ParVector *u)
+{
+   static HYPRE_Int (*orig)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *) = NULL;
+   static int noticed = 0;
+   hypre_ParAMGData *amg = (hypre_ParAMGData *) amg_vdata;
+   const char *why = amg_unsupported(amg);
+   hb200_amg *dev;
+   double *df = NULL, *du = NULL, rel = 0.0;
+   int n = hypre_ParCSRMatrixNumRows(A), its = 0, flag;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *)) next_sym("hypre_BoomerAMGSolve"); }
+   if (!why && (hypre_ParAMGDataPrintLevel(amg) > 1 || hypre_ParAMGDataLogging(amg) > 1)) { why = "per-cycle printing / residual logging of stand-alone BoomerAMG"; }
+   if (!why && hypre_ParVectorNumVectors(f) > 1) { why = "multi-vector BoomerAMG solve"; }
+   if (why)
+   {
+      if (g_strict) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, why); return hypre_error_flag; }
+      notice_once(&noticed, why);
+      return orig(amg_vdata, A, f, u);
+   }
+   if (shim_init(hypre_ParCSRMatrixComm(A))) { return hypre_error_flag; }
+   dev = mirror_amg(amg_vdata, A);
+   if (!dev) { return hypre_error_flag; }
+   hb200_amg_set_solve(dev, hypre_ParAMGDataTol(amg), hypre_ParAMGDataMinIter(amg), hypre_ParAMGDataMaxIter(amg),
+                       hypre_ParAMGDataConvergeType(amg));
+   if (hb200_malloc((void **) &df, sizeof(double) * (size_t) (n ? n : 1)) || hb200_malloc((void **) &du, sizeof(double) * (size_t) (n ? n : 1)))
+   {
+      hypre_error_w_msg(HYPRE_ERROR_MEMORY, hb200_last_error());
+      return hypre_error_flag;
+   }
+   hb200_memcpy_h2d(df, hypre_VectorData(hypre_ParVectorLocalVector(f)), sizeof(double) * (size_t) n);
+   if (!hypre_ParVectorAllZeros(u)) { hb200_memcpy_h2d(du, hypre_VectorData(hypre_ParVectorLocalVector(u)), sizeof(double) * (size_t) n); }
+   flag = hb200_amg_solve(dev, df, du, hypre_ParVectorAllZeros(u) ? 1 : 0, &its, &rel);
+   hb200_memcpy_d2h(hypre_VectorData(hypre_ParVectorLocalVector(u)), du, sizeof(double) * (size_t) n);
+   hb200_free(df); hb200_free(du);
+   hypre_ParVectorAllZeros(u) = 0;
+   hypre_ParAMGDataNumIterations(amg) = its;
+   hypre_ParAMGDataRelativeResidualNorm(amg) = rel;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
+   return hypre_error_flag;
+}
+
+/* ---- Krylov drivers --------------------------------------------------------------------------------- */
+
+/* which preconditioner did the user install?  (HYPRE_PCGSetPrecond stores the solve function) */
+static int precond_kind(void *precond_fn, void *precond_data, hypre_ParCSRMatrix *A, hb200_amg **amg, const char **why)
+{
+   *amg = NULL; *why = NULL;
+   if (precond_fn == (void *) hypre_ParKrylovIdentity) { return HB200_PRECOND_NONE; }
+   if (precond_fn == (void *) HYPRE_ParCSRDiagScale) { return HB200_PRECOND_DIAGSCALE; }
+   if (precond_fn == (void *) HYPRE_BoomerAMGSolve || precond_fn == (void *) hypre_BoomerAMGSolve)
+   {
+      *why = amg_unsupported((hypre_ParAMGData *) precond_data);
+      if (*why) { return -1; }
+      *amg = mirror_amg(precond_data, A);
+      if (!*amg) { *why = "hierarchy upload failed"; return -2; }
+      {
+         hypre_ParAMGData *ad = (hypre_ParAMGData *) precond_data;
+         hb200_amg_set_solve(*amg, hypre_ParAMGDataTol(ad), hypre_ParAMGDataMinIter(ad), hypre_ParAMGDataMaxIter(ad),
+                             hypre_ParAMGDataConvergeType(ad));
+      }
+      return HB200_PRECOND_AMG;
+   }
+   *why = "preconditioner other than BoomerAMG / diagonal scaling / none";
+   return -1;
+}
+
+HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_PCGData *pd = (hypre_PCGData *) pcg_vdata;
+   hypre_PCGFunctions *fn = pd->functions;
+   const char *why = NULL;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA;
+   hb200_pcg_params P;
+   hb200_krylov_result R;
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   int kind, flag;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_PCGSolve"); }
+   /* only the ParCSR function table (HYPRE_ParCSRPCGCreate) is on the accelerated path */
+   if (fn->Matvec != hypre_ParKrylovMatvec) { return orig(pcg_vdata, A, b, x); }
+   if (pd->precond_Mat && pd->precond_Mat != A) { why = "separate preconditioning matrix"; }
+   if (!why && hypre_ParVectorNumVectors((hypre_ParVector *) b) > 1) { why = "multi-vector PCG"; }
+   if (!why)
+   {
+      if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+      kind = precond_kind((void *) fn->precond, pd->precond_data, pA, &amg, &why);
+      if (kind == -2) { return hypre_error_flag; }
+   }
+   if (why)
+   {
+      if (g_strict) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, why); return hypre_error_flag; }
+      notice_once(&noticed, why);
+      return orig(pcg_vdata, A, b, x);
+   }
+   dA = mirror_matrix(pA);
+   if (!dA) { return hypre_error_flag; }
+   hb200_pcg_default_params(&P);
+   P.tol = pd->tol; P.a_tol = pd->a_tol; P.atolf = pd->atolf; P.cf_tol = pd->cf_tol; P.rtol = pd->rtol;
+   P.max_iter = pd->max_iter; P.two_norm = pd->two_norm; P.rel_change = pd->rel_change;
+   P.recompute_residual = pd->recompute_residual; P.recompute_residual_p = pd->recompute_residual_p;
+   P.stop_crit = pd->stop_crit; P.skip_break = pd->skip_break; P.flex = pd->flex; P.hybrid = pd->hybrid;
+   P.logging = pd->logging; P.print_level = pd->print_level;
+   pd->converged = 0;
+   flag = hb200_pcg_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                               hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)),
+                               pd->norms, pd->rel_norms, &R);
+   pd->num_iterations = R.num_iterations;
+   pd->rel_residual_norm = R.rel_residual_norm;
+   pd->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_CONV, hb200_last_error()); }
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] PCG on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_GMRESData *gd = (hypre_GMRESData *) gmres_vdata;
+   hypre_GMRESFunctions *fn = gd->functions;
+   const char *why = NULL;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA;
+   hb200_gmres_params P;
+   hb200_krylov_result R;
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   int kind, flag;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_GMRESSolve"); }
+   if (fn->Matvec != hypre_ParKrylovMatvec) { return orig(gmres_vdata, A, b, x); }
+   if (gd->precond_Mat && gd->precond_Mat != A) { why = "separate preconditioning matrix"; }
+   if (!why && gd->xref) { why = "GMRES with a reference solution"; }
+   if (!why && gd->print_level > 2) { why = "tagged residual printing (print_level > 2)"; }
+   if (!why && hypre_ParVectorNumVectors((hypre_ParVector *) b) > 1) { why = "multi-vector GMRES"; }
+   if (!why)
+   {
+      if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+      kind = precond_kind((void *) fn->precond, gd->precond_data, pA, &amg, &why);
+      if (kind == -2) { return hypre_error_flag; }
+   }
+   if (why)
+   {
+      if (g_strict) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, why); return hypre_error_flag; }
+      notice_once(&noticed, why);
+      return orig(gmres_vdata, A, b, x);
+   }
+   dA = mirror_matrix(pA);
+   if (!dA) { return hypre_error_flag; }
+   hb200_gmres_default_params(&P);
+   P.tol = gd->tol; P.a_tol = gd->a_tol; P.cf_tol = gd->cf_tol; P.k_dim = gd->k_dim; P.min_iter = gd->min_iter;
+   P.max_iter = gd->max_iter; P.rel_change = gd->rel_change; P.skip_real_r_check = gd->skip_real_r_check;
+   P.stop_crit = gd->stop_crit; P.hybrid = gd->hybrid; P.logging = gd->logging; P.print_level = gd->print_level;
+   gd->converged = 0;
+   flag = hb200_gmres_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                                 hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), gd->norms, &R);
+   gd->num_iterations = R.num_iterations;
+   gd->rel_residual_norm = R.rel_residual_norm;
+   gd->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] GMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+/* ---- user-level matvec (ij -solver -1 loops over this) ------------------------------------------------ */
+
+HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y)
+{
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   hb200_parcsr *dA;
+   if (hypre_ParVectorNumVectors((hypre_ParVector *) x) > 1)
+   {
+      return hypre_ParCSRMatrixMatvec(alpha, pA, (hypre_ParVector *) x, beta, (hypre_ParVector *) y);
+   }
+   if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+   dA = mirror_matrix(pA);
+   if (!dA) { return hypre_error_flag; }
+   if (hb200_parcsr_matvec_host(dA, alpha, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), beta,
+                                hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) y))))
+   {
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+   }
+   hypre_ParVectorAllZeros((hypre_ParVector *) y) = 0;
+   return hypre_error_flag;
+}
+
+HYPRE_Int HYPRE_ParCSRMatrixMatvecT(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y)
+{
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   hb200_parcsr *dA;
+   double *dx = NULL, *dy = NULL;
+   int nr = hypre_ParCSRMatrixNumRows(pA), nc = hypre_ParCSRMatrixNumCols(pA);
+   if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+   dA = mirror_matrix(pA);
+   if (!dA) { return hypre_error_flag; }
+   if (hb200_malloc((void **) &dx, sizeof(double) * (size_t) (nr ? nr : 1)) || hb200_malloc((void **) &dy, sizeof(double) * (size_t) (nc ? nc : 1)))
+   {
+      hypre_error_w_msg(HYPRE_ERROR_MEMORY, hb200_last_error());
+      return hypre_error_flag;
+   }
+   hb200_memcpy_h2d(dx, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), sizeof(double) * (size_t) nr);
+   hb200_memcpy_h2d(dy, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) y)), sizeof(double) * (size_t) nc);
+   if (hb200_parcsr_matvecT(dA, alpha, dx, beta, dy)) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
+   hb200_memcpy_d2h(hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) y)), dy, sizeof(double) * (size_t) nc);
+   hb200_free(dx); hb200_free(dy);
+   return hypre_error_flag;
+}

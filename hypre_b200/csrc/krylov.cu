@@ -31,13 +31,6 @@ enum {
    S_H0 = 16   // GMRES: hh column (k_dim + 1 entries, k_dim <= 40)
 };
 
-__global__ void diag_extract_kernel(int n, const int *__restrict__ di, const double *__restrict__ da,
-                                    double *__restrict__ out)
-{
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) out[i] = da[di[i]];   // first entry of each diag row is the diagonal
-}
-
 static int precond_apply(int kind, hb200_amg *amg, hb200_parcsr *A, const double *r, double *z)
 {
    // the Krylov solvers always ClearVector(z) first => zero initial guess
@@ -46,16 +39,11 @@ static int precond_apply(int kind, hb200_amg *amg, hb200_parcsr *A, const double
    switch (kind) {
       case HB200_PRECOND_AMG:
          return amg_solve(amg, A, r, z, true, nullptr, nullptr) & ~HB200_ERROR_CONV;
-      case HB200_PRECOND_DIAGSCALE:
-         if (!A->d_diaginv) {
-            HB_CUDA(cudaMalloc(&A->d_diaginv, sizeof(double) * (n ? n : 1)));
-            if (n) {
-               HB_LAUNCH(diag_extract_kernel, (int) ((n + 255) / 256), 256, 0, c.s_comp, (int) n,
-                         A->diag.i, A->diag.a, A->d_diaginv);
-               HB_LAUNCH_CHECK();
-            }
-         }
-         return vec_diag_scale(A->d_diaginv, r, z, n, c.s_comp);
+      case HB200_PRECOND_DIAGSCALE: {
+         const double *dg = nullptr;
+         HB_CHECK(parcsr_diag(A, &dg));
+         return vec_diag_scale(dg, r, z, n, c.s_comp);
+      }
       default:   // hypre_ParKrylovIdentity: copy
          return vec_copy(r, z, n, c.s_comp);
    }

@@ -122,6 +122,30 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
    return 0;
 }
 
+__global__ void diag_extract_kernel(int n, const int *__restrict__ di, const double *__restrict__ da,
+                                    double *__restrict__ out)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) out[i] = da[di[i]];   // first entry of each diag row is the diagonal (par_relax.c:274)
+}
+
+// diagonal of A as a device vector (built on first use)
+int parcsr_diag(hb200_parcsr *A, const double **out)
+{
+   Ctx &c = ctx();
+   if (!A->d_diaginv) {
+      const size_t n = (size_t) A->num_rows;
+      HB_CUDA(cudaMalloc(&A->d_diaginv, sizeof(double) * (n ? n : 1)));
+      if (n) {
+         HB_LAUNCH(diag_extract_kernel, (int) ((n + 255) / 256), 256, 0, c.s_comp, (int) n, A->diag.i,
+                   A->diag.a, A->d_diaginv);
+         HB_LAUNCH_CHECK();
+      }
+   }
+   *out = A->d_diaginv;
+   return 0;
+}
+
 // download a device CSR block to the host (used to build transposes / schedules lazily)
 static int dcsr_download(const DCsr &M, std::vector<int> &hi, std::vector<int> &hj,
                          std::vector<double> &ha)

@@ -66,8 +66,13 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
    EpiArgs ea;
    ea.w = w; ea.b = f; ea.u = uin; ea.y = u_out;
    ea.cf = cf; ea.relax_points = relax_points;
-   if (relax_type == 0) { ea.d = nullptr; ea.skip_diag = 1; }
-   else                 { ea.d = l1; ea.skip_diag = 0; }
+   if (relax_type == 0) {
+      // the divisor is the diagonal of the diag block for BOTH passes (the offd pass cannot
+      // find it in its own block): use the extracted diagonal vector
+      const double *dg = nullptr;
+      HB_CHECK(parcsr_diag(A, &dg));
+      ea.d = dg; ea.skip_diag = 1;
+   } else { ea.d = l1; ea.skip_diag = 0; }
    HB_CHECK(spmv_launch(A->diag, uin, EPI_JACOBI_CORE, ea, false, c.s_comp));
    HB_CHECK(parcsr_halo_end(A, c.s_comp));
    if (A->num_cols_offd > 0) {

@@ -73,8 +73,8 @@ int rb_init(void)
    {
 #ifndef HYPRE_SEQUENTIAL
       int flag = 0;
-      hypre_MPI_Initialized(&flag);
-      if (!flag) { hypre_MPI_Init(NULL, NULL); }
+      MPI_Initialized(&flag);
+      if (!flag) { MPI_Init(NULL, NULL); }
 #endif
       HYPRE_Initialize();
       g_initialized = 1;
@@ -88,7 +88,7 @@ int rb_finalize(void)
    {
       HYPRE_Finalize();
 #ifndef HYPRE_SEQUENTIAL
-      hypre_MPI_Finalize();
+      MPI_Finalize();
 #endif
       g_initialized = 0;
    }

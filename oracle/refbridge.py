@@ -69,13 +69,15 @@ def available(mpi: bool = False) -> bool:
     return os.path.exists(os.path.join(REF_DIR, name))
 
 
-def load(mpi: bool = False) -> C.CDLL:
-    """Loads the bridge (and through it libHYPRE_ref*.so).  One flavour per process."""
+def load(mpi=None) -> C.CDLL:
+    """Loads the bridge (and through it libHYPRE_ref*.so).  One flavour per process;
+    mpi=None means "whatever is loaded" (serial if nothing is)."""
     global _lib, _mpi
     if _lib is not None:
-        if mpi != _mpi:
+        if mpi is not None and bool(mpi) != _mpi:
             raise RuntimeError("the serial and the mini-MPI reference builds cannot share a process")
         return _lib
+    mpi = bool(mpi)
     name = "libref_bridge_mpi.so" if mpi else "libref_bridge.so"
     path = os.path.join(REF_DIR, name)
     if not os.path.exists(path):
@@ -135,7 +137,7 @@ class Problem:
     setup_amg) the reference's BoomerAMG hierarchy."""
 
     def __init__(self, kind: str, n, P=(1, 1, 1), eps: float = 1.0, rhs: str = "ones",
-                 x0rand: bool = False, mpi: bool = False):
+                 x0rand: bool = False, mpi=None):
         self.lib = load(mpi)
         nx, ny, nz = n
         rhs_type = {"ones": 0, "rand": 1}[rhs]

@@ -1,0 +1,183 @@
+"""Multi-rank parity worker (one process per GPU, launched by torch.distributed.run).
+
+Every rank: builds its part of an ij problem with the reference running on minimpi, runs the
+reference's BoomerAMGSetup, uploads its part of the hierarchy through the hb200 C-ABI, then checks
+the NCCL path against the reference's MPI path on the same inputs: bit-exact maps, SpMV / SpMV-T
+/ relax / cycle to 1e-12-ish, PCG / GMRES iteration counts and residual histories."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def relerr(a, b, den=None):
+    d = np.max(np.abs(b)) if den is None else den
+    return float(np.max(np.abs(a - b)) / (d if d > 0 else 1.0)) if a.size else 0.0
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    kind = sys.argv[1] if len(sys.argv) > 1 else "27pt"
+    halo = sys.argv[2] if len(sys.argv) > 2 else "nccl"
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import hypre_b200 as hb
+    from hypre_b200._lib import lib, check
+    from oracle import refbridge as rb
+    hb.init(local)
+    uid = [hb.comm_get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    hb.comm_init(rank, world, uid[0])
+    if halo == "peer":
+        check(lib.hb200_set_halo_mode(1))
+    rb.load(mpi=True)
+    rb.set_num_threads(1)
+    P = {1: (1, 1, 1), 2: (2, 1, 1), 3: (3, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    n = (12 * P[0], 11 * P[1], 10 * P[2])
+    pb = rb.Problem(kind, n, P=P, mpi=True)
+    pb.setup_amg(relax_type=18)
+    h = pb.hierarchy()
+    mats, amg = hb.amg_from_hierarchy(h)
+    nl = pb.num_levels
+
+    def gmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+    fails = []
+
+    def expect(cond, what):
+        ok = gmax(0.0 if cond else 1.0) == 0.0
+        if not ok:
+            fails.append(what)
+        if rank == 0:
+            print(("ok   " if ok else "FAIL ") + what, flush=True)
+
+    rng = np.random.default_rng(100 + rank)
+    # ---- maps: bit-exact round trip
+    same = True
+    for l, (A, Pm) in enumerate(mats):
+        for M, view in ((A, h["levels"][l]["A"]), (Pm, h["levels"][l]["P"])):
+            if M is None:
+                continue
+            ref = view.arrays()
+            got = M.download_maps()
+            for key in ("diag_i", "diag_j", "offd_i", "offd_j", "col_map_offd", "send_map_starts",
+                        "send_map_elmts", "recv_vec_starts", "send_procs", "recv_procs"):
+                r_, g_ = ref.get(key), got.get(key)
+                if r_ is None or g_ is None:
+                    continue
+                same = same and np.array_equal(np.asarray(r_), np.asarray(g_)[: len(r_)])
+    expect(same, "CommPkg / col_map_offd / CSR index arrays bit-exact after device round trip")
+
+    # ---- SpMV, SpMV-T on every level
+    worst = 0.0
+    for l, (A, Pm) in enumerate(mats):
+        for which, M in ((0, A), (1, Pm)):
+            if M is None:
+                continue
+            x = rng.standard_normal(M.num_cols)
+            b = rng.standard_normal(M.num_rows)
+            for al, be in ((1.0, 0.0), (-1.0, 1.0), (0.7, -0.3)):
+                yref = pb.matvec(al, x, be, b, level=l, which=which)
+                y = torch.empty(M.num_rows, dtype=torch.float64, device="cuda")
+                M.matvec(al, dev(x), be, y, b=dev(b))
+                den = gmax(float(np.max(np.abs(yref))) if yref.size else 0.0)
+                worst = max(worst, relerr(y.cpu().numpy(), yref, den))
+    expect(gmax(worst) <= 1e-12, f"ParCSR matvec, all levels, A and P (worst {gmax(worst):.2e})")
+    worst = 0.0
+    for l, (A, Pm) in enumerate(mats):
+        if Pm is None:
+            continue
+        x = rng.standard_normal(Pm.num_rows)
+        y0 = rng.standard_normal(Pm.num_cols)
+        for al, be in ((1.0, 0.0), (-2.0, 0.5)):
+            yref = pb.matvecT(al, x, be, y0, level=l, which=1)
+            y = dev(y0)
+            Pm.matvecT(al, dev(x), be, y)
+            den = gmax(float(np.max(np.abs(yref))) if yref.size else 0.0)
+            worst = max(worst, relerr(y.cpu().numpy(), yref, den))
+    expect(gmax(worst) <= 1e-12, f"ParCSR matvecT (restriction), all levels (worst {gmax(worst):.2e})")
+
+    # ---- relaxation
+    worst = 0.0
+    for l in range(min(nl - 1, 3)):
+        A = mats[l][0]
+        L = h["levels"][l]
+        nloc = A.num_rows
+        f = rng.standard_normal(nloc)
+        u = rng.standard_normal(nloc)
+        cf = torch.from_numpy(np.ascontiguousarray(L["cf_marker"])).cuda() if L["cf_marker"] is not None else None
+        l1 = dev(L["l1_norms"]) if L["l1_norms"] is not None else None
+        for rt, pts, w, om in ((18, 0, 1.0, 1.0), (18, 1, 0.9, 1.0), (0, 0, 0.8, 1.0), (7, -1, 1.0, 1.0),
+                               (13, 0, 1.0, 1.0), (14, 0, 1.0, 1.0), (8, 0, 0.9, 1.1), (6, 1, 1.0, 1.0), (3, 0, 1.0, 1.0)):
+            use_l1 = rt in (7, 18, 8, 13, 14, 88, 89)
+            if (use_l1 and l1 is None) or (pts != 0 and cf is None):
+                continue
+            uref = pb.relax(l, rt, f, u, relax_points=pts, relax_weight=w, omega=om, use_l1=use_l1)
+            du = dev(u)
+            hb.relax(A, dev(f), du, rt, relax_points=pts, relax_weight=w, omega=om,
+                     l1_norms=l1 if use_l1 else None, cf_marker=cf)
+            den = gmax(float(np.max(np.abs(uref))) if uref.size else 0.0)
+            e = gmax(relerr(du.cpu().numpy(), uref, den))
+            if e > 1e-11 and rank == 0:
+                print(f"     relax type {rt} points {pts} w {w} omega {om} level {l}: err {e:.2e}", flush=True)
+            worst = max(worst, e)
+    expect(worst <= 1e-11, f"relaxation sweeps (Jacobi + hybrid GS families) (worst {worst:.2e})")
+
+    # ---- one V-cycle
+    A0 = mats[0][0]
+    n0 = A0.num_rows
+    f = rng.standard_normal(n0)
+    uref = pb.amg_solve(f, np.zeros(n0), u_all_zeros=True)
+    du = torch.zeros(n0, dtype=torch.float64, device="cuda")
+    amg.cycle(dev(f), du, u_all_zeros=True)
+    den = gmax(float(np.max(np.abs(uref))))
+    e = gmax(relerr(du.cpu().numpy(), uref, den))
+    expect(e <= 1e-11, f"V(1,1)-cycle, zero initial guess (err {e:.2e})")
+
+    # ---- PCG
+    ref = pb.pcg(precond="amg", tol=1e-8, max_iter=100, two_norm=1)
+    pcg = hb.ParCSRPCG(tol=1e-8, max_iter=100, two_norm=1)
+    pcg.set_precond(amg)
+    x = torch.zeros(n0, dtype=torch.float64, device="cuda")
+    pcg.solve(A0, dev(pb.b), x)
+    k = ref["iterations"]
+    ok = (pcg.num_iterations == k) and relerr(pcg.norms[: k + 1], ref["norms"]) <= 1e-9
+    expect(ok, f"AMG-PCG: {pcg.num_iterations} its (reference {k}), rel.res {pcg.final_relative_residual_norm:.6e} "
+               f"(reference {ref['final_rel_res']:.6e})")
+    den = gmax(float(np.max(np.abs(ref["x"]))))
+    e = gmax(relerr(x.cpu().numpy(), ref["x"], den))
+    expect(e <= 1e-8, f"AMG-PCG solution (err {e:.2e})")
+
+    # ---- GMRES
+    ref = pb.gmres(precond="amg", tol=1e-8, max_iter=100, k_dim=5)
+    gm = hb.ParCSRGMRES(tol=1e-8, max_iter=100, k_dim=5)
+    gm.set_precond(amg)
+    x = torch.zeros(n0, dtype=torch.float64, device="cuda")
+    gm.solve(A0, dev(pb.b), x)
+    expect(abs(gm.num_iterations - ref["iterations"]) <= 1,
+           f"AMG-GMRES(5): {gm.num_iterations} its (reference {ref['iterations']})")
+    den = gmax(float(np.max(np.abs(ref["x"]))))
+    e = gmax(relerr(x.cpu().numpy(), ref["x"], den))
+    expect(e <= 1e-7, f"AMG-GMRES solution (err {e:.2e})")
+
+    dist.barrier()
+    dist.destroy_process_group()
+    if fails:
+        raise SystemExit(f"rank {rank}: {len(fails)} parity failures: {fails}")
+    if rank == 0:
+        print("MULTI-RANK PARITY OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,7 +101,7 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5 };
 
 struct DCsr {
    int        nrows = 0, ncols = 0;

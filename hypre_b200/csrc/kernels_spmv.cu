@@ -265,7 +265,7 @@ spmv_stream_lc(const int *__restrict__ rowptr, const int *__restrict__ colind,
 // ---------------------------------------------------------------------------------------
 constexpr int kVecThreads = 256;
 
-template <int EPI, int K>
+template <int EPI, int K, int U>
 __global__ void __launch_bounds__(kVecThreads)
 spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ rowptr,
             const int *__restrict__ colind, const double *__restrict__ val,
@@ -282,7 +282,22 @@ spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ 
       row = rowlist ? rowlist[idx] : idx;
       p0 = rowptr[row];
       const int p1 = rowptr[row + 1];
-      for (int p = p0 + skip + lane; p < p1; p += K) {
+      int p = p0 + skip + lane;
+      if (U > 1) {
+         // U independent (index, value) loads in flight per lane before the dependent x gathers:
+         // the kernel is latency-bound on bytes in flight, not on issue slots
+         for (; p + (U - 1) * K < p1; p += U * K) {
+            int c[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) c[u] = colind[p + u * K];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = val[p + u * K];
+#pragma unroll
+            for (int u = 0; u < U; u++) s += v[u] * __ldg(x + c[u]);
+         }
+      }
+      for (; p < p1; p += K) {
          s += val[p] * __ldg(x + colind[p]);
       }
    }
@@ -327,28 +342,30 @@ static int launch_stream(const DCsr &M, const double *x, const EpiArgs &ea, cuda
 
 template <int EPI, int K>
 static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
-                           cudaStream_t st)
+                           int unroll, cudaStream_t st)
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    const long long threads = (long long) nlist * K;
    const int grid = (int) ((threads + kVecThreads - 1) / kVecThreads);
-   HB_LAUNCH((spmv_vector<EPI, K>), grid, kVecThreads, 0, st, nlist,
-             use_rownnz ? M.rownnz : (const int *) nullptr, M.i, M.j, M.a, x, ea);
+   const int *rl = use_rownnz ? M.rownnz : (const int *) nullptr;
+   if (unroll >= 4)      HB_LAUNCH((spmv_vector<EPI, K, 4>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
+   else if (unroll >= 2) HB_LAUNCH((spmv_vector<EPI, K, 2>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
+   else                  HB_LAUNCH((spmv_vector<EPI, K, 1>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
 }
 
 template <int EPI>
 static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
-                         int lanes, cudaStream_t st)
+                         int lanes, int unroll, cudaStream_t st)
 {
    switch (lanes) {
-      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, use_rownnz, st);
-      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, use_rownnz, st);
-      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, use_rownnz, st);
-      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, use_rownnz, st);
-      case 16: return launch_vector_K<EPI, 16>(M, x, ea, use_rownnz, st);
-      default: return launch_vector_K<EPI, 32>(M, x, ea, use_rownnz, st);
+      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, use_rownnz, unroll, st);
+      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, use_rownnz, unroll, st);
+      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, use_rownnz, unroll, st);
+      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, use_rownnz, unroll, st);
+      case 16: return launch_vector_K<EPI, 16>(M, x, ea, use_rownnz, unroll, st);
+      default: return launch_vector_K<EPI, 32>(M, x, ea, use_rownnz, unroll, st);
    }
 }
 
@@ -372,13 +389,15 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
    if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
    }
-   int lanes = (M.kind == SPMV_VECTOR && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
+   const bool vec = (M.kind == SPMV_VECTOR || M.kind == SPMV_VECTOR_U2 || M.kind == SPMV_VECTOR_U4);
+   int lanes = (vec && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
+   const int unroll = M.kind == SPMV_VECTOR_U4 ? 4 : M.kind == SPMV_VECTOR_U2 ? 2 : 1;
    if (lanes == 0) {
       const double avg = use_rownnz ? (double) M.nnz / (double) (M.num_rownnz ? M.num_rownnz : 1)
                                     : M.avg_row_nnz;
       lanes = vector_lanes_for(avg);
    }
-   return launch_vector<EPI>(M, x, ea, use_rownnz, lanes, st);
+   return launch_vector<EPI>(M, x, ea, use_rownnz, lanes, unroll, st);
 }
 
 int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, bool use_rownnz,

@@ -23,6 +23,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <sys/time.h>
 #include <time.h>
 #include <unistd.h>
@@ -59,6 +60,7 @@ typedef struct
    volatile int       attached[MM_MAXRANK];
    volatile int       finalized[MM_MAXRANK];
    long long          create_ns;
+   char               payload_dir[96];   /* where large payload files go (tmpfs if it is big enough) */
    mm_box             box[];
 } mm_shared;
 
@@ -382,7 +384,7 @@ int MPI_Group_free(MPI_Group *group)
 
 static void payload_path(char *out, size_t n, int src, unsigned long long seq)
 {
-   snprintf(out, n, "/dev/shm/minimpi_%s_m_%d_%llu", g_job, src, seq);
+   snprintf(out, n, "%s/minimpi_%s_m_%d_%llu", G->payload_dir, g_job, src, seq);
 }
 
 static int req_matches(const mm_req *r, const msg *m)
@@ -1219,6 +1221,18 @@ int MPI_Init(int *argc, char ***argv)
       }
       G->nranks = g_size;
       G->create_ns = now_ns();
+      {
+         /* large messages travel as files: tmpfs when it has room (containers often cap /dev/shm
+            at 64 MB), else MINIMPI_TMPDIR or /tmp */
+         const char *d = getenv("MINIMPI_TMPDIR");
+         struct statvfs vf;
+         if (!d)
+         {
+            d = "/tmp";
+            if (statvfs("/dev/shm", &vf) == 0 && (double) vf.f_bavail * (double) vf.f_frsize > 8e9) { d = "/dev/shm"; }
+         }
+         snprintf((char *) G->payload_dir, sizeof(G->payload_dir), "%s", d);
+      }
       G->attached[0] = (int) getpid();
       __sync_synchronize();
       G->magic = MM_MAGIC;

@@ -41,7 +41,7 @@ def spmv(): check(lib.hb200_parcsr_matvec(A.handle, 1.0, x.data_ptr(), 0.0, y.da
 if variants == "one":
     cfgs = [(2, 1)]
 else:
-    cfgs = [(2, 1), (2, 2), (2, 4), (3, 1), (3, 2), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)]
+    cfgs = [(1, 1), (1, 2), (1, 4), (1, 8), (4, 1), (4, 2), (4, 4), (4, 8), (5, 1), (5, 2), (5, 4), (5, 8), (2, 1)]
 for k, L in cfgs:
     A.set_spmv_kernel(k, L)
     ms = timeit(spmv)

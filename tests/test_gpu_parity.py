@@ -125,7 +125,7 @@ def test_matvec_bit_exact_fine_level(lap27, torch):
     A.set_spmv_kernel(0, 0)
 
 
-@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8)])
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32)])
 def test_matvec_kernel_variants(lap27, torch, kind, lanes):
     rng = np.random.default_rng(5)
     for l in (0, 2):
@@ -411,3 +411,55 @@ def test_multi_gpu_parity_4ranks(torch):
     if torch.cuda.device_count() < 4:
         pytest.skip("needs 4 GPUs")
     _run_workers(4, "laplacian")
+
+
+# ----------------------------------------------------------------------------------------
+# drop-in: the UNMODIFIED reference driver (src/test/ij.c) linked in front of libHYPRE_b200.so
+# ----------------------------------------------------------------------------------------
+def _ij(binary, args, nprocs=1, env_extra=None):
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref")
+    exe = os.path.join(ref, binary)
+    if not os.path.exists(exe):
+        pytest.skip(f"{binary} not built (needs /root/reference at build time)")
+    env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
+    env.update(env_extra or {})
+    cmd = [exe, *args.split()]
+    if nprocs > 1:
+        cmd = [os.path.join(ref, "mpirun"), "-np", str(nprocs)] + cmd
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ref, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    its = re.findall(r"Iterations = (\d+)", r.stdout)
+    res = re.findall(r"Final (?:GMRES )?Relative Residual Norm = ([0-9.eE+-]+)", r.stdout)
+    return (int(its[-1]) if its else None, float(res[-1]) if res else None, r.stdout, r.stderr)
+
+
+@pytest.mark.parametrize("args", ["-laplacian -n 40 40 40 -solver 1 -rlx 18",
+                                  "-27pt -n 30 30 30 -solver 1 -rlx 18",
+                                  "-27pt -n 24 24 24 -solver 1",
+                                  "-vardifconv -n 30 30 30 -solver 3 -rlx 18",
+                                  "-laplacian -n 30 30 30 -solver 2",
+                                  "-laplacian -n 30 30 30 -solver 1 -rlx 16",
+                                  "-laplacian -n 30 30 30 -solver 1 -rlx 18 -CF 1 -mu 2"])
+def test_ij_dropin_matches_reference(args):
+    its_ref, res_ref, _, _ = _ij("ij_ref", args)
+    its_dev, res_dev, out, err = _ij("ij_b200", args)
+    assert "on device" in err, err[-1500:]          # the solve really ran through libhb200
+    assert its_dev == its_ref, (args, its_dev, its_ref)
+    # PCG: final residual to the 7 digits the reference's regression suite compares; GMRES: the
+    # Givens-recurrence residual estimate is only reproducible to a few per cent at 1e-9
+    rtol = 5e-2 if "-solver 3" in args else 2e-6
+    assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
+
+
+def test_ij_dropin_two_ranks(torch):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    args = "-27pt -n 40 30 30 -P 2 1 1 -solver 1 -rlx 18"
+    its_ref, res_ref, _, _ = _ij("ij_refmpi", args, nprocs=2)
+    its_dev, res_dev, out, err = _ij("ij_b200_mpi", args, nprocs=2)
+    assert "on device" in err, err[-1500:]
+    assert its_dev == its_ref and abs(res_dev - res_ref) <= 2e-6 * res_ref, (its_dev, its_ref, res_dev, res_ref)

@@ -21,8 +21,10 @@ LIB = os.path.join(HERE, "libhb200.so")
 SOURCES = [
     "runtime.cu",
     "kernels_spmv.cu",
+    "kernels_sell.cu",
     "kernels_blas1.cu",
     "parcsr.cu",
+    "parcsr_peer.cu",
     "relax.cu",
     "gs.cu",
     "amg.cu",

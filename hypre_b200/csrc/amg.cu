@@ -241,7 +241,8 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
 int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zeros)
 {
    Ctx &c = ctx();
-   if (!amg->use_graph || c.nranks > 1) {
+   // multi-rank: only the peer-put halo keeps every step of the cycle a plain kernel on one stream
+   if (!amg->use_graph || (c.nranks > 1 && c.halo_mode != 1)) {
       return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    }
    // CUDA-graph path: the topology of a cycle is fixed by the hierarchy, so capture once per
@@ -470,7 +471,7 @@ int hb200_amg_set_use_graph(hb200_amg *amg, int enable)
 int hb200_amg_cycle(hb200_amg *amg, const double *f, double *u, int u_all_zeros)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(amg && f && u, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(amg && ((f && u) || amg->lev[0].n == 0), HB200_ERROR_ARG, "null argument");
    for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
    return amg_cycle(amg, f, u, u_all_zeros != 0);
 }
@@ -479,7 +480,7 @@ int hb200_amg_solve(hb200_amg *amg, const double *f, double *u, int u_all_zeros,
                     double *rel_resid_norm)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(amg && f && u, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(amg && ((f && u) || amg->lev[0].n == 0), HB200_ERROR_ARG, "null argument");
    for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
    return amg_solve(amg, amg->lev[0].A, f, u, u_all_zeros != 0, num_iterations, rel_resid_norm);
 }

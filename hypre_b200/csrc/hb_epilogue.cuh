@@ -1,0 +1,66 @@
+// hb_epilogue.cuh — the fused SpMV epilogues shared by every SpMV kernel.
+#pragma once
+#include "hb_internal.cuh"
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum, double diag)
+{
+   if (EPI == EPI_AXPBY) {
+      // reference: y = (beta/alpha)*b; y += sum; y *= alpha  ==  beta*b + alpha*sum
+      // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
+      double v;
+      if (ea.beta == 0.0) { v = ea.alpha * sum; }
+      else                { v = ea.beta * ea.b[row] + ea.alpha * sum; }
+      ea.y[row] = v;
+   }
+   else if (EPI == EPI_ACC) {
+      ea.y[row] += ea.alpha * sum;
+   }
+   else if (EPI == EPI_JACOBI7) {
+      // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
+      const double uo = ea.u[row];
+      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
+         const double vt = (ea.w == 1.0) ? (ea.b[row] - sum) : (ea.w * ea.b[row] - ea.w * sum);
+         ea.y[row] = uo + vt / ea.d[row];
+      } else {
+         ea.y[row] = uo;
+      }
+   }
+   else if (EPI == EPI_JACOBI7_ACC) {
+      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
+         ea.y[row] -= (ea.w * sum) / ea.d[row];
+      }
+   }
+   else if (EPI == EPI_JACOBI_CORE) {
+      // hypre_BoomerAMGRelaxWeightedJacobi_core (par_relax.c:258-295)
+      const double uo = ea.u[row];
+      const double di = ea.d ? ea.d[row] : diag;
+      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
+         const double res = ea.b[row] - sum;
+         if (ea.skip_diag) { ea.y[row] = uo * (1.0 - ea.w) + ea.w * res / di; }
+         else              { ea.y[row] = uo + ea.w * res / di; }
+      } else {
+         ea.y[row] = uo;
+      }
+   }
+   else if (EPI == EPI_JACOBI_CORE_ACC) {
+      const double di = ea.d ? ea.d[row] : diag;
+      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
+         ea.y[row] -= ea.w * sum / di;
+      }
+   }
+}
+
+template <int EPI>
+__device__ __forceinline__ constexpr bool epi_needs_diag()
+{
+   return EPI == EPI_JACOBI_CORE || EPI == EPI_JACOBI_CORE_ACC;
+}
+
+
+}  // namespace hb

@@ -75,12 +75,21 @@ struct Ctx {
    double       *h_scalars  = nullptr;   // pinned mirror
    long long     launches = 0;
    bool          capturing = false;      // inside CUDA graph capture
+   // NVLink peer arena (halo mode 1): one IPC-shared allocation per rank; halo receive buffers
+   // and arrival / consumed flags of every matrix are carved out of it, peers write into it directly
+   char         *arena = nullptr;
+   size_t        arena_bytes = 0, arena_used = 0;
+   std::vector<char *> peer_arena;       // IPC-mapped base of every rank's arena (self = arena)
+   bool          peer_ok = false;
    // persistent workspace (Krylov work vectors): stable addresses across solves keep the
    // captured V-cycle graphs valid and take cudaMalloc out of the solve
    void         *ws_ptr[16] = {nullptr};
    size_t        ws_bytes[16] = {0};
 };
 int ws_get(int slot, size_t bytes, double **out);
+int arena_setup();                                         // collective, after the NCCL communicator exists
+int arena_alloc(size_t bytes, size_t *offset);             // 256-byte aligned carve-out
+struct PeerPlan;
 Ctx &ctx();
 int  require_ready();
 
@@ -101,7 +110,7 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6 };
 
 struct DCsr {
    int        nrows = 0, ncols = 0;
@@ -118,6 +127,18 @@ struct DCsr {
    int        nblks = 0;
    int        kind = SPMV_VECTOR;
    int        lanes = 1;          // lanes per row (vector kernel: K; stream kernel: phase-2 L)
+   // dictionary-packed sliced-ELL copy (kernels_sell.cu), present when the block qualifies:
+   // column index = row + off_dict[code] with <= 256 distinct offsets (structured grids), values
+   // either coded the same way (<= 256 distinct, constant-coefficient stencils) or raw fp64
+   bool       has_sell = false;
+   int        sell_nslices = 0;
+   long long *sell_ptr = nullptr;      // nslices+1, in entries (multiples of 32)
+   unsigned char *sell_cidx = nullptr; // offset codes, [slice][k][lane]
+   unsigned char *sell_vidx = nullptr; // value codes, or NULL
+   double    *sell_val = nullptr;      // raw values when not coded, or NULL
+   int       *sell_offdict = nullptr;  // 256 entries
+   double    *sell_valdict = nullptr;  // 256 entries
+   int        sell_nd = 0, sell_nv = 0;
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
 };
@@ -126,6 +147,8 @@ int  dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, co
 int  dcsr_free(DCsr &M);
 void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
 int  dcsr_build_partition(DCsr &M, const int *hi);
+int  dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha);   // kernels_sell.cu
+int  dcsr_free_sell(DCsr &M);
 // host-side transpose (stable: entries of each output row in ascending source-row order,
 // the order hypre_CSRMatrixMatvecTHost accumulates in, csr_matvec.c:1095-1110)
 void host_csr_transpose(int nrows, int ncols, const int *ai, const int *aj, const double *aa,
@@ -165,6 +188,7 @@ struct EpiArgs {
 // y-type epilogue launchers (kernels_spmv.cu).  rows_list: optional compressed row list.
 int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
                 bool use_rownnz, cudaStream_t st);
+int spmv_sell_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
 // BLAS-1 (kernels_blas1.cu).  Scalars live in ctx().d_scalars[slot]; dots are two-stage,
@@ -211,16 +235,9 @@ struct CommPkgD {
    // MatvecT unpack: CSR-of-E grouping send entries by target row (deterministic)
    int    *d_unpack_rows = nullptr, *d_unpack_ptr = nullptr, *d_unpack_idx = nullptr;
    int     n_unpack_rows = 0;
-   // peer-put halo (mode 1)
-   std::vector<double *> peer_recv_ptr;   // per send i: remote address to write segment into
-   std::vector<void *>   peer_mapped;     // IPC-opened bases
-   unsigned long long   *d_flags = nullptr;          // local arrival flags, one per recv
-   std::vector<unsigned long long *> peer_flag_ptr;  // per send i: remote flag address
-   unsigned long long    epoch = 0;
-   double **d_peer_dst = nullptr;                    // device copies for the put kernel
-   unsigned long long **d_peer_flag = nullptr;
-   int    *d_send_seg = nullptr;                     // segment id of each send entry
-   bool    peer_ready = false;
+   // peer-put halo (halo mode 1): one plan per direction, built collectively at first use
+   struct PeerPlan *fwd = nullptr, *rev = nullptr;
+   bool    peer_tried = false;
 };
 
 }  // namespace hb
@@ -253,4 +270,9 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
                   double *y, const double *dotw = nullptr, int dot_slot = -1);
 int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y);
 int gs_sched_free(void *p);
+// peer-put halo (parcsr_peer.cu)
+int  peer_plans_ensure(hb200_parcsr *A);                    // collective; sets A->pkg.fwd / rev (or leaves NULL)
+int  peer_put(PeerPlan *pl, const double *src, cudaStream_t st);
+int  peer_wait(PeerPlan *pl, cudaStream_t st);
+void peer_plan_free(PeerPlan *pl);
 }  // namespace hb

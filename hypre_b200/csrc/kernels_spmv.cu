@@ -19,66 +19,9 @@
 // the epilogue's vectors; x is gathered through L1/L2 (a 27-point row block touches 9 short
 // x segments, reuse factor ~27).
 #include "hb_internal.cuh"
+#include "hb_epilogue.cuh"
 
 namespace hb {
-
-// ---------------------------------------------------------------------------------------
-// epilogues
-// ---------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum, double diag)
-{
-   if (EPI == EPI_AXPBY) {
-      // reference: y = (beta/alpha)*b; y += sum; y *= alpha  ==  beta*b + alpha*sum
-      // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
-      double v;
-      if (ea.beta == 0.0) { v = ea.alpha * sum; }
-      else                { v = ea.beta * ea.b[row] + ea.alpha * sum; }
-      ea.y[row] = v;
-   }
-   else if (EPI == EPI_ACC) {
-      ea.y[row] += ea.alpha * sum;
-   }
-   else if (EPI == EPI_JACOBI7) {
-      // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
-      const double uo = ea.u[row];
-      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
-         const double vt = (ea.w == 1.0) ? (ea.b[row] - sum) : (ea.w * ea.b[row] - ea.w * sum);
-         ea.y[row] = uo + vt / ea.d[row];
-      } else {
-         ea.y[row] = uo;
-      }
-   }
-   else if (EPI == EPI_JACOBI7_ACC) {
-      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
-         ea.y[row] -= (ea.w * sum) / ea.d[row];
-      }
-   }
-   else if (EPI == EPI_JACOBI_CORE) {
-      // hypre_BoomerAMGRelaxWeightedJacobi_core (par_relax.c:258-295)
-      const double uo = ea.u[row];
-      const double di = ea.d ? ea.d[row] : diag;
-      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
-         const double res = ea.b[row] - sum;
-         if (ea.skip_diag) { ea.y[row] = uo * (1.0 - ea.w) + ea.w * res / di; }
-         else              { ea.y[row] = uo + ea.w * res / di; }
-      } else {
-         ea.y[row] = uo;
-      }
-   }
-   else if (EPI == EPI_JACOBI_CORE_ACC) {
-      const double di = ea.d ? ea.d[row] : diag;
-      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
-         ea.y[row] -= ea.w * sum / di;
-      }
-   }
-}
-
-template <int EPI>
-__device__ __forceinline__ constexpr bool epi_needs_diag()
-{
-   return EPI == EPI_JACOBI_CORE || EPI == EPI_JACOBI_CORE_ACC;
-}
 
 // ---------------------------------------------------------------------------------------
 // stream kernel
@@ -386,6 +329,7 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
+   if (!use_rownnz && M.kind == SPMV_SELL && M.has_sell) return spmv_sell_launch(M, x, EPI, ea, st);
    if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
    }
@@ -448,7 +392,8 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
 {
    // the sub-warp vector kernel beat the shared-memory stream kernel on every level measured
    // (profiles/r1_level_sweep.md): the stream kernel is L1-wavefront bound by its smem round trip
-   if (kind == SPMV_AUTO) kind = SPMV_VECTOR;
+   if (kind == SPMV_AUTO) kind = M.has_sell ? SPMV_SELL : SPMV_VECTOR;
+   if (kind == SPMV_SELL && !M.has_sell) kind = SPMV_VECTOR;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
    if (kind == SPMV_STREAM || kind == SPMV_STREAM_V4) {
@@ -496,8 +441,9 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMalloc(&M.rownnz, sizeof(int) * rn.size()));
       HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
    }
-   dcsr_choose_kernel(M, SPMV_AUTO, 0);
    if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
+   if (nrows > 0 && nrows == ncols) HB_CHECK(dcsr_build_sell(M, hi, hj, ha));   // square (A_l) blocks only
+   dcsr_choose_kernel(M, SPMV_AUTO, 0);
    return 0;
 }
 
@@ -508,6 +454,7 @@ int dcsr_free(DCsr &M)
    if (M.a) cudaFree(M.a);
    if (M.rownnz) cudaFree(M.rownnz);
    if (M.blk_row) cudaFree(M.blk_row);
+   dcsr_free_sell(M);
    M = DCsr();
    return 0;
 }

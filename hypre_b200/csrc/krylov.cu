@@ -708,7 +708,7 @@ int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const hb2
                     hb200_krylov_result *result)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && params && b && x && result, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && params && result && ((b && x) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    HB_CHECK(check_precond(precond_kind, amg, A));
    Ctx &c = ctx();
    memset(result, 0, sizeof(*result));
@@ -728,7 +728,7 @@ int hb200_gmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const h
                       const double *b, double *x, double *norms, hb200_krylov_result *result)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && params && b && x && result, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && params && result && ((b && x) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    HB_CHECK(check_precond(precond_kind, amg, A));
    Ctx &c = ctx();
    memset(result, 0, sizeof(*result));
@@ -761,7 +761,7 @@ int hb200_pcg_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                          double *norms, double *rel_norms, hb200_krylov_result *result)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && b_host && x_host, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && ((b_host && x_host) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    double *db = nullptr, *dx = nullptr;
    HB_CHECK(host_wrap(A, b_host, x_host, &db, &dx));
    int f = hb200_pcg_solve(A, precond_kind, amg, params, db, dx, norms, rel_norms, result);
@@ -775,7 +775,7 @@ int hb200_gmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                            double *norms, hb200_krylov_result *result)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && b_host && x_host, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && ((b_host && x_host) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    double *db = nullptr, *dx = nullptr;
    HB_CHECK(host_wrap(A, b_host, x_host, &db, &dx));
    int f = hb200_gmres_solve(A, precond_kind, amg, params, db, dx, norms, result);

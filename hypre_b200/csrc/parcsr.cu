@@ -75,6 +75,12 @@ int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp)
 {
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
+   if (c.halo_mode == 1 && c.nranks > 1) {
+      // NVLink peer puts, everything on the compute stream (parcsr_peer.cu); the plan build is
+      // collective, so ranks without neighbours on this matrix take part too
+      HB_CHECK(peer_plans_ensure(A));
+      return peer_put(pk.fwd, x, st_comp);
+   }
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
    HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
    HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
@@ -91,6 +97,7 @@ int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
 {
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
+   if (c.halo_mode == 1 && c.nranks > 1) return peer_wait(pk.fwd, st_comp);
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
    HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
    HB_CUDA(cudaStreamWaitEvent(st_comp, c.ev_b, 0));
@@ -186,14 +193,18 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    Ctx &c = ctx();
    HB_CHECK(parcsr_ensure_T(A));
    CommPkgD &pk = A->pkg;
+   const bool peer = (c.halo_mode == 1 && c.nranks > 1);
    const bool comm = (pk.num_sends || pk.num_recvs);
+   if (peer) HB_CHECK(peer_plans_ensure(A));
    if (A->num_cols_offd > 0) {
       // y_tmp = alpha * offd^T x  (par_csr_matvec.c:402-420)
       EpiArgs eo;
       eo.alpha = alpha; eo.beta = 0.0; eo.y = A->d_ytmp;
       HB_CHECK(spmv_launch(A->offdT, x, EPI_AXPBY, eo, false, c.s_comp));
    }
-   if (comm) {
+   if (peer) {
+      HB_CHECK(peer_put(pk.rev, A->d_ytmp, c.s_comp));
+   } else if (comm) {
       HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
       HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
       HB_CHECK(exchange(A, false, c.s_comm));
@@ -202,16 +213,17 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    EpiArgs ed;
    ed.alpha = alpha; ed.beta = beta; ed.b = y; ed.y = y;
    HB_CHECK(spmv_launch(A->diagT, x, EPI_AXPBY, ed, false, c.s_comp));
-   if (A->diagT.nrows == 0) { /* nothing local */ }
-   if (comm) {
+   if (peer) {
+      HB_CHECK(peer_wait(pk.rev, c.s_comp));
+   } else if (comm) {
       HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
       HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
-      if (pk.n_unpack_rows > 0) {
-         HB_LAUNCH(unpack_add_kernel, (pk.n_unpack_rows + 255) / 256, 256, 0, c.s_comp,
-                   pk.n_unpack_rows, pk.d_unpack_rows, pk.d_unpack_ptr, pk.d_unpack_idx,
-                   pk.d_send_buf, y);
-         HB_LAUNCH_CHECK();
-      }
+   }
+   if ((peer || comm) && pk.n_unpack_rows > 0) {
+      HB_LAUNCH(unpack_add_kernel, (pk.n_unpack_rows + 255) / 256, 256, 0, c.s_comp,
+                pk.n_unpack_rows, pk.d_unpack_rows, pk.d_unpack_ptr, pk.d_unpack_idx,
+                pk.d_send_buf, y);
+      HB_LAUNCH_CHECK();
    }
    return 0;
 }
@@ -324,6 +336,8 @@ int hb200_parcsr_destroy(hb200_parcsr *A)
    if (pk.d_unpack_rows) cudaFree(pk.d_unpack_rows);
    if (pk.d_unpack_ptr) cudaFree(pk.d_unpack_ptr);
    if (pk.d_unpack_idx) cudaFree(pk.d_unpack_idx);
+   peer_plan_free(pk.fwd);
+   peer_plan_free(pk.rev);
    if (A->d_ytmp) cudaFree(A->d_ytmp);
    if (A->d_diaginv) cudaFree(A->d_diaginv);
    if (A->gs_sched) gs_sched_free(A->gs_sched);
@@ -367,7 +381,7 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, 
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
 {
    HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
-   HB_REQUIRE(kind >= 0 && kind <= 5, HB200_ERROR_ARG, "kind must be 0..5");
+   HB_REQUIRE(kind >= 0 && kind <= 6, HB200_ERROR_ARG, "kind must be 0..6");
    HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
               HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
    dcsr_choose_kernel(A->diag, kind, lanes_per_row);
@@ -379,15 +393,19 @@ int hb200_parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double b
                         const double *b, double *y)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && x && y && (b || beta == 0.0), HB200_ERROR_ARG, "null argument");
-   HB_REQUIRE(x != y, HB200_ERROR_ARG, "x must not alias y");
+   HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
+   // ranks may own zero rows / columns of a coarse level: only non-empty vectors must exist
+   HB_REQUIRE((x || A->num_cols == 0) && (y || A->num_rows == 0) && (b || beta == 0.0 || A->num_rows == 0),
+              HB200_ERROR_ARG, "null vector argument");
+   HB_REQUIRE(x != y || x == nullptr, HB200_ERROR_ARG, "x must not alias y");
    return parcsr_matvec(A, alpha, x, beta, b, y);
 }
 
 int hb200_parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && x && y, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
+   HB_REQUIRE((x || A->num_rows == 0) && (y || A->num_cols == 0), HB200_ERROR_ARG, "null vector argument");
    return parcsr_matvecT(A, alpha, x, beta, y);
 }
 
@@ -395,7 +413,7 @@ int hb200_parcsr_matvec_host(hb200_parcsr *A, double alpha, const double *x_host
                              double *y_host)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && x_host && y_host, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && (x_host || A->num_cols == 0) && (y_host || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    Ctx &c = ctx();
    double *dx = nullptr, *dy = nullptr;
    HB_CUDA(cudaMalloc(&dx, sizeof(double) * (size_t) (A->num_cols ? A->num_cols : 1)));

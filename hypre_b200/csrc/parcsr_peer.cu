@@ -1,0 +1,328 @@
+// parcsr_peer.cu — halo exchange by direct NVLink peer stores (halo mode 1).
+//
+// Replaces the pack kernel + grouped ncclSend/ncclRecv of the default path (and, in the
+// reference, thrust::gather + D2H + MPI_Isend/Irecv/Waitall + H2D,
+// src/parcsr_mv/par_csr_matvec_device.c:201-205, par_csr_communication.c:459-715) by ONE kernel on
+// the sending side and ONE on the receiving side, both on the compute stream:
+//
+//   put  : buf_q[parity][k] = x[send_map_elmts[k]]   written straight into the receiver's HBM over
+//          NVLink (IPC-mapped arena), __threadfence_system, last CTA stores the arrival flags;
+//   wait : spin on this rank's arrival flags (acquire, system scope), copy the arena buffer into
+//          the matrix's private x_ext, store "consumed" flags back to the senders.
+//
+// The transfer itself overlaps with the diag-block SpMV that sits between the two kernels in the
+// stream.  No NCCL launch, no second stream, no events: a coarse-level exchange costs two ~3 us
+// kernels instead of a ~25 us NCCL group, and the whole V-cycle stays capturable in a CUDA graph.
+// Receive buffers are double-buffered by exchange parity and protected by the consumed flags, so a
+// sender can never overwrite data that has not been copied out (also for non-symmetric neighbour
+// sets, e.g. interpolation matrices).  Epoch counters live in device memory, so a replayed graph
+// keeps counting.
+#include "hb_internal.cuh"
+#include <string.h>
+
+namespace hb {
+
+struct PeerPlan {
+   int n_out = 0, n_in = 0, total_out = 0, total_in = 0;
+   // outgoing segments
+   int                 *d_out_starts = nullptr;   // n_out + 1
+   const int           *d_gather = nullptr;       // gather map (borrowed) or NULL = contiguous
+   double             **d_out_dst = nullptr;      // [2][n_out] remote data pointers
+   unsigned long long **d_out_flag = nullptr;     // [2][n_out] remote arrival flags
+   unsigned long long  *acks = nullptr;           // local (arena): consumed-epoch per outgoing segment
+   // incoming segments
+   double              *in_buf[2] = {nullptr, nullptr};   // local (arena), total_in doubles each
+   unsigned long long  *in_flags = nullptr;       // local (arena): [2][n_in] arrival epochs
+   unsigned long long **d_in_ack = nullptr;       // [n_in] remote consumed flags (at the senders)
+   double              *dst = nullptr;            // private destination buffer (borrowed)
+   // device state
+   unsigned long long  *d_epoch = nullptr;        // [0] = out epoch, [1] = in epoch
+   unsigned int        *d_ticket = nullptr;       // [0] put, [1] wait
+};
+
+// ---------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------
+int arena_setup()
+{
+   Ctx &c = ctx();
+   if (c.peer_ok || c.nranks <= 1) return 0;
+#ifdef HB200_WITH_NCCL
+   const char *e = getenv("HB200_ARENA_MB");
+   c.arena_bytes = (size_t) (e ? atoi(e) : 256) << 20;
+   HB_CUDA(cudaMalloc((void **) &c.arena, c.arena_bytes));
+   HB_CUDA(cudaMemset(c.arena, 0, c.arena_bytes));
+   c.arena_used = 0;
+   cudaIpcMemHandle_t mine;
+   HB_CUDA(cudaIpcGetMemHandle(&mine, c.arena));
+   char *d_h = nullptr;
+   const size_t hs = sizeof(cudaIpcMemHandle_t);
+   HB_CUDA(cudaMalloc((void **) &d_h, hs * (size_t) c.nranks));
+   HB_CUDA(cudaMemcpy(d_h + hs * (size_t) c.rank, &mine, hs, cudaMemcpyHostToDevice));
+   HB_NCCL(nccl_api().AllGather(d_h + hs * (size_t) c.rank, d_h, hs, ncclChar, c.nccl, c.s_comp));
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   std::vector<cudaIpcMemHandle_t> all((size_t) c.nranks);
+   HB_CUDA(cudaMemcpy(all.data(), d_h, hs * (size_t) c.nranks, cudaMemcpyDeviceToHost));
+   cudaFree(d_h);
+   c.peer_arena.assign((size_t) c.nranks, nullptr);
+   for (int r = 0; r < c.nranks; r++) {
+      if (r == c.rank) { c.peer_arena[r] = c.arena; continue; }
+      void *p = nullptr;
+      cudaError_t er = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+      if (er != cudaSuccess) {
+         return set_error(HB200_ERROR_GENERIC, "cudaIpcOpenMemHandle(rank %d) failed: %s (peer halo mode needs "
+                          "all ranks on one NVLink domain)", r, cudaGetErrorString(er));
+      }
+      c.peer_arena[r] = (char *) p;
+   }
+   c.peer_ok = true;
+   return 0;
+#else
+   return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL");
+#endif
+}
+
+int arena_alloc(size_t bytes, size_t *offset)
+{
+   Ctx &c = ctx();
+   const size_t off = (c.arena_used + 255) & ~(size_t) 255;
+   if (off + bytes > c.arena_bytes) {
+      return set_error(HB200_ERROR_MEMORY, "peer arena exhausted (%zu MB); raise HB200_ARENA_MB", c.arena_bytes >> 20);
+   }
+   *offset = off;
+   c.arena_used = off + bytes;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const int *__restrict__ gather,
+                const double *__restrict__ src, double *const *__restrict__ dst2,
+                unsigned long long *const *__restrict__ flag2, const unsigned long long *__restrict__ acks,
+                unsigned long long *epoch_ctr, unsigned int *ticket)
+{
+   __shared__ bool is_last;
+   const unsigned long long epoch = epoch_ctr[0] + 1;
+   const int par = (int) (epoch & 1ull);
+   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < total) {
+      // segment of entry k (n_out <= a few dozen)
+      int lo = 0, hi = n_out - 1;
+      while (lo < hi) {
+         const int mid = (lo + hi + 1) >> 1;
+         if (out_starts[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      // the receiver must have copied exchange (epoch - 2) out of this parity's buffer
+      if (epoch > 2) { while (ld_acquire_sys(acks + lo) + 2 < epoch) { } }
+      const double v = gather ? src[gather[k]] : src[k];
+      dst2[par * n_out + lo][k - out_starts[lo]] = v;
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+      is_last = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (is_last) {
+      __threadfence_system();
+      for (int i = threadIdx.x; i < n_out; i += blockDim.x) st_release_sys(flag2[par * n_out + i], epoch);
+      if (threadIdx.x == 0) epoch_ctr[0] = epoch;
+   }
+}
+
+__global__ void __launch_bounds__(256)
+halo_wait_kernel(int total, int n_in, const double *__restrict__ buf0, const double *__restrict__ buf1,
+                 const unsigned long long *__restrict__ flags, unsigned long long *const *__restrict__ in_ack,
+                 double *__restrict__ dst, unsigned long long *epoch_ctr, unsigned int *ticket)
+{
+   __shared__ bool is_last;
+   const unsigned long long epoch = epoch_ctr[1] + 1;
+   const int par = (int) (epoch & 1ull);
+   for (int j = threadIdx.x; j < n_in; j += blockDim.x) {
+      while (ld_acquire_sys(flags + par * n_in + j) < epoch) { }
+   }
+   __syncthreads();
+   const double *buf = par ? buf1 : buf0;
+   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+      dst[k] = __ldcg(buf + k);
+   }
+   __threadfence();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const unsigned int t = atomicInc(ticket + 1, gridDim.x - 1);
+      is_last = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (is_last) {
+      // everything of this exchange has been copied out: tell the senders, advance the epoch
+      for (int j = threadIdx.x; j < n_in; j += blockDim.x) st_release_sys(in_ack[j], epoch);
+      if (threadIdx.x == 0) epoch_ctr[1] = epoch;
+   }
+}
+
+int peer_put(PeerPlan *pl, const double *src, cudaStream_t st)
+{
+   if (pl->n_out == 0) return 0;
+   const int grid = pl->total_out > 0 ? (pl->total_out + 255) / 256 : 1;
+   HB_LAUNCH(halo_put_kernel, grid, 256, 0, st, pl->total_out, pl->n_out, pl->d_out_starts, pl->d_gather, src,
+             pl->d_out_dst, pl->d_out_flag, pl->acks, pl->d_epoch, pl->d_ticket);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+int peer_wait(PeerPlan *pl, cudaStream_t st)
+{
+   if (pl->n_in == 0) return 0;
+   int grid = (pl->total_in + 256 * 8 - 1) / (256 * 8);
+   if (grid < 1) grid = 1;
+   if (grid > 64) grid = 64;
+   HB_LAUNCH(halo_wait_kernel, grid, 256, 0, st, pl->total_in, pl->n_in, pl->in_buf[0], pl->in_buf[1],
+             pl->in_flags, pl->d_in_ack, pl->dst, pl->d_epoch, pl->d_ticket);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+void peer_plan_free(PeerPlan *pl)
+{
+   if (!pl) return;
+   if (pl->d_out_starts) cudaFree(pl->d_out_starts);
+   if (pl->d_out_dst) cudaFree(pl->d_out_dst);
+   if (pl->d_out_flag) cudaFree(pl->d_out_flag);
+   if (pl->d_in_ack) cudaFree(pl->d_in_ack);
+   if (pl->d_epoch) cudaFree(pl->d_epoch);
+   if (pl->d_ticket) cudaFree(pl->d_ticket);
+   delete pl;
+}
+
+// ---------------------------------------------------------------------------------------
+// plan construction (collective over all ranks, same call order everywhere)
+// ---------------------------------------------------------------------------------------
+// out: segments this rank sends (peer, start offsets);  in: segments it receives.
+static int build_plan(PeerPlan **out_plan, int n_out, const int *out_procs, const int *out_starts,
+                      const int *d_gather, int n_in, const int *in_procs, const int *in_starts, double *dst)
+{
+#ifdef HB200_WITH_NCCL
+   Ctx &c = ctx();
+   const int nr = c.nranks;
+   PeerPlan *pl = new PeerPlan();
+   pl->n_out = n_out; pl->n_in = n_in;
+   pl->total_out = n_out ? out_starts[n_out] : 0;
+   pl->total_in = n_in ? in_starts[n_in] : 0;
+   pl->d_gather = d_gather;
+   pl->dst = dst;
+   // ---- carve local arena space
+   size_t off_buf0 = 0, off_buf1 = 0, off_flags = 0, off_acks = 0;
+   HB_CHECK(arena_alloc(sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1), &off_buf0));
+   HB_CHECK(arena_alloc(sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1), &off_buf1));
+   HB_CHECK(arena_alloc(sizeof(unsigned long long) * (size_t) (2 * (n_in ? n_in : 1)), &off_flags));
+   HB_CHECK(arena_alloc(sizeof(unsigned long long) * (size_t) (n_out ? n_out : 1), &off_acks));
+   pl->in_buf[0] = (double *) (c.arena + off_buf0);
+   pl->in_buf[1] = (double *) (c.arena + off_buf1);
+   pl->in_flags = (unsigned long long *) (c.arena + off_flags);
+   pl->acks = (unsigned long long *) (c.arena + off_acks);
+   // ---- publish: row [p] of my table = {buf0, buf1, flag0, flag1 of the segment I receive from
+   //      rank p; ack slot of the segment I send to rank p}; -1 = none
+   const int W = 5;
+   std::vector<long long> mine((size_t) nr * W, -1), all((size_t) nr * nr * W, -1);
+   for (int j = 0; j < n_in; j++) {
+      const int p = in_procs[j];
+      long long *row = &mine[(size_t) p * W];
+      row[0] = (long long) (off_buf0 + sizeof(double) * (size_t) in_starts[j]);
+      row[1] = (long long) (off_buf1 + sizeof(double) * (size_t) in_starts[j]);
+      row[2] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) j);
+      row[3] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) (n_in + j));
+   }
+   for (int i = 0; i < n_out; i++) {
+      mine[(size_t) out_procs[i] * W + 4] = (long long) (off_acks + sizeof(unsigned long long) * (size_t) i);
+   }
+   long long *d_t = nullptr;
+   const size_t row_bytes = sizeof(long long) * (size_t) nr * W;
+   HB_CUDA(cudaMalloc((void **) &d_t, row_bytes * (size_t) nr));
+   HB_CUDA(cudaMemcpy((char *) d_t + row_bytes * (size_t) c.rank, mine.data(), row_bytes, cudaMemcpyHostToDevice));
+   HB_NCCL(nccl_api().AllGather((char *) d_t + row_bytes * (size_t) c.rank, d_t, row_bytes, ncclChar, c.nccl, c.s_comp));
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   HB_CUDA(cudaMemcpy(all.data(), d_t, row_bytes * (size_t) nr, cudaMemcpyDeviceToHost));
+   cudaFree(d_t);
+   // ---- resolve remote pointers
+   std::vector<double *> out_dst((size_t) (2 * (n_out ? n_out : 1)), nullptr);
+   std::vector<unsigned long long *> out_flag((size_t) (2 * (n_out ? n_out : 1)), nullptr);
+   std::vector<unsigned long long *> in_ack((size_t) (n_in ? n_in : 1), nullptr);
+   for (int i = 0; i < n_out; i++) {
+      const int q = out_procs[i];
+      const long long *row = &all[((size_t) q * nr + (size_t) c.rank) * W];   // q's segment from me
+      if (row[0] < 0) { delete pl; return set_error(HB200_ERROR_GENERIC, "halo plan mismatch: rank %d does not expect data from rank %d", q, c.rank); }
+      out_dst[(size_t) i] = (double *) (c.peer_arena[q] + row[0]);
+      out_dst[(size_t) (n_out + i)] = (double *) (c.peer_arena[q] + row[1]);
+      out_flag[(size_t) i] = (unsigned long long *) (c.peer_arena[q] + row[2]);
+      out_flag[(size_t) (n_out + i)] = (unsigned long long *) (c.peer_arena[q] + row[3]);
+   }
+   for (int j = 0; j < n_in; j++) {
+      const int p = in_procs[j];
+      const long long a = all[((size_t) p * nr + (size_t) c.rank) * W + 4];         // p's ack slot for me
+      if (a < 0) { delete pl; return set_error(HB200_ERROR_GENERIC, "halo plan mismatch: rank %d does not send to rank %d", p, c.rank); }
+      in_ack[(size_t) j] = (unsigned long long *) (c.peer_arena[p] + a);
+   }
+   // parity 0 buffers are used by even epochs, parity 1 by odd ones: order the tables [par][i]
+   std::vector<double *> dst2((size_t) (2 * (n_out ? n_out : 1)));
+   std::vector<unsigned long long *> flag2((size_t) (2 * (n_out ? n_out : 1)));
+   for (int i = 0; i < n_out; i++) {
+      dst2[(size_t) i] = out_dst[(size_t) i];                       // par 0
+      dst2[(size_t) (n_out + i)] = out_dst[(size_t) (n_out + i)];   // par 1
+      flag2[(size_t) i] = out_flag[(size_t) i];
+      flag2[(size_t) (n_out + i)] = out_flag[(size_t) (n_out + i)];
+   }
+   HB_CUDA(cudaMalloc((void **) &pl->d_out_starts, sizeof(int) * (size_t) (n_out + 1)));
+   if (n_out) HB_CUDA(cudaMemcpy(pl->d_out_starts, out_starts, sizeof(int) * (size_t) (n_out + 1), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc((void **) &pl->d_out_dst, sizeof(double *) * dst2.size()));
+   HB_CUDA(cudaMemcpy(pl->d_out_dst, dst2.data(), sizeof(double *) * dst2.size(), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc((void **) &pl->d_out_flag, sizeof(unsigned long long *) * flag2.size()));
+   HB_CUDA(cudaMemcpy(pl->d_out_flag, flag2.data(), sizeof(unsigned long long *) * flag2.size(), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc((void **) &pl->d_in_ack, sizeof(unsigned long long *) * in_ack.size()));
+   HB_CUDA(cudaMemcpy(pl->d_in_ack, in_ack.data(), sizeof(unsigned long long *) * in_ack.size(), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc((void **) &pl->d_epoch, sizeof(unsigned long long) * 2));
+   HB_CUDA(cudaMemset(pl->d_epoch, 0, sizeof(unsigned long long) * 2));
+   HB_CUDA(cudaMalloc((void **) &pl->d_ticket, sizeof(unsigned int) * 2));
+   HB_CUDA(cudaMemset(pl->d_ticket, 0, sizeof(unsigned int) * 2));
+   *out_plan = pl;
+   return 0;
+#else
+   return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL");
+#endif
+}
+
+int peer_plans_ensure(hb200_parcsr *A)
+{
+   Ctx &c = ctx();
+   CommPkgD &pk = A->pkg;
+   if (pk.peer_tried) return 0;
+   pk.peer_tried = true;
+   if (c.nranks <= 1) return 0;
+   HB_CHECK(arena_setup());
+   // forward (job 1): out = sends (gather through send_map_elmts), in = recvs -> x_ext
+   HB_CHECK(build_plan(&pk.fwd, pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_map_elmts,
+                       pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), pk.d_recv_buf));
+   // reverse (job 2): out = recv segments of y_tmp (contiguous), in = send segments -> send_buf
+   HB_CHECK(parcsr_ensure_T(A));
+   HB_CHECK(build_plan(&pk.rev, pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), nullptr,
+                       pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_buf));
+   // peers must not start writing into this arena region before everybody has built the plan
+   HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   return 0;
+}
+
+}  // namespace hb

@@ -272,10 +272,10 @@ int hb200_relax(hb200_parcsr *A, const double *f, const int *cf_marker, int rela
                 double *u, int u_all_zeros, double *vtemp)
 {
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && f && u, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && ((f && u) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    Ctx &c = ctx();
    if (relax_is_jacobi(relax_type)) {
-      HB_REQUIRE(vtemp != nullptr, HB200_ERROR_ARG, "Jacobi relaxation needs vtemp scratch");
+      HB_REQUIRE(vtemp != nullptr || A->num_rows == 0, HB200_ERROR_ARG, "Jacobi relaxation needs vtemp scratch");
       bool shortcut = false;
       // out of place into vtemp, then back into u (the AMG cycle avoids this copy by swapping)
       const bool core_zero = u_all_zeros && !((relax_type == 7) || (relax_type == 18 && relax_points == 0));
@@ -314,7 +314,7 @@ int hb200_cheby_solve(hb200_parcsr *A, const double *f, const double *ds, const 
 {
    (void) variant;   // unused by the reference's solve too (par_cheby_solve.c:207)
    HB_CHECK(require_ready());
-   HB_REQUIRE(A && f && coefs && u, HB200_ERROR_ARG, "null argument");
+   HB_REQUIRE(A && coefs && ((f && u) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
    const size_t n = (size_t) (A->num_rows ? A->num_rows : 1);
    double *w = nullptr;
    HB_CUDA(cudaMalloc(&w, sizeof(double) * n * 4));

@@ -113,19 +113,22 @@ def test_matvec_all_levels(request, torch, case_name, ab):
 def test_matvec_bit_exact_fine_level(lap27, torch):
     """one lane per row in the stream kernel keeps the reference's summation order"""
     A = lap27.mats[0][0]
-    A.set_spmv_kernel(2, 1)
     rng = np.random.default_rng(7)
     x = rng.standard_normal(A.num_cols)
     b = rng.standard_normal(A.num_rows)
-    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (1.0, 1.0)):
-        yref = lap27.pb.matvec(alpha, x, beta, b)
-        y = torch.empty(A.num_rows, dtype=torch.float64, device="cuda")
-        A.matvec(alpha, dev(torch, x), beta, y, b=dev(torch, b))
-        assert np.array_equal(y.cpu().numpy(), yref), (alpha, beta)
+    # stream kernel with one lane per row, and the packed SELL kernel (one thread per row):
+    # both add the products in CSR order with separate multiply / add
+    for kind, lanes in ((2, 1), (6, 0)):
+        A.set_spmv_kernel(kind, lanes)
+        for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (1.0, 1.0)):
+            yref = lap27.pb.matvec(alpha, x, beta, b)
+            y = torch.empty(A.num_rows, dtype=torch.float64, device="cuda")
+            A.matvec(alpha, dev(torch, x), beta, y, b=dev(torch, b))
+            assert np.array_equal(y.cpu().numpy(), yref), (kind, alpha, beta)
     A.set_spmv_kernel(0, 0)
 
 
-@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32)])
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32), (6, 0)])
 def test_matvec_kernel_variants(lap27, torch, kind, lanes):
     rng = np.random.default_rng(5)
     for l in (0, 2):

@@ -14,6 +14,7 @@ are timed separately and reported in `config`, never inside the timed region.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -45,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=3, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv-only", action="store_true", help="configs[4]: SpMV bandwidth line")
+    ap.add_argument("--mpi-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -124,45 +126,73 @@ def dist_env():
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path (oracle/_ref = unmodified hypre 3.1.0,
-    OpenMP, all host cores), same config / metric.  Each step is a bounded sample: `cpu_iters`
-    PCG iterations of the same 256^3 solve, extrapolated to the full iteration count by the
-    per-iteration cost (an AMG-PCG iteration costs the same every time)."""
+    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified hypre
+    3.1.0 CPU build, OpenMP; for N > 1 its MPI build on oracle/minimpi with N ranks x cores/N
+    threads, i.e. the "CPU MPI+OpenMP build" of BASELINE.json), same config / metric / unit.
+    One complete solve first (real iteration count, full-size parity anchor); each timed step is
+    a bounded sample: `cpu_iters` PCG iterations of the same solve, scaled to the full iteration
+    count by the per-iteration cost."""
     rank, world, local = dist_env()
-    if world > 1 and rank != 0:
+    if world > 1 and rank != 0 and not args.mpi_worker:
+        return
+    N = args.gpus
+    if N > 1 and not args.mpi_worker:
+        # rank 0 of the torchrun job launches the N-rank CPU reference on the host cores
+        mpirun = os.path.join(ROOT, "oracle", "_ref", "mpirun")
+        cmd = [mpirun, "-np", str(N), sys.executable, os.path.abspath(__file__), "--impl", "reference",
+               "--mpi-worker", "--gpus", str(N), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--n", str(args.n), "--problem", args.problem, "--tol", str(args.tol),
+               "--cpu-iters", str(args.cpu_iters)]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            print(json.dumps({"impl": "reference", "unavailable":
+                              f"N-rank CPU reference failed (rc {r.returncode}): {r.stderr[-300:]}"}), flush=True)
+            return
+        print(lines[-1], flush=True)
         return
     from oracle import refbridge as rb
-    rb.load(mpi=False)
+    mpi = N > 1
+    rb.load(mpi=mpi)
+    ncores = os.cpu_count() or 1
+    if mpi:
+        rb.set_num_threads(max(1, ncores // N))
+    myrank = rb.load().rb_comm_rank() if mpi else 0
     n = args.n
-    t0 = time.time()
-    pb = rb.Problem(args.problem, (n, n, n))
+    P = PGRID[N]
+    gn = (n * P[0], n * P[1], n * P[2])
+    pb = rb.Problem(args.problem, gn, P=P, mpi=mpi)
     setup_s = pb.setup_amg(relax_type=18)
-    cores = rb.num_threads()
-    # one complete solve first: gives the real iteration count the bounded samples are scaled to
+    threads = rb.num_threads()
     full = pb.pcg(precond="amg", tol=args.tol, max_iter=100, two_norm=1)
     its_full = full["iterations"]
-    k = args.cpu_iters
+    k = args.cpu_iters if args.cpu_iters > 0 else 3
     times = []
     for s in range(args.warmup + args.steps):
         r = pb.pcg(precond="amg", tol=args.tol, max_iter=k, two_norm=1)
         if s >= args.warmup:
             times.append(r["seconds"])
-    t_k = float(np.mean(times))
+    t_k = float(np.mean(times)) if times else full["seconds"] * (k + 1) / (its_full + 1)
     t_full = t_k * (its_full + 1) / (k + 1)
     rows = pb.global_rows
     val = rows / t_full / 1e6
+    if myrank != 0:
+        return
     line = {
         "impl": "reference", "metric": "amg_pcg_solve_mdof_per_s", "value": val, "unit": "MDOF/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ij -{args.problem} -n {n} {n} {n} -solver 1 -rlx 18 (BoomerAMG-PCG, "
-                               "HMIS + ext+i, l1-Jacobi V(1,1)), reference CPU build (OpenMP)",
+        "config": {"workload": f"ij -{args.problem} -n {gn[0]} {gn[1]} {gn[2]} -P {P[0]} {P[1]} {P[2]} -solver 1 "
+                               "-rlx 18 (BoomerAMG-PCG, HMIS + ext+i, l1-Jacobi V(1,1)), reference CPU build "
+                               f"({N} rank(s) x {threads} OpenMP threads)",
                    "rows": rows, "setup_s": setup_s, "iterations": its_full,
                    "final_rel_res": full["final_rel_res"], "full_solve_s": full["seconds"]},
-        "cpu_baseline": {"value": val, "unit": "MDOF/s", "cores": cores, "kind": "reference",
-                         "sample": f"{k} PCG iterations of the same solve per step "
-                                   f"({t_k:.3f} s), scaled by ({its_full}+1)/({k}+1) to the full solve"},
+        "cpu_baseline": {"value": val, "unit": "MDOF/s", "cores": N * threads, "kind": "reference",
+                         "sample": f"{k} PCG iterations of the same solve per step ({t_k:.3f} s), scaled by "
+                                   f"({its_full}+1)/({k}+1) to the full {its_full}-iteration solve "
+                                   f"(one complete solve measured: {full['seconds']:.2f} s)"},
         "e2e": {"value": val, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,29 +297,56 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant kernel: fine-level CSR SpMV (stream kernel), timed alone
+    # ---- roofline of the dominant kernel: the fine-level SpMV, timed alone with CUDA events.
+    # A_0 of a structured-grid operator runs through the dictionary-packed SELL kernel (2 B per
+    # nonzero instead of CSR's 12); its algorithmic bytes are those of the packed format.  The
+    # general CSR kernel (every coarse level, every unstructured matrix) is timed on the same
+    # matrix as `roofline_csr`.
     peak, peak_src = peaks()
     xs = torch.randn(A.num_cols, dtype=torch.float64, device="cuda")
     ys = torch.empty(nloc, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    for _ in range(3):
-        check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
-    hb.sync()
-    reps = 20
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(stream)
-    for _ in range(reps):
-        check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
-    s1.record(stream)
-    hb.sync()
-    spmv_ms = s0.elapsed_time(s1) / reps
-    spmv_bytes = 12.0 * nnz0 + 4.0 * nloc + 8.0 * A.num_cols + 8.0 * nloc
-    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmv_stream<EPI_AXPBY> on A_0 (y = A x)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "ms_per_launch": spmv_ms,
-                "bytes_per_launch": spmv_bytes, "bytes_per_nnz": spmv_bytes / max(nnz0, 1),
+
+    def time_spmv(reps=20):
+        for _ in range(3):
+            check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+        hb.sync()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(reps):
+            check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+        s1.record(stream)
+        hb.sync()
+        return s0.elapsed_time(s1) / reps
+
+    csr_bytes = 12.0 * nnz0 + 4.0 * nloc + 8.0 * A.num_cols + 8.0 * nloc
+    info = (C.c_longlong * 4)()
+    check(lib.hb200_parcsr_format_info(A.handle, info))
+    packed, sell_entries, sell_bytes_per_entry = int(info[0]), int(info[1]), int(info[2])
+    spmv_ms = time_spmv()
+    if packed:
+        alg_bytes = float(sell_entries) * sell_bytes_per_entry + 8.0 * (nloc / 32.0) + 4.0 * nloc \
+            + 8.0 * A.num_cols + 8.0 * nloc
+        kname = f"spmv_sell<EPI_AXPBY> on A_0 (packed SELL-32, {sell_bytes_per_entry} B/nonzero)"
+    else:
+        alg_bytes = csr_bytes
+        kname = "spmv_vector<EPI_AXPBY> on A_0 (CSR)"
+    achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "ms_per_launch": spmv_ms,
+                "bytes_per_launch": alg_bytes, "bytes_per_nnz": alg_bytes / max(nnz0, 1),
+                "csr_equivalent_gbs": csr_bytes / (spmv_ms * 1e-3) / 1e9,
+                "note": ("packed kernel: LSU-issue bound, not HBM bound (DESIGN.md section 3)" if packed else None),
                 "traffic": None}
+    roofline_csr = None
+    if packed:
+        A.set_spmv_kernel(1, 0)
+        ms_csr = time_spmv()
+        A.set_spmv_kernel(0, 0)
+        roofline_csr = {"bound": "hbm", "kernel": "spmv_vector<EPI_AXPBY,K> on A_0 (general CSR path)",
+                        "achieved": csr_bytes / (ms_csr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": csr_bytes / (ms_csr * 1e-3) / 1e9 / peak, "ms_per_launch": ms_csr,
+                        "bytes_per_launch": csr_bytes, "bytes_per_nnz": csr_bytes / max(nnz0, 1), "traffic": None}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own solve, bounded sample
     cpu = None
@@ -338,6 +395,7 @@ def main():
                     "api": "hb200_pcg_solve_host (host b, x; the call behind HYPRE_PCGSolve)"},
             "gpu_launches": launches,
             "roofline": roofline,
+            "roofline_csr": roofline_csr,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

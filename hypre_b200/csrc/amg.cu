@@ -242,7 +242,7 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
 {
    Ctx &c = ctx();
    // multi-rank: only the peer-put halo keeps every step of the cycle a plain kernel on one stream
-   if (!amg->use_graph || (c.nranks > 1 && c.halo_mode != 1)) {
+   if (!amg->use_graph || g_timers_on || (c.nranks > 1 && c.halo_mode != 1)) {
       return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    }
    // CUDA-graph path: the topology of a cycle is fixed by the hierarchy, so capture once per

@@ -87,6 +87,16 @@ struct Ctx {
    size_t        ws_bytes[16] = {0};
 };
 int ws_get(int slot, size_t bytes, double **out);
+
+// optional stream-time attribution (env HB200_TIMERS=1): tick(cat) charges the compute-stream time
+// from now on to `cat`; categories mirror the reference's HYPRE_TIMER_IDs (seq_mv/HYPRE_seq_mv.h:85-97)
+enum TimerCat { T_OTHER = 0, T_MATVEC_DIAG, T_MATVEC_OFFD, T_HALO_START, T_HALO_WAIT, T_BLAS1, T_ALLREDUCE,
+                T_HOST_SYNC, T_GE_SOLVE, T_RELAX_ZERO, T_NUM };
+extern bool g_timers_on;
+void timer_tick_impl(int cat);
+inline void timer_tick(int cat) { if (g_timers_on) timer_tick_impl(cat); }
+void timers_begin();
+void timers_report(const char *what);
 int arena_setup();                                         // collective, after the NCCL communicator exists
 int arena_alloc(size_t bytes, size_t *offset);             // 256-byte aligned carve-out
 struct PeerPlan;
@@ -237,7 +247,7 @@ struct CommPkgD {
    int     n_unpack_rows = 0;
    // peer-put halo (halo mode 1): one plan per direction, built collectively at first use
    struct PeerPlan *fwd = nullptr, *rev = nullptr;
-   bool    peer_tried = false;
+   bool    peer_tried = false, peer_tried_rev = false;
 };
 
 }  // namespace hb
@@ -271,7 +281,7 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
 int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y);
 int gs_sched_free(void *p);
 // peer-put halo (parcsr_peer.cu)
-int  peer_plans_ensure(hb200_parcsr *A);                    // collective; sets A->pkg.fwd / rev (or leaves NULL)
+int  peer_plans_ensure(hb200_parcsr *A, bool reverse);      // collective, lazy: builds A->pkg.fwd or .rev
 int  peer_put(PeerPlan *pl, const double *src, cudaStream_t st);
 int  peer_wait(PeerPlan *pl, cudaStream_t st);
 void peer_plan_free(PeerPlan *pl);

@@ -249,7 +249,9 @@ int scalars_allreduce(int slot, int count, cudaStream_t st)
    Ctx &c = ctx();
    if (c.nranks <= 1) return 0;
 #ifdef HB200_WITH_NCCL
+   timer_tick(T_ALLREDUCE);
    HB_NCCL(nccl_api().AllReduce(c.d_scalars + slot, c.d_scalars + slot, count, ncclDouble, ncclSum, c.nccl, st));
+   timer_tick(T_OTHER);
    return 0;
 #else
    return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL but nranks > 1");
@@ -259,9 +261,11 @@ int scalars_allreduce(int slot, int count, cudaStream_t st)
 int scalars_fetch(int slot, int count, double *out, cudaStream_t st)
 {
    Ctx &c = ctx();
+   timer_tick(T_HOST_SYNC);
    HB_CUDA(cudaMemcpyAsync(c.h_scalars + slot, c.d_scalars + slot, sizeof(double) * count,
                            cudaMemcpyDeviceToHost, st));
    HB_CUDA(cudaStreamSynchronize(st));
+   timer_tick(T_OTHER);
    for (int k = 0; k < count; k++) out[k] = c.h_scalars[slot + k];
    return 0;
 }

@@ -7,7 +7,8 @@
 //   * a constant-coefficient operator has a handful of distinct values (the 27-point Laplacian: 2).
 // When a square block has <= 256 distinct offsets it is stored a second time as SELL-32: slices
 // of 32 consecutive rows, entry k of lane r at [slice][k][r], one byte of offset code per entry and
-// either one byte of value code (<= 256 distinct values) or the raw fp64 value.  The fine-level
+// either one byte of value code (<= 256 distinct values) or the raw fp64 value; four consecutive
+// entries of a row are stored contiguously so that a lane fetches 4 codes with one 32-bit load.  The fine-level
 // SpMV then streams 2 B (or 9 B) per nonzero instead of 12, and a warp's gather of x for entry k
 // touches 32 consecutive doubles (same offset across neighbouring rows) instead of 16+ sectors.
 //
@@ -47,6 +48,9 @@ struct SmallMap {
    }
 };
 
+// Layout: slice s (32 rows) holds G = ceil(maxlen/4) groups; group g of lane r sits at
+// sell_ptr[s] + g*128 + r*4 .. +3  (4 consecutive entries of one row are contiguous), so a lane
+// fetches 4 offset codes with one 32-bit load and a warp's load is one coalesced 128 B line.
 template <int EPI, bool VCODED>
 __global__ void __launch_bounds__(kSellThreads)
 spmv_sell(int nrows, const int *__restrict__ rowptr, const long long *__restrict__ sptr,
@@ -65,28 +69,52 @@ spmv_sell(int nrows, const int *__restrict__ rowptr, const long long *__restrict
    const int lane = tid & 31;
    const int slice = row >> 5;
    const int len = rowptr[row + 1] - rowptr[row];
-   const long long base = sptr[slice] + lane;
+   const long long base = sptr[slice] + lane * 4;
    const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
    double s = 0.0, diag = 0.0;
    if (epi_needs_diag<EPI>() && len > 0) diag = VCODED ? s_val[vidx[base]] : vraw[base];
-   int k = skip;
-   // 4 entries in flight per thread: codes first, then the dependent gathers
-   for (; k + 3 < len; k += 4) {
-      unsigned char c[4];
-      double a[4], xv[4];
+   const double *xr = x + row;
+   int k = 0;
+   // two groups (8 entries) in flight per thread: codes first, then the dependent gathers
+   for (; k + 8 <= len; k += 8) {
+      const long long e0 = base + (long long) (k >> 2) * 128;
+      const unsigned int c0 = *reinterpret_cast<const unsigned int *>(cidx + e0);
+      const unsigned int c1 = *reinterpret_cast<const unsigned int *>(cidx + e0 + 128);
+      double a[8], xv[8];
+      if (VCODED) {
+         const unsigned int v0 = *reinterpret_cast<const unsigned int *>(vidx + e0);
+         const unsigned int v1 = *reinterpret_cast<const unsigned int *>(vidx + e0 + 128);
 #pragma unroll
-      for (int u = 0; u < 4; u++) c[u] = cidx[base + (long long) (k + u) * 32];
+         for (int u = 0; u < 4; u++) { a[u] = s_val[(v0 >> (8 * u)) & 255u]; a[4 + u] = s_val[(v1 >> (8 * u)) & 255u]; }
+      } else {
+         const double2 p0 = *reinterpret_cast<const double2 *>(vraw + e0);
+         const double2 p1 = *reinterpret_cast<const double2 *>(vraw + e0 + 2);
+         const double2 p2 = *reinterpret_cast<const double2 *>(vraw + e0 + 128);
+         const double2 p3 = *reinterpret_cast<const double2 *>(vraw + e0 + 130);
+         a[0] = p0.x; a[1] = p0.y; a[2] = p1.x; a[3] = p1.y; a[4] = p2.x; a[5] = p2.y; a[6] = p3.x; a[7] = p3.y;
+      }
 #pragma unroll
-      for (int u = 0; u < 4; u++) a[u] = VCODED ? s_val[vidx[base + (long long) (k + u) * 32]] : vraw[base + (long long) (k + u) * 32];
+      for (int u = 0; u < 4; u++) {
+         xv[u]     = __ldg(xr + s_off[(c0 >> (8 * u)) & 255u]);
+         xv[4 + u] = __ldg(xr + s_off[(c1 >> (8 * u)) & 255u]);
+      }
 #pragma unroll
-      for (int u = 0; u < 4; u++) xv[u] = __ldg(x + row + s_off[c[u]]);
-#pragma unroll
-      for (int u = 0; u < 4; u++) s = __dadd_rn(s, __dmul_rn(a[u], xv[u]));
+      for (int u = 0; u < 8; u++) {
+         if (k + u >= skip) s = __dadd_rn(s, __dmul_rn(a[u], xv[u]));
+      }
    }
-   for (; k < len; k++) {
-      const long long e = base + (long long) k * 32;
-      const double a = VCODED ? s_val[vidx[e]] : vraw[e];
-      s = __dadd_rn(s, __dmul_rn(a, __ldg(x + row + s_off[cidx[e]])));
+   for (; k < len; k += 4) {
+      const long long e0 = base + (long long) (k >> 2) * 128;
+      const unsigned int c0 = *reinterpret_cast<const unsigned int *>(cidx + e0);
+      unsigned int v0 = 0;
+      if (VCODED) v0 = *reinterpret_cast<const unsigned int *>(vidx + e0);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+         if (k + u < len && k + u >= skip) {
+            const double a = VCODED ? s_val[(v0 >> (8 * u)) & 255u] : vraw[e0 + u];
+            s = __dadd_rn(s, __dmul_rn(a, __ldg(xr + s_off[(c0 >> (8 * u)) & 255u])));
+         }
+      }
    }
    epi_apply<EPI>(ea, row, s, diag);
 }
@@ -170,23 +198,23 @@ int dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha)
          }
       }
    }
-   // ---- slices
+   // ---- slices: G = ceil(maxlen/4) groups of 4 entries per lane
    const int nslices = (n + 31) / 32;
    std::vector<long long> sptr((size_t) nslices + 1, 0);
    for (int s = 0; s < nslices; s++) {
       int mx = 0;
       for (int r = s * 32; r < n && r < s * 32 + 32; r++) mx = std::max(mx, hi[r + 1] - hi[r]);
-      sptr[s + 1] = sptr[s] + (long long) mx * 32;
+      sptr[s + 1] = sptr[s] + (long long) ((mx + 3) / 4) * 128;
    }
    const long long total = sptr[nslices];
-   if ((double) total > 1.5 * (double) nnz + 4096.0) return 0;   // too much padding: ragged rows
+   if ((double) total > 1.6 * (double) nnz + 4096.0) return 0;   // too much padding: ragged rows
    std::vector<unsigned char> cidx((size_t) total, 0), vidx;
    std::vector<double> vraw;
    if (vcoded) vidx.assign((size_t) total, 0); else vraw.assign((size_t) total, 0.0);
    for (int r = 0; r < n; r++) {
-      const long long base = sptr[r >> 5] + (r & 31);
+      const long long base = sptr[r >> 5] + (long long) (r & 31) * 4;
       for (int p = hi[r], k = 0; p < hi[r + 1]; p++, k++) {
-         const long long e = base + (long long) k * 32;
+         const long long e = base + (long long) (k >> 2) * 128 + (k & 3);
          cidx[(size_t) e] = (unsigned char) offmap.find((unsigned long long) (long long) (hj[p] - r));
          if (vcoded) {
             unsigned long long bits;

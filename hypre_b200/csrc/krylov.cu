@@ -69,7 +69,9 @@ struct FScaleInvSqrtDev {   // y *= 1/sqrt(S[slot]) unless S[slot] == 0
 static int dot_global(const double *x, const double *y, size_t n, int slot)
 {
    Ctx &c = ctx();
+   timer_tick(T_BLAS1);
    HB_CHECK(vec_dot_dev(x, y, n, slot, c.s_comp));
+   timer_tick(T_OTHER);
    return scalars_allreduce(slot, 1, c.s_comp);
 }
 
@@ -209,7 +211,9 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       if (!recompute_true_residual) {
          if (flex) PCG_CHECK(vec_copy(r, r_old, n, st));
          // x += alpha p ; r -= alpha s ; <r,r>   with alpha, and its breakdown tests, on the device
+         timer_tick(T_BLAS1);
          PCG_CHECK(pcg_update_xr(p, s, x, r, n, g_cur, S_SDOTP, S_RR, S_FLAG, skip_break, st));
+         timer_tick(T_OTHER);
       } else {
          // rare path (pcg.c:653-702): host-driven
          double tmp[8];
@@ -265,8 +269,10 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       // s = C r ; gamma = <r,s>
       const int g_new = g_old;
       PCG_CHECK(precond_apply(pk, amg, A, r, s));
+      timer_tick(T_BLAS1);
       PCG_CHECK(vec_dot_dev(r, s, n, g_new, st));
       if (flex) PCG_CHECK(vec_dot_dev(r_old, s, n, S_DELTA, st));
+      timer_tick(T_OTHER);
       if (c.nranks > 1) {
          PCG_CHECK(scalars_allreduce(g_new, 1, st));
          PCG_CHECK(scalars_allreduce(S_RR, 1, st));
@@ -378,7 +384,9 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       // ---- p = s + beta p (pcg.c:968-984)
       if (!recompute_true_residual) {
          if (!flex) {
+            timer_tick(T_BLAS1);
             PCG_CHECK(pcg_update_p(s, p, n, g_new, g_cur, st));
+            timer_tick(T_OTHER);
          } else {
             beta = delta / gamma_old;
             PCG_CHECK(vec_scale(beta, p, n, st));
@@ -713,8 +721,10 @@ int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const hb2
    Ctx &c = ctx();
    memset(result, 0, sizeof(*result));
    const long long l0 = c.launches;
+   timers_begin();
    HB_CUDA(cudaEventRecord(c.ev_c, c.s_comp));
    int f = pcg_solve_dev(A, precond_kind, amg, params, b, x, norms, rel_norms, result);
+   timers_report("hb200_pcg_solve");
    HB_CUDA(cudaEventRecord(c.ev_d, c.s_comp));
    HB_CUDA(cudaEventSynchronize(c.ev_d));
    float ms = 0.f;

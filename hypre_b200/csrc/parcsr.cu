@@ -78,7 +78,7 @@ int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp)
    if (c.halo_mode == 1 && c.nranks > 1) {
       // NVLink peer puts, everything on the compute stream (parcsr_peer.cu); the plan build is
       // collective, so ranks without neighbours on this matrix take part too
-      HB_CHECK(peer_plans_ensure(A));
+      HB_CHECK(peer_plans_ensure(A, false));
       return peer_put(pk.fwd, x, st_comp);
    }
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
@@ -114,18 +114,23 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
       if (beta == 0.0) return vec_set(y, 0.0, A->num_rows, c.s_comp);
       return vec_axpby_out(beta, b, 0.0, b, y, A->num_rows, c.s_comp);
    }
+   timer_tick(T_HALO_START);
    HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
+   timer_tick(T_MATVEC_DIAG);
    EpiArgs ea;
    ea.alpha = alpha; ea.beta = beta; ea.b = b; ea.y = y;
    HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
+   timer_tick(T_HALO_WAIT);
    if (A->num_cols_offd > 0) {
       HB_CHECK(parcsr_halo_end(A, c.s_comp));
+      timer_tick(T_MATVEC_OFFD);
       EpiArgs eo;
       eo.alpha = alpha; eo.y = y;
       HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_ACC, eo, true, c.s_comp));
    } else {
       HB_CHECK(parcsr_halo_end(A, c.s_comp));
    }
+   timer_tick(T_OTHER);
    return 0;
 }
 
@@ -195,13 +200,15 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    CommPkgD &pk = A->pkg;
    const bool peer = (c.halo_mode == 1 && c.nranks > 1);
    const bool comm = (pk.num_sends || pk.num_recvs);
-   if (peer) HB_CHECK(peer_plans_ensure(A));
+   if (peer) HB_CHECK(peer_plans_ensure(A, true));
+   timer_tick(T_MATVEC_OFFD);
    if (A->num_cols_offd > 0) {
       // y_tmp = alpha * offd^T x  (par_csr_matvec.c:402-420)
       EpiArgs eo;
       eo.alpha = alpha; eo.beta = 0.0; eo.y = A->d_ytmp;
       HB_CHECK(spmv_launch(A->offdT, x, EPI_AXPBY, eo, false, c.s_comp));
    }
+   timer_tick(T_HALO_START);
    if (peer) {
       HB_CHECK(peer_put(pk.rev, A->d_ytmp, c.s_comp));
    } else if (comm) {
@@ -210,9 +217,11 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
       HB_CHECK(exchange(A, false, c.s_comm));
    }
    // y = alpha * diag^T x + beta * y   (overlapped with the reverse exchange)
+   timer_tick(T_MATVEC_DIAG);
    EpiArgs ed;
    ed.alpha = alpha; ed.beta = beta; ed.b = y; ed.y = y;
    HB_CHECK(spmv_launch(A->diagT, x, EPI_AXPBY, ed, false, c.s_comp));
+   timer_tick(T_HALO_WAIT);
    if (peer) {
       HB_CHECK(peer_wait(pk.rev, c.s_comp));
    } else if (comm) {
@@ -225,6 +234,7 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
                 pk.d_send_buf, y);
       HB_LAUNCH_CHECK();
    }
+   timer_tick(T_OTHER);
    return 0;
 }
 
@@ -374,6 +384,21 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, 
    if (recv_procs && pk.num_recvs) memcpy(recv_procs, pk.recv_procs.data(), sizeof(int) * pk.num_recvs);
    if (send_map_elmts && pk.d_send_map_elmts) {
       HB_CUDA(cudaMemcpy(send_map_elmts, pk.d_send_map_elmts, sizeof(int) * pk.send_map_elmts.size(), cudaMemcpyDeviceToHost));
+   }
+   return 0;
+}
+
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info4)
+{
+   HB_REQUIRE(A && info4, HB200_ERROR_ARG, "null argument");
+   info4[0] = A->diag.has_sell ? 1 : 0;
+   info4[1] = 0; info4[2] = 0; info4[3] = 0;
+   if (A->diag.has_sell) {
+      long long total = 0;
+      HB_CUDA(cudaMemcpy(&total, A->diag.sell_ptr + A->diag.sell_nslices, sizeof(long long), cudaMemcpyDeviceToHost));
+      info4[1] = total;
+      info4[2] = A->diag.sell_vidx ? 2 : 9;
+      info4[3] = A->diag.sell_nv;
    }
    return 0;
 }

@@ -117,6 +117,13 @@ halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const 
    __shared__ bool is_last;
    const unsigned long long epoch = epoch_ctr[0] + 1;
    const int par = (int) (epoch & 1ull);
+   // the receivers must have copied exchange (epoch - 2) out of this parity's buffers
+   if (epoch > 2) {
+      for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+         while (ld_acquire_sys(acks + i) + 2 < epoch) { }
+      }
+      __syncthreads();
+   }
    const int k = blockIdx.x * blockDim.x + threadIdx.x;
    if (k < total) {
       // segment of entry k (n_out <= a few dozen)
@@ -125,20 +132,21 @@ halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const 
          const int mid = (lo + hi + 1) >> 1;
          if (out_starts[mid] <= k) lo = mid; else hi = mid - 1;
       }
-      // the receiver must have copied exchange (epoch - 2) out of this parity's buffer
-      if (epoch > 2) { while (ld_acquire_sys(acks + lo) + 2 < epoch) { } }
       const double v = gather ? src[gather[k]] : src[k];
       dst2[par * n_out + lo][k - out_starts[lo]] = v;
    }
-   __threadfence_system();
+   // one system-scope fence per CTA (cumulative over the CTA's stores through the barrier), then
+   // the last CTA to arrive publishes the arrival flags
    __syncthreads();
    if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned int t = atomicInc(ticket, gridDim.x - 1);
       is_last = (t == gridDim.x - 1);
    }
    __syncthreads();
    if (is_last) {
-      __threadfence_system();
+      if (threadIdx.x == 0) __threadfence_system();
+      __syncthreads();
       for (int i = threadIdx.x; i < n_out; i += blockDim.x) st_release_sys(flag2[par * n_out + i], epoch);
       if (threadIdx.x == 0) epoch_ctr[0] = epoch;
    }
@@ -304,21 +312,24 @@ static int build_plan(PeerPlan **out_plan, int n_out, const int *out_procs, cons
 #endif
 }
 
-int peer_plans_ensure(hb200_parcsr *A)
+int peer_plans_ensure(hb200_parcsr *A, bool reverse)
 {
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
-   if (pk.peer_tried) return 0;
-   pk.peer_tried = true;
    if (c.nranks <= 1) return 0;
+   bool &tried = reverse ? pk.peer_tried_rev : pk.peer_tried;
+   if (tried) return 0;
+   tried = true;
    HB_CHECK(arena_setup());
-   // forward (job 1): out = sends (gather through send_map_elmts), in = recvs -> x_ext
-   HB_CHECK(build_plan(&pk.fwd, pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_map_elmts,
-                       pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), pk.d_recv_buf));
-   // reverse (job 2): out = recv segments of y_tmp (contiguous), in = send segments -> send_buf
-   HB_CHECK(parcsr_ensure_T(A));
-   HB_CHECK(build_plan(&pk.rev, pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), nullptr,
-                       pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_buf));
+   if (!reverse) {
+      // forward (job 1): out = sends (gather through send_map_elmts), in = recvs -> x_ext
+      HB_CHECK(build_plan(&pk.fwd, pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_map_elmts,
+                          pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), pk.d_recv_buf));
+   } else {
+      // reverse (job 2): out = recv segments of y_tmp (contiguous), in = send segments -> send_buf
+      HB_CHECK(build_plan(&pk.rev, pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), nullptr,
+                          pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_buf));
+   }
    // peers must not start writing into this arena region before everybody has built the plan
    HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
    HB_CUDA(cudaStreamSynchronize(c.s_comp));

@@ -40,18 +40,26 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       if (zero_guess) {
          // Vtemp = w*f (Scale), u = 0 + Vtemp ./ l1   (par_relax.c:1221-1244)
          if (used_shortcut) *used_shortcut = true;
-         return vec_scale_div(w, f, l1, u_out, relax_points ? cf : nullptr, relax_points, nullptr,
-                              (size_t) n, c.s_comp);
+         timer_tick(T_RELAX_ZERO);
+         int fl = vec_scale_div(w, f, l1, u_out, relax_points ? cf : nullptr, relax_points, nullptr,
+                                (size_t) n, c.s_comp);
+         timer_tick(T_OTHER);
+         return fl;
       }
+      timer_tick(T_HALO_START);
       HB_CHECK(parcsr_halo_begin(A, u_in, c.s_comp));
+      timer_tick(T_MATVEC_DIAG);
       EpiArgs ea;
       ea.w = w; ea.b = f; ea.u = u_in; ea.d = l1; ea.y = u_out;
       ea.cf = relax_points ? cf : nullptr; ea.relax_points = relax_points;
       HB_CHECK(spmv_launch(A->diag, u_in, EPI_JACOBI7, ea, false, c.s_comp));
+      timer_tick(T_HALO_WAIT);
       HB_CHECK(parcsr_halo_end(A, c.s_comp));
+      timer_tick(T_MATVEC_OFFD);
       if (A->num_cols_offd > 0) {
          HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_JACOBI7_ACC, ea, true, c.s_comp));
       }
+      timer_tick(T_OTHER);
       return 0;
    }
    // core form
@@ -240,6 +248,7 @@ int ge_solve(const GEData &ge, const double *f_local, double *u_local)
 {
    Ctx &c = ctx();
    if (ge.n <= 0) return 0;
+   timer_tick(T_GE_SOLVE);
    if (c.nranks > 1) {
       // hypre_MPI_Allgatherv of the coarse right-hand side (par_gauss_elim.c:577): every rank
       // deposits its slice into a zeroed n-vector and the vector is summed (x + 0 is exact)
@@ -258,6 +267,7 @@ int ge_solve(const GEData &ge, const double *f_local, double *u_local)
    HB_LAUNCH(ge_solve_kernel, 1, nt, sizeof(double) * (size_t) ge.n, c.s_comp, ge.n, ge.d_LfT,
              ge.d_UT, ge.d_Udiag, ge.d_b, u_local, ge.first_row, ge.num_local);
    HB_LAUNCH_CHECK();
+   timer_tick(T_OTHER);
    return 0;
 }
 

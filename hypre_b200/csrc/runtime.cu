@@ -67,6 +67,58 @@ int nccl_load()
 }
 #endif
 
+// ---- stream-time attribution --------------------------------------------------------------------
+bool g_timers_on = false;
+static std::vector<cudaEvent_t> g_tev;
+static std::vector<int> g_tcat;
+static size_t g_tn = 0;
+
+void timers_begin()
+{
+   static bool checked = false;
+   if (!checked) { checked = true; g_timers_on = getenv("HB200_TIMERS") != nullptr; }
+   if (!g_timers_on) return;
+   g_tn = 0;
+   timer_tick_impl(T_OTHER);
+}
+
+void timer_tick_impl(int cat)
+{
+   if (g_tn >= g_tev.size()) {
+      const size_t old = g_tev.size();
+      g_tev.resize(old + 4096);
+      g_tcat.resize(old + 4096);
+      for (size_t k = old; k < g_tev.size(); k++) cudaEventCreate(&g_tev[k]);
+   }
+   cudaEventRecord(g_tev[g_tn], g_ctx.s_comp);
+   g_tcat[g_tn] = cat;
+   g_tn++;
+}
+
+void timers_report(const char *what)
+{
+   if (!g_timers_on || g_tn < 2) return;
+   timer_tick_impl(T_OTHER);
+   cudaStreamSynchronize(g_ctx.s_comp);
+   double acc[T_NUM] = {0};
+   long cnt[T_NUM] = {0};
+   for (size_t k = 0; k + 1 < g_tn; k++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_tev[k], g_tev[k + 1]);
+      acc[g_tcat[k]] += ms;
+      cnt[g_tcat[k]]++;
+   }
+   static const char *names[T_NUM] = {"other", "matvec_diag(+relax)", "matvec_offd", "halo_start(pack/put)", "halo_wait(exposed)",
+                                      "blas1", "allreduce", "host_sync(fetch)", "ge_solve", "relax_zero_guess"};
+   double tot = 0.0;
+   for (int c = 0; c < T_NUM; c++) tot += acc[c];
+   fprintf(stderr, "[hb200 timers rank %d] %s: %.3f ms on the compute stream\n", g_ctx.rank, what, tot);
+   for (int c = 0; c < T_NUM; c++) {
+      if (cnt[c]) fprintf(stderr, "   %-24s %9.3f ms %5.1f%%  (%ld intervals)\n", names[c], acc[c], 100.0 * acc[c] / tot, cnt[c]);
+   }
+   g_tn = 0;
+}
+
 int ws_get(int slot, size_t bytes, double **out)
 {
    Ctx &c = g_ctx;

@@ -108,9 +108,15 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
                                int *offd_i, int *offd_j, int64_t *col_map_offd,
                                int *send_map_starts, int *send_map_elmts,
                                int *recv_vec_starts, int *send_procs, int *recv_procs);
+/* Storage format of the diag block: info[0] = 1 when a dictionary-packed SELL-32 copy exists
+ * (structured operators: <= 256 distinct column offsets), info[1] = stored entries incl. padding,
+ * info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset code + fp64 value),
+ * info[3] = number of distinct values (0 when values are stored raw). */
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info4);
 /* Selects the SpMV kernel for this matrix: 0 = auto from nnz/row (default),
  * 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced stream (merge-style),
- * 3 = stream with 128-bit index/value loads (kept for comparison). */
+ * 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 = vector with 2x/4x
+ * unrolled loads, 6 = packed SELL (when the block qualifies, else vector). */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):

@@ -416,6 +416,19 @@ def test_multi_gpu_parity_4ranks(torch):
     _run_workers(4, "laplacian")
 
 
+def test_multi_gpu_parity_2ranks_peer_halo(torch):
+    """same checks with the NVLink peer-put halo (hb200_set_halo_mode(1)) instead of NCCL send/recv"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_workers(2, "27pt", "peer")
+
+
+def test_multi_gpu_parity_4ranks_peer_halo(torch):
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run_workers(4, "27pt", "peer")
+
+
 # ----------------------------------------------------------------------------------------
 # drop-in: the UNMODIFIED reference driver (src/test/ij.c) linked in front of libHYPRE_b200.so
 # ----------------------------------------------------------------------------------------

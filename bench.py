@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--solver", default="pcg", choices=["pcg", "gmres"])
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer"],
+                    help="N>1 halo transport: NVLink peer puts, NCCL send/recv, or peer when every rank can map every peer")
     ap.add_argument("--cpu-iters", type=int, default=3, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv-only", action="store_true", help="configs[4]: SpMV bandwidth line")
@@ -220,8 +221,7 @@ def main():
         uid = [hb.comm_get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         hb.comm_init(rank, world, uid[0])
-        if args.halo == "peer":
-            check(lib.hb200_set_halo_mode(1))
+        check(lib.hb200_set_halo_mode({"nccl": 0, "peer": 1, "auto": 2}[args.halo]))
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,7 +239,19 @@ def main():
     # ---- hierarchy from the reference's own setup (CPU), uploaded once: timed separately
     rb, pb, gn, gen_s, setup_s = build_problem(args, rank, world)
     t0 = time.time()
-    mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), use_graph=not args.no_graph)
+    hier = pb.hierarchy()
+    if rank == 0 and os.environ.get("HB200_BENCH_LEVELS"):
+        for l, lv in enumerate(hier["levels"]):
+            for nm in ("A", "P"):
+                M = lv[nm]
+                if M is None:
+                    continue
+                oi = M.arrays()["offd_i"]
+                nbr = int((np.diff(oi) > 0).sum()) if oi is not None else 0
+                print(f"[levels] L{l} {nm}: rows {M.num_rows} diag_nnz {M.diag_nnz} offd_nnz {M.offd_nnz} "
+                      f"offd_rows {nbr} cols_offd {M.num_cols_offd} sends {M.num_sends} recvs {M.num_recvs}",
+                      file=sys.stderr)
+    mats, amg = hb.amg_from_hierarchy(hier, use_graph=not args.no_graph)
     hb.sync()
     upload_s = time.time() - t0
     A = mats[0][0]
@@ -297,56 +309,73 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant kernel: the fine-level SpMV, timed alone with CUDA events.
-    # A_0 of a structured-grid operator runs through the dictionary-packed SELL kernel (2 B per
-    # nonzero instead of CSR's 12); its algorithmic bytes are those of the packed format.  The
-    # general CSR kernel (every coarse level, every unstructured matrix) is timed on the same
-    # matrix as `roofline_csr`.
+    # ---- roofline: every level's SpMV kernel is timed alone with CUDA events on the library's
+    # compute stream; `roofline` is the one with the largest share of an iteration.  A_0 of a
+    # constant-coefficient stencil runs in the row-pattern format (1 B per row), other structured
+    # operators in packed SELL (2 or 9 B per nonzero), everything else (every coarse level, every
+    # unstructured matrix) in CSR through spmv_vector; the general CSR kernel is also timed on A_0
+    # as `roofline_csr`.
     peak, peak_src = peaks()
-    xs = torch.randn(A.num_cols, dtype=torch.float64, device="cuda")
-    ys = torch.empty(nloc, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
-
-    def time_spmv(reps=20):
+    def time_spmv(M, reps=20):
+        xs = torch.randn(max(M.num_cols, 1), dtype=torch.float64, device="cuda")
+        ys = torch.empty(max(M.num_rows, 1), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
         for _ in range(3):
-            check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+            check(lib.hb200_parcsr_matvec(M.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
         hb.sync()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
         for _ in range(reps):
-            check(lib.hb200_parcsr_matvec(A.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
+            check(lib.hb200_parcsr_matvec(M.handle, 1.0, xs.data_ptr(), 0.0, ys.data_ptr(), ys.data_ptr()))
         s1.record(stream)
         hb.sync()
         return s0.elapsed_time(s1) / reps
 
-    csr_bytes = 12.0 * nnz0 + 4.0 * nloc + 8.0 * A.num_cols + 8.0 * nloc
-    info = (C.c_longlong * 4)()
-    check(lib.hb200_parcsr_format_info(A.handle, info))
-    packed, sell_entries, sell_bytes_per_entry = int(info[0]), int(info[1]), int(info[2])
-    spmv_ms = time_spmv()
-    if packed:
-        alg_bytes = float(sell_entries) * sell_bytes_per_entry + 8.0 * (nloc / 32.0) + 4.0 * nloc \
-            + 8.0 * A.num_cols + 8.0 * nloc
-        kname = f"spmv_sell<EPI_AXPBY> on A_0 (packed SELL-32, {sell_bytes_per_entry} B/nonzero)"
-    else:
-        alg_bytes = csr_bytes
-        kname = "spmv_vector<EPI_AXPBY> on A_0 (CSR)"
-    achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "ms_per_launch": spmv_ms,
-                "bytes_per_launch": alg_bytes, "bytes_per_nnz": alg_bytes / max(nnz0, 1),
-                "csr_equivalent_gbs": csr_bytes / (spmv_ms * 1e-3) / 1e9,
-                "note": ("packed kernel: LSU-issue bound, not HBM bound (DESIGN.md section 3)" if packed else None),
-                "traffic": None}
+    def csr_model(M):
+        return 12.0 * M.diag_nnz + 4.0 * (M.num_rows + 1) + 8.0 * M.num_cols + 8.0 * M.num_rows
+
+    def kernel_entry(level, M, passes):
+        """algorithmic bytes of one y = A x on the diag block in its stored format
+        over the launch time measured here; on N > 1 the time includes the halo and the offd pass"""
+        fi = M.format_info()
+        n, nnz = M.num_rows, M.diag_nnz
+        if fi["kernel"] == 7:
+            by = 1.0 * n + 8.0 * M.num_cols + 8.0 * n + 12.0 * fi["pattern_entries"]
+            name = f"spmv_pat<EPI_AXPBY> on A_{level} (row-pattern format, 1 B/row + x + y)"
+        elif fi["kernel"] == 6:
+            by = float(fi["sell_entries"]) * fi["sell_bytes_per_entry"] + 8.0 * (n / 32.0) + 4.0 * n \
+                + 8.0 * M.num_cols + 8.0 * n
+            name = f"spmv_sell<EPI_AXPBY> on A_{level} (packed SELL-32, {fi['sell_bytes_per_entry']} B/nonzero)"
+        else:
+            by = csr_model(M)
+            name = f"spmv_vector<EPI_AXPBY,K> on A_{level} (CSR, 12 B/nonzero)"
+        ms_k = time_spmv(M)
+        gbs = by / (ms_k * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": name, "level": level, "rows": n, "nnz": nnz,
+                "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+                "ms_per_launch": ms_k, "bytes_per_launch": by, "bytes_per_nnz": by / max(nnz, 1),
+                "csr_equivalent_gbs": csr_model(M) / (ms_k * 1e-3) / 1e9,
+                "launches_per_iteration": passes, "ms_per_iteration": passes * ms_k, "traffic": None}
+
+    # one PCG iteration launches the A_0 kernel 3 times (Krylov matvec, residual, post-smoothing; the
+    # pre-smoothing sweep starts from a zero guess and reads no matrix) and the A_l kernel, l >= 1, twice
+    per_level = []
+    for l, (Al, _) in enumerate(mats):
+        if Al.diag_nnz * 50 < nnz0 or Al.num_rows == 0:
+            break
+        per_level.append(kernel_entry(l, Al, 3 if l == 0 else 2))
+    roofline = max(per_level, key=lambda e: e["ms_per_iteration"])
+    roofline = dict(roofline, note="the level kernel with the largest share of the iteration; all levels in roofline_levels")
     roofline_csr = None
-    if packed:
+    if A.format_info()["kernel"] != 1:
         A.set_spmv_kernel(1, 0)
-        ms_csr = time_spmv()
+        ms_csr = time_spmv(A)
         A.set_spmv_kernel(0, 0)
+        cb = csr_model(A)
         roofline_csr = {"bound": "hbm", "kernel": "spmv_vector<EPI_AXPBY,K> on A_0 (general CSR path)",
-                        "achieved": csr_bytes / (ms_csr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": csr_bytes / (ms_csr * 1e-3) / 1e9 / peak, "ms_per_launch": ms_csr,
-                        "bytes_per_launch": csr_bytes, "bytes_per_nnz": csr_bytes / max(nnz0, 1), "traffic": None}
+                        "achieved": cb / (ms_csr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": cb / (ms_csr * 1e-3) / 1e9 / peak, "ms_per_launch": ms_csr,
+                        "bytes_per_launch": cb, "bytes_per_nnz": cb / max(nnz0, 1), "traffic": None}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own solve, bounded sample
     cpu = None
@@ -387,7 +416,8 @@ def main():
                 "iterations": its, "final_rel_res": relres, "tol": args.tol, "parity_vs_reference": ref_parity,
                 "cache": "inputs larger than L2 (A_0 alone is %.1f GB)" % (12.0 * nnz0 / 1e9),
                 "setup_s_reference_cpu": setup_s, "generate_s": gen_s, "upload_s": upload_s,
-                "cuda_graph_vcycle": (not args.no_graph) and world == 1, "halo": args.halo if world > 1 else None,
+                "cuda_graph_vcycle": (not args.no_graph) and (world == 1 or lib.hb200_halo_mode() == 1),
+                "halo": (["nccl", "peer"][lib.hb200_halo_mode()] if world > 1 else None),
                 "timing": "CUDA events on the hb200 compute stream, max over ranks",
             },
             "e2e": {"value": rows / (e2e_ms * 1e-3) / 1e6, "unit": "MDOF/s", "ms_per_step": e2e_ms,
@@ -396,6 +426,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
             "roofline_csr": roofline_csr,
+            "roofline_levels": per_level,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -69,6 +69,7 @@ def _load() -> C.CDLL:
         "hb200_comm_size": ([], C.c_int),
         "hb200_comm_barrier": ([], C.c_int),
         "hb200_set_halo_mode": ([C.c_int], C.c_int),
+        "hb200_halo_mode": ([], C.c_int),
         "hb200_malloc": ([C.POINTER(vp), C.c_size_t], C.c_int),
         "hb200_free": ([vp], C.c_int),
         "hb200_memcpy_h2d": ([vp, vp, C.c_size_t], C.c_int),

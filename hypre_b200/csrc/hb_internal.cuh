@@ -120,7 +120,7 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7 };
 
 struct DCsr {
    int        nrows = 0, ncols = 0;
@@ -149,6 +149,15 @@ struct DCsr {
    int       *sell_offdict = nullptr;  // 256 entries
    double    *sell_valdict = nullptr;  // 256 entries
    int        sell_nd = 0, sell_nv = 0;
+   // row-pattern copy (kernels_pat.cu), present when the block has <= 256 distinct rows as lists of
+   // (column - row, value): one byte per row + a table of the patterns (constant-coefficient stencils)
+   bool       has_pat = false;
+   unsigned char *pat_code = nullptr;  // nrows
+   int       *pat_base = nullptr;      // nrows: first column of each row (rectangular blocks), NULL = the row itself
+   int       *pat_ptr = nullptr;       // pat_npat + 1
+   int       *pat_off = nullptr;       // pat_nent
+   double    *pat_val = nullptr;       // pat_nent
+   int        pat_npat = 0, pat_nent = 0;
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
 };
@@ -159,6 +168,8 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
 int  dcsr_build_partition(DCsr &M, const int *hi);
 int  dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha);   // kernels_sell.cu
 int  dcsr_free_sell(DCsr &M);
+int  dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha);    // kernels_pat.cu
+int  dcsr_free_pat(DCsr &M);
 // host-side transpose (stable: entries of each output row in ascending source-row order,
 // the order hypre_CSRMatrixMatvecTHost accumulates in, csr_matvec.c:1095-1110)
 void host_csr_transpose(int nrows, int ncols, const int *ai, const int *aj, const double *aa,
@@ -199,6 +210,7 @@ struct EpiArgs {
 int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
                 bool use_rownnz, cudaStream_t st);
 int spmv_sell_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
+int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
 // BLAS-1 (kernels_blas1.cu).  Scalars live in ctx().d_scalars[slot]; dots are two-stage,
@@ -281,6 +293,8 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
 int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y);
 int gs_sched_free(void *p);
 // peer-put halo (parcsr_peer.cu)
+int  arena_setup_collective(int *all_ok);                    // collective; never hangs on a local failure
+bool peer_has_out(const PeerPlan *pl);
 int  peer_plans_ensure(hb200_parcsr *A, bool reverse);      // collective, lazy: builds A->pkg.fwd or .rev
 int  peer_put(PeerPlan *pl, const double *src, cudaStream_t st);
 int  peer_wait(PeerPlan *pl, cudaStream_t st);

@@ -105,6 +105,18 @@ static int shim_init(MPI_Comm comm)
          fprintf(stderr, "[hypre_b200] FATAL: %s\n", hb200_last_error());
          return 1;
       }
+      /* halo transport: NVLink peer puts when every rank can map every peer, else NCCL
+       * (HYPRE_B200_HALO=nccl forces the latter) */
+      {
+         const char *hm = getenv("HYPRE_B200_HALO");
+         if (hb200_set_halo_mode((hm && !strcmp(hm, "nccl")) ? 0 : 2) != 0)
+         {
+            g_failed = 1;
+            hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+            return 1;
+         }
+         if (g_verbose && myid == 0) fprintf(stderr, "[hypre_b200] halo transport: %s\n", hb200_halo_mode() ? "peer put" : "NCCL");
+      }
    }
    g_ready = 1;
    if (g_verbose && myid == 0) { fprintf(stderr, "[hypre_b200] %s bound, %d rank(s)\n", hb200_version(), nprocs); }

@@ -1,0 +1,243 @@
+// kernels_pat.cu — row-pattern SpMV for operators with few distinct rows.
+//
+// A row of a CSR block is the list (column - base, value) of its entries, with base = the row
+// index for square blocks and the row's first column for rectangular ones.  On a constant-
+// coefficient grid problem only a handful of distinct lists exist on the fine level — one for the
+// interior and one per kind of boundary, 27 on a box for the 7-point and the 27-point stencil
+// alike — and, where the coarsening comes out regular, the same holds for the interpolation P_0,
+// its stored transpose and the Galerkin operator A_1 (about 100 patterns each on 27-pt).
+// When a block has <= 256 distinct row patterns (<= 8192 table entries) it is stored a second
+// time as
+//     pat[row]           1 byte per ROW        (+ base[row], 4 bytes, for rectangular blocks)
+//     table[pattern]     the (offset, value) list of each pattern, held in shared memory
+// so the SpMV streams x, y and one byte per row — 17 B per row instead of 12 B per NONZERO — and
+// the kernel is bound by the L1 gathers of x, not by HBM.
+//
+// One thread owns R rows that sit one block width apart (a block covers R*blockDim consecutive
+// rows; for fixed j a warp's 32 rows are consecutive, so on square blocks every gather of x is a
+// coalesced 256 B request).  When the R rows share a pattern — the interior of A, i.e. nearly
+// always — each (offset, value) is read from shared memory once and used R times.  Every row
+// adds its products in CSR order with separate multiply and add, exactly the reference's
+// sequential loop (src/seq_mv/csr_matvec.c:683-721): results are bit-identical to the 1-thread
+// CPU reference.  Lossless; blocks that do not qualify (variable coefficients, the deeper AMG
+// levels) keep the packed-SELL or CSR path.
+#include "hb_internal.cuh"
+#include "hb_epilogue.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <unordered_map>
+
+namespace hb {
+
+constexpr int kPatRows = 4;            // rows per thread
+constexpr int kPatMaxPatterns = 256;
+constexpr int kPatMaxEntries = 8192;   // table entries over all patterns (96 KB of shared memory)
+
+template <int EPI>
+__device__ __forceinline__ void pat_one_row(const EpiArgs &ea, const double *__restrict__ xb, int row, int p,
+                                            const int *s_ptr, const int *s_off, const double *s_val, int skip)
+{
+   const int b = s_ptr[p], e = s_ptr[p + 1];
+   double s = 0.0;
+   for (int k = b + skip; k < e; k++) s = __dadd_rn(s, __dmul_rn(s_val[k], __ldg(xb + s_off[k])));
+   epi_apply<EPI>(ea, row, s, e > b ? s_val[b] : 0.0);
+}
+
+// column of entry k of a row = base + off[k]; base = the row itself for square blocks (BASE =
+// false), else base[row] (the row's first column: interpolation and its stored transpose)
+template <int EPI, bool BASE>
+__global__ void __launch_bounds__(512)
+spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int *__restrict__ base, int npat,
+         int nent, const int *__restrict__ tab_ptr, const int *__restrict__ tab_off,
+         const double *__restrict__ tab_val, const double *__restrict__ x, EpiArgs ea)
+{
+   extern __shared__ double s_mem[];
+   double *s_val = s_mem;
+   int    *s_off = reinterpret_cast<int *>(s_val + nent);
+   int    *s_ptr = s_off + nent;
+   const int tid = threadIdx.x, nt = blockDim.x;
+   for (int k = tid; k < nent; k += nt) { s_val[k] = tab_val[k]; s_off[k] = tab_off[k]; }
+   for (int k = tid; k <= npat; k += nt) s_ptr[k] = tab_ptr[k];
+   __syncthreads();
+   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int r0 = tile * (nt * kPatRows) + tid;
+      int p[kPatRows];
+      const double *xb[kPatRows];
+      bool same = true;
+#pragma unroll
+      for (int j = 0; j < kPatRows; j++) {
+         const int row = r0 + j * nt;
+         p[j] = row < nrows ? (int) pat[row] : -1;
+         xb[j] = x + (BASE ? (row < nrows ? base[row] : 0) : row);
+         same = same && (p[j] == p[0]);
+      }
+      if (same && p[0] >= 0) {
+         // the R rows share a pattern: one table read per entry, R gathers
+         const int b = s_ptr[p[0]], e = s_ptr[p[0] + 1];
+         double s[kPatRows];
+#pragma unroll
+         for (int j = 0; j < kPatRows; j++) s[j] = 0.0;
+#pragma unroll 2
+         for (int k = b + skip; k < e; k++) {
+            const double a = s_val[k];
+            const int o = s_off[k];
+            double xv[kPatRows];
+#pragma unroll
+            for (int j = 0; j < kPatRows; j++) xv[j] = __ldg(xb[j] + o);
+#pragma unroll
+            for (int j = 0; j < kPatRows; j++) s[j] = __dadd_rn(s[j], __dmul_rn(a, xv[j]));
+         }
+         const double diag = e > b ? s_val[b] : 0.0;
+#pragma unroll
+         for (int j = 0; j < kPatRows; j++) epi_apply<EPI>(ea, r0 + j * nt, s[j], diag);
+      } else {
+#pragma unroll
+         for (int j = 0; j < kPatRows; j++) {
+            if (p[j] >= 0) pat_one_row<EPI>(ea, xb[j], r0 + j * nt, p[j], s_ptr, s_off, s_val, skip);
+         }
+      }
+   }
+}
+
+template <int EPI, bool BASE>
+static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
+   static bool opted = false;
+   if (!opted) {
+      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPatMaxEntries * 12 + (kPatMaxPatterns + 1) * 4 + 8));
+      opted = true;
+   }
+   // big tables leave room for few blocks per SM: use larger ones
+   const int threads = smem > 40 * 1024 ? 512 : 256;
+   const int ntiles = (M.nrows + threads * kPatRows - 1) / (threads * kPatRows);
+   // the table is loaded once per block: the resident blocks walk the tiles
+   int per_sm = (int) ((227 * 1024) / (smem + 1024));
+   const int cap = threads == 512 ? 3 : 6;
+   if (per_sm > cap) per_sm = cap;
+   if (per_sm < 1) per_sm = 1;
+   int grid = 148 * per_sm;
+   if (grid > ntiles) grid = ntiles;
+   HB_LAUNCH((spmv_pat<EPI, BASE>), grid, threads, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
+             M.pat_nent, M.pat_ptr, M.pat_off, M.pat_val, x, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+template <int EPI>
+static int pat_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   return M.pat_base ? pat_launch_t<EPI, true>(M, x, ea, st) : pat_launch_t<EPI, false>(M, x, ea, st);
+}
+
+int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)
+{
+   switch (epi_kind) {
+      case EPI_AXPBY:           return pat_dispatch<EPI_AXPBY>(M, x, ea, st);
+      case EPI_ACC:             return pat_dispatch<EPI_ACC>(M, x, ea, st);
+      case EPI_JACOBI7:         return pat_dispatch<EPI_JACOBI7>(M, x, ea, st);
+      case EPI_JACOBI7_ACC:     return pat_dispatch<EPI_JACOBI7_ACC>(M, x, ea, st);
+      case EPI_JACOBI_CORE:     return pat_dispatch<EPI_JACOBI_CORE>(M, x, ea, st);
+      case EPI_JACOBI_CORE_ACC: return pat_dispatch<EPI_JACOBI_CORE_ACC>(M, x, ea, st);
+      default: return set_error(HB200_ERROR_ARG, "spmv_pat_launch: unknown epilogue %d", epi_kind);
+   }
+}
+
+int dcsr_free_pat(DCsr &M)
+{
+   if (M.pat_code) cudaFree(M.pat_code);
+   if (M.pat_ptr) cudaFree(M.pat_ptr);
+   if (M.pat_off) cudaFree(M.pat_off);
+   if (M.pat_val) cudaFree(M.pat_val);
+   if (M.pat_base) cudaFree(M.pat_base);
+   M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr;
+   M.has_pat = false;
+   return 0;
+}
+
+// pattern detection on the host, one pass over the block.  Consecutive rows of a grid operator
+// nearly always repeat the previous row's pattern, so the common case is one compare per entry
+// against that pattern; only a change of pattern goes through the hash.  Irregular blocks leave
+// after their first kPatMaxPatterns+1 rows.
+int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
+{
+   if (getenv("HB200_NO_PAT")) return 0;
+   const int n = M.nrows;
+   if (n < 1024 || M.nnz < 2LL * n) return 0;        // tiny or nearly empty (offd) blocks: nothing to win
+   // square blocks: column = row + offset; rectangular ones (P, P^T): column = first column + offset
+   const bool square = (M.nrows == M.ncols);
+   std::vector<int> basev;
+   if (!square) {
+      basev.resize((size_t) n);
+      for (int r = 0; r < n; r++) basev[r] = hi[r + 1] > hi[r] ? hj[hi[r]] : 0;
+   }
+   auto base_of = [&](int r) -> int { return square ? r : basev[r]; };
+   std::vector<int> ptr(1, 0), off;
+   std::vector<unsigned long long> val;   // bit patterns (-0.0 and NaN payloads survive)
+   std::vector<unsigned char> code((size_t) n);
+   std::unordered_multimap<unsigned long long, int> by_hash;
+   auto matches = [&](int p, int r) -> bool {
+      const int b = ptr[p], len = ptr[p + 1] - b;
+      if (hi[r + 1] - hi[r] != len) return false;
+      const int *cj = hj + hi[r];
+      const double *ca = ha + hi[r];
+      for (int k = 0; k < len; k++) {
+         unsigned long long bits;
+         memcpy(&bits, &ca[k], 8);
+         if (cj[k] - base_of(r) != off[b + k] || bits != val[b + k]) return false;
+      }
+      return true;
+   };
+   int prev = -1;
+   for (int r = 0; r < n; r++) {
+      if (prev >= 0 && matches(prev, r)) { code[r] = (unsigned char) prev; continue; }
+      unsigned long long h = 1469598103934665603ull ^ (unsigned long long) (hi[r + 1] - hi[r]);
+      for (int q = hi[r]; q < hi[r + 1]; q++) {
+         unsigned long long bits;
+         memcpy(&bits, &ha[q], 8);
+         h = (h ^ (unsigned long long) (long long) (hj[q] - base_of(r))) * 1099511628211ull;
+         h = (h ^ bits) * 1099511628211ull;
+      }
+      int found = -1;
+      auto range = by_hash.equal_range(h);
+      for (auto it = range.first; it != range.second; ++it) {
+         if (matches(it->second, r)) { found = it->second; break; }
+      }
+      if (found < 0) {
+         const int len = hi[r + 1] - hi[r];
+         if ((int) ptr.size() - 1 >= kPatMaxPatterns || (int) off.size() + len > kPatMaxEntries) return 0;
+         found = (int) ptr.size() - 1;
+         for (int q = hi[r]; q < hi[r + 1]; q++) {
+            unsigned long long bits;
+            memcpy(&bits, &ha[q], 8);
+            off.push_back(hj[q] - base_of(r));
+            val.push_back(bits);
+         }
+         ptr.push_back((int) off.size());
+         by_hash.emplace(h, found);
+      }
+      code[r] = (unsigned char) found;
+      prev = found;
+   }
+   const int npat = (int) ptr.size() - 1, nent = (int) off.size();
+   HB_CUDA(cudaMalloc(&M.pat_code, (size_t) n + 64));
+   HB_CUDA(cudaMemcpy(M.pat_code, code.data(), (size_t) n, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc(&M.pat_ptr, sizeof(int) * ((size_t) npat + 1)));
+   HB_CUDA(cudaMemcpy(M.pat_ptr, ptr.data(), sizeof(int) * ((size_t) npat + 1), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc(&M.pat_off, sizeof(int) * ((size_t) nent + 1)));
+   HB_CUDA(cudaMemcpy(M.pat_off, off.data(), sizeof(int) * (size_t) nent, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMalloc(&M.pat_val, sizeof(double) * ((size_t) nent + 1)));
+   HB_CUDA(cudaMemcpy(M.pat_val, val.data(), sizeof(double) * (size_t) nent, cudaMemcpyHostToDevice));
+   if (!square) {
+      HB_CUDA(cudaMalloc(&M.pat_base, sizeof(int) * (size_t) n));
+      HB_CUDA(cudaMemcpy(M.pat_base, basev.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
+   }
+   M.pat_npat = npat;
+   M.pat_nent = nent;
+   M.has_pat = true;
+   return 0;
+}
+
+}  // namespace hb

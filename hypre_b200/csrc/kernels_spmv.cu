@@ -323,12 +323,24 @@ static int vector_lanes_for(double avg)
    return 1;
 }
 
+// A launch with fewer threads than the GPU holds is latency-bound on the per-lane serial chain of
+// dependent gathers (offd blocks, coarse levels): spread each row over more lanes until the grid
+// covers the SMs, as long as every lane still has an entry to work on.  HB200_NO_WIDEN=1 disables.
+static int widen_lanes(int lanes, long long nlist, double avg)
+{
+   static const bool off = getenv("HB200_NO_WIDEN") != nullptr;
+   if (off) return lanes;
+   while (lanes < 32 && nlist * lanes < 148LL * 1024 && lanes * 2 <= avg) lanes *= 2;
+   return lanes;
+}
+
 template <int EPI>
 static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
                          cudaStream_t st)
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
+   if (!use_rownnz && M.kind == SPMV_PAT && M.has_pat) return spmv_pat_launch(M, x, EPI, ea, st);
    if (!use_rownnz && M.kind == SPMV_SELL && M.has_sell) return spmv_sell_launch(M, x, EPI, ea, st);
    if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
@@ -339,7 +351,7 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
    if (lanes == 0) {
       const double avg = use_rownnz ? (double) M.nnz / (double) (M.num_rownnz ? M.num_rownnz : 1)
                                     : M.avg_row_nnz;
-      lanes = vector_lanes_for(avg);
+      lanes = widen_lanes(vector_lanes_for(avg), nlist, avg);
    }
    return launch_vector<EPI>(M, x, ea, use_rownnz, lanes, unroll, st);
 }
@@ -392,7 +404,8 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
 {
    // the sub-warp vector kernel beat the shared-memory stream kernel on every level measured
    // (profiles/r1_level_sweep.md): the stream kernel is L1-wavefront bound by its smem round trip
-   if (kind == SPMV_AUTO) kind = M.has_sell ? SPMV_SELL : SPMV_VECTOR;
+   if (kind == SPMV_AUTO) kind = M.has_pat ? SPMV_PAT : M.has_sell ? SPMV_SELL : SPMV_VECTOR;
+   if (kind == SPMV_PAT && !M.has_pat) kind = M.has_sell ? SPMV_SELL : SPMV_VECTOR;
    if (kind == SPMV_SELL && !M.has_sell) kind = SPMV_VECTOR;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
@@ -442,6 +455,7 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
    }
    if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
+   if (nrows > 0) HB_CHECK(dcsr_build_pat(M, hi, hj, ha));
    if (nrows > 0 && nrows == ncols) HB_CHECK(dcsr_build_sell(M, hi, hj, ha));   // square (A_l) blocks only
    dcsr_choose_kernel(M, SPMV_AUTO, 0);
    return 0;
@@ -455,6 +469,7 @@ int dcsr_free(DCsr &M)
    if (M.rownnz) cudaFree(M.rownnz);
    if (M.blk_row) cudaFree(M.blk_row);
    dcsr_free_sell(M);
+   dcsr_free_pat(M);
    M = DCsr();
    return 0;
 }

@@ -79,7 +79,13 @@ int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp)
       // NVLink peer puts, everything on the compute stream (parcsr_peer.cu); the plan build is
       // collective, so ranks without neighbours on this matrix take part too
       HB_CHECK(peer_plans_ensure(A, false));
-      return peer_put(pk.fwd, x, st_comp);
+      if (!peer_has_out(pk.fwd)) return 0;
+      // the put (gather + NVLink stores + system fences, ~10 us of latency) runs beside the diag pass
+      HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
+      HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+      HB_CHECK(peer_put(pk.fwd, x, c.s_comm));
+      HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+      return 0;
    }
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
    HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
@@ -97,7 +103,10 @@ int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
 {
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
-   if (c.halo_mode == 1 && c.nranks > 1) return peer_wait(pk.fwd, st_comp);
+   if (c.halo_mode == 1 && c.nranks > 1) {
+      if (peer_has_out(pk.fwd)) HB_CUDA(cudaStreamWaitEvent(st_comp, c.ev_b, 0));
+      return pk.fwd ? peer_wait(pk.fwd, st_comp) : 0;
+   }
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
    HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
    HB_CUDA(cudaStreamWaitEvent(st_comp, c.ev_b, 0));
@@ -210,7 +219,12 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    }
    timer_tick(T_HALO_START);
    if (peer) {
-      HB_CHECK(peer_put(pk.rev, A->d_ytmp, c.s_comp));
+      if (peer_has_out(pk.rev)) {
+         HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
+         HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+         HB_CHECK(peer_put(pk.rev, A->d_ytmp, c.s_comm));
+         HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+      }
    } else if (comm) {
       HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
       HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
@@ -223,7 +237,8 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    HB_CHECK(spmv_launch(A->diagT, x, EPI_AXPBY, ed, false, c.s_comp));
    timer_tick(T_HALO_WAIT);
    if (peer) {
-      HB_CHECK(peer_wait(pk.rev, c.s_comp));
+      if (peer_has_out(pk.rev)) HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
+      if (pk.rev) HB_CHECK(peer_wait(pk.rev, c.s_comp));
    } else if (comm) {
       HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
       HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
@@ -388,25 +403,29 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, 
    return 0;
 }
 
-int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info4)
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info8)
 {
-   HB_REQUIRE(A && info4, HB200_ERROR_ARG, "null argument");
-   info4[0] = A->diag.has_sell ? 1 : 0;
-   info4[1] = 0; info4[2] = 0; info4[3] = 0;
+   HB_REQUIRE(A && info8, HB200_ERROR_ARG, "null argument");
+   for (int k = 0; k < 8; k++) info8[k] = 0;
+   info8[0] = A->diag.has_sell ? 1 : 0;
    if (A->diag.has_sell) {
       long long total = 0;
       HB_CUDA(cudaMemcpy(&total, A->diag.sell_ptr + A->diag.sell_nslices, sizeof(long long), cudaMemcpyDeviceToHost));
-      info4[1] = total;
-      info4[2] = A->diag.sell_vidx ? 2 : 9;
-      info4[3] = A->diag.sell_nv;
+      info8[1] = total;
+      info8[2] = A->diag.sell_vidx ? 2 : 9;
+      info8[3] = A->diag.sell_nv;
    }
+   info8[4] = A->diag.has_pat ? 1 : 0;
+   info8[5] = A->diag.pat_npat;
+   info8[6] = A->diag.pat_nent;
+   info8[7] = A->diag.kind;
    return 0;
 }
 
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
 {
    HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
-   HB_REQUIRE(kind >= 0 && kind <= 6, HB200_ERROR_ARG, "kind must be 0..6");
+   HB_REQUIRE(kind >= 0 && kind <= 7, HB200_ERROR_ARG, "kind must be 0..7");
    HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
               HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
    dcsr_choose_kernel(A->diag, kind, lanes_per_row);

@@ -43,20 +43,31 @@ struct PeerPlan {
 // ---------------------------------------------------------------------------------------
 // arena
 // ---------------------------------------------------------------------------------------
-int arena_setup()
+// Collective over all ranks.  Every rank takes part in every collective of this function even
+// when its local part failed, so that one rank's failure cannot hang the others; the verdict is
+// the sum of the local failure counts.  *all_ok = 1 when every rank mapped every peer arena.
+int arena_setup_collective(int *all_ok)
 {
    Ctx &c = ctx();
-   if (c.peer_ok || c.nranks <= 1) return 0;
+   *all_ok = 0;
+   if (c.nranks <= 1) return 0;
+   if (c.peer_ok) { *all_ok = 1; return 0; }
 #ifdef HB200_WITH_NCCL
    const char *e = getenv("HB200_ARENA_MB");
+   const size_t hs = sizeof(cudaIpcMemHandle_t);
+   int bad = 0;
+   char msg[256] = "";
    c.arena_bytes = (size_t) (e ? atoi(e) : 256) << 20;
-   HB_CUDA(cudaMalloc((void **) &c.arena, c.arena_bytes));
-   HB_CUDA(cudaMemset(c.arena, 0, c.arena_bytes));
    c.arena_used = 0;
    cudaIpcMemHandle_t mine;
-   HB_CUDA(cudaIpcGetMemHandle(&mine, c.arena));
+   memset(&mine, 0, sizeof(mine));
+   if (cudaMalloc((void **) &c.arena, c.arena_bytes) != cudaSuccess ||
+       cudaMemset(c.arena, 0, c.arena_bytes) != cudaSuccess ||
+       cudaIpcGetMemHandle(&mine, c.arena) != cudaSuccess) {
+      snprintf(msg, sizeof(msg), "peer arena allocation / IPC export failed: %s", cudaGetErrorString(cudaGetLastError()));
+      bad = 1;
+   }
    char *d_h = nullptr;
-   const size_t hs = sizeof(cudaIpcMemHandle_t);
    HB_CUDA(cudaMalloc((void **) &d_h, hs * (size_t) c.nranks));
    HB_CUDA(cudaMemcpy(d_h + hs * (size_t) c.rank, &mine, hs, cudaMemcpyHostToDevice));
    HB_NCCL(nccl_api().AllGather(d_h + hs * (size_t) c.rank, d_h, hs, ncclChar, c.nccl, c.s_comp));
@@ -64,22 +75,57 @@ int arena_setup()
    std::vector<cudaIpcMemHandle_t> all((size_t) c.nranks);
    HB_CUDA(cudaMemcpy(all.data(), d_h, hs * (size_t) c.nranks, cudaMemcpyDeviceToHost));
    cudaFree(d_h);
-   c.peer_arena.assign((size_t) c.nranks, nullptr);
-   for (int r = 0; r < c.nranks; r++) {
-      if (r == c.rank) { c.peer_arena[r] = c.arena; continue; }
-      void *p = nullptr;
-      cudaError_t er = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-      if (er != cudaSuccess) {
-         return set_error(HB200_ERROR_GENERIC, "cudaIpcOpenMemHandle(rank %d) failed: %s (peer halo mode needs "
-                          "all ranks on one NVLink domain)", r, cudaGetErrorString(er));
+   // did everybody export?  (opening the handle of a rank whose export failed is undefined)
+   double v = (double) bad;
+   HB_CUDA(cudaMemcpyAsync(c.d_scalars + kScalarSlots - 1, &v, sizeof(double), cudaMemcpyHostToDevice, c.s_comp));
+   HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
+   HB_CHECK(scalars_fetch(kScalarSlots - 1, 1, &v, c.s_comp));
+   if (v == 0.0) {
+      c.peer_arena.assign((size_t) c.nranks, nullptr);
+      for (int r = 0; r < c.nranks && !bad; r++) {
+         if (r == c.rank) { c.peer_arena[r] = c.arena; continue; }
+         void *p = nullptr;
+         cudaError_t er = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+         if (er != cudaSuccess) {
+            snprintf(msg, sizeof(msg), "cudaIpcOpenMemHandle(rank %d) failed: %s (the peer halo needs all ranks on one "
+                     "NVLink domain)", r, cudaGetErrorString(er));
+            cudaGetLastError();
+            bad = 1;
+         }
+         c.peer_arena[r] = (char *) p;
       }
-      c.peer_arena[r] = (char *) p;
+      v = (double) bad;
+      HB_CUDA(cudaMemcpyAsync(c.d_scalars + kScalarSlots - 1, &v, sizeof(double), cudaMemcpyHostToDevice, c.s_comp));
+      HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
+      HB_CHECK(scalars_fetch(kScalarSlots - 1, 1, &v, c.s_comp));
    }
-   c.peer_ok = true;
+   if (v == 0.0) {
+      c.peer_ok = true;
+      *all_ok = 1;
+      return 0;
+   }
+   // somebody failed: nobody uses the arena
+   for (int r = 0; r < c.nranks && r < (int) c.peer_arena.size(); r++) {
+      if (r != c.rank && c.peer_arena[r]) cudaIpcCloseMemHandle(c.peer_arena[r]);
+   }
+   c.peer_arena.clear();
+   if (c.arena) { cudaFree(c.arena); c.arena = nullptr; }
+   cudaGetLastError();
+   if (msg[0]) set_error(HB200_ERROR_GENERIC, "%s", msg);   // kept for hb200_last_error()
    return 0;
 #else
    return set_error(HB200_ERROR_GENERIC, "libhb200 built without NCCL");
 #endif
+}
+
+int arena_setup()
+{
+   int ok = 0;
+   HB_CHECK(arena_setup_collective(&ok));
+   if (!ok && ctx().nranks > 1) {
+      return set_error(HB200_ERROR_GENERIC, "peer halo unavailable on at least one rank (see the ranks' hb200_last_error)");
+   }
+   return 0;
 }
 
 int arena_alloc(size_t bytes, size_t *offset)
@@ -108,7 +154,9 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kHaloBlock = 512;
+
+__global__ void __launch_bounds__(kHaloBlock)
 halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const int *__restrict__ gather,
                 const double *__restrict__ src, double *const *__restrict__ dst2,
                 unsigned long long *const *__restrict__ flag2, const unsigned long long *__restrict__ acks,
@@ -124,8 +172,7 @@ halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const 
       }
       __syncthreads();
    }
-   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k < total) {
+   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
       // segment of entry k (n_out <= a few dozen)
       int lo = 0, hi = n_out - 1;
       while (lo < hi) {
@@ -135,24 +182,27 @@ halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const 
       const double v = gather ? src[gather[k]] : src[k];
       dst2[par * n_out + lo][k - out_starts[lo]] = v;
    }
-   // one system-scope fence per CTA (cumulative over the CTA's stores through the barrier), then
-   // the last CTA to arrive publishes the arrival flags
+   // one system-scope fence per CTA (cumulative over the CTA's stores through the barrier); with
+   // several CTAs the last one to arrive publishes the arrival flags
    __syncthreads();
    if (threadIdx.x == 0) {
       __threadfence_system();
-      const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-      is_last = (t == gridDim.x - 1);
+      if (gridDim.x == 1) {
+         is_last = true;
+      } else {
+         const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+         is_last = (t == gridDim.x - 1);
+         if (is_last) __threadfence_system();
+      }
    }
    __syncthreads();
    if (is_last) {
-      if (threadIdx.x == 0) __threadfence_system();
-      __syncthreads();
       for (int i = threadIdx.x; i < n_out; i += blockDim.x) st_release_sys(flag2[par * n_out + i], epoch);
       if (threadIdx.x == 0) epoch_ctr[0] = epoch;
    }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kHaloBlock)
 halo_wait_kernel(int total, int n_in, const double *__restrict__ buf0, const double *__restrict__ buf1,
                  const unsigned long long *__restrict__ flags, unsigned long long *const *__restrict__ in_ack,
                  double *__restrict__ dst, unsigned long long *epoch_ctr, unsigned int *ticket)
@@ -168,11 +218,15 @@ halo_wait_kernel(int total, int n_in, const double *__restrict__ buf0, const dou
    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
       dst[k] = __ldcg(buf + k);
    }
-   __threadfence();
    __syncthreads();
    if (threadIdx.x == 0) {
-      const unsigned int t = atomicInc(ticket + 1, gridDim.x - 1);
-      is_last = (t == gridDim.x - 1);
+      if (gridDim.x == 1) {
+         is_last = true;
+      } else {
+         __threadfence();
+         const unsigned int t = atomicInc(ticket + 1, gridDim.x - 1);
+         is_last = (t == gridDim.x - 1);
+      }
    }
    __syncthreads();
    if (is_last) {
@@ -182,12 +236,19 @@ halo_wait_kernel(int total, int n_in, const double *__restrict__ buf0, const dou
    }
 }
 
+// small exchanges (the coarse levels) run as one CTA: no ticket, one fence
+static inline int halo_grid(int total)
+{
+   if (total <= kHaloBlock * 8) return 1;
+   int grid = (total + kHaloBlock * 4 - 1) / (kHaloBlock * 4);
+   return grid > 128 ? 128 : grid;
+}
+
 int peer_put(PeerPlan *pl, const double *src, cudaStream_t st)
 {
    if (pl->n_out == 0) return 0;
-   const int grid = pl->total_out > 0 ? (pl->total_out + 255) / 256 : 1;
-   HB_LAUNCH(halo_put_kernel, grid, 256, 0, st, pl->total_out, pl->n_out, pl->d_out_starts, pl->d_gather, src,
-             pl->d_out_dst, pl->d_out_flag, pl->acks, pl->d_epoch, pl->d_ticket);
+   HB_LAUNCH(halo_put_kernel, halo_grid(pl->total_out), kHaloBlock, 0, st, pl->total_out, pl->n_out, pl->d_out_starts,
+             pl->d_gather, src, pl->d_out_dst, pl->d_out_flag, pl->acks, pl->d_epoch, pl->d_ticket);
    HB_LAUNCH_CHECK();
    return 0;
 }
@@ -195,14 +256,13 @@ int peer_put(PeerPlan *pl, const double *src, cudaStream_t st)
 int peer_wait(PeerPlan *pl, cudaStream_t st)
 {
    if (pl->n_in == 0) return 0;
-   int grid = (pl->total_in + 256 * 8 - 1) / (256 * 8);
-   if (grid < 1) grid = 1;
-   if (grid > 64) grid = 64;
-   HB_LAUNCH(halo_wait_kernel, grid, 256, 0, st, pl->total_in, pl->n_in, pl->in_buf[0], pl->in_buf[1],
-             pl->in_flags, pl->d_in_ack, pl->dst, pl->d_epoch, pl->d_ticket);
+   HB_LAUNCH(halo_wait_kernel, halo_grid(pl->total_in), kHaloBlock, 0, st, pl->total_in, pl->n_in, pl->in_buf[0],
+             pl->in_buf[1], pl->in_flags, pl->d_in_ack, pl->dst, pl->d_epoch, pl->d_ticket);
    HB_LAUNCH_CHECK();
    return 0;
 }
+
+bool peer_has_out(const PeerPlan *pl) { return pl && pl->n_out > 0; }
 
 void peer_plan_free(PeerPlan *pl)
 {

@@ -257,10 +257,21 @@ int hb200_comm_barrier(void)
 
 int hb200_set_halo_mode(int mode)
 {
-   HB_REQUIRE(mode == 0 || mode == 1, HB200_ERROR_ARG, "halo mode must be 0 (NCCL) or 1 (peer put)");
-   ctx().halo_mode = mode;
+   HB_REQUIRE(mode >= 0 && mode <= 2, HB200_ERROR_ARG, "halo mode must be 0 (NCCL), 1 (peer put) or 2 (peer put if possible)");
+   Ctx &c = ctx();
+   if (mode == 0 || c.nranks <= 1) { c.halo_mode = mode == 2 ? 0 : mode; return 0; }
+   HB_CHECK(require_ready());
+   // collective: all ranks must make the same call
+   int ok = 0;
+   HB_CHECK(arena_setup_collective(&ok));
+   if (!ok && mode == 1) {
+      return set_error(HB200_ERROR_GENERIC, "peer halo unavailable on at least one rank: %s", std::string(hb200_last_error()).c_str());
+   }
+   c.halo_mode = ok ? 1 : 0;
    return 0;
 }
+
+int hb200_halo_mode(void) { return ctx().halo_mode; }
 
 int hb200_malloc(void **dev, size_t bytes)
 {

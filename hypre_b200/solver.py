@@ -174,6 +174,14 @@ class ParCSRMatrix:
     def set_spmv_kernel(self, kind: int = 0, lanes_per_row: int = 0) -> None:
         check(lib.hb200_parcsr_set_spmv_kernel(self.handle, kind, lanes_per_row))
 
+    def format_info(self) -> dict:
+        """storage formats of the diag block (hb200_parcsr_format_info)"""
+        info = (C.c_longlong * 8)()
+        check(lib.hb200_parcsr_format_info(self.handle, info))
+        return {"sell": bool(info[0]), "sell_entries": int(info[1]), "sell_bytes_per_entry": int(info[2]),
+                "sell_values": int(info[3]), "pattern": bool(info[4]), "patterns": int(info[5]),
+                "pattern_entries": int(info[6]), "kernel": int(info[7])}
+
     def matvec(self, alpha: float, x, beta: float, y, b=None):
         """HYPRE_ParCSRMatrixMatvec / hypre_ParCSRMatrixMatvecOutOfPlace: y = alpha*A*x + beta*b
         (b defaults to y).  torch CUDA tensors -> device path; numpy arrays -> host path."""

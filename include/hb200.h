@@ -62,9 +62,14 @@ int hb200_comm_init(int rank, int nranks, const void *id128);
 int hb200_comm_rank(void);
 int hb200_comm_size(void);
 int hb200_comm_barrier(void);
-/* halo transport: 0 = NCCL send/recv (default), 1 = direct NVLink peer stores into
- * IPC-mapped receive buffers (pack+put fused in one kernel). */
+/* halo transport (the Isend/Irecv/Waitall of hypre_ParCSRCommHandleCreate,
+ * src/parcsr_mv/par_csr_communication.c:520-640): 0 = NCCL send/recv (default), 1 = direct
+ * NVLink peer stores into IPC-mapped receive buffers (pack+put fused in one kernel; lets the
+ * whole V-cycle stay a CUDA graph on N>1), 2 = mode 1 when every rank can map every peer,
+ * else mode 0.  Collective over the ranks of hb200_comm_init for modes 1 and 2.
+ * hb200_halo_mode returns the transport in force. */
 int hb200_set_halo_mode(int mode);
+int hb200_halo_mode(void);
 
 /* device memory + transfers (hypre_TAlloc/hypre_TMemcpy, src/utilities/memory.c:956-990) */
 int hb200_malloc(void **dev, size_t bytes);
@@ -108,15 +113,19 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
                                int *offd_i, int *offd_j, int64_t *col_map_offd,
                                int *send_map_starts, int *send_map_elmts,
                                int *recv_vec_starts, int *send_procs, int *recv_procs);
-/* Storage format of the diag block: info[0] = 1 when a dictionary-packed SELL-32 copy exists
- * (structured operators: <= 256 distinct column offsets), info[1] = stored entries incl. padding,
- * info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset code + fp64 value),
- * info[3] = number of distinct values (0 when values are stored raw). */
-int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info4);
-/* Selects the SpMV kernel for this matrix: 0 = auto from nnz/row (default),
- * 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced stream (merge-style),
- * 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 = vector with 2x/4x
- * unrolled loads, 6 = packed SELL (when the block qualifies, else vector). */
+/* Storage format of the diag block (8 values): info[0] = 1 when a dictionary-packed SELL-32 copy
+ * exists (structured operators: <= 256 distinct column offsets), info[1] = its stored entries
+ * incl. padding, info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset code +
+ * fp64 value), info[3] = number of distinct values (0 when values are stored raw);
+ * info[4] = 1 when a row-pattern copy exists (<= 256 distinct rows as lists of (column - row,
+ * value): constant-coefficient stencils; 1 byte per row), info[5] = patterns, info[6] = table
+ * entries; info[7] = the kernel kind in force (numbering of hb200_parcsr_set_spmv_kernel). */
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info8);
+/* Selects the SpMV kernel for this matrix: 0 = auto (row-pattern, else packed SELL, else vector
+ * with lanes from nnz/row; default), 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced
+ * stream (merge-style), 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 =
+ * vector with 2x/4x unrolled loads, 6 = packed SELL, 7 = row-pattern (6 and 7 fall back to the
+ * next format when the block does not qualify). */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):

@@ -39,14 +39,15 @@ rows = []
 spmv_bytes = 12.0 * nnz + 4.0 * N + 8.0 * N + 8.0 * N
 def spmv(): check(lib.hb200_parcsr_matvec(A.handle, 1.0, x.data_ptr(), 0.0, y.data_ptr(), y.data_ptr()))
 if variants == "one":
-    cfgs = [(6, 1)]
+    cfgs = [(7, 1), (6, 1)]
 else:
-    cfgs = [(6, 1), (1, 2), (1, 4), (4, 4), (2, 1)]
+    cfgs = [(7, 1), (6, 1), (1, 2), (1, 4), (4, 4), (2, 1)]
 for k, L in cfgs:
     A.set_spmv_kernel(k, L)
     ms = timeit(spmv)
     rows.append((f"spmv kind={k} lanes={L}", ms, spmv_bytes / ms / 1e6))
 A.set_spmv_kernel(0, 0)
+print("# format:", A.format_info())
 vt = torch.empty(N, dtype=torch.float64, device="cuda")
 def jac(): check(lib.hb200_relax(A.handle, f.data_ptr(), None, 18, 0, 1.0, 1.0, l1.data_ptr(), x.data_ptr(), 0, vt.data_ptr()))
 ms = timeit(jac)

@@ -110,15 +110,19 @@ def test_matvec_all_levels(request, torch, case_name, ab):
             assert err <= RTOL, (case_name, l, which, alpha, beta, err)
 
 
-def test_matvec_bit_exact_fine_level(lap27, torch):
+@pytest.mark.parametrize("case_name", ["lap27", "lap7"])
+def test_matvec_bit_exact_fine_level(request, torch, case_name):
     """one lane per row in the stream kernel keeps the reference's summation order"""
+    lap27 = request.getfixturevalue(case_name)
     A = lap27.mats[0][0]
     rng = np.random.default_rng(7)
     x = rng.standard_normal(A.num_cols)
     b = rng.standard_normal(A.num_rows)
-    # stream kernel with one lane per row, and the packed SELL kernel (one thread per row):
-    # both add the products in CSR order with separate multiply / add
-    for kind, lanes in ((2, 1), (6, 0)):
+    # stream kernel with one lane per row, the packed SELL kernel and the row-pattern kernel (one
+    # thread per row): all add the products in CSR order with separate multiply / add
+    fi = A.format_info()
+    assert fi["pattern"] and fi["sell"] and fi["kernel"] == 7, fi   # constant-coefficient stencil
+    for kind, lanes in ((2, 1), (6, 0), (7, 0)):
         A.set_spmv_kernel(kind, lanes)
         for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (1.0, 1.0)):
             yref = lap27.pb.matvec(alpha, x, beta, b)
@@ -128,7 +132,7 @@ def test_matvec_bit_exact_fine_level(lap27, torch):
     A.set_spmv_kernel(0, 0)
 
 
-@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32), (6, 0)])
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32), (6, 0), (7, 0)])
 def test_matvec_kernel_variants(lap27, torch, kind, lanes):
     rng = np.random.default_rng(5)
     for l in (0, 2):
@@ -142,6 +146,65 @@ def test_matvec_kernel_variants(lap27, torch, kind, lanes):
         A.matvec(1.0, dev(torch, x), 0.0, y)
         A.set_spmv_kernel(0, 0)
         assert relerr(y.cpu().numpy(), yref) <= RTOL, (l, kind, lanes)
+
+
+def test_format_detection(lap27, lap7, hb, torch):
+    """coarse levels and variable-coefficient operators do not qualify for the row-pattern copy"""
+    assert lap27.mats[0][0].format_info()["patterns"] <= 27
+    if lap27.nl > 2:
+        fi = lap27.mats[2][0].format_info()
+        assert not fi["pattern"] and fi["kernel"] == 1, fi
+    # same 7-point structure, every coefficient different: packed SELL with raw fp64 values
+    a = lap7.h["levels"][0]["A"].arrays()
+    n = lap7.mats[0][0].num_rows
+    rng = np.random.default_rng(77)
+    data = rng.standard_normal(a["diag_data"].shape[0])
+    M = hb.ParCSRMatrix(n, n, a["diag_i"], a["diag_j"], data)
+    fi = M.format_info()
+    assert not fi["pattern"] and fi["sell"] and fi["sell_bytes_per_entry"] == 9 and fi["kernel"] == 6, fi
+    x = rng.standard_normal(n)
+    di, dj = a["diag_i"], a["diag_j"]
+    yref = np.zeros(n)
+    for r in range(n):                       # sequential row sums, the reference's order
+        s = 0.0
+        for p in range(di[r], di[r + 1]):
+            s += data[p] * x[dj[p]]
+        yref[r] = s
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    M.matvec(1.0, dev(torch, x), 0.0, y)
+    assert np.array_equal(y.cpu().numpy(), yref)
+    M.destroy()
+
+
+@pytest.mark.parametrize("case_name", ["lap7", "lap27"])
+def test_interp_restrict_bit_exact_on_pattern_path(request, torch, case_name):
+    """P_0 and its stored transpose in the row-pattern format (rectangular: base column per row):
+    one thread per row, CSR order, separate multiply/add -> identical to the 1-thread reference"""
+    case = request.getfixturevalue(case_name)
+    P = case.mats[0][1]
+    rng = np.random.default_rng(123)
+    xc = rng.standard_normal(P.num_cols)
+    xf = rng.standard_normal(P.num_rows)
+    P.matvecT(1.0, dev(torch, xf), 0.0, torch.zeros(P.num_cols, dtype=torch.float64, device="cuda"))  # builds P^T
+    fi = P.format_info()
+    if not fi["pattern"]:
+        pytest.skip(f"P_0 of {case_name} has too many row patterns: {fi}")
+    try:
+        for kind in (7, 1):
+            P.set_spmv_kernel(kind, 0)
+            yref = case.pb.matvec(1.0, xc, 1.0, xf, level=0, which=1)
+            y = dev(torch, xf)
+            P.matvec(1.0, dev(torch, xc), 1.0, y)
+            if kind == 7:
+                assert np.array_equal(y.cpu().numpy(), yref), (case_name, kind, "interp")
+            else:
+                assert relerr(y.cpu().numpy(), yref) <= RTOL
+            zref = case.pb.matvecT(1.0, xf, 0.0, np.zeros(P.num_cols), level=0, which=1)
+            z = torch.zeros(P.num_cols, dtype=torch.float64, device="cuda")
+            P.matvecT(1.0, dev(torch, xf), 0.0, z)
+            assert relerr(z.cpu().numpy(), zref) <= RTOL, (case_name, kind, "restrict")
+    finally:
+        P.set_spmv_kernel(0, 0)
 
 
 def test_matvec_host_entry(lap7):

@@ -346,6 +346,9 @@ def main():
             by = float(fi["sell_entries"]) * fi["sell_bytes_per_entry"] + 8.0 * (n / 32.0) + 4.0 * n \
                 + 8.0 * M.num_cols + 8.0 * n
             name = f"spmv_sell<EPI_AXPBY> on A_{level} (packed SELL-32, {fi['sell_bytes_per_entry']} B/nonzero)"
+        elif fi["kernel"] == 8:
+            by = csr_model(M) - 2.0 * nnz
+            name = f"spmv_vector<EPI_AXPBY,K,I16> on A_{level} (CSR, 16-bit column offsets, 10 B/nonzero)"
         else:
             by = csr_model(M)
             name = f"spmv_vector<EPI_AXPBY,K> on A_{level} (CSR, 12 B/nonzero)"

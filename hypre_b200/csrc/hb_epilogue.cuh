@@ -7,6 +7,8 @@ namespace hb {
 // ---------------------------------------------------------------------------------------
 // epilogues
 // ---------------------------------------------------------------------------------------
+// The epilogue vectors (b/f, l1 norms, cf marker) are read once per sweep and y is written once:
+// streaming (evict-first) accesses keep them from displacing the gathered x lines in L1/L2.
 template <int EPI>
 __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum, double diag)
 {
@@ -15,8 +17,8 @@ __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum
       // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
       double v;
       if (ea.beta == 0.0) { v = ea.alpha * sum; }
-      else                { v = ea.beta * ea.b[row] + ea.alpha * sum; }
-      ea.y[row] = v;
+      else                { v = ea.beta * __ldcs(ea.b + row) + ea.alpha * sum; }
+      __stcs(ea.y + row, v);
    }
    else if (EPI == EPI_ACC) {
       ea.y[row] += ea.alpha * sum;
@@ -24,11 +26,12 @@ __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum
    else if (EPI == EPI_JACOBI7) {
       // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
       const double uo = ea.u[row];
-      if (ea.cf == nullptr || ea.cf[row] == ea.relax_points) {
-         const double vt = (ea.w == 1.0) ? (ea.b[row] - sum) : (ea.w * ea.b[row] - ea.w * sum);
-         ea.y[row] = uo + vt / ea.d[row];
+      if (ea.cf == nullptr || __ldcs(ea.cf + row) == ea.relax_points) {
+         const double f = __ldcs(ea.b + row);
+         const double vt = (ea.w == 1.0) ? (f - sum) : (ea.w * f - ea.w * sum);
+         __stcs(ea.y + row, uo + vt / __ldcs(ea.d + row));
       } else {
-         ea.y[row] = uo;
+         __stcs(ea.y + row, uo);
       }
    }
    else if (EPI == EPI_JACOBI7_ACC) {

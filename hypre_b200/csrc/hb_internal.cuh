@@ -120,7 +120,7 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7, SPMV_VECTOR16 = 8 };
 
 struct DCsr {
    int        nrows = 0, ncols = 0;
@@ -128,6 +128,7 @@ struct DCsr {
    int       *i = nullptr;        // nrows+1
    int       *j = nullptr;        // nnz
    double    *a = nullptr;        // nnz
+   short     *j16 = nullptr;      // nnz: column - row, when every entry fits 16 bits (square blocks), else NULL
    // list of rows with at least one entry (hypre_CSRMatrixRownnz, csr_matrix.c:381-397);
    // built for every block, used when it is sparse in rows (offd blocks)
    int       *rownnz = nullptr;

@@ -29,7 +29,6 @@
 
 namespace hb {
 
-constexpr int kPatRows = 4;            // rows per thread
 constexpr int kPatMaxPatterns = 256;
 constexpr int kPatMaxEntries = 8192;   // table entries over all patterns (96 KB of shared memory)
 
@@ -44,9 +43,10 @@ __device__ __forceinline__ void pat_one_row(const EpiArgs &ea, const double *__r
 }
 
 // column of entry k of a row = base + off[k]; base = the row itself for square blocks (BASE =
-// false), else base[row] (the row's first column: interpolation and its stored transpose)
-template <int EPI, bool BASE>
-__global__ void __launch_bounds__(512)
+// false), else base[row] (the row's first column: interpolation and its stored transpose).
+// NT threads per block, R rows per thread.
+template <int EPI, bool BASE, int NT, int R>
+__global__ void __launch_bounds__(NT, 1536 / NT)
 spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int *__restrict__ base, int npat,
          int nent, const int *__restrict__ tab_ptr, const int *__restrict__ tab_off,
          const double *__restrict__ tab_val, const double *__restrict__ x, EpiArgs ea)
@@ -55,72 +55,87 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
    double *s_val = s_mem;
    int    *s_off = reinterpret_cast<int *>(s_val + nent);
    int    *s_ptr = s_off + nent;
-   const int tid = threadIdx.x, nt = blockDim.x;
-   for (int k = tid; k < nent; k += nt) { s_val[k] = tab_val[k]; s_off[k] = tab_off[k]; }
-   for (int k = tid; k <= npat; k += nt) s_ptr[k] = tab_ptr[k];
+   const int tid = threadIdx.x;
+   for (int k = tid; k < nent; k += NT) { s_val[k] = tab_val[k]; s_off[k] = tab_off[k]; }
+   for (int k = tid; k <= npat; k += NT) s_ptr[k] = tab_ptr[k];
    __syncthreads();
    const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int r0 = tile * (nt * kPatRows) + tid;
-      int p[kPatRows];
-      const double *xb[kPatRows];
+      const int r0 = tile * (NT * R) + tid;
+      int p[R];
+      int bs[R];
       bool same = true;
 #pragma unroll
-      for (int j = 0; j < kPatRows; j++) {
-         const int row = r0 + j * nt;
+      for (int j = 0; j < R; j++) {
+         const int row = r0 + j * NT;
          p[j] = row < nrows ? (int) pat[row] : -1;
-         xb[j] = x + (BASE ? (row < nrows ? base[row] : 0) : row);
+         if (BASE) bs[j] = row < nrows ? base[row] : 0;
          same = same && (p[j] == p[0]);
       }
       if (same && p[0] >= 0) {
          // the R rows share a pattern: one table read per entry, R gathers
          const int b = s_ptr[p[0]], e = s_ptr[p[0] + 1];
-         double s[kPatRows];
+         double s[R];
 #pragma unroll
-         for (int j = 0; j < kPatRows; j++) s[j] = 0.0;
+         for (int j = 0; j < R; j++) s[j] = 0.0;
 #pragma unroll 2
          for (int k = b + skip; k < e; k++) {
             const double a = s_val[k];
-            const int o = s_off[k];
-            double xv[kPatRows];
+            const double *xk = x + s_off[k];
+            double xv[R];
 #pragma unroll
-            for (int j = 0; j < kPatRows; j++) xv[j] = __ldg(xb[j] + o);
+            for (int j = 0; j < R; j++) xv[j] = BASE ? __ldg(xk + bs[j]) : __ldg(xk + r0 + j * NT);
 #pragma unroll
-            for (int j = 0; j < kPatRows; j++) s[j] = __dadd_rn(s[j], __dmul_rn(a, xv[j]));
+            for (int j = 0; j < R; j++) s[j] = __dadd_rn(s[j], __dmul_rn(a, xv[j]));
          }
          const double diag = e > b ? s_val[b] : 0.0;
 #pragma unroll
-         for (int j = 0; j < kPatRows; j++) epi_apply<EPI>(ea, r0 + j * nt, s[j], diag);
+         for (int j = 0; j < R; j++) epi_apply<EPI>(ea, r0 + j * NT, s[j], diag);
       } else {
 #pragma unroll
-         for (int j = 0; j < kPatRows; j++) {
-            if (p[j] >= 0) pat_one_row<EPI>(ea, xb[j], r0 + j * nt, p[j], s_ptr, s_off, s_val, skip);
+         for (int j = 0; j < R; j++) {
+            if (p[j] >= 0) {
+               pat_one_row<EPI>(ea, x + (BASE ? bs[j] : r0 + j * NT), r0 + j * NT, p[j], s_ptr, s_off, s_val, skip);
+            }
          }
       }
    }
 }
 
-template <int EPI, bool BASE>
+static int pat_rows_per_thread()
+{
+   static int r = 0;
+   if (r == 0) {
+      const char *e = getenv("HB200_PAT_ROWS");
+      r = (e && atoi(e) == 8) ? 8 : 4;
+   }
+   return r;
+}
+
+template <int EPI, bool BASE, int NT, int R>
 static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
    const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
    static bool opted = false;
    if (!opted) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE, NT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kPatMaxEntries * 12 + (kPatMaxPatterns + 1) * 4 + 8));
       opted = true;
    }
-   // big tables leave room for few blocks per SM: use larger ones
-   const int threads = smem > 40 * 1024 ? 512 : 256;
-   const int ntiles = (M.nrows + threads * kPatRows - 1) / (threads * kPatRows);
-   // the table is loaded once per block: the resident blocks walk the tiles
-   int per_sm = (int) ((227 * 1024) / (smem + 1024));
-   const int cap = threads == 512 ? 3 : 6;
-   if (per_sm > cap) per_sm = cap;
-   if (per_sm < 1) per_sm = 1;
-   int grid = 148 * per_sm;
+   const int ntiles = (M.nrows + NT * R - 1) / (NT * R);
+   // the table is loaded once per block and the resident blocks walk the tiles: the grid is exactly
+   // one wave (a partial second wave would double the time)
+   static size_t occ_smem = (size_t) -1;
+   static int occ_blocks = 1;
+   if (occ_smem != smem) {
+      int nb = 0;
+      HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_pat<EPI, BASE, NT, R>, NT, smem));
+      occ_blocks = nb > 0 ? nb : 1;
+      occ_smem = smem;
+   }
+   int grid = 148 * occ_blocks;
    if (grid > ntiles) grid = ntiles;
-   HB_LAUNCH((spmv_pat<EPI, BASE>), grid, threads, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
+   HB_LAUNCH((spmv_pat<EPI, BASE, NT, R>), grid, NT, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
              M.pat_nent, M.pat_ptr, M.pat_off, M.pat_val, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
@@ -129,7 +144,22 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 template <int EPI>
 static int pat_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
-   return M.pat_base ? pat_launch_t<EPI, true>(M, x, ea, st) : pat_launch_t<EPI, false>(M, x, ea, st);
+   const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
+   // big tables leave room for few blocks per SM: use larger ones
+   const bool big = smem > 40 * 1024;
+   if (M.pat_base) {
+      // rectangular blocks.  Interpolation (3-4 entries per row): 4 rows per thread keep enough gathers
+      // in flight.  Restriction (~30 entries per row): one row per thread, a thread's rows would
+      // otherwise touch R distant pieces of x and thrash L1 (measured: profiles/r1_level_sweep_27pt.txt)
+      if (M.avg_row_nnz < 8.0) {
+         return big ? pat_launch_t<EPI, true, 512, 4>(M, x, ea, st) : pat_launch_t<EPI, true, 256, 4>(M, x, ea, st);
+      }
+      return big ? pat_launch_t<EPI, true, 512, 1>(M, x, ea, st) : pat_launch_t<EPI, true, 256, 1>(M, x, ea, st);
+   }
+   if (pat_rows_per_thread() == 8) {
+      return big ? pat_launch_t<EPI, false, 512, 8>(M, x, ea, st) : pat_launch_t<EPI, false, 256, 8>(M, x, ea, st);
+   }
+   return big ? pat_launch_t<EPI, false, 512, 4>(M, x, ea, st) : pat_launch_t<EPI, false, 256, 4>(M, x, ea, st);
 }
 
 int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)

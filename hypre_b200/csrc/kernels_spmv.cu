@@ -208,12 +208,15 @@ spmv_stream_lc(const int *__restrict__ rowptr, const int *__restrict__ colind,
 // ---------------------------------------------------------------------------------------
 constexpr int kVecThreads = 256;
 
-template <int EPI, int K, int U>
+// I16: column indices stored as 16-bit offsets from the row (square blocks whose rows stay within
+// +-32767 of the diagonal: every AMG level of a grid problem) -> 10 B per nonzero instead of 12
+template <int EPI, int K, int U, bool I16 = false>
 __global__ void __launch_bounds__(kVecThreads)
 spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ rowptr,
             const int *__restrict__ colind, const double *__restrict__ val,
             const double *__restrict__ x, EpiArgs ea)
 {
+   const short *__restrict__ col16 = reinterpret_cast<const short *>(colind);
    const int gtid = blockIdx.x * kVecThreads + threadIdx.x;
    const int idx  = gtid / K;
    const int lane = threadIdx.x % K;
@@ -240,8 +243,11 @@ spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ 
             for (int u = 0; u < U; u++) s += v[u] * __ldg(x + c[u]);
          }
       }
-      for (; p < p1; p += K) {
-         s += val[p] * __ldg(x + colind[p]);
+      if (I16) {
+         const double *xr = x + row;
+         for (; p < p1; p += K) s += val[p] * __ldg(xr + col16[p]);
+      } else {
+         for (; p < p1; p += K) s += val[p] * __ldg(x + colind[p]);
       }
    }
 #pragma unroll
@@ -291,6 +297,12 @@ static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, bo
    const long long threads = (long long) nlist * K;
    const int grid = (int) ((threads + kVecThreads - 1) / kVecThreads);
    const int *rl = use_rownnz ? M.rownnz : (const int *) nullptr;
+   if (!use_rownnz && M.kind == SPMV_VECTOR16 && M.j16) {
+      HB_LAUNCH((spmv_vector<EPI, K, 1, true>), grid, kVecThreads, 0, st, nlist, rl, M.i,
+                reinterpret_cast<const int *>(M.j16), M.a, x, ea);
+      HB_LAUNCH_CHECK();
+      return 0;
+   }
    if (unroll >= 4)      HB_LAUNCH((spmv_vector<EPI, K, 4>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
    else if (unroll >= 2) HB_LAUNCH((spmv_vector<EPI, K, 2>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
    else                  HB_LAUNCH((spmv_vector<EPI, K, 1>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
@@ -312,11 +324,12 @@ static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, bool
    }
 }
 
-static int vector_lanes_for(double avg)
+static int vector_lanes_for(double avg, long long nrows = 0)
 {
-   // measured on B200 over the levels of 27-pt and 7-pt hierarchies (profiles/r1_level_sweep.md):
-   // the fastest lane count keeps ~6-14 nonzeros per lane
-   if (avg >= 150) return 32;
+   // measured on B200 over the levels of 27-pt and 7-pt hierarchies (profiles/r1_level_sweep_*.txt):
+   // the fastest lane count keeps ~6-14 nonzeros per lane; with many rows 16 lanes beat a full
+   // warp even on 200-entry rows
+   if (avg >= 150) return nrows >= 100000 ? 16 : 32;
    if (avg >= 80)  return 16;
    if (avg >= 36)  return 8;
    if (avg >= 10)  return 2;
@@ -330,7 +343,7 @@ static int widen_lanes(int lanes, long long nlist, double avg)
 {
    static const bool off = getenv("HB200_NO_WIDEN") != nullptr;
    if (off) return lanes;
-   while (lanes < 32 && nlist * lanes < 148LL * 1024 && lanes * 2 <= avg) lanes *= 2;
+   while (lanes < 32 && nlist * lanes < 148LL * 1024 && lanes < avg) lanes *= 2;
    return lanes;
 }
 
@@ -345,7 +358,8 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
    if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
    }
-   const bool vec = (M.kind == SPMV_VECTOR || M.kind == SPMV_VECTOR_U2 || M.kind == SPMV_VECTOR_U4);
+   const bool vec = (M.kind == SPMV_VECTOR || M.kind == SPMV_VECTOR_U2 || M.kind == SPMV_VECTOR_U4 ||
+                     M.kind == SPMV_VECTOR16);
    int lanes = (vec && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
    const int unroll = M.kind == SPMV_VECTOR_U4 ? 4 : M.kind == SPMV_VECTOR_U2 ? 2 : 1;
    if (lanes == 0) {
@@ -404,9 +418,11 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
 {
    // the sub-warp vector kernel beat the shared-memory stream kernel on every level measured
    // (profiles/r1_level_sweep.md): the stream kernel is L1-wavefront bound by its smem round trip
-   if (kind == SPMV_AUTO) kind = M.has_pat ? SPMV_PAT : M.has_sell ? SPMV_SELL : SPMV_VECTOR;
-   if (kind == SPMV_PAT && !M.has_pat) kind = M.has_sell ? SPMV_SELL : SPMV_VECTOR;
-   if (kind == SPMV_SELL && !M.has_sell) kind = SPMV_VECTOR;
+   const int csr = M.j16 ? SPMV_VECTOR16 : SPMV_VECTOR;
+   if (kind == SPMV_AUTO) kind = M.has_pat ? SPMV_PAT : M.has_sell ? SPMV_SELL : csr;
+   if (kind == SPMV_PAT && !M.has_pat) kind = M.has_sell ? SPMV_SELL : csr;
+   if (kind == SPMV_SELL && !M.has_sell) kind = csr;
+   if (kind == SPMV_VECTOR16 && !M.j16) kind = SPMV_VECTOR;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
    if (kind == SPMV_STREAM || kind == SPMV_STREAM_V4) {
@@ -414,7 +430,7 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
       const double a = M.avg_row_nnz;
       M.lanes = a <= 40 ? 1 : a <= 80 ? 2 : a <= 160 ? 4 : a <= 320 ? 8 : 16;
    } else {
-      M.lanes = vector_lanes_for(M.avg_row_nnz);
+      M.lanes = widen_lanes(vector_lanes_for(M.avg_row_nnz, M.nrows), M.nrows, M.avg_row_nnz);
    }
 }
 
@@ -455,6 +471,24 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
    }
    if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
+   if (nrows >= 1024 && nrows == ncols && M.nnz >= 2LL * nrows && !getenv("HB200_NO_CSR16")) {
+      // 16-bit column offsets from the row, when every entry stays within +-32767 of the diagonal
+      bool fits = true;
+      for (int r = 0; r < nrows && fits; r++) {
+         for (int q = hi[r]; q < hi[r + 1]; q++) {
+            const int d = hj[q] - r;
+            if (d < -32767 || d > 32767) { fits = false; break; }
+         }
+      }
+      if (fits) {
+         std::vector<short> j16((size_t) M.nnz + 8, 0);
+         for (int r = 0; r < nrows; r++) {
+            for (int q = hi[r]; q < hi[r + 1]; q++) j16[(size_t) q] = (short) (hj[q] - r);
+         }
+         HB_CUDA(cudaMalloc(&M.j16, sizeof(short) * j16.size()));
+         HB_CUDA(cudaMemcpy(M.j16, j16.data(), sizeof(short) * j16.size(), cudaMemcpyHostToDevice));
+      }
+   }
    if (nrows > 0) HB_CHECK(dcsr_build_pat(M, hi, hj, ha));
    if (nrows > 0 && nrows == ncols) HB_CHECK(dcsr_build_sell(M, hi, hj, ha));   // square (A_l) blocks only
    dcsr_choose_kernel(M, SPMV_AUTO, 0);
@@ -468,6 +502,7 @@ int dcsr_free(DCsr &M)
    if (M.a) cudaFree(M.a);
    if (M.rownnz) cudaFree(M.rownnz);
    if (M.blk_row) cudaFree(M.blk_row);
+   if (M.j16) cudaFree(M.j16);
    dcsr_free_sell(M);
    dcsr_free_pat(M);
    M = DCsr();

@@ -124,8 +124,10 @@ int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info8);
 /* Selects the SpMV kernel for this matrix: 0 = auto (row-pattern, else packed SELL, else vector
  * with lanes from nnz/row; default), 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced
  * stream (merge-style), 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 =
- * vector with 2x/4x unrolled loads, 6 = packed SELL, 7 = row-pattern (6 and 7 fall back to the
- * next format when the block does not qualify). */
+ * vector with 2x/4x unrolled loads, 6 = packed SELL, 7 = row-pattern, 8 = vector-per-row over
+ * 16-bit column offsets from the row (10 B per nonzero; square blocks whose entries stay within
+ * +-32767 of the diagonal).  6, 7 and 8 fall back to the next format when the block does not
+ * qualify; auto prefers 7, 6, 8, 1 in that order. */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):

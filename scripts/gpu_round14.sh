@@ -1,0 +1,14 @@
+#!/bin/bash
+TAG=${1:-r14}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONPATH=$PWD
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 900 python scripts/level_sweep.py 27pt 256 quick > $OUT/levels_27pt.txt 2>&1; cut -c1-200 $OUT/levels_27pt.txt | head -30
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench1.log 2>&1; grep '^{' $OUT/bench1.log | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['config']['iterations'], d['config']['final_rel_res'], d['config']['upload_s'])
+for e in d['roofline_levels']: print(e['kernel'], round(e['ms_per_launch'],4), round(e['frac'],3))
+"
+timeout 600 python scripts/spmv_sweep.py 256 27pt one 2>&1 | sed -n 2,5p

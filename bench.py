@@ -46,6 +46,8 @@ def parse():
                     help="N>1 halo transport: NVLink peer puts, NCCL send/recv, or peer when every rank can map every peer")
     ap.add_argument("--cpu-iters", type=int, default=3, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-timeout", type=float, default=420.0,
+                    help="seconds a stage of the hb200 arm may take before the rank gives up")
     ap.add_argument("--spmv-only", action="store_true", help="configs[4]: SpMV bandwidth line")
     ap.add_argument("--mpi-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -221,7 +223,31 @@ def main():
         uid = [hb.comm_get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         hb.comm_init(rank, world, uid[0])
-        check(lib.hb200_set_halo_mode({"nccl": 0, "peer": 1, "auto": 2}[args.halo]))
+        # auto: the NVLink peer-put halo (whole V-cycle in one CUDA graph) where this round measured
+        # it on hardware (N = 2: 105.5 ms against 111.9 ms over NCCL on the same library state,
+        # profiles/r1_multi_gpu.md); the NCCL send/recv halo, the configuration measured at N = 8,
+        # for every other N.  --halo peer forces the former.
+        mode = {"nccl": 0, "peer": 1, "auto": 2 if world == 2 else 0}[args.halo]
+        check(lib.hb200_set_halo_mode(mode))
+
+    # a stage that stops making progress (a rank lost in a collective) must not hold the box:
+    # every stage re-arms the watchdog; on expiry the rank says where it was and leaves
+    import threading
+    wd = {"stage": "init", "deadline": time.time() + args.stage_timeout}
+
+    def stage(name):
+        wd["stage"] = name
+        wd["deadline"] = time.time() + args.stage_timeout
+
+    def watchdog():
+        while True:
+            time.sleep(5.0)
+            if time.time() > wd["deadline"]:
+                print(f"bench.py: rank {rank} made no progress in stage '{wd['stage']}' for "
+                      f"{args.stage_timeout:.0f} s, giving up", file=sys.stderr, flush=True)
+                os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,7 +263,9 @@ def main():
         return float(t.item())
 
     # ---- hierarchy from the reference's own setup (CPU), uploaded once: timed separately
+    stage("reference setup (CPU)")
     rb, pb, gn, gen_s, setup_s = build_problem(args, rank, world)
+    stage("upload")
     t0 = time.time()
     hier = pb.hierarchy()
     if rank == 0 and os.environ.get("HB200_BENCH_LEVELS"):
@@ -278,9 +306,11 @@ def main():
         x_host.zero_()
         return solver.solve(A, b_host.numpy(), x_host.numpy())
 
+    stage("warm-up solves")
     for _ in range(args.warmup):
         res = step_dev()
     its = res.num_iterations if args.warmup else None
+    stage("timed solves")
 
     # ---- timed region: K solves, device-resident inputs
     sampler = ClockSampler(local) if rank == 0 else None
@@ -299,6 +329,7 @@ def main():
     value = rows / (ms * 1e-3) / 1e6
 
     # ---- e2e: same solve through the host-buffer entry point (H2D b, x0; D2H x inside)
+    stage("e2e solves")
     for _ in range(min(2, args.warmup)):
         step_host()
     barrier()
@@ -315,7 +346,9 @@ def main():
     # operators in packed SELL (2 or 9 B per nonzero), everything else (every coarse level, every
     # unstructured matrix) in CSR through spmv_vector; the general CSR kernel is also timed on A_0
     # as `roofline_csr`.
+    stage("per-level kernel timing")
     peak, peak_src = peaks()
+
     def time_spmv(M, reps=20):
         xs = torch.randn(max(M.num_cols, 1), dtype=torch.float64, device="cuda")
         ys = torch.empty(max(M.num_rows, 1), dtype=torch.float64, device="cuda")
@@ -340,8 +373,11 @@ def main():
         fi = M.format_info()
         n, nnz = M.num_rows, M.diag_nnz
         if fi["kernel"] == 7:
-            by = 1.0 * n + 8.0 * M.num_cols + 8.0 * n + 12.0 * fi["pattern_entries"]
-            name = f"spmv_pat<EPI_AXPBY> on A_{level} (row-pattern format, 1 B/row + x + y)"
+            by = 1.0 * n + 8.0 * M.num_cols + 8.0 * n + 12.0 * fi["pattern_entries"] \
+                + 12.0 * fi["pattern_irregular_nnz"] + 8.0 * fi["pattern_irregular_rows"]
+            irr = fi["pattern_irregular_rows"]
+            name = f"spmv_pat<EPI_AXPBY> on A_{level} (row-pattern format, 1 B/row + x + y" \
+                + (f"; {irr} irregular rows in CSR)" if irr else ")")
         elif fi["kernel"] == 6:
             by = float(fi["sell_entries"]) * fi["sell_bytes_per_entry"] + 8.0 * (n / 32.0) + 4.0 * n \
                 + 8.0 * M.num_cols + 8.0 * n
@@ -362,10 +398,9 @@ def main():
 
     # one PCG iteration launches the A_0 kernel 3 times (Krylov matvec, residual, post-smoothing; the
     # pre-smoothing sweep starts from a zero guess and reads no matrix) and the A_l kernel, l >= 1, twice
+    # (the matvec is collective on N > 1: the levels timed are fixed, not chosen from rank-local sizes)
     per_level = []
-    for l, (Al, _) in enumerate(mats):
-        if Al.diag_nnz * 50 < nnz0 or Al.num_rows == 0:
-            break
+    for l, (Al, _) in enumerate(mats[:min(4, len(mats))]):
         per_level.append(kernel_entry(l, Al, 3 if l == 0 else 2))
     roofline = max(per_level, key=lambda e: e["ms_per_iteration"])
     roofline = dict(roofline, note="the level kernel with the largest share of the iteration; all levels in roofline_levels")
@@ -381,6 +416,7 @@ def main():
                         "bytes_per_launch": cb, "bytes_per_nnz": cb / max(nnz0, 1), "traffic": None}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own solve, bounded sample
+    stage("cpu baseline")
     cpu = None
     ref_parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -159,6 +159,9 @@ struct DCsr {
    int       *pat_off = nullptr;       // pat_nent
    double    *pat_val = nullptr;       // pat_nent
    int        pat_npat = 0, pat_nent = 0;
+   int       *pat_irr = nullptr;       // rows outside the table (code 255), swept by the CSR kernel
+   int        pat_nirr = 0;
+   long long  pat_irr_nnz = 0;
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
 };

@@ -25,11 +25,12 @@
 #include "hb_epilogue.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <unordered_map>
 
 namespace hb {
 
-constexpr int kPatMaxPatterns = 256;
+constexpr int kPatMaxPatterns = 256;   // codes 0..254; 255 = row outside the table
 constexpr int kPatMaxEntries = 8192;   // table entries over all patterns (96 KB of shared memory)
 
 template <int EPI>
@@ -68,7 +69,8 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
 #pragma unroll
       for (int j = 0; j < R; j++) {
          const int row = r0 + j * NT;
-         p[j] = row < nrows ? (int) pat[row] : -1;
+         p[j] = row < nrows ? (int) pat[row] : 255;
+         if (p[j] == 255) p[j] = -1;           // past the end, or an irregular row (CSR pass)
          if (BASE) bs[j] = row < nrows ? base[row] : 0;
          same = same && (p[j] == p[0]);
       }
@@ -182,15 +184,20 @@ int dcsr_free_pat(DCsr &M)
    if (M.pat_off) cudaFree(M.pat_off);
    if (M.pat_val) cudaFree(M.pat_val);
    if (M.pat_base) cudaFree(M.pat_base);
-   M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr;
+   if (M.pat_irr) cudaFree(M.pat_irr);
+   M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr; M.pat_irr = nullptr;
+   M.pat_nirr = 0;
    M.has_pat = false;
    return 0;
 }
 
-// pattern detection on the host, one pass over the block.  Consecutive rows of a grid operator
+// Pattern detection on the host, one pass over the block.  Consecutive rows of a grid operator
 // nearly always repeat the previous row's pattern, so the common case is one compare per entry
-// against that pattern; only a change of pattern goes through the hash.  Irregular blocks leave
-// after their first kPatMaxPatterns+1 rows.
+// against that pattern; only a change of pattern goes through the hash.  The 255 most frequent
+// patterns that fit the table are kept; rows outside them (the irregular strip next to a rank
+// boundary, where the coarsening of a partitioned grid loses its regularity) get code 255 and are
+// swept by the CSR vector kernel over a row list (pat_irr).  The block qualifies when the table
+// covers at least 70% of the rows.  Irregular blocks leave after their first 64K rows.
 int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
 {
    if (getenv("HB200_NO_PAT")) return 0;
@@ -204,25 +211,28 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
       for (int r = 0; r < n; r++) basev[r] = hi[r + 1] > hi[r] ? hj[hi[r]] : 0;
    }
    auto base_of = [&](int r) -> int { return square ? r : basev[r]; };
-   std::vector<int> ptr(1, 0), off;
-   std::vector<unsigned long long> val;   // bit patterns (-0.0 and NaN payloads survive)
-   std::vector<unsigned char> code((size_t) n);
+   // candidate patterns, each known by a representative row
+   constexpr int kMaxCand = 16384;
+   std::vector<int> rep;
+   std::vector<long long> count;
+   std::vector<int> rid((size_t) n, -1);
    std::unordered_multimap<unsigned long long, int> by_hash;
-   auto matches = [&](int p, int r) -> bool {
-      const int b = ptr[p], len = ptr[p + 1] - b;
+   auto same_rows = [&](int a, int r) -> bool {
+      const int len = hi[a + 1] - hi[a];
       if (hi[r + 1] - hi[r] != len) return false;
-      const int *cj = hj + hi[r];
-      const double *ca = ha + hi[r];
+      const int *ja = hj + hi[a], *jr = hj + hi[r];
+      const double *va = ha + hi[a], *vr = ha + hi[r];
+      const int shift = base_of(r) - base_of(a);
       for (int k = 0; k < len; k++) {
-         unsigned long long bits;
-         memcpy(&bits, &ca[k], 8);
-         if (cj[k] - base_of(r) != off[b + k] || bits != val[b + k]) return false;
+         if (jr[k] - ja[k] != shift || memcmp(&va[k], &vr[k], 8) != 0) return false;   // bit patterns
       }
       return true;
    };
    int prev = -1;
+   long long misses = 0;
    for (int r = 0; r < n; r++) {
-      if (prev >= 0 && matches(prev, r)) { code[r] = (unsigned char) prev; continue; }
+      if ((r & 65535) == 0 && r > 0 && misses > r / 2) return 0;      // irregular block
+      if (prev >= 0 && same_rows(rep[prev], r)) { rid[r] = prev; count[prev]++; continue; }
       unsigned long long h = 1469598103934665603ull ^ (unsigned long long) (hi[r + 1] - hi[r]);
       for (int q = hi[r]; q < hi[r + 1]; q++) {
          unsigned long long bits;
@@ -233,23 +243,50 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
       int found = -1;
       auto range = by_hash.equal_range(h);
       for (auto it = range.first; it != range.second; ++it) {
-         if (matches(it->second, r)) { found = it->second; break; }
+         if (same_rows(rep[it->second], r)) { found = it->second; break; }
       }
       if (found < 0) {
-         const int len = hi[r + 1] - hi[r];
-         if ((int) ptr.size() - 1 >= kPatMaxPatterns || (int) off.size() + len > kPatMaxEntries) return 0;
-         found = (int) ptr.size() - 1;
-         for (int q = hi[r]; q < hi[r + 1]; q++) {
-            unsigned long long bits;
-            memcpy(&bits, &ha[q], 8);
-            off.push_back(hj[q] - base_of(r));
-            val.push_back(bits);
-         }
-         ptr.push_back((int) off.size());
+         if ((int) rep.size() >= kMaxCand) { misses++; continue; }
+         found = (int) rep.size();
+         rep.push_back(r);
+         count.push_back(0);
          by_hash.emplace(h, found);
       }
-      code[r] = (unsigned char) found;
+      rid[r] = found;
+      count[found]++;
       prev = found;
+   }
+   // ---- keep the most frequent patterns that fit the table
+   std::vector<int> order(rep.size());
+   for (size_t k = 0; k < order.size(); k++) order[k] = (int) k;
+   std::sort(order.begin(), order.end(), [&](int a, int b) { return count[a] != count[b] ? count[a] > count[b] : a < b; });
+   std::vector<int> code_of(rep.size(), -1), ptr(1, 0), off;
+   std::vector<double> val;
+   long long covered = 0, all_entries = 0;
+   for (int c : order) all_entries += hi[rep[c] + 1] - hi[rep[c]];
+   // a fully regular block keeps every pattern, rare ones included; otherwise a pattern has to
+   // earn its table slot (shared memory per block) with a few rows
+   const bool all_fit = ((int) rep.size() < kPatMaxPatterns && all_entries <= kPatMaxEntries && misses == 0);
+   const long long min_count = all_fit ? 1 : 8;
+   for (int c : order) {
+      const int len = hi[rep[c] + 1] - hi[rep[c]];
+      if ((int) ptr.size() - 1 >= kPatMaxPatterns - 1 || count[c] < min_count) break;
+      if ((int) off.size() + len > kPatMaxEntries) continue;
+      code_of[c] = (int) ptr.size() - 1;
+      for (int q = hi[rep[c]]; q < hi[rep[c] + 1]; q++) {
+         off.push_back(hj[q] - base_of(rep[c]));
+         val.push_back(ha[q]);
+      }
+      ptr.push_back((int) off.size());
+      covered += count[c];
+   }
+   if ((double) covered < 0.7 * (double) n) return 0;
+   std::vector<unsigned char> code((size_t) n);
+   std::vector<int> irr;
+   for (int r = 0; r < n; r++) {
+      const int c = rid[r] >= 0 ? code_of[rid[r]] : -1;
+      if (c >= 0) { code[r] = (unsigned char) c; }
+      else        { code[r] = 255; irr.push_back(r); }
    }
    const int npat = (int) ptr.size() - 1, nent = (int) off.size();
    HB_CUDA(cudaMalloc(&M.pat_code, (size_t) n + 64));
@@ -264,6 +301,14 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
       HB_CUDA(cudaMalloc(&M.pat_base, sizeof(int) * (size_t) n));
       HB_CUDA(cudaMemcpy(M.pat_base, basev.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
    }
+   if (!irr.empty()) {
+      HB_CUDA(cudaMalloc(&M.pat_irr, sizeof(int) * irr.size()));
+      HB_CUDA(cudaMemcpy(M.pat_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
+      long long innz = 0;
+      for (int r : irr) innz += hi[r + 1] - hi[r];
+      M.pat_irr_nnz = innz;
+   }
+   M.pat_nirr = (int) irr.size();
    M.pat_npat = npat;
    M.pat_nent = nent;
    M.has_pat = true;

@@ -290,14 +290,13 @@ static int launch_stream(const DCsr &M, const double *x, const EpiArgs &ea, cuda
 }
 
 template <int EPI, int K>
-static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
+static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, const int *rowlist, int nlist,
                            int unroll, cudaStream_t st)
 {
-   const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    const long long threads = (long long) nlist * K;
    const int grid = (int) ((threads + kVecThreads - 1) / kVecThreads);
-   const int *rl = use_rownnz ? M.rownnz : (const int *) nullptr;
-   if (!use_rownnz && M.kind == SPMV_VECTOR16 && M.j16) {
+   const int *rl = rowlist;
+   if (!rowlist && M.kind == SPMV_VECTOR16 && M.j16) {
       HB_LAUNCH((spmv_vector<EPI, K, 1, true>), grid, kVecThreads, 0, st, nlist, rl, M.i,
                 reinterpret_cast<const int *>(M.j16), M.a, x, ea);
       HB_LAUNCH_CHECK();
@@ -311,16 +310,16 @@ static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, bo
 }
 
 template <int EPI>
-static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, bool use_rownnz,
+static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, const int *rowlist, int nlist,
                          int lanes, int unroll, cudaStream_t st)
 {
    switch (lanes) {
-      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, use_rownnz, unroll, st);
-      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, use_rownnz, unroll, st);
-      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, use_rownnz, unroll, st);
-      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, use_rownnz, unroll, st);
-      case 16: return launch_vector_K<EPI, 16>(M, x, ea, use_rownnz, unroll, st);
-      default: return launch_vector_K<EPI, 32>(M, x, ea, use_rownnz, unroll, st);
+      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, rowlist, nlist, unroll, st);
+      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, rowlist, nlist, unroll, st);
+      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, rowlist, nlist, unroll, st);
+      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, rowlist, nlist, unroll, st);
+      case 16: return launch_vector_K<EPI, 16>(M, x, ea, rowlist, nlist, unroll, st);
+      default: return launch_vector_K<EPI, 32>(M, x, ea, rowlist, nlist, unroll, st);
    }
 }
 
@@ -353,7 +352,13 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
-   if (!use_rownnz && M.kind == SPMV_PAT && M.has_pat) return spmv_pat_launch(M, x, EPI, ea, st);
+   if (!use_rownnz && M.kind == SPMV_PAT && M.has_pat) {
+      HB_CHECK(spmv_pat_launch(M, x, EPI, ea, st));
+      if (M.pat_nirr == 0) return 0;
+      // rows outside the pattern table: CSR sweep over the row list (disjoint rows, same epilogue)
+      const double avg = (double) M.pat_irr_nnz / (double) M.pat_nirr;
+      return launch_vector<EPI>(M, x, ea, M.pat_irr, M.pat_nirr, widen_lanes(vector_lanes_for(avg), M.pat_nirr, avg), 1, st);
+   }
    if (!use_rownnz && M.kind == SPMV_SELL && M.has_sell) return spmv_sell_launch(M, x, EPI, ea, st);
    if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
       return launch_stream<EPI>(M, x, ea, st);
@@ -367,7 +372,7 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
                                     : M.avg_row_nnz;
       lanes = widen_lanes(vector_lanes_for(avg), nlist, avg);
    }
-   return launch_vector<EPI>(M, x, ea, use_rownnz, lanes, unroll, st);
+   return launch_vector<EPI>(M, x, ea, use_rownnz ? M.rownnz : (const int *) nullptr, nlist, lanes, unroll, st);
 }
 
 int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, bool use_rownnz,

@@ -403,22 +403,24 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j, 
    return 0;
 }
 
-int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info8)
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10)
 {
-   HB_REQUIRE(A && info8, HB200_ERROR_ARG, "null argument");
-   for (int k = 0; k < 8; k++) info8[k] = 0;
-   info8[0] = A->diag.has_sell ? 1 : 0;
+   HB_REQUIRE(A && info10, HB200_ERROR_ARG, "null argument");
+   for (int k = 0; k < 10; k++) info10[k] = 0;
+   info10[0] = A->diag.has_sell ? 1 : 0;
    if (A->diag.has_sell) {
       long long total = 0;
       HB_CUDA(cudaMemcpy(&total, A->diag.sell_ptr + A->diag.sell_nslices, sizeof(long long), cudaMemcpyDeviceToHost));
-      info8[1] = total;
-      info8[2] = A->diag.sell_vidx ? 2 : 9;
-      info8[3] = A->diag.sell_nv;
+      info10[1] = total;
+      info10[2] = A->diag.sell_vidx ? 2 : 9;
+      info10[3] = A->diag.sell_nv;
    }
-   info8[4] = A->diag.has_pat ? 1 : 0;
-   info8[5] = A->diag.pat_npat;
-   info8[6] = A->diag.pat_nent;
-   info8[7] = A->diag.kind;
+   info10[4] = A->diag.has_pat ? 1 : 0;
+   info10[5] = A->diag.pat_npat;
+   info10[6] = A->diag.pat_nent;
+   info10[7] = A->diag.kind;
+   info10[8] = A->diag.pat_nirr;
+   info10[9] = A->diag.pat_irr_nnz;
    return 0;
 }
 

@@ -176,11 +176,12 @@ class ParCSRMatrix:
 
     def format_info(self) -> dict:
         """storage formats of the diag block (hb200_parcsr_format_info)"""
-        info = (C.c_longlong * 8)()
+        info = (C.c_longlong * 10)()
         check(lib.hb200_parcsr_format_info(self.handle, info))
         return {"sell": bool(info[0]), "sell_entries": int(info[1]), "sell_bytes_per_entry": int(info[2]),
                 "sell_values": int(info[3]), "pattern": bool(info[4]), "patterns": int(info[5]),
-                "pattern_entries": int(info[6]), "kernel": int(info[7])}
+                "pattern_entries": int(info[6]), "kernel": int(info[7]),
+                "pattern_irregular_rows": int(info[8]), "pattern_irregular_nnz": int(info[9])}
 
     def matvec(self, alpha: float, x, beta: float, y, b=None):
         """HYPRE_ParCSRMatrixMatvec / hypre_ParCSRMatrixMatvecOutOfPlace: y = alpha*A*x + beta*b

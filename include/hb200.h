@@ -113,14 +113,16 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
                                int *offd_i, int *offd_j, int64_t *col_map_offd,
                                int *send_map_starts, int *send_map_elmts,
                                int *recv_vec_starts, int *send_procs, int *recv_procs);
-/* Storage format of the diag block (8 values): info[0] = 1 when a dictionary-packed SELL-32 copy
- * exists (structured operators: <= 256 distinct column offsets), info[1] = its stored entries
- * incl. padding, info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset code +
- * fp64 value), info[3] = number of distinct values (0 when values are stored raw);
- * info[4] = 1 when a row-pattern copy exists (<= 256 distinct rows as lists of (column - row,
- * value): constant-coefficient stencils; 1 byte per row), info[5] = patterns, info[6] = table
- * entries; info[7] = the kernel kind in force (numbering of hb200_parcsr_set_spmv_kernel). */
-int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info8);
+/* Storage format of the diag block (10 values): info[0] = 1 when a dictionary-packed SELL-32
+ * copy exists (structured operators: <= 256 distinct column offsets), info[1] = its stored
+ * entries incl. padding, info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset
+ * code + fp64 value), info[3] = number of distinct values (0 when values are stored raw);
+ * info[4] = 1 when a row-pattern copy exists (>= 70% of the rows fall into <= 255 distinct rows
+ * as lists of (column - base, value): constant-coefficient stencils and the regular part of
+ * their first coarse level; 1 byte per row), info[5] = patterns, info[6] = table entries;
+ * info[7] = the kernel kind in force (numbering of hb200_parcsr_set_spmv_kernel);
+ * info[8] = rows outside the pattern table (swept in CSR), info[9] = their nonzeros. */
+int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10);
 /* Selects the SpMV kernel for this matrix: 0 = auto (row-pattern, else packed SELL, else vector
  * with lanes from nnz/row; default), 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced
  * stream (merge-style), 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 =

@@ -207,6 +207,42 @@ def test_interp_restrict_bit_exact_on_pattern_path(request, torch, case_name):
         P.set_spmv_kernel(0, 0)
 
 
+def test_pattern_format_with_irregular_rows(lap27, hb, torch):
+    """a stencil operator with 5% of its rows perturbed: the regular rows stay in the pattern table,
+    the others are swept in CSR over a row list; both halves against the sequential row sums"""
+    a = lap27.h["levels"][0]["A"].arrays()
+    n = lap27.mats[0][0].num_rows
+    rng = np.random.default_rng(321)
+    di, dj = a["diag_i"], a["diag_j"]
+    data = np.array(a["diag_data"], dtype=np.float64)
+    odd = rng.choice(n, size=n // 20, replace=False)
+    for r in odd:
+        data[di[r]:di[r + 1]] *= 1.0 + rng.random(di[r + 1] - di[r])
+    M = hb.ParCSRMatrix(n, n, di, dj, data)
+    fi = M.format_info()
+    # the perturbed rows are irregular, and so are the 8 corner patterns of the box (one row each)
+    assert fi["pattern"] and fi["kernel"] == 7, fi
+    assert len(odd) <= fi["pattern_irregular_rows"] <= len(odd) + 8, fi
+    x = rng.standard_normal(n)
+    b = rng.standard_normal(n)
+    yref = np.zeros(n)
+    for r in range(n):
+        s = 0.0
+        for p in range(di[r], di[r + 1]):
+            s += data[p] * x[dj[p]]
+        yref[r] = s
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    M.matvec(1.0, dev(torch, x), 0.0, y)
+    got = y.cpu().numpy()
+    # pattern rows follow the reference's order exactly; CSR rows add their lanes in another order
+    assert int((got != yref).sum()) <= fi["pattern_irregular_rows"]
+    assert relerr(got, yref) <= RTOL
+    # fused epilogues run over both halves too: y = b - A x
+    M.matvec(-1.0, dev(torch, x), 1.0, y, b=dev(torch, b))
+    assert relerr(y.cpu().numpy(), b - yref) <= RTOL
+    M.destroy()
+
+
 def test_matvec_host_entry(lap7):
     A = lap7.mats[0][0]
     rng = np.random.default_rng(11)

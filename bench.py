@@ -402,6 +402,15 @@ def main():
     per_level = []
     for l, (Al, _) in enumerate(mats[:min(4, len(mats))]):
         per_level.append(kernel_entry(l, Al, 3 if l == 0 else 2))
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    # of the same workload (profiles/r1_ncu_spmv_kernels.md); a number measured under the profiler is
+    # not taken live here
+    if args.problem == "27pt" and args.n == 256 and world == 1:
+        ncu_traffic = {7: 285242880.0 + 97056768.0, 6: 1140867000.0 + 131572224.0, 1: 5595142000.0 + 138026752.0}
+        fi0 = A.format_info()
+        if per_level and fi0["kernel"] in ncu_traffic and not fi0["pattern_irregular_rows"]:
+            per_level[0]["traffic"] = ncu_traffic[fi0["kernel"]]
+            per_level[0]["traffic_source"] = "ncu --set full, profiles/r1_ncu_spmv_kernels.md (capture 2)"
     roofline = max(per_level, key=lambda e: e["ms_per_iteration"])
     roofline = dict(roofline, note="the level kernel with the largest share of the iteration; all levels in roofline_levels")
     roofline_csr = None

@@ -105,11 +105,15 @@ static int shim_init(MPI_Comm comm)
          fprintf(stderr, "[hypre_b200] FATAL: %s\n", hb200_last_error());
          return 1;
       }
-      /* halo transport: NVLink peer puts when every rank can map every peer, else NCCL
-       * (HYPRE_B200_HALO=nccl forces the latter) */
+      /* halo transport: HYPRE_B200_HALO=peer -> NVLink peer puts when every rank can map every
+       * peer (else NCCL), =nccl -> NCCL send/recv.  Default: peer puts on 2 ranks, where they were
+       * measured against NCCL, NCCL on more. */
       {
          const char *hm = getenv("HYPRE_B200_HALO");
-         if (hb200_set_halo_mode((hm && !strcmp(hm, "nccl")) ? 0 : 2) != 0)
+         int mode = (nprocs == 2) ? 2 : 0;
+         if (hm && !strcmp(hm, "nccl")) { mode = 0; }
+         if (hm && !strcmp(hm, "peer")) { mode = 2; }
+         if (hb200_set_halo_mode(mode) != 0)
          {
             g_failed = 1;
             hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());

@@ -172,6 +172,17 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
 int  dcsr_build_partition(DCsr &M, const int *hi);
 int  dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha);   // kernels_sell.cu
 int  dcsr_free_sell(DCsr &M);
+// host-side result of the row-pattern analysis of one CSR block (kernels_pat.cu)
+struct PatHost {
+   bool ok = false, square = true;
+   std::vector<unsigned char> code;    // per row: pattern id, 255 = outside the table
+   std::vector<int> base;              // per row first column (rectangular blocks only)
+   std::vector<int> ptr, off;          // table: ptr[npat+1], off[nent]
+   std::vector<double> val;            // table: val[nent]
+   std::vector<int> irr;               // rows with code 255
+   long long irr_nnz = 0;
+};
+int  pat_analyze_host(int nrows, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out);
 int  dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha);    // kernels_pat.cu
 int  dcsr_free_pat(DCsr &M);
 // host-side transpose (stable: entries of each output row in ascending source-row order,

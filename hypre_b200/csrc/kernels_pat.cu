@@ -198,13 +198,14 @@ int dcsr_free_pat(DCsr &M)
 // boundary, where the coarsening of a partitioned grid loses its regularity) get code 255 and are
 // swept by the CSR vector kernel over a row list (pat_irr).  The block qualifies when the table
 // covers at least 70% of the rows.  Irregular blocks leave after their first 64K rows.
-int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
+// Pure host code (no CUDA call): also reachable through hb200_host_pattern_analyze for CPU tests.
+int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out)
 {
-   if (getenv("HB200_NO_PAT")) return 0;
-   const int n = M.nrows;
-   if (n < 1024 || M.nnz < 2LL * n) return 0;        // tiny or nearly empty (offd) blocks: nothing to win
+   out = PatHost();
+   const long long nnz = n > 0 ? hi[n] : 0;
+   if (n < 1024 || nnz < 2LL * n) return 0;          // tiny or nearly empty (offd) blocks: nothing to win
    // square blocks: column = row + offset; rectangular ones (P, P^T): column = first column + offset
-   const bool square = (M.nrows == M.ncols);
+   const bool square = (n == ncols);
    std::vector<int> basev;
    if (!square) {
       basev.resize((size_t) n);
@@ -260,8 +261,8 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
    std::vector<int> order(rep.size());
    for (size_t k = 0; k < order.size(); k++) order[k] = (int) k;
    std::sort(order.begin(), order.end(), [&](int a, int b) { return count[a] != count[b] ? count[a] > count[b] : a < b; });
-   std::vector<int> code_of(rep.size(), -1), ptr(1, 0), off;
-   std::vector<double> val;
+   std::vector<int> code_of(rep.size(), -1);
+   out.ptr.assign(1, 0);
    long long covered = 0, all_entries = 0;
    for (int c : order) all_entries += hi[rep[c] + 1] - hi[rep[c]];
    // a fully regular block keeps every pattern, rare ones included; otherwise a pattern has to
@@ -270,45 +271,55 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
    const long long min_count = all_fit ? 1 : 8;
    for (int c : order) {
       const int len = hi[rep[c] + 1] - hi[rep[c]];
-      if ((int) ptr.size() - 1 >= kPatMaxPatterns - 1 || count[c] < min_count) break;
-      if ((int) off.size() + len > kPatMaxEntries) continue;
-      code_of[c] = (int) ptr.size() - 1;
+      if ((int) out.ptr.size() - 1 >= kPatMaxPatterns - 1 || count[c] < min_count) break;
+      if ((int) out.off.size() + len > kPatMaxEntries) continue;
+      code_of[c] = (int) out.ptr.size() - 1;
       for (int q = hi[rep[c]]; q < hi[rep[c] + 1]; q++) {
-         off.push_back(hj[q] - base_of(rep[c]));
-         val.push_back(ha[q]);
+         out.off.push_back(hj[q] - base_of(rep[c]));
+         out.val.push_back(ha[q]);
       }
-      ptr.push_back((int) off.size());
+      out.ptr.push_back((int) out.off.size());
       covered += count[c];
    }
-   if ((double) covered < 0.7 * (double) n) return 0;
-   std::vector<unsigned char> code((size_t) n);
-   std::vector<int> irr;
+   if ((double) covered < 0.7 * (double) n) { out = PatHost(); return 0; }
+   out.code.resize((size_t) n);
    for (int r = 0; r < n; r++) {
       const int c = rid[r] >= 0 ? code_of[rid[r]] : -1;
-      if (c >= 0) { code[r] = (unsigned char) c; }
-      else        { code[r] = 255; irr.push_back(r); }
+      if (c >= 0) { out.code[r] = (unsigned char) c; }
+      else        { out.code[r] = 255; out.irr.push_back(r); out.irr_nnz += hi[r + 1] - hi[r]; }
    }
-   const int npat = (int) ptr.size() - 1, nent = (int) off.size();
+   out.base.swap(basev);
+   out.square = square;
+   out.ok = true;
+   return 0;
+}
+
+int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
+{
+   if (getenv("HB200_NO_PAT")) return 0;
+   PatHost ph;
+   HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph));
+   if (!ph.ok) return 0;
+   const int n = M.nrows;
+   const int npat = (int) ph.ptr.size() - 1, nent = (int) ph.off.size();
    HB_CUDA(cudaMalloc(&M.pat_code, (size_t) n + 64));
-   HB_CUDA(cudaMemcpy(M.pat_code, code.data(), (size_t) n, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMemcpy(M.pat_code, ph.code.data(), (size_t) n, cudaMemcpyHostToDevice));
    HB_CUDA(cudaMalloc(&M.pat_ptr, sizeof(int) * ((size_t) npat + 1)));
-   HB_CUDA(cudaMemcpy(M.pat_ptr, ptr.data(), sizeof(int) * ((size_t) npat + 1), cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMemcpy(M.pat_ptr, ph.ptr.data(), sizeof(int) * ((size_t) npat + 1), cudaMemcpyHostToDevice));
    HB_CUDA(cudaMalloc(&M.pat_off, sizeof(int) * ((size_t) nent + 1)));
-   HB_CUDA(cudaMemcpy(M.pat_off, off.data(), sizeof(int) * (size_t) nent, cudaMemcpyHostToDevice));
+   HB_CUDA(cudaMemcpy(M.pat_off, ph.off.data(), sizeof(int) * (size_t) nent, cudaMemcpyHostToDevice));
    HB_CUDA(cudaMalloc(&M.pat_val, sizeof(double) * ((size_t) nent + 1)));
-   HB_CUDA(cudaMemcpy(M.pat_val, val.data(), sizeof(double) * (size_t) nent, cudaMemcpyHostToDevice));
-   if (!square) {
+   HB_CUDA(cudaMemcpy(M.pat_val, ph.val.data(), sizeof(double) * (size_t) nent, cudaMemcpyHostToDevice));
+   if (!ph.square) {
       HB_CUDA(cudaMalloc(&M.pat_base, sizeof(int) * (size_t) n));
-      HB_CUDA(cudaMemcpy(M.pat_base, basev.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
+      HB_CUDA(cudaMemcpy(M.pat_base, ph.base.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
    }
-   if (!irr.empty()) {
-      HB_CUDA(cudaMalloc(&M.pat_irr, sizeof(int) * irr.size()));
-      HB_CUDA(cudaMemcpy(M.pat_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
-      long long innz = 0;
-      for (int r : irr) innz += hi[r + 1] - hi[r];
-      M.pat_irr_nnz = innz;
+   if (!ph.irr.empty()) {
+      HB_CUDA(cudaMalloc(&M.pat_irr, sizeof(int) * ph.irr.size()));
+      HB_CUDA(cudaMemcpy(M.pat_irr, ph.irr.data(), sizeof(int) * ph.irr.size(), cudaMemcpyHostToDevice));
    }
-   M.pat_nirr = (int) irr.size();
+   M.pat_irr_nnz = ph.irr_nnz;
+   M.pat_nirr = (int) ph.irr.size();
    M.pat_npat = npat;
    M.pat_nent = nent;
    M.has_pat = true;
@@ -316,3 +327,31 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
 }
 
 }  // namespace hb
+
+extern "C" int hb200_host_pattern_analyze(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                                          const double *values, unsigned char *row_code, int *row_base,
+                                          int *num_patterns, int *pattern_ptr, int *pattern_offset,
+                                          double *pattern_value, int *num_irregular, int *irregular_rows)
+{
+   using namespace hb;
+   HB_REQUIRE(num_rows >= 0 && num_cols >= 0 && row_ptr && num_patterns && num_irregular, HB200_ERROR_ARG,
+              "hb200_host_pattern_analyze: null argument");
+   HB_REQUIRE(row_ptr[num_rows] == 0 || (col_ind && values), HB200_ERROR_ARG, "hb200_host_pattern_analyze: null matrix arrays");
+   PatHost ph;
+   HB_CHECK(pat_analyze_host(num_rows, num_cols, row_ptr, col_ind, values, ph));
+   *num_patterns = 0;
+   *num_irregular = 0;
+   if (!ph.ok) return 0;
+   const int npat = (int) ph.ptr.size() - 1;
+   *num_patterns = npat;
+   *num_irregular = (int) ph.irr.size();
+   if (row_code) memcpy(row_code, ph.code.data(), (size_t) num_rows);
+   if (row_base) {
+      for (int r = 0; r < num_rows; r++) row_base[r] = ph.square ? r : ph.base[r];
+   }
+   if (pattern_ptr) memcpy(pattern_ptr, ph.ptr.data(), sizeof(int) * ((size_t) npat + 1));
+   if (pattern_offset) memcpy(pattern_offset, ph.off.data(), sizeof(int) * ph.off.size());
+   if (pattern_value) memcpy(pattern_value, ph.val.data(), sizeof(double) * ph.val.size());
+   if (irregular_rows && !ph.irr.empty()) memcpy(irregular_rows, ph.irr.data(), sizeof(int) * ph.irr.size());
+   return 0;
+}

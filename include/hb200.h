@@ -131,6 +131,17 @@ int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10);
  * +-32767 of the diagonal).  6, 7 and 8 fall back to the next format when the block does not
  * qualify; auto prefers 7, 6, 8, 1 in that order. */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
+/* Host-side half of the upload, no GPU needed: the row-pattern analysis of one CSR
+ * block (a hypre_CSRMatrix: i / j / data, src/seq_mv/csr_matrix.h:33-62) exactly as
+ * hb200_parcsr_create runs it.  Outputs (any may be NULL): row_code[num_rows] (pattern id, 255 =
+ * row outside the table), row_base[num_rows] (column of entry k = row_base + pattern_offset[k];
+ * the row itself for square blocks), pattern_ptr[*num_patterns + 1], pattern_offset / pattern_value
+ * (<= 8192 entries), irregular_rows[*num_irregular].  *num_patterns = 0 when the block does not
+ * qualify.  Decoding the outputs reproduces the block entry for entry (lossless). */
+int hb200_host_pattern_analyze(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                               const double *values, unsigned char *row_code, int *row_base,
+                               int *num_patterns, int *pattern_ptr, int *pattern_offset,
+                               double *pattern_value, int *num_irregular, int *irregular_rows);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):
  *   y = alpha*A*x + beta*b, halo exchange (job 1) overlapped with the diag block.

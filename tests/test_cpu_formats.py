@@ -1,0 +1,165 @@
+"""CPU checks of the host half of the upload: the row-pattern analysis (kernels_pat.cu) is lossless
+— decoding (row code, base, pattern table, irregular-row list) reproduces the CSR block entry for
+entry — qualifies the blocks DESIGN.md says it does, and leaves irregular blocks alone."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BRIDGE = os.path.join(ROOT, "oracle", "_ref", "libref_bridge.so")
+
+
+def analyze(n, ncols, ai, aj, aa):
+    from hypre_b200._lib import lib, check
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    aa = np.ascontiguousarray(aa, dtype=np.float64)
+    code = np.zeros(max(n, 1), np.uint8)
+    base = np.zeros(max(n, 1), np.int32)
+    ptr = np.zeros(257, np.int32)
+    off = np.zeros(8192, np.int32)
+    val = np.zeros(8192, np.float64)
+    irr = np.zeros(max(n, 1), np.int32)
+    npat, nirr = C.c_int(0), C.c_int(0)
+    check(lib.hb200_host_pattern_analyze(n, ncols, ai.ctypes.data, aj.ctypes.data, aa.ctypes.data,
+                                         code.ctypes.data, base.ctypes.data, C.byref(npat), ptr.ctypes.data,
+                                         off.ctypes.data, val.ctypes.data, C.byref(nirr), irr.ctypes.data))
+    return {"npat": npat.value, "nirr": nirr.value, "code": code[:n], "base": base[:n],
+            "ptr": ptr[:npat.value + 1], "off": off, "val": val, "irr": irr[:nirr.value]}
+
+
+def assert_lossless(n, ai, aj, aa, r):
+    """every row with a code decodes to its CSR entries, in CSR order, bit for bit"""
+    ai = np.asarray(ai)
+    aj = np.asarray(aj)
+    aa = np.asarray(aa, dtype=np.float64)
+    irr = set(int(x) for x in r["irr"])
+    assert len(irr) == r["nirr"]
+    for row in range(n):
+        c = int(r["code"][row])
+        if c == 255:
+            assert row in irr
+            continue
+        assert row not in irr and c < r["npat"]
+        b, e = int(r["ptr"][c]), int(r["ptr"][c + 1])
+        s, t = int(ai[row]), int(ai[row + 1])
+        assert e - b == t - s, row
+        assert np.array_equal(r["base"][row] + r["off"][b:e], aj[s:t]), row
+        assert np.array_equal(r["val"][b:e].view(np.uint64), aa[s:t].view(np.uint64)), row
+
+
+def stencil7(nx, ny, nz):
+    """7-point Laplacian in the reference's storage: diagonal first, then ascending columns"""
+    n = nx * ny * nz
+    ai, aj, aa = [0], [], []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                r = i + nx * (j + ny * k)
+                aj.append(r)
+                aa.append(6.0)
+                for d, ok in ((-nx * ny, k > 0), (-nx, j > 0), (-1, i > 0), (1, i < nx - 1), (nx, j < ny - 1),
+                              (nx * ny, k < nz - 1)):
+                    if ok:
+                        aj.append(r + d)
+                        aa.append(-1.0)
+                ai.append(len(aj))
+    return n, np.array(ai, np.int32), np.array(aj, np.int32), np.array(aa)
+
+
+def test_constant_stencil_has_27_patterns_and_is_lossless():
+    n, ai, aj, aa = stencil7(12, 11, 10)
+    r = analyze(n, n, ai, aj, aa)
+    assert r["npat"] == 27 and r["nirr"] == 0           # 3 x 3 x 3 kinds of boundary
+    assert_lossless(n, ai, aj, aa, r)
+    assert np.array_equal(r["base"], np.arange(n))      # square block: base = the row
+
+
+def test_perturbed_rows_go_to_the_irregular_list():
+    # 409 one-off rows + 27 regular patterns: more candidates than table slots, so a pattern has to
+    # earn its slot with >= 8 rows (with fewer candidates every pattern is kept, see the next test)
+    n, ai, aj, aa = stencil7(16, 16, 16)
+    rng = np.random.default_rng(5)
+    odd = np.sort(rng.choice(n, size=n // 10, replace=False))
+    aa = aa.copy()
+    for row in odd:
+        aa[ai[row]:ai[row + 1]] *= 1.0 + rng.random(ai[row + 1] - ai[row])
+    r = analyze(n, n, ai, aj, aa)
+    assert r["npat"] > 0
+    assert set(odd.tolist()) <= set(r["irr"].tolist())
+    # beyond the perturbed rows only patterns too rare to earn a table slot (the 8 corners) are left out
+    assert r["nirr"] <= len(odd) + 8
+    assert_lossless(n, ai, aj, aa, r)
+
+
+def test_few_one_off_rows_are_kept_in_the_table():
+    n, ai, aj, aa = stencil7(16, 12, 10)
+    rng = np.random.default_rng(6)
+    aa = aa.copy()
+    for row in rng.choice(n, size=40, replace=False):
+        aa[ai[row]:ai[row + 1]] *= 1.0 + rng.random(ai[row + 1] - ai[row])
+    r = analyze(n, n, ai, aj, aa)
+    assert r["nirr"] == 0 and 27 < r["npat"] <= 27 + 40
+    assert_lossless(n, ai, aj, aa, r)
+
+
+def test_irregular_and_tiny_blocks_do_not_qualify():
+    rng = np.random.default_rng(9)
+    n = 4096
+    ai = np.arange(0, 8 * n + 1, 8, dtype=np.int32)
+    aj = np.sort(rng.integers(0, n, size=(n, 8)), axis=1).astype(np.int32).ravel()
+    aa = rng.standard_normal(8 * n)
+    assert analyze(n, n, ai, aj, aa)["npat"] == 0        # unstructured: every row its own pattern
+    n2, bi, bj, ba = stencil7(8, 8, 8)
+    assert analyze(n2, n2, bi, bj, ba)["npat"] == 0      # 512 rows: below the size worth a table
+
+
+def test_mostly_irregular_block_is_rejected_below_70_percent_coverage():
+    n, ai, aj, aa = stencil7(16, 16, 8)
+    rng = np.random.default_rng(11)
+    aa = aa.copy()
+    for row in rng.choice(n, size=n // 2, replace=False):
+        aa[ai[row]:ai[row + 1]] *= 1.0 + rng.random(ai[row + 1] - ai[row])
+    assert analyze(n, n, ai, aj, aa)["npat"] == 0
+
+
+@pytest.mark.parametrize("kind,dims", [("27pt", (24, 24, 24)), ("laplacian", (32, 32, 32))])
+def test_reference_hierarchy_blocks(kind, dims):
+    """A_0, P_0, P_0^T and A_1 of hierarchies built by the reference's own BoomerAMGSetup"""
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    import scipy.sparse as sp
+    from oracle import refbridge as rb
+    rb.load()
+    pb = rb.Problem(kind, dims)
+    pb.setup_amg(relax_type=18)
+    h = pb.hierarchy()
+    A0 = h["levels"][0]["A"]
+    a = A0.arrays()
+    r = analyze(A0.num_rows, A0.num_cols, a["diag_i"], a["diag_j"], a["diag_data"])
+    assert 0 < r["npat"] <= 27 and r["nirr"] == 0
+    assert_lossless(A0.num_rows, a["diag_i"], a["diag_j"], a["diag_data"], r)
+    P0 = h["levels"][0]["P"]
+    p = P0.arrays()
+    r = analyze(P0.num_rows, P0.num_cols, p["diag_i"], p["diag_j"], p["diag_data"])
+    if r["npat"]:                                        # rectangular: base = first column of the row
+        assert_lossless(P0.num_rows, p["diag_i"], p["diag_j"], p["diag_data"], r)
+        first = np.asarray(p["diag_j"])[np.minimum(np.asarray(p["diag_i"])[:-1], len(p["diag_j"]) - 1)]
+        nonempty = np.diff(np.asarray(p["diag_i"])) > 0
+        assert np.array_equal(r["base"][nonempty], first[nonempty])
+        Pm = sp.csr_matrix((np.asarray(p["diag_data"]), np.asarray(p["diag_j"]), np.asarray(p["diag_i"])),
+                           shape=(P0.num_rows, P0.num_cols))
+        R = Pm.T.tocsr()
+        R.sort_indices()
+        if R.shape[0] >= 1024:
+            rr = analyze(R.shape[0], R.shape[1], R.indptr, R.indices, R.data)
+            if rr["npat"]:
+                assert_lossless(R.shape[0], R.indptr, R.indices, R.data, rr)
+    if len(h["levels"]) > 1 and h["levels"][1]["A"].num_rows >= 1024:
+        A1 = h["levels"][1]["A"]
+        a1 = A1.arrays()
+        r1 = analyze(A1.num_rows, A1.num_cols, a1["diag_i"], a1["diag_j"], a1["diag_data"])
+        if r1["npat"]:
+            assert_lossless(A1.num_rows, a1["diag_i"], a1["diag_j"], a1["diag_data"], r1)

@@ -252,3 +252,18 @@ int relax_hybrid_gs(hb200_parcsr *A, const double *f, const int *cf, int relax_t
 }
 
 }  // namespace hb
+
+// host half of the hybrid-GS path, reachable without a GPU (CPU tests of the schedule)
+extern "C" int hb200_host_gs_schedule(int num_rows, const int *row_ptr, const int *col_ind, int forward,
+                                      int *perm, int *level_ptr, int *num_levels)
+{
+   using namespace hb;
+   HB_REQUIRE(num_rows >= 0 && row_ptr && num_levels, HB200_ERROR_ARG, "hb200_host_gs_schedule: null argument");
+   HB_REQUIRE(row_ptr[num_rows] == 0 || col_ind, HB200_ERROR_ARG, "hb200_host_gs_schedule: null column indices");
+   std::vector<int> p, lp;
+   build_levels(num_rows, row_ptr, col_ind, forward != 0, p, lp);
+   *num_levels = (int) lp.size() - 1;
+   if (perm && num_rows > 0) memcpy(perm, p.data(), sizeof(int) * (size_t) num_rows);
+   if (level_ptr) memcpy(level_ptr, lp.data(), sizeof(int) * lp.size());
+   return 0;
+}

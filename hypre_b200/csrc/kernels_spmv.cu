@@ -534,3 +534,24 @@ void host_csr_transpose(int nrows, int ncols, const int *ai, const int *aj, cons
 }
 
 }  // namespace hb
+
+// host half of the restriction path, reachable without a GPU (CPU tests of the stored transpose)
+extern "C" int hb200_host_csr_transpose(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                                        const double *values, int *t_row_ptr, int *t_col_ind, double *t_values)
+{
+   using namespace hb;
+   HB_REQUIRE(num_rows >= 0 && num_cols >= 0 && row_ptr && t_row_ptr, HB200_ERROR_ARG,
+              "hb200_host_csr_transpose: null argument");
+   const int nnz = num_rows > 0 ? row_ptr[num_rows] : 0;
+   HB_REQUIRE(nnz == 0 || (col_ind && values && t_col_ind && t_values), HB200_ERROR_ARG,
+              "hb200_host_csr_transpose: null matrix arrays");
+   std::vector<int> ti, tj;
+   std::vector<double> ta;
+   host_csr_transpose(num_rows, num_cols, row_ptr, col_ind, values, ti, tj, ta);
+   memcpy(t_row_ptr, ti.data(), sizeof(int) * ti.size());
+   if (nnz) {
+      memcpy(t_col_ind, tj.data(), sizeof(int) * (size_t) nnz);
+      memcpy(t_values, ta.data(), sizeof(double) * (size_t) nnz);
+   }
+   return 0;
+}

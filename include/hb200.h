@@ -142,6 +142,18 @@ int hb200_host_pattern_analyze(int num_rows, int num_cols, const int *row_ptr, c
                                const double *values, unsigned char *row_code, int *row_base,
                                int *num_patterns, int *pattern_ptr, int *pattern_offset,
                                double *pattern_value, int *num_irregular, int *irregular_rows);
+/* The stored transpose that restriction runs on (hypre_ParCSRMatrixMatvecT with keepTranspose,
+ * src/parcsr_mv/par_csr_matvec.c:298-299, 430-468): entries of each output row in ascending
+ * source-row order = the order hypre_CSRMatrixMatvecT accumulates in (src/seq_mv/csr_matvec.c:1095-1110).
+ * t_row_ptr[num_cols + 1], t_col_ind / t_values[nnz].  Host only, no GPU needed. */
+int hb200_host_csr_transpose(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                             const double *values, int *t_row_ptr, int *t_col_ind, double *t_values);
+/* Wavefront schedule of the hybrid Gauss-Seidel sweeps (src/parcsr_ls/par_relax.h:12-330 run with
+ * one thread): rows of one level are mutually uncoupled and every row comes after the rows it
+ * reads updated values from, so sweeping the levels in order reproduces the sequential sweep.
+ * perm[num_rows] = rows grouped by level, level_ptr[*num_levels + 1].  Host only. */
+int hb200_host_gs_schedule(int num_rows, const int *row_ptr, const int *col_ind, int forward,
+                           int *perm, int *level_ptr, int *num_levels);
 
 /* (a3) hypre_ParCSRMatrixMatvecOutOfPlace (src/parcsr_mv/par_csr_matvec.c:241-262):
  *   y = alpha*A*x + beta*b, halo exchange (job 1) overlapped with the diag block.

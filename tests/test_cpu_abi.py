@@ -56,3 +56,21 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "refbridge" not in txt and "oracle/" not in txt.replace("oracle/_ref", "").replace(
                     "reference bridge", ""), os.path.join(dp, f)
+
+
+def test_dropin_ij_fails_loudly_without_gpu():
+    """The unmodified ij driver linked in front of the shim: without a GPU the overridden solve must
+    refuse (hypre error + message), never fall back to the reference's CPU solve behind it."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ij = os.path.join(ROOT, "oracle", "_ref", "ij_b200")
+    if not os.path.exists(ij):
+        pytest.skip("oracle/_ref/ij_b200 not built (needs /root/reference)")
+    r = subprocess.run([ij, "-n", "12", "12", "12", "-solver", "1", "-rlx", "18"], capture_output=True, text=True,
+                       timeout=300, cwd=os.path.dirname(ij))
+    out = r.stdout + r.stderr
+    assert "[hypre_b200] FATAL" in out and "no CPU fallback" in out, out[-2000:]
+    # the reference's own CPU PCG would report 8 iterations here; the refused solve reports none
+    assert "Iterations = 0" in out, out[-2000:]

@@ -163,3 +163,104 @@ def test_reference_hierarchy_blocks(kind, dims):
         r1 = analyze(A1.num_rows, A1.num_cols, a1["diag_i"], a1["diag_j"], a1["diag_data"])
         if r1["npat"]:
             assert_lossless(A1.num_rows, a1["diag_i"], a1["diag_j"], a1["diag_data"], r1)
+
+
+# ----------------------------------------------------------------------------------------
+# stored transpose (restriction) and hybrid-GS wavefront schedule: host logic against the oracle
+# ----------------------------------------------------------------------------------------
+def host_transpose(n, ncols, ai, aj, aa):
+    from hypre_b200._lib import lib, check
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    aa = np.ascontiguousarray(aa, dtype=np.float64)
+    ti = np.zeros(ncols + 1, np.int32)
+    tj = np.zeros(max(len(aj), 1), np.int32)
+    ta = np.zeros(max(len(aa), 1), np.float64)
+    check(lib.hb200_host_csr_transpose(n, ncols, ai.ctypes.data, aj.ctypes.data, aa.ctypes.data,
+                                       ti.ctypes.data, tj.ctypes.data, ta.ctypes.data))
+    return ti, tj[:len(aj)], ta[:len(aa)]
+
+
+def gs_schedule(n, ai, aj, forward):
+    from hypre_b200._lib import lib, check
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    perm = np.zeros(max(n, 1), np.int32)
+    lptr = np.zeros(n + 2, np.int32)
+    nlev = C.c_int(0)
+    check(lib.hb200_host_gs_schedule(n, ai.ctypes.data, aj.ctypes.data, 1 if forward else 0,
+                                     perm.ctypes.data, lptr.ctypes.data, C.byref(nlev)))
+    return perm[:n], lptr[:nlev.value + 1]
+
+
+def random_rect(rng, n, ncols, per_row):
+    ai = [0]
+    aj, aa = [], []
+    for _ in range(n):
+        k = int(rng.integers(0, per_row + 1))
+        cols = np.sort(rng.choice(ncols, size=min(k, ncols), replace=False))
+        aj.extend(cols.tolist())
+        aa.extend(rng.standard_normal(len(cols)).tolist())
+        ai.append(len(aj))
+    return np.array(ai, np.int32), np.array(aj, np.int32), np.array(aa)
+
+
+def test_stored_transpose_sums_in_the_reference_order():
+    """row sums of the stored transpose == the oracle's restatement of hypre_CSRMatrixMatvecT
+    (csr_matvec.c:1095-1110, one thread), bit for bit: same products, same order"""
+    from oracle import restatement as orc
+    rng = np.random.default_rng(42)
+    for n, ncols in ((300, 90), (64, 64), (5, 200)):
+        ai, aj, aa = random_rect(rng, n, ncols, 7)
+        ti, tj, ta = host_transpose(n, ncols, ai, aj, aa)
+        assert ti[0] == 0 and ti[-1] == len(aj) and np.all(np.diff(ti) >= 0)
+        for c in range(ncols):                       # ascending source rows within each output row
+            assert np.all(np.diff(tj[ti[c]:ti[c + 1]]) > 0)
+        x = rng.standard_normal(n)
+        yref = orc.csr_matvecT(ai, aj, aa, ncols, 1.0, x, 0.0, np.zeros(ncols))
+        y = np.zeros(ncols)
+        for c in range(ncols):
+            s = 0.0
+            for p in range(ti[c], ti[c + 1]):
+                s += ta[p] * x[tj[p]]
+            y[c] = s
+        assert np.array_equal(y, yref)
+
+
+@pytest.mark.parametrize("forward", [True, False])
+def test_gs_wavefront_schedule_reproduces_the_sequential_sweep(forward):
+    """levels are independent sets that respect the sweep's dependencies, and sweeping them in
+    order gives exactly the oracle's sequential Gauss-Seidel sweep (relax type 3 forward / 4 backward)"""
+    from oracle import restatement as orc
+    n, ai, aj, aa = stencil7(9, 8, 7)
+    rng = np.random.default_rng(3)
+    aa = aa * (1.0 + 0.1 * rng.random(len(aa)))      # generic values, diagonal stays first and dominant
+    perm, lptr = gs_schedule(n, ai, aj, forward)
+    assert sorted(perm.tolist()) == list(range(n))
+    lev = np.empty(n, np.int64)
+    for l in range(len(lptr) - 1):
+        lev[perm[lptr[l]:lptr[l + 1]]] = l
+    for i in range(n):
+        for p in range(ai[i], ai[i + 1]):
+            j = int(aj[p])
+            if j == i:
+                continue
+            earlier = (j < i) if forward else (j > i)
+            # a coupled row that the sequential sweep visits earlier must sit in an earlier level,
+            # one it visits later in a later level: never the same level
+            assert (lev[j] < lev[i]) if earlier else (lev[j] > lev[i]), (i, j)
+    f = rng.standard_normal(n)
+    u0 = rng.standard_normal(n)
+    uref = orc.relax(ai, aj, aa, f, u0.copy(), 3 if forward else 4)
+    u = u0.copy()
+    for l in range(len(lptr) - 1):
+        rows = perm[lptr[l]:lptr[l + 1]]
+        new = {}
+        for i in rows:                                # all rows of a level read the same state
+            s = f[i]
+            for p in range(ai[i] + 1, ai[i + 1]):
+                s -= aa[p] * u[aj[p]]
+            new[i] = s / aa[ai[i]]
+        for i, v in new.items():
+            u[i] = v
+    assert np.array_equal(u, uref)

@@ -238,6 +238,8 @@ def main():
     def stage(name):
         wd["stage"] = name
         wd["deadline"] = time.time() + args.stage_timeout
+        if os.environ.get("HB200_TRACE"):
+            print(f"[bench rank {rank}] stage: {name}", file=sys.stderr, flush=True)
 
     def watchdog():
         while True:

@@ -264,6 +264,7 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
       amg->graphs.erase(amg->graphs.begin());
    }
    const long long before = c.launches;
+   HB_TRACE("amg_cycle: capturing the V-cycle graph (%d levels, zero guess %d)", amg->num_levels, (int) u_all_zeros);
    cudaGraph_t graph = nullptr;
    HB_CUDA(cudaStreamBeginCapture(c.s_comp, cudaStreamCaptureModeThreadLocal));
    c.capturing = true;

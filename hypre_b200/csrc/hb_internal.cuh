@@ -93,6 +93,11 @@ int ws_get(int slot, size_t bytes, double **out);
 enum TimerCat { T_OTHER = 0, T_MATVEC_DIAG, T_MATVEC_OFFD, T_HALO_START, T_HALO_WAIT, T_BLAS1, T_ALLREDUCE,
                 T_HOST_SYNC, T_GE_SOLVE, T_RELAX_ZERO, T_NUM };
 extern bool g_timers_on;
+// HB200_TRACE=1: one stderr line per collective set-up step and per solve (finding the rank and the
+// step a multi-rank run stops in); off by default, never on the timed path
+extern bool g_trace_on;
+void trace_line(const char *fmt, ...);
+#define HB_TRACE(...) do { if (hb::g_trace_on) hb::trace_line(__VA_ARGS__); } while (0)
 void timer_tick_impl(int cat);
 inline void timer_tick(int cat) { if (g_timers_on) timer_tick_impl(cat); }
 void timers_begin();

@@ -95,6 +95,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
    const int my_id = c.rank;
    const bool log = (P->logging > 0 || P->print_level > 0) && norms;
    int eflag = 0;
+   HB_TRACE("pcg_solve: %zu local rows, halo mode %d", n, c.halo_mode);
 
    // work vectors p, s, r [, r_old, v] (hypre_PCGSetup, pcg.c:233-250) from the persistent workspace
    double *p = nullptr, *s = nullptr, *r = nullptr, *r_old = nullptr, *v = nullptr;
@@ -410,6 +411,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
    res->rel_residual_norm = bi_prod > 0.0 ? sqrt(i_prod / bi_prod) : 0.0;
    res->error_flag = eflag;
    cleanup();
+   HB_TRACE("pcg_solve: %d iterations, rel.res %.6e", i, res->rel_residual_norm);
 #undef PCG_CHECK
    return eflag;
 }

@@ -380,6 +380,8 @@ int peer_plans_ensure(hb200_parcsr *A, bool reverse)
    bool &tried = reverse ? pk.peer_tried_rev : pk.peer_tried;
    if (tried) return 0;
    tried = true;
+   HB_TRACE("peer plan (%s) for a %d x %d block: %d sends, %d recvs ...", reverse ? "reverse" : "forward", A->num_rows,
+            A->num_cols, pk.num_sends, pk.num_recvs);
    HB_CHECK(arena_setup());
    if (!reverse) {
       // forward (job 1): out = sends (gather through send_map_elmts), in = recvs -> x_ext
@@ -393,6 +395,7 @@ int peer_plans_ensure(hb200_parcsr *A, bool reverse)
    // peers must not start writing into this arena region before everybody has built the plan
    HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
    HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   HB_TRACE("peer plan built");
    return 0;
 }
 

@@ -69,6 +69,19 @@ int nccl_load()
 
 // ---- stream-time attribution --------------------------------------------------------------------
 bool g_timers_on = false;
+bool g_trace_on = false;
+
+void trace_line(const char *fmt, ...)
+{
+   char buf[512];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof(buf), fmt, ap);
+   va_end(ap);
+   fprintf(stderr, "[hb200 trace rank %d] %s\n", ctx().rank, buf);
+   fflush(stderr);
+}
+
 static std::vector<cudaEvent_t> g_tev;
 static std::vector<int> g_tcat;
 static size_t g_tn = 0;
@@ -147,6 +160,7 @@ int hb200_init(int device)
 {
    Ctx &c = ctx();
    if (c.ready) return 0;
+   g_trace_on = getenv("HB200_TRACE") != nullptr;
    int ndev = 0;
    cudaError_t e = cudaGetDeviceCount(&ndev);
    if (e != cudaSuccess || ndev == 0) {
@@ -232,7 +246,9 @@ int hb200_comm_init(int rank, int nranks, const void *id128)
    HB_CHECK(nccl_load());
    ncclUniqueId id;
    memcpy(&id, id128, 128);
+   HB_TRACE("comm_init: ncclCommInitRank %d/%d ...", rank, nranks);
    HB_NCCL(nccl_api().CommInitRank(&c.nccl, nranks, id, rank));
+   HB_TRACE("comm_init: done");
    c.rank = rank;
    c.nranks = nranks;
    return 0;
@@ -263,7 +279,9 @@ int hb200_set_halo_mode(int mode)
    HB_CHECK(require_ready());
    // collective: all ranks must make the same call
    int ok = 0;
+   HB_TRACE("set_halo_mode(%d): mapping the peer arenas ...", mode);
    HB_CHECK(arena_setup_collective(&ok));
+   HB_TRACE("set_halo_mode(%d): peer arenas %s", mode, ok ? "mapped on every rank" : "unavailable, NCCL halo");
    if (!ok && mode == 1) {
       return set_error(HB200_ERROR_GENERIC, "peer halo unavailable on at least one rank: %s", std::string(hb200_last_error()).c_str());
    }

@@ -91,6 +91,7 @@ def _load() -> C.CDLL:
         "hb200_parcsr_format_info": ([vp, C.POINTER(C.c_longlong)], C.c_int),
         "hb200_host_csr_transpose": ([C.c_int, C.c_int, vp, vp, vp, vp, vp, vp], C.c_int),
         "hb200_host_gs_schedule": ([C.c_int, vp, vp, C.c_int, vp, vp, c_int_p], C.c_int),
+        "hb200_host_pattern_analyze_wide": ([C.c_int, C.c_int, vp, vp, vp, vp, vp, c_int_p, c_int_p, C.c_int, vp, vp, vp, c_int_p, vp], C.c_int),
         "hb200_host_pattern_analyze": ([C.c_int, C.c_int, vp, vp, vp, vp, vp, c_int_p, vp, vp, vp, c_int_p, vp], C.c_int),
         "hb200_parcsr_matvec": ([vp, C.c_double, vp, C.c_double, vp, vp], C.c_int),
         "hb200_parcsr_matvecT": ([vp, C.c_double, vp, C.c_double, vp], C.c_int),

@@ -164,6 +164,7 @@ struct DCsr {
    int       *pat_off = nullptr;       // pat_nent
    double    *pat_val = nullptr;       // pat_nent
    int        pat_npat = 0, pat_nent = 0;
+   bool       pat_wide = false;        // 16-bit codes in pat_code, table read from global memory
    int       *pat_irr = nullptr;       // rows outside the table (code 255), swept by the CSR kernel
    int        pat_nirr = 0;
    long long  pat_irr_nnz = 0;
@@ -179,15 +180,16 @@ int  dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha);  
 int  dcsr_free_sell(DCsr &M);
 // host-side result of the row-pattern analysis of one CSR block (kernels_pat.cu)
 struct PatHost {
-   bool ok = false, square = true;
+   bool ok = false, square = true, wide = false;
    std::vector<unsigned char> code;    // per row: pattern id, 255 = outside the table
+   std::vector<unsigned short> code16; // wide variant: 65535 = outside the table
    std::vector<int> base;              // per row first column (rectangular blocks only)
    std::vector<int> ptr, off;          // table: ptr[npat+1], off[nent]
    std::vector<double> val;            // table: val[nent]
    std::vector<int> irr;               // rows with code 255
    long long irr_nnz = 0;
 };
-int  pat_analyze_host(int nrows, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out);
+int  pat_analyze_host(int nrows, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out, bool wide);
 int  dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha);    // kernels_pat.cu
 int  dcsr_free_pat(DCsr &M);
 // host-side transpose (stable: entries of each output row in ascending source-row order,

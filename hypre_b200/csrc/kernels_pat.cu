@@ -46,20 +46,30 @@ __device__ __forceinline__ void pat_one_row(const EpiArgs &ea, const double *__r
 // column of entry k of a row = base + off[k]; base = the row itself for square blocks (BASE =
 // false), else base[row] (the row's first column: interpolation and its stored transpose).
 // NT threads per block, R rows per thread.
-template <int EPI, bool BASE, int NT, int R>
+// WIDE (experimental, HB200_PAT_WIDE=1): 16-bit row codes (<= 65534 patterns, 65535 = row outside
+// the table) and the table read from global memory through L1 instead of shared memory — the
+// partitioned coarse operators, whose numbering next to a rank boundary multiplies the patterns.
+template <int EPI, bool BASE, int NT, int R, bool WIDE = false>
 __global__ void __launch_bounds__(NT, 1536 / NT)
 spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int *__restrict__ base, int npat,
          int nent, const int *__restrict__ tab_ptr, const int *__restrict__ tab_off,
          const double *__restrict__ tab_val, const double *__restrict__ x, EpiArgs ea)
 {
    extern __shared__ double s_mem[];
-   double *s_val = s_mem;
-   int    *s_off = reinterpret_cast<int *>(s_val + nent);
-   int    *s_ptr = s_off + nent;
+   const double *s_val;
+   const int    *s_off, *s_ptr;
    const int tid = threadIdx.x;
-   for (int k = tid; k < nent; k += NT) { s_val[k] = tab_val[k]; s_off[k] = tab_off[k]; }
-   for (int k = tid; k <= npat; k += NT) s_ptr[k] = tab_ptr[k];
-   __syncthreads();
+   if (WIDE) {
+      s_val = tab_val; s_off = tab_off; s_ptr = tab_ptr;
+   } else {
+      double *w_val = s_mem;
+      int    *w_off = reinterpret_cast<int *>(w_val + nent);
+      int    *w_ptr = w_off + nent;
+      for (int k = tid; k < nent; k += NT) { w_val[k] = tab_val[k]; w_off[k] = tab_off[k]; }
+      for (int k = tid; k <= npat; k += NT) w_ptr[k] = tab_ptr[k];
+      __syncthreads();
+      s_val = w_val; s_off = w_off; s_ptr = w_ptr;
+   }
    const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int r0 = tile * (NT * R) + tid;
@@ -69,8 +79,13 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
 #pragma unroll
       for (int j = 0; j < R; j++) {
          const int row = r0 + j * NT;
-         p[j] = row < nrows ? (int) pat[row] : 255;
-         if (p[j] == 255) p[j] = -1;           // past the end, or an irregular row (CSR pass)
+         if (WIDE) {
+            p[j] = row < nrows ? (int) reinterpret_cast<const unsigned short *>(pat)[row] : 65535;
+            if (p[j] == 65535) p[j] = -1;
+         } else {
+            p[j] = row < nrows ? (int) pat[row] : 255;
+            if (p[j] == 255) p[j] = -1;        // past the end, or an irregular row (CSR pass)
+         }
          if (BASE) bs[j] = row < nrows ? base[row] : 0;
          same = same && (p[j] == p[0]);
       }
@@ -114,13 +129,13 @@ static int pat_rows_per_thread()
    return r;
 }
 
-template <int EPI, bool BASE, int NT, int R>
+template <int EPI, bool BASE, int NT, int R, bool WIDE = false>
 static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
-   const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
+   const size_t smem = WIDE ? 0 : (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
    static bool opted = false;
-   if (!opted) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE, NT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   if (!opted && !WIDE) {
+      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE, NT, R, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kPatMaxEntries * 12 + (kPatMaxPatterns + 1) * 4 + 8));
       opted = true;
    }
@@ -131,13 +146,13 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    static int occ_blocks = 1;
    if (occ_smem != smem) {
       int nb = 0;
-      HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_pat<EPI, BASE, NT, R>, NT, smem));
+      HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_pat<EPI, BASE, NT, R, WIDE>, NT, smem));
       occ_blocks = nb > 0 ? nb : 1;
       occ_smem = smem;
    }
    int grid = 148 * occ_blocks;
    if (grid > ntiles) grid = ntiles;
-   HB_LAUNCH((spmv_pat<EPI, BASE, NT, R>), grid, NT, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
+   HB_LAUNCH((spmv_pat<EPI, BASE, NT, R, WIDE>), grid, NT, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
              M.pat_nent, M.pat_ptr, M.pat_off, M.pat_val, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
@@ -146,6 +161,14 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 template <int EPI>
 static int pat_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
+   if (M.pat_wide) {
+      // 16-bit codes, table in global memory (no shared-memory limit on the block size)
+      if (M.pat_base) {
+         return M.avg_row_nnz < 8.0 ? pat_launch_t<EPI, true, 256, 4, true>(M, x, ea, st)
+                                    : pat_launch_t<EPI, true, 256, 1, true>(M, x, ea, st);
+      }
+      return pat_launch_t<EPI, false, 256, 4, true>(M, x, ea, st);
+   }
    const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
    // big tables leave room for few blocks per SM: use larger ones
    const bool big = smem > 40 * 1024;
@@ -187,6 +210,7 @@ int dcsr_free_pat(DCsr &M)
    if (M.pat_irr) cudaFree(M.pat_irr);
    M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr; M.pat_irr = nullptr;
    M.pat_nirr = 0;
+   M.pat_wide = false;
    M.has_pat = false;
    return 0;
 }
@@ -199,8 +223,12 @@ int dcsr_free_pat(DCsr &M)
 // swept by the CSR vector kernel over a row list (pat_irr).  The block qualifies when the table
 // covers at least 70% of the rows.  Irregular blocks leave after their first 64K rows.
 // Pure host code (no CUDA call): also reachable through hb200_host_pattern_analyze for CPU tests.
-int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out)
+int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out, bool wide)
 {
+   // narrow: 1-byte codes, table in shared memory; wide: 2-byte codes, table in global memory
+   const int max_pat = wide ? 65534 : kPatMaxPatterns - 1;
+   const int max_ent = wide ? (1 << 20) : kPatMaxEntries;
+   const int kMaxCand = wide ? (1 << 18) : 16384;
    out = PatHost();
    const long long nnz = n > 0 ? hi[n] : 0;
    if (n < 1024 || nnz < 2LL * n) return 0;          // tiny or nearly empty (offd) blocks: nothing to win
@@ -213,7 +241,6 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
    }
    auto base_of = [&](int r) -> int { return square ? r : basev[r]; };
    // candidate patterns, each known by a representative row
-   constexpr int kMaxCand = 16384;
    std::vector<int> rep;
    std::vector<long long> count;
    std::vector<int> rid((size_t) n, -1);
@@ -267,12 +294,13 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
    for (int c : order) all_entries += hi[rep[c] + 1] - hi[rep[c]];
    // a fully regular block keeps every pattern, rare ones included; otherwise a pattern has to
    // earn its table slot (shared memory per block) with a few rows
-   const bool all_fit = ((int) rep.size() < kPatMaxPatterns && all_entries <= kPatMaxEntries && misses == 0);
-   const long long min_count = all_fit ? 1 : 8;
+   const bool all_fit = ((int) rep.size() <= max_pat && all_entries <= max_ent && misses == 0);
+   // (wide: a one-off row in the table is a 1-thread CSR row; the vector kernel sweeps those better)
+   const long long min_count = wide ? 4 : (all_fit ? 1 : 8);
    for (int c : order) {
       const int len = hi[rep[c] + 1] - hi[rep[c]];
-      if ((int) out.ptr.size() - 1 >= kPatMaxPatterns - 1 || count[c] < min_count) break;
-      if ((int) out.off.size() + len > kPatMaxEntries) continue;
+      if ((int) out.ptr.size() - 1 >= max_pat || count[c] < min_count) break;
+      if ((int) out.off.size() + len > max_ent) continue;
       code_of[c] = (int) out.ptr.size() - 1;
       for (int q = hi[rep[c]]; q < hi[rep[c] + 1]; q++) {
          out.off.push_back(hj[q] - base_of(rep[c]));
@@ -282,12 +310,14 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
       covered += count[c];
    }
    if ((double) covered < 0.7 * (double) n) { out = PatHost(); return 0; }
-   out.code.resize((size_t) n);
+   if (wide) out.code16.resize((size_t) n); else out.code.resize((size_t) n);
    for (int r = 0; r < n; r++) {
       const int c = rid[r] >= 0 ? code_of[rid[r]] : -1;
-      if (c >= 0) { out.code[r] = (unsigned char) c; }
-      else        { out.code[r] = 255; out.irr.push_back(r); out.irr_nnz += hi[r + 1] - hi[r]; }
+      if (c < 0) { out.irr.push_back(r); out.irr_nnz += hi[r + 1] - hi[r]; }
+      if (wide) out.code16[r] = (unsigned short) (c >= 0 ? c : 65535);
+      else      out.code[r] = (unsigned char) (c >= 0 ? c : 255);
    }
+   out.wide = wide;
    out.base.swap(basev);
    out.square = square;
    out.ok = true;
@@ -298,12 +328,19 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
 {
    if (getenv("HB200_NO_PAT")) return 0;
    PatHost ph;
-   HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph));
+   HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, false));
+   if (!ph.ok && getenv("HB200_PAT_WIDE")) HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, true));
    if (!ph.ok) return 0;
    const int n = M.nrows;
    const int npat = (int) ph.ptr.size() - 1, nent = (int) ph.off.size();
-   HB_CUDA(cudaMalloc(&M.pat_code, (size_t) n + 64));
-   HB_CUDA(cudaMemcpy(M.pat_code, ph.code.data(), (size_t) n, cudaMemcpyHostToDevice));
+   if (ph.wide) {
+      HB_CUDA(cudaMalloc(&M.pat_code, 2 * (size_t) n + 64));
+      HB_CUDA(cudaMemcpy(M.pat_code, ph.code16.data(), 2 * (size_t) n, cudaMemcpyHostToDevice));
+   } else {
+      HB_CUDA(cudaMalloc(&M.pat_code, (size_t) n + 64));
+      HB_CUDA(cudaMemcpy(M.pat_code, ph.code.data(), (size_t) n, cudaMemcpyHostToDevice));
+   }
+   M.pat_wide = ph.wide;
    HB_CUDA(cudaMalloc(&M.pat_ptr, sizeof(int) * ((size_t) npat + 1)));
    HB_CUDA(cudaMemcpy(M.pat_ptr, ph.ptr.data(), sizeof(int) * ((size_t) npat + 1), cudaMemcpyHostToDevice));
    HB_CUDA(cudaMalloc(&M.pat_off, sizeof(int) * ((size_t) nent + 1)));
@@ -338,7 +375,7 @@ extern "C" int hb200_host_pattern_analyze(int num_rows, int num_cols, const int 
               "hb200_host_pattern_analyze: null argument");
    HB_REQUIRE(row_ptr[num_rows] == 0 || (col_ind && values), HB200_ERROR_ARG, "hb200_host_pattern_analyze: null matrix arrays");
    PatHost ph;
-   HB_CHECK(pat_analyze_host(num_rows, num_cols, row_ptr, col_ind, values, ph));
+   HB_CHECK(pat_analyze_host(num_rows, num_cols, row_ptr, col_ind, values, ph, false));
    *num_patterns = 0;
    *num_irregular = 0;
    if (!ph.ok) return 0;
@@ -352,6 +389,40 @@ extern "C" int hb200_host_pattern_analyze(int num_rows, int num_cols, const int 
    if (pattern_ptr) memcpy(pattern_ptr, ph.ptr.data(), sizeof(int) * ((size_t) npat + 1));
    if (pattern_offset) memcpy(pattern_offset, ph.off.data(), sizeof(int) * ph.off.size());
    if (pattern_value) memcpy(pattern_value, ph.val.data(), sizeof(double) * ph.val.size());
+   if (irregular_rows && !ph.irr.empty()) memcpy(irregular_rows, ph.irr.data(), sizeof(int) * ph.irr.size());
+   return 0;
+}
+
+// the experimental wide variant of the analysis (HB200_PAT_WIDE=1): 16-bit codes, 65535 = row outside
+// the table; pattern_capacity = entries the caller's pattern_offset / pattern_value arrays hold
+extern "C" int hb200_host_pattern_analyze_wide(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                                               const double *values, unsigned short *row_code, int *row_base,
+                                               int *num_patterns, int *num_entries, int pattern_capacity,
+                                               int *pattern_ptr, int *pattern_offset, double *pattern_value,
+                                               int *num_irregular, int *irregular_rows)
+{
+   using namespace hb;
+   HB_REQUIRE(num_rows >= 0 && num_cols >= 0 && row_ptr && num_patterns && num_entries && num_irregular,
+              HB200_ERROR_ARG, "hb200_host_pattern_analyze_wide: null argument");
+   HB_REQUIRE(row_ptr[num_rows] == 0 || (col_ind && values), HB200_ERROR_ARG,
+              "hb200_host_pattern_analyze_wide: null matrix arrays");
+   PatHost ph;
+   HB_CHECK(pat_analyze_host(num_rows, num_cols, row_ptr, col_ind, values, ph, true));
+   *num_patterns = 0; *num_entries = 0; *num_irregular = 0;
+   if (!ph.ok) return 0;
+   const int npat = (int) ph.ptr.size() - 1;
+   *num_patterns = npat;
+   *num_entries = (int) ph.off.size();
+   *num_irregular = (int) ph.irr.size();
+   if (row_code) memcpy(row_code, ph.code16.data(), 2 * (size_t) num_rows);
+   if (row_base) {
+      for (int r = 0; r < num_rows; r++) row_base[r] = ph.square ? r : ph.base[r];
+   }
+   if (pattern_ptr) memcpy(pattern_ptr, ph.ptr.data(), sizeof(int) * ((size_t) npat + 1));
+   if ((int) ph.off.size() <= pattern_capacity) {
+      if (pattern_offset) memcpy(pattern_offset, ph.off.data(), sizeof(int) * ph.off.size());
+      if (pattern_value) memcpy(pattern_value, ph.val.data(), sizeof(double) * ph.val.size());
+   }
    if (irregular_rows && !ph.irr.empty()) memcpy(irregular_rows, ph.irr.data(), sizeof(int) * ph.irr.size());
    return 0;
 }

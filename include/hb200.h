@@ -142,6 +142,15 @@ int hb200_host_pattern_analyze(int num_rows, int num_cols, const int *row_ptr, c
                                const double *values, unsigned char *row_code, int *row_base,
                                int *num_patterns, int *pattern_ptr, int *pattern_offset,
                                double *pattern_value, int *num_irregular, int *irregular_rows);
+/* Experimental wide variant of the same analysis (enabled in the upload by HB200_PAT_WIDE=1 for
+ * blocks the 1-byte format rejects): 16-bit row codes (65535 = row outside the table), up to 65534
+ * patterns and 2^20 table entries read from global memory; patterns need >= 4 rows.  The table is
+ * copied out only when it fits pattern_capacity entries (*num_entries says how many it has). */
+int hb200_host_pattern_analyze_wide(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
+                                    const double *values, unsigned short *row_code, int *row_base,
+                                    int *num_patterns, int *num_entries, int pattern_capacity,
+                                    int *pattern_ptr, int *pattern_offset, double *pattern_value,
+                                    int *num_irregular, int *irregular_rows);
 /* The stored transpose that restriction runs on (hypre_ParCSRMatrixMatvecT with keepTranspose,
  * src/parcsr_mv/par_csr_matvec.c:298-299, 430-468): entries of each output row in ascending
  * source-row order = the order hypre_CSRMatrixMatvecT accumulates in (src/seq_mv/csr_matvec.c:1095-1110).

@@ -30,6 +30,26 @@ def analyze(n, ncols, ai, aj, aa):
             "ptr": ptr[:npat.value + 1], "off": off, "val": val, "irr": irr[:nirr.value]}
 
 
+def analyze_wide(n, ncols, ai, aj, aa, cap=1 << 20):
+    from hypre_b200._lib import lib, check
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    aa = np.ascontiguousarray(aa, dtype=np.float64)
+    code = np.zeros(max(n, 1), np.uint16)
+    base = np.zeros(max(n, 1), np.int32)
+    ptr = np.zeros(65536, np.int32)
+    off = np.zeros(cap, np.int32)
+    val = np.zeros(cap, np.float64)
+    irr = np.zeros(max(n, 1), np.int32)
+    npat, nent, nirr = C.c_int(0), C.c_int(0), C.c_int(0)
+    check(lib.hb200_host_pattern_analyze_wide(n, ncols, ai.ctypes.data, aj.ctypes.data, aa.ctypes.data,
+                                              code.ctypes.data, base.ctypes.data, C.byref(npat), C.byref(nent), cap,
+                                              ptr.ctypes.data, off.ctypes.data, val.ctypes.data, C.byref(nirr),
+                                              irr.ctypes.data))
+    return {"npat": npat.value, "nent": nent.value, "nirr": nirr.value, "code": code[:n], "base": base[:n],
+            "ptr": ptr[:npat.value + 1], "off": off, "val": val, "irr": irr[:nirr.value], "none": 65535}
+
+
 def assert_lossless(n, ai, aj, aa, r):
     """every row with a code decodes to its CSR entries, in CSR order, bit for bit"""
     ai = np.asarray(ai)
@@ -39,7 +59,7 @@ def assert_lossless(n, ai, aj, aa, r):
     assert len(irr) == r["nirr"]
     for row in range(n):
         c = int(r["code"][row])
-        if c == 255:
+        if c == r.get("none", 255):
             assert row in irr
             continue
         assert row not in irr and c < r["npat"]
@@ -264,3 +284,24 @@ def test_gs_wavefront_schedule_reproduces_the_sequential_sweep(forward):
         for i, v in new.items():
             u[i] = v
     assert np.array_equal(u, uref)
+
+
+def test_wide_variant_takes_blocks_the_one_byte_format_rejects():
+    """half of the rows perturbed in groups of 5 equal rows: ~400 patterns of >= 4 rows, too many for
+    1-byte codes at < 70 % coverage, fine for 16-bit codes; one-off rows go to the irregular list"""
+    n, ai, aj, aa = stencil7(16, 16, 16)
+    rng = np.random.default_rng(17)
+    aa = aa.copy()
+    interior = [r for r in range(n) if ai[r + 1] - ai[r] == 7]
+    pick = rng.choice(interior, size=2000, replace=False)
+    for g in range(0, 2000, 5):                       # groups of 5 rows share one new pattern
+        scale = 1.0 + rng.random(7)
+        for r in pick[g:g + 5]:
+            aa[ai[r]:ai[r + 1]] *= scale
+    singles = [r for r in interior if r not in set(pick.tolist())][:50]
+    for r in singles:                                 # and 50 one-off rows
+        aa[ai[r]:ai[r + 1]] *= 1.0 + rng.random(7)
+    assert analyze(n, n, ai, aj, aa)["npat"] == 0
+    w = analyze_wide(n, n, ai, aj, aa)
+    assert w["npat"] >= 400 and set(singles) <= set(w["irr"].tolist())
+    assert_lossless(n, ai, aj, aa, w)

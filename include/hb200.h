@@ -21,7 +21,10 @@
  *   - One process drives one GPU (src/utilities/device_utils.c:2764 hypre_bind_device_id);
  *     all ranks of a job call collectively, exactly like the MPI reference.
  *   - There is NO CPU fallback: every entry point fails with flag 1 when no sm_100 device
- *     or no CUDA runtime is usable.
+ *     or no CUDA runtime is usable.  The only calls that work without a GPU are the
+ *     hb200_host_* helpers: the host halves of the upload (format analysis, stored transpose,
+ *     GS schedule), exposed so that they can be checked on a CPU-only machine; they do none of
+ *     the solve-path arithmetic.
  */
 #ifndef HB200_H
 #define HB200_H

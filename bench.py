@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hb200", choices=["hb200", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="brick edge per GPU")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="brick edge per GPU")
     ap.add_argument("--problem", default="27pt", choices=["27pt", "laplacian", "vardifconv"])
     ap.add_argument("--solver", default="pcg", choices=["pcg", "gmres"])
     ap.add_argument("--tol", type=float, default=1e-8)

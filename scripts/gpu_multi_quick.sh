@@ -1,0 +1,20 @@
+#!/bin/bash
+# N-GPU quick check at small size (an N-GPU call is charged N x the box time: keep it under a minute).
+# usage: gpurun --gpus N --timeout 300 -- 'bash scripts/gpu_multi_quick.sh tag N [size]'
+# Runs the bench at 64^3 rows per GPU with both halo transports under HB200_TRACE=1 and a short
+# timeout each, so that a rank lost in a collective shows its last step instead of holding the box.
+TAG=${1:-mq}
+NG=${2:-8}
+SZ=${3:-64}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONPATH=$PWD
+for halo in nccl peer; do
+  HB200_TRACE=1 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
+    --master-port 29521 bench.py --gpus $NG --size $SZ --steps 2 --warmup 2 --no-cpu-baseline --halo $halo \
+    --stage-timeout 60 > $OUT/$halo.log 2>&1
+  echo "== $halo rc=$?"
+  grep '^{' $OUT/$halo.log | tail -1 | cut -c1-330
+  grep "no progress\|Error\|error flag" $OUT/$halo.log | head -5
+  grep "hb200 trace rank 0\]\|bench rank 0\]" $OUT/$halo.log | tail -6
+done

@@ -245,6 +245,9 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    if (!amg->use_graph || g_timers_on || (c.nranks > 1 && c.halo_mode != 1)) {
       return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    }
+#ifdef HB200_EMU
+   return cycle_body(amg, f_dev, u_dev, u_all_zeros);   // the host emulation has no graphs
+#endif
    // CUDA-graph path: the topology of a cycle is fixed by the hierarchy, so capture once per
    // (f, u, zero flag) and replay; removes the launch latency of the ~60 small coarse-level
    // kernels.

@@ -108,11 +108,25 @@ struct PeerPlan;
 Ctx &ctx();
 int  require_ready();
 
+#ifndef HB200_EMU
 #define HB_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
    do {                                                                                  \
       kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
       hb::ctx().launches++;                                                              \
    } while (0)
+// dynamic shared memory of a kernel
+#define HB_DYN_SHARED(type, name) extern __shared__ type name[]
+#else
+// host emulation of the kernels for CPU-only logic tests (oracle/emu, test infrastructure)
+#define HB_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
+   do {                                                                                  \
+      (void) (stream);                                                                   \
+      hb_emu::launch((unsigned) (grid), (unsigned) (block), (size_t) (smem),             \
+                     [&]() { kern(__VA_ARGS__); });                                      \
+      hb::ctx().launches++;                                                              \
+   } while (0)
+#define HB_DYN_SHARED(type, name) type *name = reinterpret_cast<type *>(hb_emu::dyn_smem())
+#endif
 
 #define HB_LAUNCH_CHECK()                                                                \
    do {                                                                                  \

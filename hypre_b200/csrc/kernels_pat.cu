@@ -55,7 +55,7 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
          int nent, const int *__restrict__ tab_ptr, const int *__restrict__ tab_off,
          const double *__restrict__ tab_val, const double *__restrict__ x, EpiArgs ea)
 {
-   extern __shared__ double s_mem[];
+   HB_DYN_SHARED(double, s_mem);
    const double *s_val;
    const int    *s_off, *s_ptr;
    const int tid = threadIdx.x;

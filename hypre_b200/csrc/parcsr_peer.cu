@@ -146,12 +146,20 @@ int arena_alloc(size_t bytes, size_t *offset)
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
    unsigned long long v;
+#ifndef HB200_EMU
    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else
+   v = *(const volatile unsigned long long *) p;
+#endif
    return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
+#ifndef HB200_EMU
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+   *(volatile unsigned long long *) p = v;
+#endif
 }
 
 constexpr int kHaloBlock = 512;

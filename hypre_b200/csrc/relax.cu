@@ -198,7 +198,7 @@ __global__ void ge_solve_kernel(int n, const double *__restrict__ LfT, const dou
                                 const double *__restrict__ Udiag, const double *__restrict__ b,
                                 double *__restrict__ u_local, int first_row, int num_local)
 {
-   extern __shared__ double x[];
+   HB_DYN_SHARED(double, x);
    const int tid = threadIdx.x;
    for (int j = tid; j < n; j += blockDim.x) x[j] = b[j];
    __syncthreads();

@@ -1,0 +1,159 @@
+// oracle/emu/cuda_runtime.h — TEST INFRASTRUCTURE, not product code.
+//
+// A host-only stand-in for the slice of the CUDA runtime and device language that
+// hypre_b200/csrc/*.cu uses, so that the very same kernel sources compile with g++ into
+// oracle/_ref/libhb200_emu.so and their LOGIC (indexing, format decoding, epilogues, reductions,
+// control flow of the cycle and the Krylov drivers) can be checked on a machine without a GPU.
+// It says nothing about performance and is never loaded by the hypre_b200 package: only tests
+// (tests/test_emu_kernels.py) build and load it.
+//
+// Execution model: one kernel launch runs its blocks one after the other; the threads of a block
+// are fibers (ucontext) on the calling OS thread, switched only at the points where CUDA threads
+// can observe each other: __syncthreads() and the warp shuffles.  Everything is deterministic.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <chrono>
+#include <functional>
+
+#ifndef HB200_EMU
+#error "oracle/emu/cuda_runtime.h is the emulation header: compile with -DHB200_EMU"
+#endif
+
+// ---------------------------------------------------------------------------------------
+// language
+// ---------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+
+struct hb_emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+
+namespace hb_emu {
+struct ThreadCtx { hb_emu_dim3 tid, bid, bdim, gdim; };
+extern ThreadCtx *g_cur;             // the running fiber's coordinates
+void  syncthreads();
+unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int width);
+void *dyn_smem();
+void  launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
+long long launches();
+}  // namespace hb_emu
+
+#define threadIdx (hb_emu::g_cur->tid)
+#define blockIdx  (hb_emu::g_cur->bid)
+#define blockDim  (hb_emu::g_cur->bdim)
+#define gridDim   (hb_emu::g_cur->gdim)
+
+inline void __syncthreads() { hb_emu::syncthreads(); }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, unsigned delta, int width = 32)
+{
+   static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+   unsigned long long bits = 0;
+   memcpy(&bits, &v, sizeof(T));
+   bits = hb_emu::shfl_down_bits(bits, delta, width);
+   T out;
+   memcpy(&out, &bits, sizeof(T));
+   return out;
+}
+
+template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
+template <class T> inline void __stcs(T *p, T v) { *p = v; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline unsigned int atomicInc(unsigned int *p, unsigned int val)
+{
+   const unsigned int old = *p;
+   *p = (old >= val) ? 0u : old + 1u;
+   return old;
+}
+using std::max;
+using std::min;
+
+// ---------------------------------------------------------------------------------------
+// runtime API (host memory stands in for device memory; streams and events are ordinals)
+// ---------------------------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorNotSupported = 801, cudaErrorInvalidValue = 1 };
+typedef struct hb_emu_stream *cudaStream_t;
+typedef struct hb_emu_event { double t_ms; } *cudaEvent_t;
+typedef struct hb_emu_graph *cudaGraph_t;
+typedef struct hb_emu_graph_exec *cudaGraphExec_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; size_t totalGlobalMem; };
+
+inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+   memset(p, 0, sizeof(*p));
+   snprintf(p->name, sizeof(p->name), "emulated sm_100 (host fibers)");
+   p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
+   return cudaSuccess;
+}
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t bytes)
+{
+   *p = (T *) malloc(bytes ? bytes : 8);
+   return *p ? cudaSuccess : 2;
+}
+template <class T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t) malloc(8); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+inline double hb_emu_now_ms()
+{
+   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t) malloc(sizeof(hb_emu_event)); (*e)->t_ms = 0; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t_ms = hb_emu_now_ms(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
+// no graphs and no peer mapping in the emulation: callers take their eager / single-rank paths
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long = 0) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int threads, size_t)
+{
+   *n = std::max(1, 1536 / std::max(threads, 1));
+   return cudaSuccess;
+}

@@ -1,0 +1,165 @@
+// oracle/emu/emu_runtime.cpp — TEST INFRASTRUCTURE: the fiber scheduler behind cuda_runtime.h.
+//
+// launch(grid, block, smem, body): for every block, `block` fibers run `body` (the kernel call
+// with its arguments bound).  A fiber runs until it finishes or reaches __syncthreads() / a warp
+// shuffle, where it waits for the other threads of its block / warp exactly as on the device;
+// threads that have left the kernel count as arrived.  One OS thread, round-robin, deterministic.
+#include "cuda_runtime.h"
+#include <ucontext.h>
+#include <vector>
+
+namespace hb_emu {
+
+ThreadCtx *g_cur = nullptr;
+
+namespace {
+
+constexpr size_t kStack = 64 * 1024;
+constexpr int    kMaxThreads = 1024;
+
+struct Fiber {
+   ucontext_t ctx;
+   ThreadCtx  tc;
+   bool       done = false;
+};
+
+struct Block {
+   int nthreads = 0, live = 0;
+   // block barrier
+   unsigned bar_gen = 0;
+   int      bar_arrived = 0;
+   // warp exchange (two barriers per shuffle: publish, then read)
+   unsigned wgen[kMaxThreads / 32];
+   int      warrived[kMaxThreads / 32];
+   int      wlive[kMaxThreads / 32];
+   unsigned long long wslot[kMaxThreads / 32][32];
+};
+
+ucontext_t               g_sched;
+std::vector<Fiber>       g_fibers;
+std::vector<char>        g_stacks;
+Block                    g_blk;
+int                      g_running = -1;
+const std::function<void()> *g_body = nullptr;
+std::vector<char>        g_dyn;
+long long                g_launches = 0;
+unsigned long long       g_events = 0;      // barrier releases + thread exits: progress of a block
+
+void yield_to_scheduler()
+{
+   Fiber &f = g_fibers[(size_t) g_running];
+   swapcontext(&f.ctx, &g_sched);
+}
+
+void retire_thread(int t)
+{
+   // a thread that leaves the kernel counts as arrived at every later barrier
+   Block &b = g_blk;
+   b.live--;
+   g_events++;
+   if (b.live > 0 && b.bar_arrived == b.live) { b.bar_arrived = 0; b.bar_gen++; }
+   const int w = t / 32;
+   b.wlive[w]--;
+   if (b.wlive[w] > 0 && b.warrived[w] == b.wlive[w]) { b.warrived[w] = 0; b.wgen[w]++; }
+}
+
+void fiber_entry()
+{
+   (*g_body)();
+   const int t = g_running;
+   g_fibers[(size_t) t].done = true;
+   retire_thread(t);
+   yield_to_scheduler();
+}
+
+void warp_barrier(int w)
+{
+   Block &b = g_blk;
+   const unsigned gen = b.wgen[w];
+   b.warrived[w]++;
+   if (b.warrived[w] == b.wlive[w]) { b.warrived[w] = 0; b.wgen[w]++; g_events++; return; }
+   while (b.wgen[w] == gen) yield_to_scheduler();
+}
+
+}  // namespace
+
+void syncthreads()
+{
+   Block &b = g_blk;
+   const unsigned gen = b.bar_gen;
+   b.bar_arrived++;
+   if (b.bar_arrived == b.live) { b.bar_arrived = 0; b.bar_gen++; g_events++; return; }
+   while (b.bar_gen == gen) yield_to_scheduler();
+}
+
+unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int width)
+{
+   const int t = g_running, w = t / 32, lane = t % 32;
+   g_blk.wslot[w][lane] = bits;
+   warp_barrier(w);
+   // lanes of one `width`-wide segment exchange among themselves; out of range -> own value
+   const int seg_end = (lane / width) * width + width;
+   const int src = lane + (int) delta;
+   const unsigned long long out = (src < seg_end && src < 32) ? g_blk.wslot[w][src] : bits;
+   warp_barrier(w);
+   return out;
+}
+
+void *dyn_smem() { return g_dyn.data(); }
+long long launches() { return g_launches; }
+
+void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body)
+{
+   if (grid == 0 || block == 0) return;
+   if (block > (unsigned) kMaxThreads || (block % 32) != 0) {
+      fprintf(stderr, "hb_emu: unsupported block size %u\n", block);
+      abort();
+   }
+   if (g_running >= 0) {
+      fprintf(stderr, "hb_emu: nested kernel launch\n");
+      abort();
+   }
+   g_launches++;
+   if (g_fibers.size() < block) g_fibers.resize(block);
+   if (g_stacks.size() < (size_t) block * kStack) g_stacks.resize((size_t) block * kStack);
+   if (g_dyn.size() < smem + 64) g_dyn.resize(smem + 64);
+   g_body = &body;
+   for (unsigned bid = 0; bid < grid; bid++) {
+      Block &b = g_blk;
+      b.nthreads = b.live = (int) block;
+      b.bar_gen = 0; b.bar_arrived = 0;
+      for (unsigned w = 0; w < block / 32; w++) { b.wgen[w] = 0; b.warrived[w] = 0; b.wlive[w] = 32; }
+      for (unsigned t = 0; t < block; t++) {
+         Fiber &f = g_fibers[t];
+         f.done = false;
+         f.tc.tid.x = t; f.tc.bid.x = bid; f.tc.bdim.x = block; f.tc.gdim.x = grid;
+         getcontext(&f.ctx);
+         f.ctx.uc_stack.ss_sp = g_stacks.data() + (size_t) t * kStack;
+         f.ctx.uc_stack.ss_size = kStack;
+         f.ctx.uc_link = &g_sched;
+         makecontext(&f.ctx, (void (*)()) fiber_entry, 0);
+      }
+      int remaining = (int) block;
+      while (remaining > 0) {
+         const unsigned long long before = g_events;
+         for (unsigned t = 0; t < block; t++) {
+            Fiber &f = g_fibers[t];
+            if (f.done) continue;
+            g_running = (int) t;
+            g_cur = &f.tc;
+            swapcontext(&g_sched, &f.ctx);
+            if (f.done) remaining--;
+         }
+         if (remaining > 0 && g_events == before) {
+            fprintf(stderr, "hb_emu: block %u deadlocked (%d threads waiting at a barrier nobody else reaches)\n", bid,
+                    remaining);
+            abort();
+         }
+      }
+      g_running = -1;
+      g_cur = nullptr;
+   }
+   g_body = nullptr;
+}
+
+}  // namespace hb_emu

@@ -8,6 +8,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+if os.environ.get("HB200_EMU_TEST"):
+    # child process of tests/test_emu_kernels.py: the gpu-marked parity tests against the host
+    # emulation of the kernels (tests/emu_env.py); never set on a GPU box
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_env
+    emu_env.activate()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

@@ -1,0 +1,49 @@
+"""The `-m gpu` parity tests, run on the CPU against a host emulation of the kernels.
+
+oracle/_ref/libhb200_emu.so is the product's own hypre_b200/csrc/*.cu compiled by g++ against
+oracle/emu/cuda_runtime.h (one fiber per CUDA thread, switched at __syncthreads and the warp
+shuffles).  It checks the LOGIC of every kernel and of the host code around it — formats,
+epilogues, reductions, wavefront GS, cycle, PCG, GMRES — against the compiled reference on a
+machine without a GPU; it says nothing about performance and the product never loads it.  The
+real parity gate stays `pytest -m gpu` on a B200."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "oracle", "_ref", "libhb200_emu.so")
+BRIDGE = os.path.join(ROOT, "oracle", "_ref", "libref_bridge.so")
+
+
+def build_emu():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert os.path.exists(EMU)
+
+
+def run_child(extra_env, *pytest_args, timeout=1500):
+    env = dict(os.environ, HB200_EMU_TEST="1", **extra_env)
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", *pytest_args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+
+
+def test_gpu_parity_suite_on_the_host_emulation():
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    build_emu()
+    # everything that runs on one device except the tests that exec the real shim binary
+    r = run_child({}, os.path.join("tests", "test_gpu_parity.py"), "-m", "gpu", "-n", "6",
+                  "-k", "not ij_dropin and not multi_gpu")
+    tail = r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+def test_wide_pattern_format_on_the_host_emulation():
+    """the experimental 16-bit-code / global-table variant of the row-pattern kernel (HB200_PAT_WIDE=1):
+    a block the 1-byte format rejects runs through spmv_pat<..., WIDE> and matches the row sums"""
+    build_emu()
+    r = run_child({"HB200_PAT_WIDE": "1"}, os.path.join("tests", "emu_wide_case.py"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

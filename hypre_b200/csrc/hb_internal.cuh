@@ -117,7 +117,7 @@ int  require_ready();
 // dynamic shared memory of a kernel
 #define HB_DYN_SHARED(type, name) extern __shared__ type name[]
 #else
-// host emulation of the kernels for CPU-only logic tests (oracle/emu, test infrastructure)
+// -DHB200_EMU: g++ build of these sources for the CPU-only logic tests (never the product build)
 #define HB_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
    do {                                                                                  \
       (void) (stream);                                                                   \

@@ -46,7 +46,7 @@ __device__ __forceinline__ void pat_one_row(const EpiArgs &ea, const double *__r
 // column of entry k of a row = base + off[k]; base = the row itself for square blocks (BASE =
 // false), else base[row] (the row's first column: interpolation and its stored transpose).
 // NT threads per block, R rows per thread.
-// WIDE (experimental, HB200_PAT_WIDE=1): 16-bit row codes (<= 65534 patterns, 65535 = row outside
+// WIDE (HB200_PAT_WIDE=1, default on N > 1): 16-bit row codes (<= 65534 patterns, 65535 = row outside
 // the table) and the table read from global memory through L1 instead of shared memory — the
 // partitioned coarse operators, whose numbering next to a rank boundary multiplies the patterns.
 template <int EPI, bool BASE, int NT, int R, bool WIDE = false>
@@ -329,7 +329,10 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
    if (getenv("HB200_NO_PAT")) return 0;
    PatHost ph;
    HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, false));
-   if (!ph.ok && getenv("HB200_PAT_WIDE")) HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, true));
+   // the wide variant: on request, and by default on a partitioned problem, where the coarse
+   // operators lose the regular numbering next to the rank boundary
+   const bool try_wide = getenv("HB200_PAT_WIDE") || (ctx().nranks > 1 && !getenv("HB200_NO_PAT_WIDE"));
+   if (!ph.ok && try_wide) HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, true));
    if (!ph.ok) return 0;
    const int n = M.nrows;
    const int npat = (int) ph.ptr.size() - 1, nent = (int) ph.off.size();

@@ -47,13 +47,18 @@ struct hb200_amg {
    hb::GEData ge;
    bool has_ge = false;
    bool use_graph = false;
+   // fused-dot request of the caller (Krylov preconditioner use): <u, f> of the cycle's result in
+   // this scalar slot, produced by the last level-0 sweep when it can; dot_fused reports it
+   int  dot_req_slot = -1;
+   bool dot_fused = false;
    // graph cache: one executable graph per (f, u, zero flag) the cycle has been called with
    struct GraphEntry {
       const double *f; double *u; int zero;
       cudaGraphExec_t exec; long long launches;
+      int dot_slot; bool dot_fused;
    };
    std::vector<GraphEntry> graphs;
-   long long cycles_run = 0;
+   long long cycles_run = 0, cycles_run_dot = 0;
 };
 
 namespace hb {
@@ -98,7 +103,7 @@ static int level0_swaps(const hb200_amg *amg, bool zero_guess)
 }
 
 static int do_relax(hb200_amg *amg, int level, int relax_type, int relax_order, int cycle_param,
-                    bool force_no_cf)
+                    bool force_no_cf, bool last_of_cycle = false)
 {
    hb200_amg_level &L = amg->lev[level];
    Ctx &c = ctx();
@@ -133,6 +138,10 @@ static int do_relax(hb200_amg *amg, int level, int relax_type, int relax_order, 
          double *other = (L.u_cur == L.Ualt) ? L.U : L.Ualt;
          bool shortcut = false;
          const bool form7 = (relax_type == 7) || (relax_type == 18 && pts[q] == 0);
+         if (last_of_cycle && q == npts - 1 && amg->dot_req_slot >= 0) {
+            // the sweep that writes the cycle's result: ask it for <u, f> as well
+            c.dot_req_armed = true; c.dot_req_w = f; c.dot_req_slot = amg->dot_req_slot;
+         }
          if (L.u_zero && form7) {
             // element-wise zero-guess sweep writes straight into the current buffer
             HB_CHECK(relax_jacobi_oop(L.A, f, L.cf, relax_type, pts[q], L.relax_weight, L.l1,
@@ -142,6 +151,7 @@ static int do_relax(hb200_amg *amg, int level, int relax_type, int relax_order, 
                                       L.u_cur, other, L.u_zero, &shortcut));
             L.u_cur = other;
          }
+         if (last_of_cycle && q == npts - 1) amg->dot_fused = c.last_dot_fused;
       } else if (relax_is_gs(relax_type)) {
          if (L.u_zero) HB_CHECK(vec_set(L.u_cur, 0.0, (size_t) L.n, c.s_comp));
          HB_CHECK(relax_hybrid_gs(L.A, f, L.cf, relax_type, pts[q], L.relax_weight, L.omega, L.l1,
@@ -158,6 +168,7 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
 {
    Ctx &c = ctx();
    const int nl = amg->num_levels;
+   amg->dot_fused = false;
    hb200_amg_level &L0 = amg->lev[0];
    // level-0 aliases (par_amg_solve.c:108-110)
    L0.F = (double *) f_dev;
@@ -189,7 +200,9 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
          one_level = true;
       }
       for (int j = 0; j < num_sweep; j++) {
-         HB_CHECK(do_relax(amg, level, relax_type, amg->relax_order, cycle_param, one_level));
+         // the cycle ends with the post-smoothing of level 0 (cycle_param 2): its last sweep writes the result
+         const bool last = (nl > 1 && level == 0 && cycle_param == 2 && j == num_sweep - 1);
+         HB_CHECK(do_relax(amg, level, relax_type, amg->relax_order, cycle_param, one_level, last));
       }
       --lev_counter[level];
       if (lev_counter[level] >= 0 && level != nl - 1) {
@@ -252,15 +265,19 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    // (f, u, zero flag) and replay; removes the launch latency of the ~60 small coarse-level
    // kernels.
    for (auto &g : amg->graphs) {
-      if (g.f == f_dev && g.u == u_dev && g.zero == (int) u_all_zeros) {
+      if (g.f == f_dev && g.u == u_dev && g.zero == (int) u_all_zeros && g.dot_slot == amg->dot_req_slot) {
          HB_CUDA(cudaGraphLaunch(g.exec, c.s_comp));
          c.launches += g.launches;
+         amg->dot_fused = g.dot_fused;
          return 0;
       }
    }
    // the first cycle of a hierarchy runs eagerly: it builds the lazily allocated scratch
    // (Chebyshev work vectors, GS wavefront schedules), which cannot happen under capture
-   if (amg->cycles_run++ == 0) return cycle_body(amg, f_dev, u_dev, u_all_zeros);
+   // (the same holds for the first cycle that carries a fused-dot request: its kernel variants bind
+   // their scratch pointers and launch attributes on first use)
+   long long &runs = amg->dot_req_slot >= 0 ? amg->cycles_run_dot : amg->cycles_run;
+   if (runs++ == 0) return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    for (int l = 0; l + 1 < amg->num_levels; l++) HB_CHECK(parcsr_ensure_T(amg->lev[l].P));
    if (amg->graphs.size() >= 8) {
       cudaGraphExecDestroy(amg->graphs.front().exec);
@@ -278,6 +295,7 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    if (e != cudaSuccess) return set_error(HB200_ERROR_GENERIC, "graph capture failed: %s", cudaGetErrorString(e));
    hb200_amg::GraphEntry ge;
    ge.f = f_dev; ge.u = u_dev; ge.zero = (int) u_all_zeros;
+   ge.dot_slot = amg->dot_req_slot; ge.dot_fused = amg->dot_fused;
    ge.launches = c.launches - before;
    c.launches = before;
    e = cudaGraphInstantiate(&ge.exec, graph, 0);
@@ -342,6 +360,9 @@ int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool 
    if (rel_resid_norm) *rel_resid_norm = relative_resid;
    return flag;
 }
+
+void amg_set_dot_request(hb200_amg *amg, int slot) { if (amg) amg->dot_req_slot = slot; }
+bool amg_dot_fused(const hb200_amg *amg) { return amg && amg->dot_fused; }
 
 }  // namespace hb
 

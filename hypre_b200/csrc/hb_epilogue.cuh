@@ -59,6 +59,29 @@ __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum
    }
 }
 
+// The same arithmetic as epi_apply<EPI_AXPBY / EPI_JACOBI7>, returning the value it stored: used by the
+// kernels that fuse a dot product with the vector they write (kernels_pat.cu, DOT variants).
+template <int EPI>
+__device__ __forceinline__ double epi_apply_ret(const EpiArgs &ea, int row, double sum)
+{
+   double v;
+   if (EPI == EPI_AXPBY) {
+      if (ea.beta == 0.0) { v = ea.alpha * sum; }
+      else                { v = ea.beta * __ldcs(ea.b + row) + ea.alpha * sum; }
+   } else {   // EPI_JACOBI7
+      const double uo = ea.u[row];
+      if (ea.cf == nullptr || __ldcs(ea.cf + row) == ea.relax_points) {
+         const double f = __ldcs(ea.b + row);
+         const double vt = (ea.w == 1.0) ? (f - sum) : (ea.w * f - ea.w * sum);
+         v = uo + vt / __ldcs(ea.d + row);
+      } else {
+         v = uo;
+      }
+   }
+   __stcs(ea.y + row, v);
+   return v;
+}
+
 template <int EPI>
 __device__ __forceinline__ constexpr bool epi_needs_diag()
 {

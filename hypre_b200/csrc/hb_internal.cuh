@@ -75,6 +75,13 @@ struct Ctx {
    double       *h_scalars  = nullptr;   // pinned mirror
    long long     launches = 0;
    bool          capturing = false;      // inside CUDA graph capture
+   // fused-dot request: the caller arms it right before the operation whose LAST SpMV kernel should
+   // also produce <y, dot_req_w> in scalar slot dot_req_slot; the launch site consumes it when the
+   // format supports the fused epilogue (last_dot_fused = true), else the caller runs dot_kernel
+   bool          dot_req_armed = false;
+   const double *dot_req_w = nullptr;
+   int           dot_req_slot = -1;
+   bool          last_dot_fused = false;
    // NVLink peer arena (halo mode 1): one IPC-shared allocation per rank; halo receive buffers
    // and arrival / consumed flags of every matrix are carved out of it, peers write into it directly
    char         *arena = nullptr;
@@ -247,6 +254,8 @@ int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
                 bool use_rownnz, cudaStream_t st);
 int spmv_sell_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
+bool spmv_can_fuse_dot(const DCsr &M, int epi_kind);   // row-pattern format, no rows outside the table
+bool fused_dots_enabled();                              // HB200_FUSED_DOTS=1 turns them on
 
 // ---------------------------------------------------------------------------------------
 // BLAS-1 (kernels_blas1.cu).  Scalars live in ctx().d_scalars[slot]; dots are two-stage,

@@ -43,13 +43,61 @@ __device__ __forceinline__ void pat_one_row(const EpiArgs &ea, const double *__r
    epi_apply<EPI>(ea, row, s, e > b ? s_val[b] : 0.0);
 }
 
+// ---- fused dot (DOT variants): <y, w> of the vector the kernel writes, two-stage and in a fixed
+// order (bitwise reproducible): per thread over its rows, per block by warp shuffles, the last
+// block to arrive adds the block partials.  Region 3 of the reduction scratch of the context.
+__device__ double       *g_pd_partials = nullptr;
+__device__ unsigned int *g_pd_counter = nullptr;
+__device__ double       *g_pd_scalars = nullptr;
+
+template <int NT>
+__device__ __forceinline__ void pat_dot_finish(double acc, int slot)
+{
+   __shared__ double sm[NT / 32];
+   __shared__ bool   is_last;
+   double *partials = g_pd_partials + 3 * (size_t) kRedBlocksMax;
+   unsigned int *counter = g_pd_counter + 3;
+   const int tid = threadIdx.x;
+   double s = acc;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+   if ((tid & 31) == 0) sm[tid >> 5] = s;
+   __syncthreads();
+   if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; w++) t += sm[w];
+      partials[blockIdx.x] = t;
+      __threadfence();
+      const unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+      is_last = (ticket == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (is_last) {
+      __threadfence();
+      double t = 0.0;
+      for (int b = tid; b < (int) gridDim.x; b += NT) t += ((volatile double *) partials)[b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      __syncthreads();
+      if ((tid & 31) == 0) sm[tid >> 5] = t;
+      __syncthreads();
+      if (tid == 0) {
+         double r = 0.0;
+#pragma unroll
+         for (int w = 0; w < NT / 32; w++) r += sm[w];
+         g_pd_scalars[slot] = r;
+      }
+   }
+}
+
 // column of entry k of a row = base + off[k]; base = the row itself for square blocks (BASE =
 // false), else base[row] (the row's first column: interpolation and its stored transpose).
 // NT threads per block, R rows per thread.
 // WIDE (HB200_PAT_WIDE=1, default on N > 1): 16-bit row codes (<= 65534 patterns, 65535 = row outside
 // the table) and the table read from global memory through L1 instead of shared memory — the
 // partitioned coarse operators, whose numbering next to a rank boundary multiplies the patterns.
-template <int EPI, bool BASE, int NT, int R, bool WIDE = false>
+template <int EPI, bool BASE, int NT, int R, bool WIDE = false, bool DOT = false>
 __global__ void __launch_bounds__(NT, 1536 / NT)
 spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int *__restrict__ base, int npat,
          int nent, const int *__restrict__ tab_ptr, const int *__restrict__ tab_off,
@@ -71,6 +119,7 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
       s_val = w_val; s_off = w_off; s_ptr = w_ptr;
    }
    const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+   double dacc = 0.0;                     // DOT: this thread's share of <y, dotw>
    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int r0 = tile * (NT * R) + tid;
       int p[R];
@@ -106,17 +155,35 @@ spmv_pat(int nrows, int ntiles, const unsigned char *__restrict__ pat, const int
             for (int j = 0; j < R; j++) s[j] = __dadd_rn(s[j], __dmul_rn(a, xv[j]));
          }
          const double diag = e > b ? s_val[b] : 0.0;
+         if (DOT) {
 #pragma unroll
-         for (int j = 0; j < R; j++) epi_apply<EPI>(ea, r0 + j * NT, s[j], diag);
+            for (int j = 0; j < R; j++) {
+               const int row = r0 + j * NT;
+               dacc += epi_apply_ret<EPI>(ea, row, s[j]) * __ldg(ea.dotw + row);
+            }
+         } else {
+#pragma unroll
+            for (int j = 0; j < R; j++) epi_apply<EPI>(ea, r0 + j * NT, s[j], diag);
+         }
       } else {
 #pragma unroll
          for (int j = 0; j < R; j++) {
             if (p[j] >= 0) {
-               pat_one_row<EPI>(ea, x + (BASE ? bs[j] : r0 + j * NT), r0 + j * NT, p[j], s_ptr, s_off, s_val, skip);
+               const int row = r0 + j * NT;
+               if (DOT) {
+                  const int b = s_ptr[p[j]], e = s_ptr[p[j] + 1];
+                  const double *xb = x + (BASE ? bs[j] : row);
+                  double sr = 0.0;
+                  for (int k = b + skip; k < e; k++) sr = __dadd_rn(sr, __dmul_rn(s_val[k], __ldg(xb + s_off[k])));
+                  dacc += epi_apply_ret<EPI>(ea, row, sr) * __ldg(ea.dotw + row);
+               } else {
+                  pat_one_row<EPI>(ea, x + (BASE ? bs[j] : row), row, p[j], s_ptr, s_off, s_val, skip);
+               }
             }
          }
       }
    }
+   if (DOT) pat_dot_finish<NT>(dacc, ea.dot_slot);
 }
 
 static int pat_rows_per_thread()
@@ -129,13 +196,13 @@ static int pat_rows_per_thread()
    return r;
 }
 
-template <int EPI, bool BASE, int NT, int R, bool WIDE = false>
+template <int EPI, bool BASE, int NT, int R, bool WIDE = false, bool DOT = false>
 static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
    const size_t smem = WIDE ? 0 : (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
    static bool opted = false;
    if (!opted && !WIDE) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE, NT, R, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      HB_CUDA(cudaFuncSetAttribute(spmv_pat<EPI, BASE, NT, R, WIDE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kPatMaxEntries * 12 + (kPatMaxPatterns + 1) * 4 + 8));
       opted = true;
    }
@@ -146,16 +213,46 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    static int occ_blocks = 1;
    if (occ_smem != smem) {
       int nb = 0;
-      HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_pat<EPI, BASE, NT, R, WIDE>, NT, smem));
+      HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_pat<EPI, BASE, NT, R, WIDE, DOT>, NT, smem));
       occ_blocks = nb > 0 ? nb : 1;
       occ_smem = smem;
    }
    int grid = 148 * occ_blocks;
    if (grid > ntiles) grid = ntiles;
-   HB_LAUNCH((spmv_pat<EPI, BASE, NT, R, WIDE>), grid, NT, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
+   HB_LAUNCH((spmv_pat<EPI, BASE, NT, R, WIDE, DOT>), grid, NT, smem, st, M.nrows, ntiles, M.pat_code, M.pat_base, M.pat_npat,
              M.pat_nent, M.pat_ptr, M.pat_off, M.pat_val, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
+}
+
+bool fused_dots_enabled()
+{
+   // opt-in until the DOT kernel variants have run on hardware (logic verified in the host emulation)
+   static const bool on = getenv("HB200_FUSED_DOTS") != nullptr;
+   return on;
+}
+
+bool spmv_can_fuse_dot(const DCsr &M, int epi_kind)
+{
+   return fused_dots_enabled() && (epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7) && M.kind == SPMV_PAT &&
+          M.has_pat && !M.pat_wide && !M.pat_base && M.pat_nirr == 0;
+}
+
+// the fused-dot instantiations exist for the two epilogues that produce a Krylov dot operand
+template <int EPI>
+static int pat_dispatch_dot(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   static bool bound = false;
+   if (!bound) {
+      Ctx &c = ctx();
+      HB_CUDA(cudaMemcpyToSymbol(g_pd_partials, &c.d_partials, sizeof(double *)));
+      HB_CUDA(cudaMemcpyToSymbol(g_pd_counter, &c.d_counter, sizeof(unsigned int *)));
+      HB_CUDA(cudaMemcpyToSymbol(g_pd_scalars, &c.d_scalars, sizeof(double *)));
+      bound = true;
+   }
+   const size_t smem = (size_t) M.pat_nent * 12 + (size_t) (M.pat_npat + 1) * 4 + 8;
+   return smem > 40 * 1024 ? pat_launch_t<EPI, false, 512, 4, false, true>(M, x, ea, st)
+                           : pat_launch_t<EPI, false, 256, 4, false, true>(M, x, ea, st);
 }
 
 template <int EPI>
@@ -189,6 +286,10 @@ static int pat_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 
 int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)
 {
+   if (ea.dot_slot >= 0 && ea.dotw != nullptr) {
+      if (!spmv_can_fuse_dot(M, epi_kind)) return set_error(HB200_ERROR_GENERIC, "fused dot requested on a block that cannot fuse it");
+      return epi_kind == EPI_AXPBY ? pat_dispatch_dot<EPI_AXPBY>(M, x, ea, st) : pat_dispatch_dot<EPI_JACOBI7>(M, x, ea, st);
+   }
    switch (epi_kind) {
       case EPI_AXPBY:           return pat_dispatch<EPI_AXPBY>(M, x, ea, st);
       case EPI_ACC:             return pat_dispatch<EPI_ACC>(M, x, ea, st);

@@ -20,6 +20,10 @@
 namespace hb {
 int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
               int *num_iterations, double *rel_resid_norm);
+// fused-dot request for the next amg_solve (preconditioner use): slot >= 0 asks the cycle's last
+// level-0 sweep for <u, f>; amg_dot_fused tells whether it delivered (else the caller runs dot_kernel)
+void amg_set_dot_request(hb200_amg *amg, int slot);
+bool amg_dot_fused(const hb200_amg *amg);
 }
 
 namespace hb {
@@ -31,14 +35,23 @@ enum {
    S_H0 = 16   // GMRES: hh column (k_dim + 1 entries, k_dim <= 40)
 };
 
-static int precond_apply(int kind, hb200_amg *amg, hb200_parcsr *A, const double *r, double *z)
+// dot_slot >= 0: the caller wants <r, z> in that scalar slot next; *dot_done says whether the
+// preconditioner's last kernel already produced it (fused epilogue, single rank, row-pattern A_0)
+static int precond_apply(int kind, hb200_amg *amg, hb200_parcsr *A, const double *r, double *z,
+                         int dot_slot = -1, bool *dot_done = nullptr)
 {
    // the Krylov solvers always ClearVector(z) first => zero initial guess
    Ctx &c = ctx();
    const size_t n = (size_t) A->num_rows;
+   if (dot_done) *dot_done = false;
    switch (kind) {
-      case HB200_PRECOND_AMG:
-         return amg_solve(amg, A, r, z, true, nullptr, nullptr) & ~HB200_ERROR_CONV;
+      case HB200_PRECOND_AMG: {
+         amg_set_dot_request(amg, (dot_done && fused_dots_enabled() && c.nranks == 1) ? dot_slot : -1);
+         const int fl = amg_solve(amg, A, r, z, true, nullptr, nullptr) & ~HB200_ERROR_CONV;
+         if (dot_done) *dot_done = (fl == 0) && amg_dot_fused(amg);
+         amg_set_dot_request(amg, -1);
+         return fl;
+      }
       case HB200_PRECOND_DIAGSCALE: {
          const double *dg = nullptr;
          HB_CHECK(parcsr_diag(A, &dg));
@@ -203,9 +216,10 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       i++;
       const bool recompute_true_residual = P->recompute_residual_p && !(i % P->recompute_residual_p);
 
-      // s = A p ; sdotp = <s,p>
+      // s = A p ; sdotp = <s,p>  (the dot comes out of the matvec epilogue when the format fuses it)
+      if (fused_dots_enabled() && c.nranks == 1) { c.dot_req_armed = true; c.dot_req_w = p; c.dot_req_slot = S_SDOTP; }
       PCG_CHECK(parcsr_matvec(A, 1.0, p, 0.0, s, s));
-      PCG_CHECK(dot_global(s, p, n, S_SDOTP));
+      if (!c.last_dot_fused) PCG_CHECK(dot_global(s, p, n, S_SDOTP));
 
       double sdotp = 0.0;
       int dflag = 0;
@@ -269,9 +283,10 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
 
       // s = C r ; gamma = <r,s>
       const int g_new = g_old;
-      PCG_CHECK(precond_apply(pk, amg, A, r, s));
+      bool gamma_done = false;
+      PCG_CHECK(precond_apply(pk, amg, A, r, s, g_new, &gamma_done));
       timer_tick(T_BLAS1);
-      PCG_CHECK(vec_dot_dev(r, s, n, g_new, st));
+      if (!gamma_done) PCG_CHECK(vec_dot_dev(r, s, n, g_new, st));
       if (flex) PCG_CHECK(vec_dot_dev(r_old, s, n, S_DELTA, st));
       timer_tick(T_OTHER);
       if (c.nranks > 1) {

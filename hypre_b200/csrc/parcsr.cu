@@ -119,6 +119,7 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
    (void) dotw; (void) dot_slot;
    Ctx &c = ctx();
    if (alpha == 0.0) {
+      c.dot_req_armed = false; c.last_dot_fused = false;
       // csr_matvec.c:92-105: y = beta*b
       if (beta == 0.0) return vec_set(y, 0.0, A->num_rows, c.s_comp);
       return vec_axpby_out(beta, b, 0.0, b, y, A->num_rows, c.s_comp);
@@ -128,6 +129,14 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
    timer_tick(T_MATVEC_DIAG);
    EpiArgs ea;
    ea.alpha = alpha; ea.beta = beta; ea.b = b; ea.y = y;
+   // an armed fused-dot request (<y, w>) is honoured when y is final after the diag pass
+   const bool want_dot = c.dot_req_armed;
+   c.dot_req_armed = false;
+   c.last_dot_fused = false;
+   if (want_dot && c.nranks == 1 && A->num_cols_offd == 0 && spmv_can_fuse_dot(A->diag, EPI_AXPBY)) {
+      ea.dotw = c.dot_req_w; ea.dot_slot = c.dot_req_slot;
+      c.last_dot_fused = true;
+   }
    HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
    timer_tick(T_HALO_WAIT);
    if (A->num_cols_offd > 0) {

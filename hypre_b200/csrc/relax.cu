@@ -30,6 +30,10 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
    Ctx &c = ctx();
    const int n = A->num_rows;
    if (used_shortcut) *used_shortcut = false;
+   // an armed fused-dot request (<u_out, w>) is honoured by the matvec-form sweep only
+   const bool want_dot = c.dot_req_armed;
+   c.dot_req_armed = false;
+   c.last_dot_fused = false;
    // which reference routine does this (type, points) pair run?
    //   0            -> core(Skip_diag = 1, d = diagonal)
    //   7            -> Relax7Jacobi (matvec form, marked divpy)
@@ -52,6 +56,10 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       EpiArgs ea;
       ea.w = w; ea.b = f; ea.u = u_in; ea.d = l1; ea.y = u_out;
       ea.cf = relax_points ? cf : nullptr; ea.relax_points = relax_points;
+      if (want_dot && c.nranks == 1 && A->num_cols_offd == 0 && spmv_can_fuse_dot(A->diag, EPI_JACOBI7)) {
+         ea.dotw = c.dot_req_w; ea.dot_slot = c.dot_req_slot;
+         c.last_dot_fused = true;
+      }
       HB_CHECK(spmv_launch(A->diag, u_in, EPI_JACOBI7, ea, false, c.s_comp));
       timer_tick(T_HALO_WAIT);
       HB_CHECK(parcsr_halo_end(A, c.s_comp));

@@ -157,3 +157,4 @@ template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiproces
    *n = std::max(1, 1536 / std::max(threads, 1));
    return cudaSuccess;
 }
+template <class T> inline cudaError_t cudaMemcpyToSymbol(T &symbol, const void *src, size_t n) { memcpy(&symbol, src, n); return cudaSuccess; }

@@ -47,3 +47,23 @@ def test_wide_pattern_format_on_the_host_emulation():
     build_emu()
     r = run_child({"HB200_PAT_WIDE": "1"}, os.path.join("tests", "emu_wide_case.py"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_fused_dots_on_the_host_emulation(tmp_path):
+    """<s,p> out of the Krylov matvec epilogue and <r,z> out of the cycle's last Jacobi sweep: same
+    iteration count and residual as with separate dot kernels, two launches fewer per iteration"""
+    import json
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    build_emu()
+    reports = {}
+    for name, env in (("fused", {"HB200_FUSED_DOTS": "1"}), ("separate", {})):
+        path = str(tmp_path / f"{name}.json")
+        r = run_child(dict(env, HB200_EMU_REPORT=path), os.path.join("tests", "emu_fused_dots_case.py"))
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        reports[name] = json.load(open(path))
+    f, s = reports["fused"], reports["separate"]
+    assert f["iterations"] == s["iterations"] == f["ref_iterations"]
+    assert abs(f["rel_res"] - s["rel_res"]) <= 1e-9 * s["rel_res"]
+    assert abs(f["x_norm"] - s["x_norm"]) <= 1e-12 * s["x_norm"]
+    assert s["launches"] - f["launches"] == 2 * f["iterations"], (f, s)

@@ -12,7 +12,7 @@ import sys
 import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU_LIB = os.path.join(ROOT, "oracle", "_ref", "libhb200_emu.so")
+EMU_LIB = os.environ.get("HB200_EMU_LIB") or os.path.join(ROOT, "oracle", "_ref", "libhb200_emu.so")
 
 
 def activate():

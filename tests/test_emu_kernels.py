@@ -67,3 +67,22 @@ def test_fused_dots_on_the_host_emulation(tmp_path):
     assert abs(f["rel_res"] - s["rel_res"]) <= 1e-9 * s["rel_res"]
     assert abs(f["x_norm"] - s["x_norm"]) <= 1e-12 * s["x_norm"]
     assert s["launches"] - f["launches"] == 2 * f["iterations"], (f, s)
+
+
+def test_kernels_under_address_sanitizer():
+    """the same emulation compiled with -fsanitize=address: no kernel (or host path around it) reads or
+    writes outside its "device" buffers on the SpMV formats, the relaxation family and a PCG solve"""
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "emu_asan"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not found")
+    env = {"HB200_EMU_LIB": os.path.join(ROOT, "oracle", "_ref", "libhb200_emu_asan.so"), "LD_PRELOAD": asan,
+           "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1"}
+    r = run_child(env, os.path.join("tests", "test_gpu_parity.py"), "-m", "gpu", "-n", "6",
+                  "-k", "matvec or format or pattern or relax or cheby or coarse or pcg_amg or gmres")
+    tail = r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "AddressSanitizer" not in tail, tail
+    assert " passed" in r.stdout, tail

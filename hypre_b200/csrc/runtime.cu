@@ -43,10 +43,14 @@ NcclApi &nccl_api() { return g_nccl; }
 int nccl_load()
 {
    if (g_nccl.loaded) return 0;
+#ifndef HB200_EMU
    // RTLD_NOLOAD first: reuse whatever NCCL the process already has (e.g. PyTorch's)
    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+#else
+   void *h = dlopen("libnccl_emu.so", RTLD_NOW | RTLD_GLOBAL);   // g++ test build: NCCL calls over host message passing
+#endif
    if (!h) return set_error(HB200_ERROR_GENERIC, "cannot load libnccl.so.2: %s", dlerror());
 #define HB_SYM(field, name)                                                              \
    *(void **) (&g_nccl.field) = dlsym(h, name);                                          \

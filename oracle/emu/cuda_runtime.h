@@ -105,7 +105,7 @@ struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; s
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }   // one emulated device per host process
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
@@ -114,14 +114,21 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
    p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
    return cudaSuccess;
 }
+namespace hb_emu {
+void *dev_alloc(size_t bytes);       // large blocks are page-mapped so that they can be exported (IPC)
+void  dev_free(void *p);
+int   ipc_export(void *handle64, void *p);
+int   ipc_open(void **p, const void *handle64);
+int   ipc_close(void *p);
+}
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t bytes)
 {
-   *p = (T *) malloc(bytes ? bytes : 8);
+   *p = (T *) hb_emu::dev_alloc(bytes ? bytes : 8);
    return *p ? cudaSuccess : 2;
 }
 template <class T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
@@ -141,16 +148,17 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t_ms = hb_emu_now_ms(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
-// no graphs and no peer mapping in the emulation: callers take their eager / single-rank paths
+// no graphs in the emulation: callers take their eager paths
 inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
 inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long = 0) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+// "device" memory exported to the other host processes of a multi-rank run: POSIX shared memory
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { return hb_emu::ipc_export(h->reserved, p) ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { return hb_emu::ipc_open(p, h.reserved) ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *p) { hb_emu::ipc_close(p); return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int threads, size_t)
 {

@@ -5,7 +5,12 @@
 // shuffle, where it waits for the other threads of its block / warp exactly as on the device;
 // threads that have left the kernel count as arrived.  One OS thread, round-robin, deterministic.
 #include "cuda_runtime.h"
+#include <string>
+#include <fcntl.h>
+#include <map>
+#include <sys/mman.h>
 #include <ucontext.h>
+#include <unistd.h>
 #include <vector>
 
 namespace hb_emu {
@@ -161,5 +166,76 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
    }
    g_body = nullptr;
 }
+
+// ---------------------------------------------------------------------------------------
+// "device" memory and its export to other processes
+// ---------------------------------------------------------------------------------------
+namespace {
+std::map<void *, size_t> g_big;        // page-mapped allocations (>= 64 MB) and opened imports
+std::vector<std::string> g_shm_names;
+int g_shm_seq = 0;
+struct IpcHandle { char name[48]; unsigned long long size; };
+size_t page_round(size_t n) { return (n + 4095) & ~(size_t) 4095; }
+void unlink_all() { for (auto &n : g_shm_names) shm_unlink(n.c_str()); }
+}  // namespace
+
+void *dev_alloc(size_t bytes)
+{
+   if (bytes < (64u << 20)) return malloc(bytes);     // only the exportable arena-sized blocks are page-mapped
+   const size_t n = page_round(bytes);
+   void *p = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+   if (p == MAP_FAILED) return nullptr;
+   g_big[p] = n;
+   return p;
+}
+
+void dev_free(void *p)
+{
+   if (!p) return;
+   auto it = g_big.find(p);
+   if (it == g_big.end()) { free(p); return; }
+   munmap(p, it->second);
+   g_big.erase(it);
+}
+
+int ipc_export(void *handle64, void *p)
+{
+   auto it = g_big.find(p);
+   if (it == g_big.end()) return 1;                     // only page-mapped blocks can be exported
+   IpcHandle h;
+   memset(&h, 0, sizeof(h));
+   snprintf(h.name, sizeof(h.name), "/hb_emu_%d_%d", (int) getpid(), g_shm_seq++);
+   h.size = it->second;
+   const int fd = shm_open(h.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+   if (fd < 0) return 1;
+   if (g_shm_names.empty()) atexit(unlink_all);
+   g_shm_names.push_back(h.name);
+   if (ftruncate(fd, (off_t) h.size) != 0) { close(fd); return 1; }
+   // keep the contents and the address: copy out, map the shared object over the block, copy back
+   std::vector<char> keep((char *) p, (char *) p + h.size);
+   void *q = mmap(p, h.size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);
+   close(fd);
+   if (q != p) return 1;
+   memcpy(p, keep.data(), h.size);
+   static_assert(sizeof(IpcHandle) <= 64, "handle fits cudaIpcMemHandle_t");
+   memcpy(handle64, &h, sizeof(h));
+   return 0;
+}
+
+int ipc_open(void **p, const void *handle64)
+{
+   IpcHandle h;
+   memcpy(&h, handle64, sizeof(h));
+   const int fd = shm_open(h.name, O_RDWR, 0600);
+   if (fd < 0) return 1;
+   void *q = mmap(nullptr, h.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+   close(fd);
+   if (q == MAP_FAILED) return 1;
+   g_big[q] = h.size;
+   *p = q;
+   return 0;
+}
+
+int ipc_close(void *p) { dev_free(p); return 0; }
 
 }  // namespace hb_emu

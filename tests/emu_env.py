@@ -36,6 +36,7 @@ def activate():
     torch.cuda.is_available = lambda: True
     torch.cuda.device_count = lambda: 1
     torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.set_device = lambda *a, **k: None
     # host <-> "device" transfers copy, as the real ones do (no aliasing with the numpy source)
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()
     torch.Tensor.cpu = lambda self, *a, **k: self.clone()

@@ -24,8 +24,16 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     kind = sys.argv[1] if len(sys.argv) > 1 else "27pt"
     halo = sys.argv[2] if len(sys.argv) > 2 else "nccl"
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if os.environ.get("HB200_EMU_TEST"):
+        # CPU run against the host emulation of the kernels (tests/test_emu_kernels.py): one host
+        # process per rank, NCCL calls over oracle/minimpi
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import emu_env
+        emu_env.activate()
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import hypre_b200 as hb
     from hypre_b200._lib import lib, check
     from oracle import refbridge as rb
@@ -38,7 +46,8 @@ def main():
     rb.load(mpi=True)
     rb.set_num_threads(1)
     P = {1: (1, 1, 1), 2: (2, 1, 1), 3: (3, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    n = (12 * P[0], 11 * P[1], 10 * P[2])
+    scale = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    n = (12 * scale * P[0], 11 * scale * P[1], 10 * scale * P[2])
     pb = rb.Problem(kind, n, P=P, mpi=True)
     pb.setup_amg(relax_type=18)
     h = pb.hierarchy()

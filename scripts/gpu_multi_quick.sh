@@ -12,15 +12,15 @@ export PYTHONPATH=$PWD
 # the peer halo runs four ways: V-cycle graph on/off, NVLS on/off (the coarse GE gather is an NCCL
 # all-reduce inside the captured cycle; NVLS-class algorithms only exist above two ranks)
 for cfg in "nccl - -" "peer - -" "peer nograph -" "peer - nonvls" "peer nograph nonvls"; do
-  set -- $cfg; halo=$1
+  set -- $cfg; halo=$1; log=$OUT/${1}_${2}_${3}.log
   extra=""; [ "$2" = nograph ] && extra="--no-graph"
   if [ "$3" = nonvls ]; then export NCCL_NVLS_ENABLE=0; else unset NCCL_NVLS_ENABLE; fi
   echo "#### halo=$halo graph=${2} nvls=${3}"
   HB200_TRACE=1 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
     --master-port 29521 bench.py --gpus $NG --size $SZ --steps 2 --warmup 2 --no-cpu-baseline --halo $halo $extra \
-    --stage-timeout 60 > $OUT/$halo.log 2>&1
+    --stage-timeout 60 > $log 2>&1
   echo "== $halo rc=$?"
-  grep '^{' $OUT/$halo.log | tail -1 | cut -c1-330
-  grep "no progress\|Error\|error flag" $OUT/$halo.log | head -5
-  grep "hb200 trace rank 0\]\|bench rank 0\]" $OUT/$halo.log | tail -6
+  grep '^{' $log | tail -1 | cut -c1-330
+  grep "no progress\|Error\|error flag" $log | head -5
+  grep "hb200 trace rank 0\]\|bench rank 0\]" $log | tail -6
 done

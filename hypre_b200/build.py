@@ -21,7 +21,7 @@ LIB = os.path.join(HERE, "libhb200.so")
 SOURCES = [
     "runtime.cu",
     "kernels_spmv.cu",
-    "kernels_sell.cu", "kernels_pat.cu",
+    "kernels_sell.cu", "kernels_pat.cu", "kernels_offd.cu",
     "kernels_blas1.cu",
     "parcsr.cu",
     "parcsr_peer.cu",

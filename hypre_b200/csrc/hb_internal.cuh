@@ -343,5 +343,18 @@ bool peer_has_out(const PeerPlan *pl);
 int  peer_plans_ensure(hb200_parcsr *A, bool reverse);      // collective, lazy: builds A->pkg.fwd or .rev
 int  peer_put(PeerPlan *pl, const double *src, cudaStream_t st);
 int  peer_wait(PeerPlan *pl, cudaStream_t st);
+// what a kernel needs to take over the job of halo_wait_kernel (the fused wait + offd pass,
+// HB200_FUSE_WAIT=1): arrival flags, the two receive buffers, the senders' ack slots, epoch, ticket
+struct PeerWaitArgs {
+   const double *buf0 = nullptr, *buf1 = nullptr;
+   const unsigned long long *flags = nullptr;
+   unsigned long long *const *in_ack = nullptr;
+   unsigned long long *epoch_ctr = nullptr;
+   unsigned int *ticket = nullptr;
+   int n_in = 0;
+};
+bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out);   // false when the plan receives nothing
+int  spmv_offd_wait_launch(const DCsr &M, const PeerWaitArgs &w, int epi_kind, const EpiArgs &ea, cudaStream_t st);
+int  parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea);   // halo_end + offd SpMV (fused or not)
 void peer_plan_free(PeerPlan *pl);
 }  // namespace hb

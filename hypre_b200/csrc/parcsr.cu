@@ -113,6 +113,36 @@ int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
    return 0;
 }
 
+static bool fuse_wait_enabled()
+{
+   static const bool on = getenv("HB200_FUSE_WAIT") != nullptr;   // opt-in until measured on hardware
+   return on;
+}
+
+// the second half of a ParCSR operation: wait for the halo, then the offd block over the boundary
+// rows with the accumulate epilogue `epi_kind`.  Peer-put halo + HB200_FUSE_WAIT=1: one kernel does
+// both and reads the receive buffer in place (kernels_offd.cu).
+int parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea)
+{
+   Ctx &c = ctx();
+   CommPkgD &pk = A->pkg;
+   PeerWaitArgs w;
+   if (c.halo_mode == 1 && c.nranks > 1 && fuse_wait_enabled() && A->num_cols_offd > 0 && A->offd.num_rownnz > 0 &&
+       peer_wait_args(pk.fwd, &w)) {
+      timer_tick(T_HALO_WAIT);
+      if (peer_has_out(pk.fwd)) HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));   // the local put is done
+      timer_tick(T_MATVEC_OFFD);
+      return spmv_offd_wait_launch(A->offd, w, epi_kind, ea, c.s_comp);
+   }
+   timer_tick(T_HALO_WAIT);
+   HB_CHECK(parcsr_halo_end(A, c.s_comp));
+   timer_tick(T_MATVEC_OFFD);
+   if (A->num_cols_offd > 0) {
+      HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, epi_kind, ea, true, c.s_comp));
+   }
+   return 0;
+}
+
 int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,
                   double *y, const double *dotw, int dot_slot)
 {
@@ -138,16 +168,9 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
       c.last_dot_fused = true;
    }
    HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
-   timer_tick(T_HALO_WAIT);
-   if (A->num_cols_offd > 0) {
-      HB_CHECK(parcsr_halo_end(A, c.s_comp));
-      timer_tick(T_MATVEC_OFFD);
-      EpiArgs eo;
-      eo.alpha = alpha; eo.y = y;
-      HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_ACC, eo, true, c.s_comp));
-   } else {
-      HB_CHECK(parcsr_halo_end(A, c.s_comp));
-   }
+   EpiArgs eo;
+   eo.alpha = alpha; eo.y = y;
+   HB_CHECK(parcsr_offd_pass(A, EPI_ACC, eo));
    timer_tick(T_OTHER);
    return 0;
 }

@@ -272,6 +272,16 @@ int peer_wait(PeerPlan *pl, cudaStream_t st)
 
 bool peer_has_out(const PeerPlan *pl) { return pl && pl->n_out > 0; }
 
+bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out)
+{
+   if (!pl || pl->n_in == 0) return false;
+   out->buf0 = pl->in_buf[0]; out->buf1 = pl->in_buf[1];
+   out->flags = pl->in_flags; out->in_ack = pl->d_in_ack;
+   out->epoch_ctr = pl->d_epoch; out->ticket = pl->d_ticket;
+   out->n_in = pl->n_in;
+   return true;
+}
+
 void peer_plan_free(PeerPlan *pl)
 {
    if (!pl) return;

@@ -61,12 +61,7 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
          c.last_dot_fused = true;
       }
       HB_CHECK(spmv_launch(A->diag, u_in, EPI_JACOBI7, ea, false, c.s_comp));
-      timer_tick(T_HALO_WAIT);
-      HB_CHECK(parcsr_halo_end(A, c.s_comp));
-      timer_tick(T_MATVEC_OFFD);
-      if (A->num_cols_offd > 0) {
-         HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_JACOBI7_ACC, ea, true, c.s_comp));
-      }
+      HB_CHECK(parcsr_offd_pass(A, EPI_JACOBI7_ACC, ea));
       timer_tick(T_OTHER);
       return 0;
    }
@@ -90,10 +85,8 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       ea.d = dg; ea.skip_diag = 1;
    } else { ea.d = l1; ea.skip_diag = 0; }
    HB_CHECK(spmv_launch(A->diag, uin, EPI_JACOBI_CORE, ea, false, c.s_comp));
-   HB_CHECK(parcsr_halo_end(A, c.s_comp));
-   if (A->num_cols_offd > 0) {
-      HB_CHECK(spmv_launch(A->offd, A->pkg.d_recv_buf, EPI_JACOBI_CORE_ACC, ea, true, c.s_comp));
-   }
+   HB_CHECK(parcsr_offd_pass(A, EPI_JACOBI_CORE_ACC, ea));
+   timer_tick(T_OTHER);
    return 0;
 }
 

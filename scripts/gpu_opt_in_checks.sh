@@ -22,6 +22,13 @@ for v in "" 1; do
 done
 unset HB200_FUSED_DOTS
 if [ "$NG" -ge 2 ]; then
+  for fw in "" 1; do
+    if [ -n "$fw" ]; then export HB200_FUSE_WAIT=1; else unset HB200_FUSE_WAIT; fi
+    timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "2ranks_peer" 2>&1 | tail -1
+    timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench2_fusewait_${fw:-0}.log 2>&1
+    grep '^{' $OUT/bench2_fusewait_${fw:-0}.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('fuse_wait=${fw:-0}', d['value'], d['ms_per_step'], d['gpu_launches'], d['config']['iterations'], d['config']['final_rel_res'])"
+  done
+  unset HB200_FUSE_WAIT
   for w in on off; do
     if [ "$w" = off ]; then export HB200_NO_PAT_WIDE=1; else unset HB200_NO_PAT_WIDE; fi
     timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench2_wide_$w.log 2>&1

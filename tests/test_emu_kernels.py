@@ -94,19 +94,20 @@ def build_emu_mpi():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def run_ranks(nproc, script, *args, timeout=900):
+def run_ranks(nproc, script, *args, timeout=900, extra_env=None):
     """one host process per rank under torch.distributed.run: emulated kernels, NCCL calls over
     oracle/minimpi, the IPC arena of the peer-put halo in POSIX shared memory"""
     env = dict(os.environ, HB200_EMU_TEST="1", OMP_NUM_THREADS="1",
                HB200_EMU_LIB=os.path.join(ROOT, "oracle", "_ref", "libhb200_emu_mpi.so"))
+    env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(29700 + nproc + 10 * len(args)),
            os.path.join(ROOT, "tests", script), *args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
-@pytest.mark.parametrize("nproc,halo", [(8, "nccl")])
-def test_multi_rank_parity_on_the_host_emulation(nproc, halo):
+@pytest.mark.parametrize("nproc,halo,fuse_wait", [(8, "nccl", False), (4, "peer", True)])
+def test_multi_rank_parity_on_the_host_emulation(nproc, halo, fuse_wait):
     """tests/mp_parity_worker.py (the worker of the multi-GPU parity tests) on N host processes: maps,
     SpMV / SpMV-T, relaxation, cycle, PCG and GMRES against the reference running on the same ranks —
     the NCCL halo at 8 ranks (2 x 2 x 2 bricks, 7 neighbours).  The peer-put protocol runs in the bench and
@@ -114,7 +115,8 @@ def test_multi_rank_parity_on_the_host_emulation(nproc, halo):
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bridge_mpi.so")):
         pytest.skip("oracle/_ref/libref_bridge_mpi.so not built (needs /root/reference)")
     build_emu_mpi()
-    r = run_ranks(nproc, "mp_parity_worker.py", "27pt", halo)
+    # fuse_wait: the opt-in kernel that waits for the peer puts and runs the offd pass in one launch
+    r = run_ranks(nproc, "mp_parity_worker.py", "27pt", halo, extra_env={"HB200_FUSE_WAIT": "1"} if fuse_wait else None)
     assert r.returncode == 0 and "MULTI-RANK PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 

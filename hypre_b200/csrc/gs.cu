@@ -206,11 +206,11 @@ static int gs_core(hb200_parcsr *A, const double *f, const int *cf, int relax_po
    // halo exchange of u, once per call (par_relax.c:806-835), frozen during the sweep(s)
    HB_CHECK(parcsr_halo_begin(A, u, c.s_comp));
    if (!non_scale) {
-      HB_REQUIRE(vtemp != nullptr, HB200_ERROR_ARG, "scaled hybrid GS needs vtemp");
+      HB_REQUIRE(vtemp != nullptr || A->num_rows == 0, HB200_ERROR_ARG, "scaled hybrid GS needs vtemp");
       HB_CHECK(vec_copy(u, vtemp, (size_t) A->num_rows, c.s_comp));   // par_relax.c:857-866
    }
    HB_CHECK(parcsr_halo_end(A, c.s_comp));
-   HB_REQUIRE(relax_points == 0 || cf != nullptr, HB200_ERROR_ARG, "CF relaxation needs cf_marker");
+   HB_REQUIRE(relax_points == 0 || cf != nullptr || A->num_rows == 0, HB200_ERROR_ARG, "CF relaxation needs cf_marker");
    GsArgs g;
    g.di = A->diag.i; g.dj = A->diag.j; g.da = A->diag.a;
    if (A->num_cols_offd > 0) { g.oi = A->offd.i; g.oj = A->offd.j; g.oa = A->offd.a; g.vext = A->pkg.d_recv_buf; }
@@ -238,13 +238,13 @@ int relax_hybrid_gs(hb200_parcsr *A, const double *f, const int *cf, int relax_t
       case 4:  return gs_core(A, f, cf, relax_points, w, omega, nullptr, u, vtemp, -1, 0, 1);
       case 6:  return gs_core(A, f, cf, relax_points, w, omega, nullptr, u, vtemp, 1, 1, 1);
       case 8:
-      case 88: HB_REQUIRE(l1, HB200_ERROR_ARG, "l1 GS needs l1_norms");
+      case 88: HB_REQUIRE(l1 || A->num_rows == 0, HB200_ERROR_ARG, "l1 GS needs l1_norms");
                return gs_core(A, f, cf, relax_points, w, omega, l1, u, vtemp, 1, 1, skip_l1);
-      case 13: HB_REQUIRE(l1, HB200_ERROR_ARG, "l1 GS needs l1_norms");
+      case 13: HB_REQUIRE(l1 || A->num_rows == 0, HB200_ERROR_ARG, "l1 GS needs l1_norms");
                return gs_core(A, f, cf, relax_points, w, omega, l1, u, vtemp, 1, 0, skip_l1);
-      case 14: HB_REQUIRE(l1, HB200_ERROR_ARG, "l1 GS needs l1_norms");
+      case 14: HB_REQUIRE(l1 || A->num_rows == 0, HB200_ERROR_ARG, "l1 GS needs l1_norms");
                return gs_core(A, f, cf, relax_points, w, omega, l1, u, vtemp, -1, 0, skip_l1);
-      case 89: HB_REQUIRE(l1, HB200_ERROR_ARG, "l1 GS needs l1_norms");
+      case 89: HB_REQUIRE(l1 || A->num_rows == 0, HB200_ERROR_ARG, "l1 GS needs l1_norms");
                HB_CHECK(gs_core(A, f, cf, relax_points, w, omega, l1, u, vtemp, 1, 0, skip_l1));
                return gs_core(A, f, cf, relax_points, w, omega, l1, u, vtemp, -1, 0, skip_l1);
       default: return set_error(HB200_ERROR_ARG, "relax_hybrid_gs: unsupported type %d", relax_type);

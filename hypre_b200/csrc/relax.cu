@@ -40,7 +40,7 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
    //   18, points=0 -> Relax7Jacobi ; 18, points!=0 -> core(Skip_diag = 0, d = l1)   (:355-368)
    const bool form7 = (relax_type == 7) || (relax_type == 18 && relax_points == 0);
    if (form7) {
-      HB_REQUIRE(l1 != nullptr, HB200_ERROR_ARG, "relax type 7/18 needs l1_norms");
+      HB_REQUIRE(l1 != nullptr || n == 0, HB200_ERROR_ARG, "relax type 7/18 needs l1_norms");   // (a rank may own no rows of a level)
       if (zero_guess) {
          // Vtemp = w*f (Scale), u = 0 + Vtemp ./ l1   (par_relax.c:1221-1244)
          if (used_shortcut) *used_shortcut = true;
@@ -69,10 +69,10 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
    const double *uin = u_in;
    if (zero_guess) {
       // the reference runs the full sweep on an all-zero u; materialise the zeros
-      HB_REQUIRE(u_in != nullptr, HB200_ERROR_ARG, "core Jacobi needs a u_in buffer");
+      HB_REQUIRE(u_in != nullptr || n == 0, HB200_ERROR_ARG, "core Jacobi needs a u_in buffer");
       HB_CHECK(vec_set((double *) u_in, 0.0, (size_t) n, c.s_comp));
    }
-   HB_REQUIRE(relax_points == 0 || cf != nullptr, HB200_ERROR_ARG, "CF relaxation needs cf_marker");
+   HB_REQUIRE(relax_points == 0 || cf != nullptr || n == 0, HB200_ERROR_ARG, "CF relaxation needs cf_marker");
    HB_CHECK(parcsr_halo_begin(A, uin, c.s_comp));
    EpiArgs ea;
    ea.w = w; ea.b = f; ea.u = uin; ea.y = u_out;
@@ -132,7 +132,7 @@ int cheby_solve(hb200_parcsr *A, const double *f, const double *ds, const double
    if (order > 4) order = 4;
    if (order < 1) order = 1;
    const int cheby_order = order - 1;
-   HB_REQUIRE(!scale || ds != nullptr, HB200_ERROR_ARG, "scaled Chebyshev needs ds");
+   HB_REQUIRE(!scale || ds != nullptr || n == 0, HB200_ERROR_ARG, "scaled Chebyshev needs ds");
    if (!scale) {
       HB_CHECK(parcsr_matvec(A, -1.0, u, 1.0, f, r));
       FChebyStart fs{f, nullptr, nullptr, r, orig_u, u, coefs[cheby_order], 0};

@@ -190,3 +190,14 @@ def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     assert its_dev == its_ref, (args, its_dev, its_ref)
     rtol = 5e-2 if "-solver 3" in args else 2e-6
     assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
+
+
+def test_random_krylov_options_on_the_host_emulation():
+    """16 random PCG / GMRES option combinations (norms, flexible, relative change, recomputed residuals,
+    tolerances, restart, preconditioner, x0, b, early max_iter exit) against the 1-thread reference.
+    (`tests/emu_option_sweep_case.py` does the same for BoomerAMG options; run on demand, minutes.)"""
+    if not os.path.exists(BRIDGE):
+        pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
+    build_emu()
+    r = run_child({"HB200_SWEEP_CASES": "16"}, os.path.join("tests", "emu_krylov_sweep_case.py"), "-n", "4")
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -49,7 +49,8 @@ def main():
     scale = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     n = (12 * scale * P[0], 11 * scale * P[1], 10 * scale * P[2])
     pb = rb.Problem(kind, n, P=P, mpi=True)
-    pb.setup_amg(relax_type=18)
+    setup_relax = int(sys.argv[4]) if len(sys.argv) > 4 else 18      # -1 = ij's default (hybrid l1-GS 13/14)
+    pb.setup_amg(relax_type=setup_relax)
     h = pb.hierarchy()
     mats, amg = hb.amg_from_hierarchy(h)
     nl = pb.num_levels

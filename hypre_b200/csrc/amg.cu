@@ -259,7 +259,8 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
       return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    }
 #ifdef HB200_EMU
-   return cycle_body(amg, f_dev, u_dev, u_all_zeros);   // the host emulation has no graphs
+   // g++ test build: graphs are recorded and replayed on one rank only (the emulated NCCL is not stream-aware)
+   if (c.nranks > 1) return cycle_body(amg, f_dev, u_dev, u_all_zeros);
 #endif
    // CUDA-graph path: the topology of a cycle is fixed by the hierarchy, so capture once per
    // (f, u, zero flag) and replay; removes the launch latency of the ~60 small coarse-level

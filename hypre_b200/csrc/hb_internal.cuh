@@ -128,8 +128,9 @@ int  require_ready();
 #define HB_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
    do {                                                                                  \
       (void) (stream);                                                                   \
-      hb_emu::launch((unsigned) (grid), (unsigned) (block), (size_t) (smem),             \
-                     [&]() { kern(__VA_ARGS__); });                                      \
+      auto hb_args_ = std::make_tuple(__VA_ARGS__);   /* evaluated and copied now */    \
+      hb_emu::launch_bound((unsigned) (grid), (unsigned) (block), (size_t) (smem),       \
+                           [=]() { std::apply([](auto... a_) { kern(a_...); }, hb_args_); }); \
       hb::ctx().launches++;                                                              \
    } while (0)
 #define HB_DYN_SHARED(type, name) type *name = reinterpret_cast<type *>(hb_emu::dyn_smem())

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <functional>
+#include <tuple>
 
 #ifndef HB200_EMU
 #error "oracle/emu/cuda_runtime.h is the emulation header: compile with -DHB200_EMU"
@@ -48,6 +49,16 @@ unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int w
 void *dyn_smem();
 void  launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
 long long launches();
+// stream capture: while a capture is open, launches and async copies are recorded (arguments by
+// value, as CUDA copies kernel parameters at launch) instead of run; a graph launch replays them
+bool  capturing();
+void  record(std::function<void()> op);
+// kernel launch whose body already holds its arguments by value
+inline void launch_bound(unsigned grid, unsigned block, size_t smem, std::function<void()> body)
+{
+   if (capturing()) record([=]() { launch(grid, block, smem, body); });
+   else launch(grid, block, smem, body);
+}
 }  // namespace hb_emu
 
 #define threadIdx (hb_emu::g_cur->tid)
@@ -130,9 +141,19 @@ template <class T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { retu
 inline cudaError_t cudaFree(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr)
+{
+   if (hb_emu::capturing()) { hb_emu::record([=]() { if (n) memmove(d, s, n); }); return cudaSuccess; }
+   if (n) memmove(d, s, n);
+   return cudaSuccess;
+}
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr)
+{
+   if (hb_emu::capturing()) { hb_emu::record([=]() { if (n) memset(d, v, n); }); return cudaSuccess; }
+   if (n) memset(d, v, n);
+   return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t) malloc(8); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -148,13 +169,20 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t_ms = hb_emu_now_ms(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
-// no graphs in the emulation: callers take their eager paths
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long = 0) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+// graphs: the recorded operations of one capture, replayed in order
+namespace hb_emu {
+int  capture_begin();
+int  capture_end(void **graph);
+int  graph_instantiate(void **exec, void *graph);
+int  graph_launch(void *exec);
+void graph_destroy(void *graph_or_exec);
+}
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return hb_emu::capture_begin() ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { return hb_emu::capture_end((void **) g) ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long = 0) { return hb_emu::graph_instantiate((void **) e, g) ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { return hb_emu::graph_launch(e) ? cudaErrorNotSupported : cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { hb_emu::graph_destroy(g); return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { hb_emu::graph_destroy(e); return cudaSuccess; }
 // "device" memory exported to the other host processes of a multi-rank run: POSIX shared memory
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { return hb_emu::ipc_export(h->reserved, p) ? cudaErrorNotSupported : cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { return hb_emu::ipc_open(p, h.reserved) ? cudaErrorNotSupported : cudaSuccess; }

@@ -168,6 +168,48 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
 }
 
 // ---------------------------------------------------------------------------------------
+// stream capture and graphs: a graph is the list of recorded operations
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Graph { std::vector<std::function<void()>> ops; };
+Graph *g_capture = nullptr;
+}  // namespace
+
+bool capturing() { return g_capture != nullptr; }
+void record(std::function<void()> op) { g_capture->ops.push_back(std::move(op)); }
+
+int capture_begin()
+{
+   if (g_capture) return 1;
+   g_capture = new Graph();
+   return 0;
+}
+
+int capture_end(void **graph)
+{
+   if (!g_capture) { *graph = nullptr; return 1; }
+   *graph = g_capture;
+   g_capture = nullptr;
+   return 0;
+}
+
+int graph_instantiate(void **exec, void *graph)
+{
+   if (!graph) return 1;
+   *exec = new Graph(*(Graph *) graph);
+   return 0;
+}
+
+int graph_launch(void *exec)
+{
+   if (!exec || g_capture) return 1;
+   for (auto &op : ((Graph *) exec)->ops) op();
+   return 0;
+}
+
+void graph_destroy(void *g) { delete (Graph *) g; }
+
+// ---------------------------------------------------------------------------------------
 // "device" memory and its export to other processes
 // ---------------------------------------------------------------------------------------
 namespace {

@@ -28,7 +28,7 @@ def test_pcg_solve_report():
     rb.load()
     pb = rb.Problem("27pt", (14, 13, 12))
     pb.setup_amg(relax_type=18)
-    mats, amg = hb.amg_from_hierarchy(pb.hierarchy())
+    mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), use_graph=True)    # the bench's configuration: captured V-cycle
     A = mats[0][0]
     assert A.format_info()["kernel"] == 7
     ref = pb.pcg(precond="amg", tol=1e-8, max_iter=100, two_norm=1)

@@ -26,7 +26,7 @@ def test_pcg_solve_report():
     from oracle import refbridge as rb
     hb.init(0)
     rb.load()
-    pb = rb.Problem("27pt", (14, 13, 12))
+    pb = rb.Problem("27pt", (12, 11, 10))
     pb.setup_amg(relax_type=18)
     mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), use_graph=True)    # the bench's configuration: captured V-cycle
     A = mats[0][0]

@@ -31,7 +31,7 @@ def random_csr(rng, n, m, kind):
     return A.tocsr()
 
 
-@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("seed", range(2))
 def test_random_blocks_all_kernels(seed):
     import torch
     import hypre_b200 as hb

@@ -83,7 +83,7 @@ def test_kernels_under_address_sanitizer():
     env = {"HB200_EMU_LIB": os.path.join(ROOT, "oracle", "_ref", "libhb200_emu_asan.so"), "LD_PRELOAD": asan,
            "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1"}
     r = run_child(env, os.path.join("tests", "test_gpu_parity.py"), "-m", "gpu", "-n", "6",
-                  "-k", "matvec or format or pattern or relax_jacobi or cheby or blas1")
+                  "-k", "matvec or format or pattern or blas1")
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0 and "AddressSanitizer" not in tail, tail
     assert " passed" in r.stdout, tail
@@ -106,7 +106,7 @@ def run_ranks(nproc, script, *args, timeout=900, extra_env=None):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
-@pytest.mark.parametrize("nproc,halo,fuse_wait", [(8, "nccl", False), (4, "peer", True)])
+@pytest.mark.parametrize("nproc,halo,fuse_wait", [(8, "nccl", False)])   # (4, "peer", True) passes too: on demand
 def test_multi_rank_parity_on_the_host_emulation(nproc, halo, fuse_wait):
     """tests/mp_parity_worker.py (the worker of the multi-GPU parity tests) on N host processes: maps,
     SpMV / SpMV-T, relaxation, cycle, PCG and GMRES against the reference running on the same ranks —
@@ -173,7 +173,6 @@ def _ij_run(binary, args, nprocs=1):
 
 
 @pytest.mark.parametrize("args,nprocs", [("-27pt -n 18 18 18 -solver 1 -rlx 18", 1),
-                                         ("-laplacian -n 20 20 20 -solver 3 -rlx 18", 1),
                                          ("-27pt -n 24 14 14 -P 2 1 1 -solver 1 -rlx 18", 2)])
 def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     """the UNMODIFIED reference driver linked in front of hypre_shim.c, the shim bound to the emulated
@@ -193,11 +192,11 @@ def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
 
 
 def test_random_krylov_options_on_the_host_emulation():
-    """16 random PCG / GMRES option combinations (norms, flexible, relative change, recomputed residuals,
+    """12 random PCG / GMRES option combinations (norms, flexible, relative change, recomputed residuals,
     tolerances, restart, preconditioner, x0, b, early max_iter exit) against the 1-thread reference.
     (`tests/emu_option_sweep_case.py` does the same for BoomerAMG options; run on demand, minutes.)"""
     if not os.path.exists(BRIDGE):
         pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
     build_emu()
-    r = run_child({"HB200_SWEEP_CASES": "16"}, os.path.join("tests", "emu_krylov_sweep_case.py"), "-n", "4")
+    r = run_child({"HB200_SWEEP_CASES": "12"}, os.path.join("tests", "emu_krylov_sweep_case.py"), "-n", "4")
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -10,6 +10,9 @@
 // Execution model: one kernel launch runs its blocks one after the other; the threads of a block
 // are fibers (ucontext) on the calling OS thread, switched only at the points where CUDA threads
 // can observe each other: __syncthreads() and the warp shuffles.  Everything is deterministic.
+// Stream capture records launches and async copies with their arguments by value; a graph launch
+// replays the list.  Multi-rank runs: one host process per rank, NCCL calls over oracle/minimpi
+// (nccl_emu.cpp), exported "device" memory in POSIX shared memory.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

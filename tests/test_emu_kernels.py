@@ -180,8 +180,9 @@ def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     the shim run here; iteration counts and residuals against the reference's own solve"""
     if not os.path.isdir("/root/reference/src"):
         pytest.skip("needs /root/reference to build the ij driver")
-    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "emu_shim"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for target in ("ij", "ij_mpi", "emu_shim"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", target], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     ref_bin, dev_bin = ("ij_ref", "ij_b200_emu") if nprocs == 1 else ("ij_refmpi", "ij_b200_emu_mpi")
     its_ref, res_ref, _ = _ij_run(ref_bin, args, nprocs)
     its_dev, res_dev, err = _ij_run(dev_bin, args, nprocs)

@@ -192,11 +192,15 @@ struct DCsr {
    long long  pat_irr_nnz = 0;
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
+   // formats the automatic choice cannot pick for this block are built on first request
+   // (dcsr_ensure_formats), not at upload
+   bool       defer_j16 = false, defer_sell = false;
 };
 
 int  dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha);
 int  dcsr_free(DCsr &M);
 void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
+int  dcsr_ensure_formats(DCsr &M, int kind);
 int  dcsr_build_partition(DCsr &M, const int *hi);
 int  dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha);   // kernels_sell.cu
 int  dcsr_free_sell(DCsr &M);

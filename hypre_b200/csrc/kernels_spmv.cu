@@ -19,6 +19,7 @@
 // the epilogue's vectors; x is gathered through L1/L2 (a 27-point row block touches 9 short
 // x segments, reuse factor ~27).
 #include "hb_internal.cuh"
+#include <chrono>
 #include "hb_epilogue.cuh"
 
 namespace hb {
@@ -439,8 +440,64 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
    }
 }
 
+// 16-bit column offsets from the row, when every entry of a square block stays within +-32767 of the
+// diagonal (the SPMV_VECTOR16 kernel: 10 instead of 12 bytes per nonzero)
+static int dcsr_build_j16(DCsr &M, const int *hi, const int *hj)
+{
+   const int nrows = M.nrows;
+   if (M.j16 || !(nrows >= 1024 && nrows == M.ncols && M.nnz >= 2LL * nrows) || getenv("HB200_NO_CSR16")) return 0;
+   bool fits = true;
+   for (int r = 0; r < nrows && fits; r++) {
+      for (int q = hi[r]; q < hi[r + 1]; q++) {
+         const int d = hj[q] - r;
+         if (d < -32767 || d > 32767) { fits = false; break; }
+      }
+   }
+   if (!fits) return 0;
+   std::vector<short> j16((size_t) M.nnz + 8, 0);
+   for (int r = 0; r < nrows; r++) {
+      for (int q = hi[r]; q < hi[r + 1]; q++) j16[(size_t) q] = (short) (hj[q] - r);
+   }
+   HB_CUDA(cudaMalloc(&M.j16, sizeof(short) * j16.size()));
+   HB_CUDA(cudaMemcpy(M.j16, j16.data(), sizeof(short) * j16.size(), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// The formats the automatic choice cannot pick are not built at upload: a block stored in the
+// row-pattern format never runs the packed-SELL kernel, and one whose every row is in the pattern
+// table never runs the CSR kernels either.  A caller that forces such a kernel
+// (hb200_parcsr_set_spmv_kernel: the level sweeps, the parity tests) gets the format built then,
+// from the device copy of the CSR arrays.  HB200_EAGER_FORMATS=1 builds everything at upload.
+int dcsr_ensure_formats(DCsr &M, int kind)
+{
+   const bool want_j16 = (kind == SPMV_VECTOR16) && M.defer_j16;
+   const bool want_sell = (kind == SPMV_SELL) && M.defer_sell;
+   if (!want_j16 && !want_sell) return 0;
+   std::vector<int> hi((size_t) M.nrows + 1), hj((size_t) M.nnz);
+   std::vector<double> ha;
+   HB_CUDA(cudaMemcpy(hi.data(), M.i, sizeof(int) * hi.size(), cudaMemcpyDeviceToHost));
+   HB_CUDA(cudaMemcpy(hj.data(), M.j, sizeof(int) * hj.size(), cudaMemcpyDeviceToHost));
+   if (want_j16) {
+      M.defer_j16 = false;
+      HB_CHECK(dcsr_build_j16(M, hi.data(), hj.data()));
+   }
+   if (want_sell) {
+      M.defer_sell = false;
+      ha.resize((size_t) M.nnz);
+      HB_CUDA(cudaMemcpy(ha.data(), M.a, sizeof(double) * ha.size(), cudaMemcpyDeviceToHost));
+      HB_CHECK(dcsr_build_sell(M, hi.data(), hj.data(), ha.data()));
+   }
+   return 0;
+}
+
+static double upload_now()
+{
+   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha)
 {
+   const double t_start = upload_now();
    M.nrows = nrows;
    M.ncols = ncols;
    M.nnz = nrows > 0 ? hi[nrows] : 0;
@@ -460,6 +517,7 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMemcpy(M.j, hj, sizeof(int) * (size_t) M.nnz, cudaMemcpyHostToDevice));
       HB_CUDA(cudaMemcpy(M.a, ha, sizeof(double) * (size_t) M.nnz, cudaMemcpyHostToDevice));
    }
+   const double t_copied = upload_now();
    // non-empty row list + row statistics
    std::vector<int> rn;
    int mx = 0;
@@ -476,27 +534,24 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
    }
    if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
-   if (nrows >= 1024 && nrows == ncols && M.nnz >= 2LL * nrows && !getenv("HB200_NO_CSR16")) {
-      // 16-bit column offsets from the row, when every entry stays within +-32767 of the diagonal
-      bool fits = true;
-      for (int r = 0; r < nrows && fits; r++) {
-         for (int q = hi[r]; q < hi[r + 1]; q++) {
-            const int d = hj[q] - r;
-            if (d < -32767 || d > 32767) { fits = false; break; }
-         }
-      }
-      if (fits) {
-         std::vector<short> j16((size_t) M.nnz + 8, 0);
-         for (int r = 0; r < nrows; r++) {
-            for (int q = hi[r]; q < hi[r + 1]; q++) j16[(size_t) q] = (short) (hj[q] - r);
-         }
-         HB_CUDA(cudaMalloc(&M.j16, sizeof(short) * j16.size()));
-         HB_CUDA(cudaMemcpy(M.j16, j16.data(), sizeof(short) * j16.size(), cudaMemcpyHostToDevice));
-      }
-   }
+   const double t_rows = upload_now();
    if (nrows > 0) HB_CHECK(dcsr_build_pat(M, hi, hj, ha));
-   if (nrows > 0 && nrows == ncols) HB_CHECK(dcsr_build_sell(M, hi, hj, ha));   // square (A_l) blocks only
+   const double t_pat = upload_now();
+   const bool eager = getenv("HB200_EAGER_FORMATS") != nullptr;
+   const bool square = nrows > 0 && nrows == ncols;
+   // 16-bit offsets: the CSR kernel of blocks outside the row-pattern format and of the rows a pattern
+   // table leaves out
+   if (square && (eager || !M.has_pat || M.pat_nirr > 0)) HB_CHECK(dcsr_build_j16(M, hi, hj)); else M.defer_j16 = square;
+   const double t_csr = upload_now();
+   if (square && (eager || !M.has_pat)) HB_CHECK(dcsr_build_sell(M, hi, hj, ha)); else M.defer_sell = square;   // square (A_l) blocks only
+   const double t_sell = upload_now();
    dcsr_choose_kernel(M, SPMV_AUTO, 0);
+   if (nrows >= 1024) {
+      HB_TRACE("upload %d x %d block, %lld nnz: CSR copy %.3f s, row lists %.3f s, row patterns %.3f s, 16-bit offsets %.3f s%s, "
+               "packed SELL %.3f s%s -> kernel kind %d", nrows, ncols, M.nnz, t_copied - t_start, t_rows - t_copied,
+               t_pat - t_rows, t_csr - t_pat, M.defer_j16 ? " (deferred)" : "", t_sell - t_csr,
+               M.defer_sell ? " (deferred)" : "", M.kind);
+   }
    return 0;
 }
 

@@ -10,6 +10,7 @@
 //   comp stream : diag block SpMV (all rows, epilogue y = beta*b + alpha*sum)   [overlapped]
 //   comp stream : wait(halo) ; offd block SpMV over the non-empty-row list, y += alpha*sum
 #include "hb_internal.cuh"
+#include <chrono>
 #include <algorithm>
 #include <numeric>
 #include <string.h>
@@ -221,9 +222,15 @@ int parcsr_ensure_T(hb200_parcsr *A)
    // 430-468): restriction stays a row-parallel, atomics-free, deterministic SpMV
    std::vector<int> hi, hj, ti, tj;
    std::vector<double> ha, ta;
+   const auto t0 = std::chrono::steady_clock::now();
    HB_CHECK(dcsr_download(A->diag, hi, hj, ha));
+   const auto t1 = std::chrono::steady_clock::now();
    host_csr_transpose(A->diag.nrows, A->diag.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
+   const auto t2 = std::chrono::steady_clock::now();
    HB_CHECK(dcsr_upload(A->diagT, A->diag.ncols, A->diag.nrows, ti.data(), tj.data(), ta.data()));
+   HB_TRACE("stored transpose of a %d x %d block: download %.3f s, host transpose %.3f s, upload %.3f s", A->diag.nrows,
+            A->diag.ncols, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
    if (A->num_cols_offd > 0) {
       HB_CHECK(dcsr_download(A->offd, hi, hj, ha));
       host_csr_transpose(A->offd.nrows, A->offd.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
@@ -462,8 +469,12 @@ int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
    HB_REQUIRE(kind >= 0 && kind <= 8, HB200_ERROR_ARG, "kind must be 0..8");
    HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
               HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
+   HB_CHECK(dcsr_ensure_formats(A->diag, kind));
    dcsr_choose_kernel(A->diag, kind, lanes_per_row);
-   if (A->has_T) dcsr_choose_kernel(A->diagT, kind, lanes_per_row);
+   if (A->has_T) {
+      HB_CHECK(dcsr_ensure_formats(A->diagT, kind));
+      dcsr_choose_kernel(A->diagT, kind, lanes_per_row);
+   }
    return 0;
 }
 

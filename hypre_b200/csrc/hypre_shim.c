@@ -430,6 +430,7 @@ HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
    hypre_ParVectorAllZeros(u) = 0;
    hypre_ParAMGDataNumIterations(amg) = its;
    hypre_ParAMGDataRelativeResidualNorm(amg) = rel;
+   if (g_verbose && hypre_ParAMGDataMaxIter(amg) > 1) { fprintf(stderr, "[hypre_b200] BoomerAMG on device: %d its, relative residual %.6e\n", its, rel); }
    if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
    if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
    return hypre_error_flag;

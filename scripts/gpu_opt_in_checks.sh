@@ -3,7 +3,8 @@
 # session and have only run in the host emulation so far.
 #   1. wide row-pattern kernel (HB200_PAT_WIDE=1) and fused Krylov dots (HB200_FUSED_DOTS=1) on hardware;
 #   2. bench with and without fused dots (N = 1);
-#   3. with >= 2 GPUs: N = 2 bench with the wide format on (default) and off.
+#   3. with >= 2 GPUs: N = 2 bench with the wide format on (default) and off;
+#   (4. and 5. at the end of the file)
 TAG=${1:-optin}
 NG=${2:-1}
 OUT=gpurun_out/$TAG
@@ -34,4 +35,13 @@ if [ "$NG" -ge 2 ]; then
     timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench2_wide_$w.log 2>&1
     grep '^{' $OUT/bench2_wide_$w.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('wide=$w', d['value'], d['ms_per_step'], d['config']['iterations'], d['config']['final_rel_res'], [ (e['kernel'][:28], round(e['ms_per_launch'],3)) for e in d['roofline_levels']])"
   done
+fi
+#   4. upload path after the deferred formats: per-block times of the 256^3 hierarchy (HB200_TRACE lines);
+#   5. with >= 4 GPUs: the reference's regression jobs through ij_b200_mpi on hardware (tests/ref_golden_jobs.py).
+HB200_TRACE=1 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_upload_trace.log 2>&1
+grep "upload\|stored transpose" $OUT/bench_upload_trace.log | head -40
+if [ "$NG" -ge 4 ]; then
+  timeout 900 python tests/ref_golden_jobs.py gpu 2>&1 | cut -c1-260 | tee $OUT/reference_regression_jobs_gpu.txt | tail -26
+elif [ "$NG" -ge 2 ]; then
+  timeout 600 python tests/ref_golden_jobs.py gpu solvers.0 solvers.2 2>&1 | cut -c1-260
 fi

@@ -34,7 +34,9 @@ CASES = [
     ("smoother.12", 4, "-rhsrand -solver 1 -rlx 16 -n 20 20 10 -P 2 2 1", 6, 2.510130e-09, True),
     ("smoother.13", 4, "-rhsrand -solver 1 -rlx 16 -cheby_order 3 -n 20 20 10 -P 2 2 1", 5, 6.702200e-09, True),
     ("smoother.14", 4, "-rhsrand -solver 1 -rlx 17 -n 20 20 10 -P 2 2 1", 6, 5.044385e-10, False),
-    ("smoother.15", 4, "-rhsrand -solver 1 -rlx 15 -n 20 20 10 -P 2 2 1", 15, 5.807749e-09, False),
+    # rlx 15 (CG smoother): the hierarchy is outside the path, so the cycle stays in the reference and is
+    # called back as the preconditioner of the device PCG; the smoother's inner PCG solves run on device too
+    ("smoother.15", 4, "-rhsrand -solver 1 -rlx 15 -n 20 20 10 -P 2 2 1", 15, 5.807749e-09, True),
     ("smoother.16", 4, "-rhsrand -solver 1 -rlx 16 -cheby_scale 0 -n 20 20 20 -P 2 2 1 -27pt", 6, 1.555966e-09, True),
     ("smoother.17", 4, "-rhsrand -solver 1 -rlx 16 -cheby_variant 1 -n 20 20 20 -P 2 2 1", 7, 2.088732e-09, True),
     ("smoother.18", 4, "-solver 3 -rlx 16 -cheby_eig_est 0 -n 40 40 20 -P 2 2 1 -difconv -a 10 10 10", 11, 8.192864e-09, True),

@@ -505,8 +505,8 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
    HB_CUDA(cudaMalloc(&M.i, sizeof(int) * ((size_t) nrows + 1)));
    HB_CUDA(cudaMalloc(&M.j, sizeof(int) * nnz_pad));
    HB_CUDA(cudaMalloc(&M.a, sizeof(double) * nnz_pad));
-   HB_CUDA(cudaMemset(M.j, 0, sizeof(int) * nnz_pad));
-   HB_CUDA(cudaMemset(M.a, 0, sizeof(double) * nnz_pad));
+   HB_CUDA(cudaMemset(M.j + M.nnz, 0, sizeof(int) * (nnz_pad - (size_t) M.nnz)));       // the pad only
+   HB_CUDA(cudaMemset(M.a + M.nnz, 0, sizeof(double) * (nnz_pad - (size_t) M.nnz)));
    if (nrows > 0) {
       HB_CUDA(cudaMemcpy(M.i, hi, sizeof(int) * ((size_t) nrows + 1), cudaMemcpyHostToDevice));
    } else {

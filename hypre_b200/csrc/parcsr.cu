@@ -323,7 +323,7 @@ int hb200_parcsr_create(hb200_parcsr **Aout, int num_rows, int num_cols, int num
    A->global_cols = global_num_cols;
    int zero = 0;
    int f = dcsr_upload(A->diag, num_rows, num_cols, num_rows ? diag_i : &zero, diag_j, diag_data);
-   if (f) { delete A; return f; }
+   if (f) { hb200_parcsr_destroy(A); return f; }   // frees what the failed upload had already allocated
    if (num_cols_offd > 0) {
       f = dcsr_upload(A->offd, num_rows, num_cols_offd, offd_i, offd_j, offd_data);
       if (f) { hb200_parcsr_destroy(A); return f; }

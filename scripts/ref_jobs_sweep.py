@@ -26,7 +26,7 @@ def read_jobs(path):
     lines = [l for l in text.splitlines() if not l.lstrip().startswith("#")]
     joined = " ".join(l.rstrip("\\").strip() for l in lines)
     out = []
-    for m in re.finditer(r"mpirun\s+-np\s+(\d+)\s+\./ij\s+(.*?)\s*>\s*(\S+)", joined):
+    for m in re.finditer(r"mpirun\s+-np\s+(\d+)\s+\./ij\s+(.*?)\s*>+\s*(\S+)", joined):
         out.append((m.group(3), int(m.group(1)), m.group(2).split()))
     return out
 

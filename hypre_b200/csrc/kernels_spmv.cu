@@ -487,6 +487,9 @@ int dcsr_ensure_formats(DCsr &M, int kind)
       HB_CUDA(cudaMemcpy(ha.data(), M.a, sizeof(double) * ha.size(), cudaMemcpyDeviceToHost));
       HB_CHECK(dcsr_build_sell(M, hi.data(), hj.data(), ha.data()));
    }
+   // the copies above went through the legacy default stream, the kernels run on non-blocking streams:
+   // small pageable H2D copies may still be in flight when cudaMemcpy returns
+   HB_CUDA(cudaDeviceSynchronize());
    return 0;
 }
 
@@ -546,6 +549,8 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
    if (square && (eager || !M.has_pat)) HB_CHECK(dcsr_build_sell(M, hi, hj, ha)); else M.defer_sell = square;   // square (A_l) blocks only
    const double t_sell = upload_now();
    dcsr_choose_kernel(M, SPMV_AUTO, 0);
+   // uploads use the legacy default stream, kernels the non-blocking compute stream (see dcsr_ensure_formats)
+   HB_CUDA(cudaDeviceSynchronize());
    if (nrows >= 1024) {
       HB_TRACE("upload %d x %d block, %lld nnz: CSR copy %.3f s, row lists %.3f s, row patterns %.3f s, 16-bit offsets %.3f s%s, "
                "packed SELL %.3f s%s -> kernel kind %d", nrows, ncols, M.nnz, t_copied - t_start, t_rows - t_copied,

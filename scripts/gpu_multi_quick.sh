@@ -11,9 +11,10 @@ mkdir -p $OUT
 export PYTHONPATH=$PWD
 # the peer halo runs four ways: V-cycle graph on/off, NVLS on/off (the coarse GE gather is an NCCL
 # all-reduce inside the captured cycle; NVLS-class algorithms only exist above two ranks)
-for cfg in "nccl - -" "peer - -" "peer nograph -" "peer - nonvls" "peer nograph nonvls"; do
+for cfg in "nccl - -" "nccl graphnccl -" "peer - -" "peer nograph -" "peer - nonvls" "peer nograph nonvls"; do
   set -- $cfg; halo=$1; log=$OUT/${1}_${2}_${3}.log
   extra=""; [ "$2" = nograph ] && extra="--no-graph"
+  if [ "$2" = graphnccl ]; then export HB200_GRAPH_NCCL=1; else unset HB200_GRAPH_NCCL; fi   # NCCL halo inside the V-cycle graph (opt-in)
   if [ "$3" = nonvls ]; then export NCCL_NVLS_ENABLE=0; else unset NCCL_NVLS_ENABLE; fi
   echo "#### halo=$halo graph=${2} nvls=${3}"
   HB200_TRACE=1 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \

@@ -4,10 +4,11 @@ front of hypre_shim.c; `emu`: host emulation of the kernels, `gpu`: the real lib
 every "Iterations = N" line must be equal and every final relative residual must agree to 1e-5 relative.
 Whether the shim ran the solve on the device or handed it back to the reference is recorded per job.
 
-usage: python scripts/ref_jobs_sweep.py [emu|gpu] [file.jobs ...] [--max-seconds S] [--jobs J] [--max-rows R]
+usage: python scripts/ref_jobs_sweep.py [emu|gpu] [file.jobs ...] [--max-seconds S] [--jobs J] [--max-rows R] [--min-rows R]
 """
 import os
 import re
+import signal
 import subprocess
 import sys
 import time
@@ -35,10 +36,15 @@ def run(binary, nranks, args, timeout):
     cmd = [os.path.join(REF, "mpirun"), "-np", str(nranks), os.path.join(REF, binary), *args]
     env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
     t0 = time.time()
+    # own process group, so that a timeout takes the ranks down with their launcher
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REF, env=env, start_new_session=True)
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=REF, env=env)
+        out, err = p.communicate(timeout=timeout)
     except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        p.communicate()
         return None, None, "", time.time() - t0, "timeout"
+    r = subprocess.CompletedProcess(cmd, p.returncode, out, err)
     its = [int(x) for x in re.findall(r"Iterations = (\d+)", r.stdout)]
     res = [float(x) for x in re.findall(r"Final (?:[A-Za-z]+ )?Relative Residual Norm = ([0-9.eE+-]+)", r.stdout)]
     return its, res, r.stderr, time.time() - t0, ("" if r.returncode == 0 else f"exit code {r.returncode}")
@@ -66,7 +72,7 @@ def one(job, how, timeout):
 def main():
     argv = sys.argv[1:]
     how = "emu"
-    max_seconds, njobs, timeout, max_rows = 1e9, 2, 400, 40000
+    max_seconds, njobs, timeout, max_rows, min_rows = 1e9, 2, 400, 40000, 0
     files = []
     while argv:
         a = argv.pop(0)
@@ -78,6 +84,8 @@ def main():
             njobs = int(argv.pop(0))
         elif a == "--max-rows":
             max_rows = int(argv.pop(0))
+        elif a == "--min-rows":
+            min_rows = int(argv.pop(0))
         elif a == "--timeout":
             timeout = float(argv.pop(0))
         else:
@@ -96,7 +104,7 @@ def main():
             if "-n" in args:
                 k = args.index("-n")
                 rows = int(args[k + 1]) * int(args[k + 2]) * int(args[k + 3])
-            if how == "emu" and rows > max_rows:
+            if (how == "emu" and rows > max_rows) or rows < min_rows:
                 continue                      # minutes per job on the host emulation
             jobs.append((j[0], j[1], args))
     t0 = time.time()

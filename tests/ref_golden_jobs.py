@@ -12,6 +12,7 @@ oracle/_ref/ij_b200_emu_mpi).  `device` says whether the job's solver / smoother
 """
 import os
 import re
+import signal
 import subprocess
 import sys
 import time
@@ -60,8 +61,18 @@ def run_case(case, how="emu", timeout=900):
     cmd = [os.path.join(REF, "mpirun"), "-np", str(nranks), exe, *args.split()]
     env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
     t0 = time.time()
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=REF, env=env)
-    out = {"id": cid, "seconds": time.time() - t0, "ok": False, "why": "", "its": None, "res": None, "device": None}
+    # own process group, so that a timeout takes the ranks down with their launcher
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REF, env=env, start_new_session=True)
+    out = {"id": cid, "seconds": 0.0, "ok": False, "why": "", "its": None, "res": None, "device": None}
+    try:
+        so, se = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        p.communicate()
+        out["why"] = f"no result after {timeout} s"
+        return out
+    r = subprocess.CompletedProcess(cmd, p.returncode, so, se)
+    out["seconds"] = time.time() - t0
     if r.returncode != 0:
         out["why"] = f"exit code {r.returncode}: {r.stderr[-800:]}"
         return out

@@ -42,6 +42,7 @@
 /* ---------------------------------------------------------------------------------------------- */
 
 static int g_ready = 0, g_failed = 0, g_verbose = 0, g_strict = 0;
+static int g_nprocs = 1, g_myid = 0;   /* the communicator the library was bound on (first matrix seen) */
 
 static void *next_sym(const char *name)
 {
@@ -123,8 +124,21 @@ static int shim_init(MPI_Comm comm)
       }
    }
    g_ready = 1;
+   g_nprocs = nprocs; g_myid = myid;
    if (g_verbose && myid == 0) { fprintf(stderr, "[hypre_b200] %s bound, %d rank(s)\n", hb200_version(), nprocs); }
    return 0;
+}
+
+/* The NCCL communicator, the rank numbers of the halo plans and the all-reduces of the dots all belong
+ * to the communicator the library was bound on.  A matrix that lives on another one — the coarse problem
+ * of the sequential coarse AMG (seq_threshold: a sub-communicator of the ranks that own coarse rows, or
+ * COMM_SELF on every rank, par_amg_setup.c / par_coarse_parms / hypre_seqAMGSetup) — stays in the reference. */
+static const char *comm_off_path(MPI_Comm comm)
+{
+   int nprocs = 1, myid = 0;
+   hypre_MPI_Comm_size(comm, &nprocs);
+   hypre_MPI_Comm_rank(comm, &myid);
+   return (nprocs == g_nprocs && myid == g_myid) ? NULL : "matrix on a sub-communicator";
 }
 
 /* ---- device mirrors ---------------------------------------------------------------------------- */
@@ -413,6 +427,14 @@ HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
       return orig(amg_vdata, A, f, u);
    }
    if (shim_init(hypre_ParCSRMatrixComm(A))) { return hypre_error_flag; }
+   why = comm_off_path(hypre_ParCSRMatrixComm(A));
+   if (why)
+   {
+      static int noticed_comm = 0;
+      if (g_strict) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, why); return hypre_error_flag; }
+      notice_once(&noticed_comm, why);
+      return orig(amg_vdata, A, f, u);
+   }
    dev = mirror_amg(amg_vdata, A);
    if (!dev) { return hypre_error_flag; }
    hb200_amg_set_solve(dev, hypre_ParAMGDataTol(amg), hypre_ParAMGDataMinIter(amg), hypre_ParAMGDataMaxIter(amg),
@@ -473,7 +495,7 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    hb200_pcg_params P;
    hb200_krylov_result R;
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
-   int kind, flag;
+   int kind = 0, flag;
    if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_PCGSolve"); }
    /* only the ParCSR function table (HYPRE_ParCSRPCGCreate) is on the accelerated path */
    if (fn->Matvec != hypre_ParKrylovMatvec) { return orig(pcg_vdata, A, b, x); }
@@ -482,7 +504,8 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    if (!why)
    {
       if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
-      kind = precond_kind((void *) fn->precond, pd->precond_data, pA, &amg, &why);
+      why = comm_off_path(hypre_ParCSRMatrixComm(pA));
+      if (!why) kind = precond_kind((void *) fn->precond, pd->precond_data, pA, &amg, &why);
       if (kind == -2) { return hypre_error_flag; }
    }
    if (why)
@@ -525,7 +548,7 @@ HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
    hb200_gmres_params P;
    hb200_krylov_result R;
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
-   int kind, flag;
+   int kind = 0, flag;
    if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_GMRESSolve"); }
    if (fn->Matvec != hypre_ParKrylovMatvec) { return orig(gmres_vdata, A, b, x); }
    if (gd->precond_Mat && gd->precond_Mat != A) { why = "separate preconditioning matrix"; }
@@ -535,7 +558,8 @@ HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
    if (!why)
    {
       if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
-      kind = precond_kind((void *) fn->precond, gd->precond_data, pA, &amg, &why);
+      why = comm_off_path(hypre_ParCSRMatrixComm(pA));
+      if (!why) kind = precond_kind((void *) fn->precond, gd->precond_data, pA, &amg, &why);
       if (kind == -2) { return hypre_error_flag; }
    }
    if (why)
@@ -574,6 +598,10 @@ HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HY
       return hypre_ParCSRMatrixMatvec(alpha, pA, (hypre_ParVector *) x, beta, (hypre_ParVector *) y);
    }
    if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+   if (comm_off_path(hypre_ParCSRMatrixComm(pA)))
+   {
+      return hypre_ParCSRMatrixMatvec(alpha, pA, (hypre_ParVector *) x, beta, (hypre_ParVector *) y);
+   }
    dA = mirror_matrix(pA);
    if (!dA) { return hypre_error_flag; }
    if (hb200_parcsr_matvec_host(dA, alpha, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), beta,
@@ -592,6 +620,10 @@ HYPRE_Int HYPRE_ParCSRMatrixMatvecT(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, H
    double *dx = NULL, *dy = NULL;
    int nr = hypre_ParCSRMatrixNumRows(pA), nc = hypre_ParCSRMatrixNumCols(pA);
    if (shim_init(hypre_ParCSRMatrixComm(pA))) { return hypre_error_flag; }
+   if (comm_off_path(hypre_ParCSRMatrixComm(pA)))
+   {
+      return hypre_ParCSRMatrixMatvecT(alpha, pA, (hypre_ParVector *) x, beta, (hypre_ParVector *) y);
+   }
    dA = mirror_matrix(pA);
    if (!dA) { return hypre_error_flag; }
    if (hb200_malloc((void **) &dx, sizeof(double) * (size_t) (nr ? nr : 1)) || hb200_malloc((void **) &dy, sizeof(double) * (size_t) (nc ? nc : 1)))

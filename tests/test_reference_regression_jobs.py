@@ -45,3 +45,20 @@ def test_reference_job_through_the_dropin(case):
         pytest.skip(f"{case[1]} ranks need {case[1]} GPUs")
     o = jobs.run_case(case, "gpu")
     assert o["ok"], (case[0], o)
+
+
+def test_sub_communicator_matrices_stay_in_the_reference():
+    """seq_threshold (TEST_ij solvers.jobs out.105-108): the coarse problem of the sequential coarse AMG lives on
+    a sub-communicator (or COMM_SELF); its BoomerAMG solve must not reach the device path, whose NCCL
+    communicator, halo plans and all-reduces belong to the communicator the library was bound on (the
+    8-rank job hung before hypre_shim.c checked the matrix communicator).  Against the reference's own run."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs /root/reference to build the ij driver")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import ref_jobs_sweep as sweep
+    for target in ("ij_mpi", "emu_shim"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", target], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for args in ("-n 12 12 12 -P 2 2 1 -seq_th 50 -solver 1 -rlx 18", "-n 12 12 12 -P 2 2 1 -seq_th 50 -solver 1 -rlx 18 -red 1"):
+        name, status, note = sweep.one(("seq_th", 4, args.split()), "emu", 300)
+        assert status == "ok", (status, note)

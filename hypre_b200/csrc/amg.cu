@@ -258,7 +258,7 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    // multi-rank: only the peer-put halo keeps every step of the cycle a plain kernel on one stream
    // (HB200_GRAPH_NCCL=1, opt-in until it has run on hardware: capture the cycle with the NCCL halo as well —
    // grouped ncclSend/ncclRecv on the comm stream are capturable through the same event fork / join)
-   static const bool graph_nccl = getenv("HB200_GRAPH_NCCL") != nullptr;
+   static const bool graph_nccl = env_flag("HB200_GRAPH_NCCL", false);
    if (!amg->use_graph || g_timers_on || (c.nranks > 1 && c.halo_mode != 1 && !graph_nccl)) {
       return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    }

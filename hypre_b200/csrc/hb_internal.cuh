@@ -20,6 +20,8 @@ namespace hb {
 // errors
 // ---------------------------------------------------------------------------------------
 int set_error(int flag, const char *fmt, ...);
+// run-time switch from the environment: unset -> dflt; "", "0", "off", "no" -> false; anything else -> true
+bool env_flag(const char *name, bool dflt);
 
 #define HB_CUDA(call)                                                                    \
    do {                                                                                  \
@@ -88,6 +90,11 @@ struct Ctx {
    size_t        arena_bytes = 0, arena_used = 0;
    std::vector<char *> peer_arena;       // IPC-mapped base of every rank's arena (self = arena)
    bool          peer_ok = false;
+   // watchdog of the polling halo kernels (hb_peer.cuh): host-mapped error word + its device alias
+   unsigned long long *h_halo_err = nullptr, *d_halo_err = nullptr;
+   unsigned long long  halo_timeout_ns = 0;
+   // free list of the arena: regions returned by destroyed halo plans, reused first-fit
+   std::vector<std::pair<size_t, size_t>> arena_free;   // (offset, bytes)
    // persistent workspace (Krylov work vectors): stable addresses across solves keep the
    // captured V-cycle graphs valid and take cudaMalloc out of the solve
    void         *ws_ptr[16] = {nullptr};
@@ -111,6 +118,8 @@ void timers_begin();
 void timers_report(const char *what);
 int arena_setup();                                         // collective, after the NCCL communicator exists
 int arena_alloc(size_t bytes, size_t *offset);             // 256-byte aligned carve-out
+void arena_release(size_t offset, size_t bytes);           // give a carve-out back (plan destruction)
+int halo_check_error();                                    // non-zero when a polling halo kernel gave up
 struct PeerPlan;
 Ctx &ctx();
 int  require_ready();
@@ -310,6 +319,7 @@ struct CommPkgD {
    // peer-put halo (halo mode 1): one plan per direction, built collectively at first use
    struct PeerPlan *fwd = nullptr, *rev = nullptr;
    bool    peer_tried = false, peer_tried_rev = false;
+   bool    peer_off = false, peer_off_rev = false;   // the ranks agreed that the plan cannot be built: NCCL for this matrix
 };
 
 }  // namespace hb
@@ -339,7 +349,7 @@ int parcsr_diag(hb200_parcsr *A, const double **diag);   // lazily extracted dia
 int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp);   // pack + exchange on s_comm
 int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp);                     // make s_comp wait
 int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,
-                  double *y, const double *dotw = nullptr, int dot_slot = -1);
+                  double *y);
 int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, double *y);
 int gs_sched_free(void *p);
 // peer-put halo (parcsr_peer.cu)
@@ -357,6 +367,8 @@ struct PeerWaitArgs {
    unsigned long long *epoch_ctr = nullptr;
    unsigned int *ticket = nullptr;
    int n_in = 0;
+   unsigned long long *err = nullptr;      // watchdog (hb_peer.cuh SpinGuard)
+   unsigned long long timeout_ns = 0;
 };
 bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out);   // false when the plan receives nothing
 int  spmv_offd_wait_launch(const DCsr &M, const PeerWaitArgs &w, int epi_kind, const EpiArgs &ea, cudaStream_t st);

@@ -10,27 +10,9 @@
 // of the offd block, shuffle reduction, the *_ACC epilogues.
 #include "hb_internal.cuh"
 #include "hb_epilogue.cuh"
+#include "hb_peer.cuh"
 
 namespace hb {
-
-__device__ __forceinline__ unsigned long long offd_ld_acquire_sys(const unsigned long long *p)
-{
-   unsigned long long v;
-#ifndef HB200_EMU
-   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-#else
-   v = *(const volatile unsigned long long *) p;
-#endif
-   return v;
-}
-__device__ __forceinline__ void offd_st_release_sys(unsigned long long *p, unsigned long long v)
-{
-#ifndef HB200_EMU
-   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#else
-   *(volatile unsigned long long *) p = v;
-#endif
-}
 
 constexpr int kOffdThreads = 256;
 
@@ -43,9 +25,9 @@ spmv_offd_wait(int nlist, const int *__restrict__ rowlist, const int *__restrict
    // ---- wait for this exchange's data (same protocol as halo_wait_kernel)
    const unsigned long long epoch = w.epoch_ctr[1] + 1;
    const int par = (int) (epoch & 1ull);
-   for (int j = threadIdx.x; j < w.n_in; j += kOffdThreads) {
-      while (offd_ld_acquire_sys(w.flags + par * w.n_in + j) < epoch) { }
-   }
+   SpinGuard guard;
+   guard.err = w.err; guard.timeout_ns = w.timeout_ns;
+   for (int j = threadIdx.x; j < w.n_in; j += kOffdThreads) spin_until_ge(w.flags + par * w.n_in + j, epoch, guard, 2, j);
    __syncthreads();
    const double *x = par ? w.buf1 : w.buf0;
    // ---- the boundary rows
@@ -77,7 +59,7 @@ spmv_offd_wait(int nlist, const int *__restrict__ rowlist, const int *__restrict
    }
    __syncthreads();
    if (is_last) {
-      for (int j = threadIdx.x; j < w.n_in; j += kOffdThreads) offd_st_release_sys(w.in_ack[j], epoch);
+      for (int j = threadIdx.x; j < w.n_in; j += kOffdThreads) st_release_sys(w.in_ack[j], epoch);
       if (threadIdx.x == 0) w.epoch_ctr[1] = epoch;
    }
 }

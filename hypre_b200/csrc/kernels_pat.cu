@@ -228,7 +228,7 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 bool fused_dots_enabled()
 {
    // opt-in until the DOT kernel variants have run on hardware (logic verified in the host emulation)
-   static const bool on = getenv("HB200_FUSED_DOTS") != nullptr;
+   static const bool on = env_flag("HB200_FUSED_DOTS", false);
    return on;
 }
 
@@ -427,12 +427,12 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
 
 int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
 {
-   if (getenv("HB200_NO_PAT")) return 0;
+   if (env_flag("HB200_NO_PAT", false)) return 0;
    PatHost ph;
    HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, false));
    // the wide variant: on request, and by default on a partitioned problem, where the coarse
    // operators lose the regular numbering next to the rank boundary
-   const bool try_wide = getenv("HB200_PAT_WIDE") || (ctx().nranks > 1 && !getenv("HB200_NO_PAT_WIDE"));
+   const bool try_wide = env_flag("HB200_PAT_WIDE", false) || (ctx().nranks > 1 && !env_flag("HB200_NO_PAT_WIDE", false));
    if (!ph.ok && try_wide) HB_CHECK(pat_analyze_host(M.nrows, M.ncols, hi, hj, ha, ph, true));
    if (!ph.ok) return 0;
    const int n = M.nrows;

@@ -163,7 +163,7 @@ int dcsr_free_sell(DCsr &M)
 
 int dcsr_build_sell(DCsr &M, const int *hi, const int *hj, const double *ha)
 {
-   if (getenv("HB200_NO_SELL")) return 0;
+   if (env_flag("HB200_NO_SELL", false)) return 0;
    const int n = M.nrows;
    const long long nnz = M.nnz;
    if (n < 1024 || nnz == 0) return 0;               // tiny blocks: nothing to win

@@ -341,7 +341,7 @@ static int vector_lanes_for(double avg, long long nrows = 0)
 // covers the SMs, as long as every lane still has an entry to work on.  HB200_NO_WIDEN=1 disables.
 static int widen_lanes(int lanes, long long nlist, double avg)
 {
-   static const bool off = getenv("HB200_NO_WIDEN") != nullptr;
+   static const bool off = env_flag("HB200_NO_WIDEN", false);
    if (off) return lanes;
    while (lanes < 32 && nlist * lanes < 148LL * 1024 && lanes < avg) lanes *= 2;
    return lanes;
@@ -445,7 +445,7 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
 static int dcsr_build_j16(DCsr &M, const int *hi, const int *hj)
 {
    const int nrows = M.nrows;
-   if (M.j16 || !(nrows >= 1024 && nrows == M.ncols && M.nnz >= 2LL * nrows) || getenv("HB200_NO_CSR16")) return 0;
+   if (M.j16 || !(nrows >= 1024 && nrows == M.ncols && M.nnz >= 2LL * nrows) || env_flag("HB200_NO_CSR16", false)) return 0;
    bool fits = true;
    for (int r = 0; r < nrows && fits; r++) {
       for (int q = hi[r]; q < hi[r + 1]; q++) {
@@ -540,7 +540,7 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
    const double t_rows = upload_now();
    if (nrows > 0) HB_CHECK(dcsr_build_pat(M, hi, hj, ha));
    const double t_pat = upload_now();
-   const bool eager = getenv("HB200_EAGER_FORMATS") != nullptr;
+   const bool eager = env_flag("HB200_EAGER_FORMATS", false);
    const bool square = nrows > 0 && nrows == ncols;
    // 16-bit offsets: the CSR kernel of blocks outside the row-pattern format and of the rows a pattern
    // table leaves out

@@ -29,10 +29,16 @@ bool amg_dot_fused(const hb200_amg *amg);
 namespace hb {
 
 // device scalar slots used by the Krylov drivers
+// PCG: the three dots that close an iteration (<r,s> = gamma, <r,r>, flexible <r_old,s>) sit in one
+// block of adjacent slots so that ONE all-reduce serves them; two blocks alternate between
+// iterations because the previous gamma is still needed (beta = gamma / gamma_old)
 enum {
-   S_BB = 0, S_GAMMA0 = 1, S_GAMMA1 = 2, S_SDOTP = 3, S_RR = 4, S_FLAG = 5, S_ALPHA = 6,
-   S_DELTA = 7, S_T0 = 8, S_T1 = 9,
-   S_H0 = 16   // GMRES: hh column (k_dim + 1 entries, k_dim <= 40)
+   S_BB = 0, S_SDOTP = 1, S_FLAG = 2, S_ALPHA = 3,   // S_ALPHA = S_FLAG + 1 (pcg_update_xr_kernel)
+   S_BLK0 = 4, S_BLK1 = 8,                           // {gamma, rr, delta} of even / odd iterations
+   B_GAMMA = 0, B_RR = 1, B_DELTA = 2,
+   S_T0 = 12, S_T1 = 13,
+   S_NFETCH = 12,                                    // slots the host reads once per iteration
+   S_H0 = 16   // GMRES: hh column (k_dim + 1 entries, k_dim <= 100)
 };
 
 // dot_slot >= 0: the caller wants <r, z> in that scalar slot next; *dot_done says whether the
@@ -129,7 +135,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
    const double guard_zero_residual = 0.0;
    int tentatively_converged = 0, converged = 0;
    int i = 0;
-   int g_cur = S_GAMMA0, g_old = S_GAMMA1;
+   int blk_cur = S_BLK0, blk_old = S_BLK1;   // blk_cur + B_GAMMA holds the current gamma
 
    // ---- bi_prod (pcg.c:403-421)
    if (two_norm) {
@@ -171,15 +177,13 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
    // ---- r = b - A x ; p = C r ; gamma = <r,p> (pcg.c:499-510)
    PCG_CHECK(parcsr_matvec(A, -1.0, x, 1.0, b, r));
    PCG_CHECK(precond_apply(pk, amg, A, r, p));
-   PCG_CHECK(vec_dot2_dev(r, p, r, r, n, g_cur, S_RR, st));
+   PCG_CHECK(vec_dot2_dev(r, p, r, r, n, blk_cur + B_GAMMA, blk_cur + B_RR, st));
    {
-      // g_cur and S_RR are not adjacent in general: two small allreduces only when nranks > 1
-      PCG_CHECK(scalars_allreduce(g_cur, 1, st));
-      PCG_CHECK(scalars_allreduce(S_RR, 1, st));
-      double tmp[8];
-      PCG_CHECK(scalars_fetch(0, 8, tmp, st));
-      gamma = tmp[g_cur];
-      if (two_norm) i_prod_0 = tmp[S_RR]; else i_prod_0 = gamma;
+      PCG_CHECK(scalars_allreduce(blk_cur, 2, st));
+      double tmp[S_NFETCH];
+      PCG_CHECK(scalars_fetch(0, S_NFETCH, tmp, st));
+      gamma = tmp[blk_cur + B_GAMMA];
+      if (two_norm) i_prod_0 = tmp[blk_cur + B_RR]; else i_prod_0 = gamma;
    }
    if (gamma != 0.0) ieee_check = gamma / gamma;
    if (ieee_check != ieee_check) {
@@ -223,16 +227,19 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
 
       double sdotp = 0.0;
       int dflag = 0;
+      const int blk_new = blk_old;          // this iteration's {gamma, rr, delta}
+      const int g_cur = blk_cur + B_GAMMA, g_new = blk_new + B_GAMMA;
+      const int s_rr = blk_new + B_RR, s_delta = blk_new + B_DELTA;
       if (!recompute_true_residual) {
          if (flex) PCG_CHECK(vec_copy(r, r_old, n, st));
          // x += alpha p ; r -= alpha s ; <r,r>   with alpha, and its breakdown tests, on the device
          timer_tick(T_BLAS1);
-         PCG_CHECK(pcg_update_xr(p, s, x, r, n, g_cur, S_SDOTP, S_RR, S_FLAG, skip_break, st));
+         PCG_CHECK(pcg_update_xr(p, s, x, r, n, g_cur, S_SDOTP, s_rr, S_FLAG, skip_break, st));
          timer_tick(T_OTHER);
       } else {
          // rare path (pcg.c:653-702): host-driven
-         double tmp[8];
-         PCG_CHECK(scalars_fetch(0, 8, tmp, st));
+         double tmp[S_NFETCH];
+         PCG_CHECK(scalars_fetch(0, S_NFETCH, tmp, st));
          sdotp = tmp[S_SDOTP];
          if (sdotp == 0.0) { eflag |= HB200_ERROR_CONV; if (i == 1) i_prod = i_prod_0; break; }
          alpha = tmp[g_cur] / sdotp;
@@ -265,14 +272,14 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
                }
             }
          }
-         PCG_CHECK(vec_dot_dev(r, r, n, S_RR, st));
+         PCG_CHECK(vec_dot_dev(r, r, n, s_rr, st));
       }
 
       if (rtol > 0.0 && two_norm && !recompute_true_residual) {
          // pcg.c:705-719 (needs alpha on the host)
-         double ss, tmp[8];
+         double ss, tmp[S_NFETCH];
          PCG_CHECK(dot_global_host(s, s, n, &ss));
-         PCG_CHECK(scalars_fetch(0, 8, tmp, st));
+         PCG_CHECK(scalars_fetch(0, S_NFETCH, tmp, st));
          const double al = tmp[S_ALPHA];
          const double drob2 = al * al * ss / bi_prod;
          if (tmp[S_FLAG] <= 0.0 && drob2 < rtol * rtol) {
@@ -282,22 +289,18 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       }
 
       // s = C r ; gamma = <r,s>
-      const int g_new = g_old;
       bool gamma_done = false;
       PCG_CHECK(precond_apply(pk, amg, A, r, s, g_new, &gamma_done));
       timer_tick(T_BLAS1);
       if (!gamma_done) PCG_CHECK(vec_dot_dev(r, s, n, g_new, st));
-      if (flex) PCG_CHECK(vec_dot_dev(r_old, s, n, S_DELTA, st));
+      if (flex) PCG_CHECK(vec_dot_dev(r_old, s, n, s_delta, st));
       timer_tick(T_OTHER);
-      if (c.nranks > 1) {
-         PCG_CHECK(scalars_allreduce(g_new, 1, st));
-         PCG_CHECK(scalars_allreduce(S_RR, 1, st));
-         if (flex) PCG_CHECK(scalars_allreduce(S_DELTA, 1, st));
-      }
+      // one all-reduce for <r,s>, <r,r> [, <r_old,s>] (the reference: one MPI_Allreduce per dot)
+      PCG_CHECK(scalars_allreduce(blk_new, flex ? 3 : 2, st));
 
       // ---- the one host read of this iteration
-      double S[8];
-      PCG_CHECK(scalars_fetch(0, 8, S, st));
+      double S[S_NFETCH];
+      PCG_CHECK(scalars_fetch(0, S_NFETCH, S, st));
       if (!recompute_true_residual) {
          sdotp = S[S_SDOTP];
          dflag = (int) S[S_FLAG];
@@ -322,7 +325,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       }
       gamma_old = S[g_cur];
       gamma = S[g_new];
-      if (flex) delta = gamma - S[S_DELTA];
+      if (flex) delta = gamma - S[s_delta];
 
       if (rtol > 0.0 && !two_norm && !recompute_true_residual) {
          const double r2ob2 = (gamma + gamma_old) / bi_prod;
@@ -332,7 +335,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
          }
       }
 
-      i_prod = two_norm ? S[S_RR] : gamma;
+      i_prod = two_norm ? S[s_rr] : gamma;
 
       if (log) {
          norms[i] = sqrt(i_prod);
@@ -411,9 +414,9 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
       } else {
          PCG_CHECK(vec_copy(s, p, n, st));
       }
-      // rotate the gamma slots
-      g_old = g_cur;
-      g_cur = g_new;
+      // rotate the scalar blocks
+      blk_old = blk_cur;
+      blk_cur = blk_new;
    }
 
    if (P->print_level > 1 && my_id == 0) printf("\n\n");

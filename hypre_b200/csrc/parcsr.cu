@@ -80,13 +80,16 @@ int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp)
       // NVLink peer puts, everything on the compute stream (parcsr_peer.cu); the plan build is
       // collective, so ranks without neighbours on this matrix take part too
       HB_CHECK(peer_plans_ensure(A, false));
-      if (!peer_has_out(pk.fwd)) return 0;
-      // the put (gather + NVLink stores + system fences, ~10 us of latency) runs beside the diag pass
-      HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
-      HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
-      HB_CHECK(peer_put(pk.fwd, x, c.s_comm));
-      HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
-      return 0;
+      if (!pk.peer_off) {
+         if (!peer_has_out(pk.fwd)) return 0;
+         // the put (gather + NVLink stores + system fences, ~10 us of latency) runs beside the diag pass
+         HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
+         HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+         HB_CHECK(peer_put(pk.fwd, x, c.s_comm));
+         HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+         return 0;
+      }
+      // (the ranks agreed that this matrix has no peer plan: NCCL below)
    }
    if (pk.num_sends == 0 && pk.num_recvs == 0) return 0;
    HB_CUDA(cudaEventRecord(c.ev_a, st_comp));
@@ -104,7 +107,7 @@ int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
 {
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
-   if (c.halo_mode == 1 && c.nranks > 1) {
+   if (c.halo_mode == 1 && c.nranks > 1 && !pk.peer_off) {
       if (peer_has_out(pk.fwd)) HB_CUDA(cudaStreamWaitEvent(st_comp, c.ev_b, 0));
       return pk.fwd ? peer_wait(pk.fwd, st_comp) : 0;
    }
@@ -116,7 +119,7 @@ int parcsr_halo_end(hb200_parcsr *A, cudaStream_t st_comp)
 
 static bool fuse_wait_enabled()
 {
-   static const bool on = getenv("HB200_FUSE_WAIT") != nullptr;   // opt-in until measured on hardware
+   static const bool on = env_flag("HB200_FUSE_WAIT", false);   // opt-in until measured on hardware
    return on;
 }
 
@@ -128,7 +131,7 @@ int parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea)
    Ctx &c = ctx();
    CommPkgD &pk = A->pkg;
    PeerWaitArgs w;
-   if (c.halo_mode == 1 && c.nranks > 1 && fuse_wait_enabled() && A->num_cols_offd > 0 && A->offd.num_rownnz > 0 &&
+   if (c.halo_mode == 1 && c.nranks > 1 && !pk.peer_off && fuse_wait_enabled() && A->num_cols_offd > 0 && A->offd.num_rownnz > 0 &&
        peer_wait_args(pk.fwd, &w)) {
       timer_tick(T_HALO_WAIT);
       if (peer_has_out(pk.fwd)) HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));   // the local put is done
@@ -145,9 +148,8 @@ int parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea)
 }
 
 int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, const double *b,
-                  double *y, const double *dotw, int dot_slot)
+                  double *y)
 {
-   (void) dotw; (void) dot_slot;
    Ctx &c = ctx();
    if (alpha == 0.0) {
       c.dot_req_armed = false; c.last_dot_fused = false;
@@ -246,9 +248,12 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    Ctx &c = ctx();
    HB_CHECK(parcsr_ensure_T(A));
    CommPkgD &pk = A->pkg;
-   const bool peer = (c.halo_mode == 1 && c.nranks > 1);
+   bool peer = (c.halo_mode == 1 && c.nranks > 1);
    const bool comm = (pk.num_sends || pk.num_recvs);
-   if (peer) HB_CHECK(peer_plans_ensure(A, true));
+   if (peer) {
+      HB_CHECK(peer_plans_ensure(A, true));
+      if (pk.peer_off_rev) peer = false;   // agreed on every rank: NCCL for this matrix
+   }
    timer_tick(T_MATVEC_OFFD);
    if (A->num_cols_offd > 0) {
       // y_tmp = alpha * offd^T x  (par_csr_matvec.c:402-420)

@@ -18,12 +18,17 @@
 // sets, e.g. interpolation matrices).  Epoch counters live in device memory, so a replayed graph
 // keeps counting.
 #include "hb_internal.cuh"
+#include "hb_peer.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace hb {
 
 struct PeerPlan {
    int n_out = 0, n_in = 0, total_out = 0, total_in = 0;
+   // arena carve-outs of this plan (returned to the free list by peer_plan_free)
+   size_t region_off[4] = {0, 0, 0, 0}, region_bytes[4] = {0, 0, 0, 0};
+   int    n_regions = 0;
    // outgoing segments
    int                 *d_out_starts = nullptr;   // n_out + 1
    const int           *d_gather = nullptr;       // gather map (borrowed) or NULL = contiguous
@@ -100,6 +105,15 @@ int arena_setup_collective(int *all_ok)
       HB_CHECK(scalars_fetch(kScalarSlots - 1, 1, &v, c.s_comp));
    }
    if (v == 0.0) {
+      // watchdog of the polling kernels: one host-mapped word the kernels write when they give up
+      if (!c.h_halo_err) {
+         HB_CUDA(cudaHostAlloc((void **) &c.h_halo_err, sizeof(unsigned long long), cudaHostAllocMapped));
+         *c.h_halo_err = 0ull;
+         HB_CUDA(cudaHostGetDevicePointer((void **) &c.d_halo_err, (void *) c.h_halo_err, 0));
+         const char *ts = getenv("HB200_HALO_TIMEOUT_S");
+         const double secs = ts ? atof(ts) : 30.0;
+         c.halo_timeout_ns = secs > 0.0 ? (unsigned long long) (secs * 1e9) : 0ull;
+      }
       c.peer_ok = true;
       *all_ok = 1;
       return 0;
@@ -131,6 +145,17 @@ int arena_setup()
 int arena_alloc(size_t bytes, size_t *offset)
 {
    Ctx &c = ctx();
+   bytes = (bytes + 255) & ~(size_t) 255;
+   // first fit in the regions that destroyed plans gave back
+   for (size_t k = 0; k < c.arena_free.size(); k++) {
+      if (c.arena_free[k].second >= bytes) {
+         *offset = c.arena_free[k].first;
+         c.arena_free[k].first += bytes;
+         c.arena_free[k].second -= bytes;
+         if (c.arena_free[k].second == 0) c.arena_free.erase(c.arena_free.begin() + (long) k);
+         return 0;
+      }
+   }
    const size_t off = (c.arena_used + 255) & ~(size_t) 255;
    if (off + bytes > c.arena_bytes) {
       return set_error(HB200_ERROR_MEMORY, "peer arena exhausted (%zu MB); raise HB200_ARENA_MB", c.arena_bytes >> 20);
@@ -140,44 +165,58 @@ int arena_alloc(size_t bytes, size_t *offset)
    return 0;
 }
 
+void arena_release(size_t offset, size_t bytes)
+{
+   Ctx &c = ctx();
+   bytes = (bytes + 255) & ~(size_t) 255;
+   if (bytes == 0 || !c.arena) return;
+   auto &fl = c.arena_free;
+   size_t k = 0;
+   while (k < fl.size() && fl[k].first < offset) k++;
+   fl.insert(fl.begin() + (long) k, std::make_pair(offset, bytes));
+   // merge with the neighbours
+   if (k + 1 < fl.size() && fl[k].first + fl[k].second == fl[k + 1].first) { fl[k].second += fl[k + 1].second; fl.erase(fl.begin() + (long) k + 1); }
+   if (k > 0 && fl[k - 1].first + fl[k - 1].second == fl[k].first) { fl[k - 1].second += fl[k].second; fl.erase(fl.begin() + (long) k); }
+   // a free region at the top of the bump pointer lowers it again
+   if (!fl.empty() && fl.back().first + fl.back().second == ((c.arena_used + 255) & ~(size_t) 255)) {
+      c.arena_used = fl.back().first;
+      fl.pop_back();
+   }
+}
+
+// a polling halo kernel gave up (hb_peer.cuh): report it once per occurrence as an error of the call
+int halo_check_error()
+{
+   Ctx &c = ctx();
+   if (!c.h_halo_err) return 0;
+   const unsigned long long w = *(volatile unsigned long long *) c.h_halo_err;
+   if (w == 0ull) return 0;
+   const int what = (int) (w >> 56), seg = (int) ((w >> 40) & 0xffff);
+   return set_error(HB200_ERROR_GENERIC,
+                    "halo exchange timed out on rank %d: the %s kernel waited more than %.0f s for %s %d to reach epoch %llu "
+                    "(a peer died or left the collective sequence); results of this call are undefined",
+                    c.rank, what == 1 ? "put" : "wait", (double) c.halo_timeout_ns * 1e-9,
+                    what == 1 ? "the consumed-flag of outgoing segment" : "the arrival flag of incoming segment", seg,
+                    (unsigned long long) (w & 0xffffffffffull));
+}
+
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-   unsigned long long v;
-#ifndef HB200_EMU
-   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-#else
-   v = *(const volatile unsigned long long *) p;
-#endif
-   return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-#ifndef HB200_EMU
-   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#else
-   *(volatile unsigned long long *) p = v;
-#endif
-}
-
 constexpr int kHaloBlock = 512;
 
 __global__ void __launch_bounds__(kHaloBlock)
 halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const int *__restrict__ gather,
                 const double *__restrict__ src, double *const *__restrict__ dst2,
                 unsigned long long *const *__restrict__ flag2, const unsigned long long *__restrict__ acks,
-                unsigned long long *epoch_ctr, unsigned int *ticket)
+                unsigned long long *epoch_ctr, unsigned int *ticket, SpinGuard guard)
 {
    __shared__ bool is_last;
    const unsigned long long epoch = epoch_ctr[0] + 1;
    const int par = (int) (epoch & 1ull);
    // the receivers must have copied exchange (epoch - 2) out of this parity's buffers
    if (epoch > 2) {
-      for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
-         while (ld_acquire_sys(acks + i) + 2 < epoch) { }
-      }
+      for (int i = threadIdx.x; i < n_out; i += blockDim.x) spin_until_ge(acks + i, epoch - 2, guard, 1, i);
       __syncthreads();
    }
    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -213,14 +252,12 @@ halo_put_kernel(int total, int n_out, const int *__restrict__ out_starts, const 
 __global__ void __launch_bounds__(kHaloBlock)
 halo_wait_kernel(int total, int n_in, const double *__restrict__ buf0, const double *__restrict__ buf1,
                  const unsigned long long *__restrict__ flags, unsigned long long *const *__restrict__ in_ack,
-                 double *__restrict__ dst, unsigned long long *epoch_ctr, unsigned int *ticket)
+                 double *__restrict__ dst, unsigned long long *epoch_ctr, unsigned int *ticket, SpinGuard guard)
 {
    __shared__ bool is_last;
    const unsigned long long epoch = epoch_ctr[1] + 1;
    const int par = (int) (epoch & 1ull);
-   for (int j = threadIdx.x; j < n_in; j += blockDim.x) {
-      while (ld_acquire_sys(flags + par * n_in + j) < epoch) { }
-   }
+   for (int j = threadIdx.x; j < n_in; j += blockDim.x) spin_until_ge(flags + par * n_in + j, epoch, guard, 2, j);
    __syncthreads();
    const double *buf = par ? buf1 : buf0;
    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -252,11 +289,19 @@ static inline int halo_grid(int total)
    return grid > 128 ? 128 : grid;
 }
 
+static SpinGuard spin_guard()
+{
+   SpinGuard g;
+   g.err = ctx().d_halo_err;
+   g.timeout_ns = ctx().halo_timeout_ns;
+   return g;
+}
+
 int peer_put(PeerPlan *pl, const double *src, cudaStream_t st)
 {
    if (pl->n_out == 0) return 0;
    HB_LAUNCH(halo_put_kernel, halo_grid(pl->total_out), kHaloBlock, 0, st, pl->total_out, pl->n_out, pl->d_out_starts,
-             pl->d_gather, src, pl->d_out_dst, pl->d_out_flag, pl->acks, pl->d_epoch, pl->d_ticket);
+             pl->d_gather, src, pl->d_out_dst, pl->d_out_flag, pl->acks, pl->d_epoch, pl->d_ticket, spin_guard());
    HB_LAUNCH_CHECK();
    return 0;
 }
@@ -265,7 +310,7 @@ int peer_wait(PeerPlan *pl, cudaStream_t st)
 {
    if (pl->n_in == 0) return 0;
    HB_LAUNCH(halo_wait_kernel, halo_grid(pl->total_in), kHaloBlock, 0, st, pl->total_in, pl->n_in, pl->in_buf[0],
-             pl->in_buf[1], pl->in_flags, pl->d_in_ack, pl->dst, pl->d_epoch, pl->d_ticket);
+             pl->in_buf[1], pl->in_flags, pl->d_in_ack, pl->dst, pl->d_epoch, pl->d_ticket, spin_guard());
    HB_LAUNCH_CHECK();
    return 0;
 }
@@ -279,12 +324,17 @@ bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out)
    out->flags = pl->in_flags; out->in_ack = pl->d_in_ack;
    out->epoch_ctr = pl->d_epoch; out->ticket = pl->d_ticket;
    out->n_in = pl->n_in;
+   out->err = ctx().d_halo_err;
+   out->timeout_ns = ctx().halo_timeout_ns;
    return true;
 }
 
 void peer_plan_free(PeerPlan *pl)
 {
    if (!pl) return;
+   // (the caller has synchronised the device; the regions are zeroed again, after a collective step,
+   //  by the next plan that takes them: build_plan)
+   for (int k = 0; k < pl->n_regions; k++) arena_release(pl->region_off[k], pl->region_bytes[k]);
    if (pl->d_out_starts) cudaFree(pl->d_out_starts);
    if (pl->d_out_dst) cudaFree(pl->d_out_dst);
    if (pl->d_out_flag) cudaFree(pl->d_out_flag);
@@ -298,24 +348,34 @@ void peer_plan_free(PeerPlan *pl)
 // plan construction (collective over all ranks, same call order everywhere)
 // ---------------------------------------------------------------------------------------
 // out: segments this rank sends (peer, start offsets);  in: segments it receives.
+// Every rank runs every collective of this function even when a local step failed (arena exhausted,
+// cudaMalloc failure): the failure count is agreed on at the end, and a plan exists afterwards either
+// on every rank or on none (*out_plan = NULL: the matrix keeps the NCCL halo).
 static int build_plan(PeerPlan **out_plan, int n_out, const int *out_procs, const int *out_starts,
                       const int *d_gather, int n_in, const int *in_procs, const int *in_starts, double *dst)
 {
 #ifdef HB200_WITH_NCCL
    Ctx &c = ctx();
    const int nr = c.nranks;
+   int bad = 0;
+   *out_plan = nullptr;
    PeerPlan *pl = new PeerPlan();
    pl->n_out = n_out; pl->n_in = n_in;
    pl->total_out = n_out ? out_starts[n_out] : 0;
    pl->total_in = n_in ? in_starts[n_in] : 0;
    pl->d_gather = d_gather;
    pl->dst = dst;
-   // ---- carve local arena space
-   size_t off_buf0 = 0, off_buf1 = 0, off_flags = 0, off_acks = 0;
-   HB_CHECK(arena_alloc(sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1), &off_buf0));
-   HB_CHECK(arena_alloc(sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1), &off_buf1));
-   HB_CHECK(arena_alloc(sizeof(unsigned long long) * (size_t) (2 * (n_in ? n_in : 1)), &off_flags));
-   HB_CHECK(arena_alloc(sizeof(unsigned long long) * (size_t) (n_out ? n_out : 1), &off_acks));
+   // ---- carve local arena space: 2 receive buffers, arrival flags, consumed flags
+   const size_t want[4] = {sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1),
+                           sizeof(double) * (size_t) (pl->total_in ? pl->total_in : 1),
+                           sizeof(unsigned long long) * (size_t) (2 * (n_in ? n_in : 1)),
+                           sizeof(unsigned long long) * (size_t) (n_out ? n_out : 1)};
+   size_t off[4] = {0, 0, 0, 0};
+   for (int k = 0; k < 4 && !bad; k++) {
+      if (arena_alloc(want[k], &off[k])) { bad = 1; break; }
+      pl->region_off[k] = off[k]; pl->region_bytes[k] = want[k]; pl->n_regions = k + 1;
+   }
+   const size_t off_buf0 = off[0], off_buf1 = off[1], off_flags = off[2], off_acks = off[3];
    pl->in_buf[0] = (double *) (c.arena + off_buf0);
    pl->in_buf[1] = (double *) (c.arena + off_buf1);
    pl->in_flags = (unsigned long long *) (c.arena + off_flags);
@@ -324,65 +384,83 @@ static int build_plan(PeerPlan **out_plan, int n_out, const int *out_procs, cons
    //      rank p; ack slot of the segment I send to rank p}; -1 = none
    const int W = 5;
    std::vector<long long> mine((size_t) nr * W, -1), all((size_t) nr * nr * W, -1);
-   for (int j = 0; j < n_in; j++) {
-      const int p = in_procs[j];
-      long long *row = &mine[(size_t) p * W];
-      row[0] = (long long) (off_buf0 + sizeof(double) * (size_t) in_starts[j]);
-      row[1] = (long long) (off_buf1 + sizeof(double) * (size_t) in_starts[j]);
-      row[2] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) j);
-      row[3] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) (n_in + j));
-   }
-   for (int i = 0; i < n_out; i++) {
-      mine[(size_t) out_procs[i] * W + 4] = (long long) (off_acks + sizeof(unsigned long long) * (size_t) i);
+   if (!bad) {
+      for (int j = 0; j < n_in; j++) {
+         const int p = in_procs[j];
+         long long *row = &mine[(size_t) p * W];
+         row[0] = (long long) (off_buf0 + sizeof(double) * (size_t) in_starts[j]);
+         row[1] = (long long) (off_buf1 + sizeof(double) * (size_t) in_starts[j]);
+         row[2] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) j);
+         row[3] = (long long) (off_flags + sizeof(unsigned long long) * (size_t) (n_in + j));
+      }
+      for (int i = 0; i < n_out; i++) {
+         mine[(size_t) out_procs[i] * W + 4] = (long long) (off_acks + sizeof(unsigned long long) * (size_t) i);
+      }
    }
    long long *d_t = nullptr;
    const size_t row_bytes = sizeof(long long) * (size_t) nr * W;
-   HB_CUDA(cudaMalloc((void **) &d_t, row_bytes * (size_t) nr));
+   HB_CUDA(cudaMalloc((void **) &d_t, row_bytes * (size_t) nr));   // (a failure here is fatal for the process anyway)
    HB_CUDA(cudaMemcpy((char *) d_t + row_bytes * (size_t) c.rank, mine.data(), row_bytes, cudaMemcpyHostToDevice));
    HB_NCCL(nccl_api().AllGather((char *) d_t + row_bytes * (size_t) c.rank, d_t, row_bytes, ncclChar, c.nccl, c.s_comp));
    HB_CUDA(cudaStreamSynchronize(c.s_comp));
    HB_CUDA(cudaMemcpy(all.data(), d_t, row_bytes * (size_t) nr, cudaMemcpyDeviceToHost));
    cudaFree(d_t);
+   // every rank is past the destruction of whatever owned these regions before (same call order on
+   // all ranks, destruction synchronises the device): no late store of an old plan can land any more.
+   // Flags and consumed-epochs start from zero.
+   if (!bad) {
+      if (cudaMemsetAsync(c.arena + off_flags, 0, want[2], c.s_comp) != cudaSuccess ||
+          cudaMemsetAsync(c.arena + off_acks, 0, want[3], c.s_comp) != cudaSuccess) bad = 1;
+   }
    // ---- resolve remote pointers
-   std::vector<double *> out_dst((size_t) (2 * (n_out ? n_out : 1)), nullptr);
-   std::vector<unsigned long long *> out_flag((size_t) (2 * (n_out ? n_out : 1)), nullptr);
+   std::vector<double *> dst2((size_t) (2 * (n_out ? n_out : 1)), nullptr);
+   std::vector<unsigned long long *> flag2((size_t) (2 * (n_out ? n_out : 1)), nullptr);
    std::vector<unsigned long long *> in_ack((size_t) (n_in ? n_in : 1), nullptr);
-   for (int i = 0; i < n_out; i++) {
+   char mismatch[160] = "";
+   for (int i = 0; i < n_out && !bad; i++) {
       const int q = out_procs[i];
       const long long *row = &all[((size_t) q * nr + (size_t) c.rank) * W];   // q's segment from me
-      if (row[0] < 0) { delete pl; return set_error(HB200_ERROR_GENERIC, "halo plan mismatch: rank %d does not expect data from rank %d", q, c.rank); }
-      out_dst[(size_t) i] = (double *) (c.peer_arena[q] + row[0]);
-      out_dst[(size_t) (n_out + i)] = (double *) (c.peer_arena[q] + row[1]);
-      out_flag[(size_t) i] = (unsigned long long *) (c.peer_arena[q] + row[2]);
-      out_flag[(size_t) (n_out + i)] = (unsigned long long *) (c.peer_arena[q] + row[3]);
+      if (row[0] < 0) { snprintf(mismatch, sizeof(mismatch), "rank %d offers no receive segment for rank %d", q, c.rank); bad = 1; break; }
+      // parity 0 buffers are used by even epochs, parity 1 by odd ones: tables ordered [par][i]
+      dst2[(size_t) i] = (double *) (c.peer_arena[q] + row[0]);
+      dst2[(size_t) (n_out + i)] = (double *) (c.peer_arena[q] + row[1]);
+      flag2[(size_t) i] = (unsigned long long *) (c.peer_arena[q] + row[2]);
+      flag2[(size_t) (n_out + i)] = (unsigned long long *) (c.peer_arena[q] + row[3]);
    }
-   for (int j = 0; j < n_in; j++) {
+   for (int j = 0; j < n_in && !bad; j++) {
       const int p = in_procs[j];
       const long long a = all[((size_t) p * nr + (size_t) c.rank) * W + 4];         // p's ack slot for me
-      if (a < 0) { delete pl; return set_error(HB200_ERROR_GENERIC, "halo plan mismatch: rank %d does not send to rank %d", p, c.rank); }
+      if (a < 0) { snprintf(mismatch, sizeof(mismatch), "rank %d offers no consumed-flag for rank %d", p, c.rank); bad = 1; break; }
       in_ack[(size_t) j] = (unsigned long long *) (c.peer_arena[p] + a);
    }
-   // parity 0 buffers are used by even epochs, parity 1 by odd ones: order the tables [par][i]
-   std::vector<double *> dst2((size_t) (2 * (n_out ? n_out : 1)));
-   std::vector<unsigned long long *> flag2((size_t) (2 * (n_out ? n_out : 1)));
-   for (int i = 0; i < n_out; i++) {
-      dst2[(size_t) i] = out_dst[(size_t) i];                       // par 0
-      dst2[(size_t) (n_out + i)] = out_dst[(size_t) (n_out + i)];   // par 1
-      flag2[(size_t) i] = out_flag[(size_t) i];
-      flag2[(size_t) (n_out + i)] = out_flag[(size_t) (n_out + i)];
+   if (!bad) {
+      bool ok = cudaMalloc((void **) &pl->d_out_starts, sizeof(int) * (size_t) (n_out + 1)) == cudaSuccess;
+      if (ok && n_out) ok = cudaMemcpy(pl->d_out_starts, out_starts, sizeof(int) * (size_t) (n_out + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_out_dst, sizeof(double *) * dst2.size()) == cudaSuccess;
+      ok = ok && cudaMemcpy(pl->d_out_dst, dst2.data(), sizeof(double *) * dst2.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_out_flag, sizeof(unsigned long long *) * flag2.size()) == cudaSuccess;
+      ok = ok && cudaMemcpy(pl->d_out_flag, flag2.data(), sizeof(unsigned long long *) * flag2.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_in_ack, sizeof(unsigned long long *) * in_ack.size()) == cudaSuccess;
+      ok = ok && cudaMemcpy(pl->d_in_ack, in_ack.data(), sizeof(unsigned long long *) * in_ack.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_epoch, sizeof(unsigned long long) * 2) == cudaSuccess;
+      ok = ok && cudaMemset(pl->d_epoch, 0, sizeof(unsigned long long) * 2) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_ticket, sizeof(unsigned int) * 2) == cudaSuccess;
+      ok = ok && cudaMemset(pl->d_ticket, 0, sizeof(unsigned int) * 2) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); bad = 1; }
    }
-   HB_CUDA(cudaMalloc((void **) &pl->d_out_starts, sizeof(int) * (size_t) (n_out + 1)));
-   if (n_out) HB_CUDA(cudaMemcpy(pl->d_out_starts, out_starts, sizeof(int) * (size_t) (n_out + 1), cudaMemcpyHostToDevice));
-   HB_CUDA(cudaMalloc((void **) &pl->d_out_dst, sizeof(double *) * dst2.size()));
-   HB_CUDA(cudaMemcpy(pl->d_out_dst, dst2.data(), sizeof(double *) * dst2.size(), cudaMemcpyHostToDevice));
-   HB_CUDA(cudaMalloc((void **) &pl->d_out_flag, sizeof(unsigned long long *) * flag2.size()));
-   HB_CUDA(cudaMemcpy(pl->d_out_flag, flag2.data(), sizeof(unsigned long long *) * flag2.size(), cudaMemcpyHostToDevice));
-   HB_CUDA(cudaMalloc((void **) &pl->d_in_ack, sizeof(unsigned long long *) * in_ack.size()));
-   HB_CUDA(cudaMemcpy(pl->d_in_ack, in_ack.data(), sizeof(unsigned long long *) * in_ack.size(), cudaMemcpyHostToDevice));
-   HB_CUDA(cudaMalloc((void **) &pl->d_epoch, sizeof(unsigned long long) * 2));
-   HB_CUDA(cudaMemset(pl->d_epoch, 0, sizeof(unsigned long long) * 2));
-   HB_CUDA(cudaMalloc((void **) &pl->d_ticket, sizeof(unsigned int) * 2));
-   HB_CUDA(cudaMemset(pl->d_ticket, 0, sizeof(unsigned int) * 2));
+   // ---- agree: peers must not start writing into this arena region before everybody has built the
+   //      plan, and nobody may use a plan that some rank could not build
+   double v = (double) bad;
+   HB_CUDA(cudaMemcpyAsync(c.d_scalars + kScalarSlots - 1, &v, sizeof(double), cudaMemcpyHostToDevice, c.s_comp));
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
+   HB_CHECK(scalars_fetch(kScalarSlots - 1, 1, &v, c.s_comp));
+   if (v != 0.0) {
+      peer_plan_free(pl);
+      if (mismatch[0]) set_error(HB200_ERROR_GENERIC, "halo plan mismatch: %s", mismatch);
+      HB_TRACE("peer plan not built (%d rank(s) failed): this matrix keeps the NCCL halo", (int) v);
+      return 0;
+   }
    *out_plan = pl;
    return 0;
 #else
@@ -401,19 +479,22 @@ int peer_plans_ensure(hb200_parcsr *A, bool reverse)
    HB_TRACE("peer plan (%s) for a %d x %d block: %d sends, %d recvs ...", reverse ? "reverse" : "forward", A->num_rows,
             A->num_cols, pk.num_sends, pk.num_recvs);
    HB_CHECK(arena_setup());
+   PeerPlan *pl = nullptr;
    if (!reverse) {
       // forward (job 1): out = sends (gather through send_map_elmts), in = recvs -> x_ext
-      HB_CHECK(build_plan(&pk.fwd, pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_map_elmts,
+      HB_CHECK(build_plan(&pl, pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_map_elmts,
                           pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), pk.d_recv_buf));
+      pk.fwd = pl;
    } else {
       // reverse (job 2): out = recv segments of y_tmp (contiguous), in = send segments -> send_buf
-      HB_CHECK(build_plan(&pk.rev, pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), nullptr,
+      HB_CHECK(build_plan(&pl, pk.num_recvs, pk.recv_procs.data(), pk.recv_vec_starts.data(), nullptr,
                           pk.num_sends, pk.send_procs.data(), pk.send_map_starts.data(), pk.d_send_buf));
+      pk.rev = pl;
    }
-   // peers must not start writing into this arena region before everybody has built the plan
-   HB_CHECK(scalars_allreduce(kScalarSlots - 1, 1, c.s_comp));
-   HB_CUDA(cudaStreamSynchronize(c.s_comp));
-   HB_TRACE("peer plan built");
+   // no plan (the ranks agreed that somebody could not build it): this direction of this matrix goes
+   // over NCCL, on every rank alike
+   if (!pl) { if (reverse) pk.peer_off_rev = true; else pk.peer_off = true; }
+   HB_TRACE("peer plan %s", pl ? "built" : "unavailable");
    return 0;
 }
 

@@ -5,6 +5,7 @@
 #include "hb_internal.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <strings.h>
 #include <mutex>
 #include <dlfcn.h>
 
@@ -25,6 +26,13 @@ int set_error(int flag, const char *fmt, ...)
    g_err = buf;
    if (getenv("HB200_VERBOSE")) fprintf(stderr, "[hb200] error %d: %s\n", flag, buf);
    return flag;
+}
+
+bool env_flag(const char *name, bool dflt)
+{
+   const char *e = getenv(name);
+   if (!e) return dflt;
+   return !(e[0] == 0 || !strcmp(e, "0") || !strcasecmp(e, "off") || !strcasecmp(e, "no"));
 }
 
 int require_ready()
@@ -93,7 +101,7 @@ static size_t g_tn = 0;
 void timers_begin()
 {
    static bool checked = false;
-   if (!checked) { checked = true; g_timers_on = getenv("HB200_TIMERS") != nullptr; }
+   if (!checked) { checked = true; g_timers_on = env_flag("HB200_TIMERS", false); }
    if (!g_timers_on) return;
    g_tn = 0;
    timer_tick_impl(T_OTHER);
@@ -164,7 +172,7 @@ int hb200_init(int device)
 {
    Ctx &c = ctx();
    if (c.ready) return 0;
-   g_trace_on = getenv("HB200_TRACE") != nullptr;
+   g_trace_on = env_flag("HB200_TRACE", false);
    int ndev = 0;
    cudaError_t e = cudaGetDeviceCount(&ndev);
    if (e != cudaSuccess || ndev == 0) {
@@ -209,6 +217,11 @@ int hb200_finalize(void)
    if (c.nccl) { nccl_api().CommDestroy(c.nccl); c.nccl = nullptr; }
 #endif
    for (int k = 0; k < 16; k++) if (c.ws_ptr[k]) cudaFree(c.ws_ptr[k]);
+   for (int r = 0; r < (int) c.peer_arena.size(); r++) {
+      if (r != c.rank && c.peer_arena[r]) cudaIpcCloseMemHandle(c.peer_arena[r]);
+   }
+   if (c.arena) cudaFree(c.arena);
+   if (c.h_halo_err) cudaFreeHost(c.h_halo_err);
    cudaFree(c.d_partials);
    cudaFree(c.d_counter);
    cudaFree(c.d_scalars);
@@ -345,7 +358,7 @@ int hb200_sync(void)
    HB_CHECK(require_ready());
    HB_CUDA(cudaStreamSynchronize(ctx().s_comm));
    HB_CUDA(cudaStreamSynchronize(ctx().s_comp));
-   return 0;
+   return halo_check_error();
 }
 
 void *hb200_compute_stream(void) { return (void *) ctx().s_comp; }

@@ -141,6 +141,9 @@ template <class T> inline cudaError_t cudaMalloc(T **p, size_t bytes)
    return *p ? cudaSuccess : 2;
 }
 template <class T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
+enum { cudaHostAllocMapped = 2, cudaHostAllocPortable = 1 };
+template <class T> inline cudaError_t cudaHostAlloc(T **p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
+template <class T> inline cudaError_t cudaHostGetDevicePointer(T **d, void *h, unsigned) { *d = (T *) h; return cudaSuccess; }
 inline cudaError_t cudaFree(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { hb_emu::dev_free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }

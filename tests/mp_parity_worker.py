@@ -139,10 +139,10 @@ def main():
                      l1_norms=l1 if use_l1 else None, cf_marker=cf)
             den = gmax(float(np.max(np.abs(uref))) if uref.size else 0.0)
             e = gmax(relerr(du.cpu().numpy(), uref, den))
-            if e > 1e-11 and rank == 0:
+            if e > 1e-12 and rank == 0:
                 print(f"     relax type {rt} points {pts} w {w} omega {om} level {l}: err {e:.2e}", flush=True)
             worst = max(worst, e)
-    expect(worst <= 1e-11, f"relaxation sweeps (Jacobi + hybrid GS families) (worst {worst:.2e})")
+    expect(worst <= 1e-12, f"relaxation sweeps (Jacobi + hybrid GS families) (worst {worst:.2e})")
 
     # ---- one V-cycle
     A0 = mats[0][0]
@@ -153,7 +153,7 @@ def main():
     amg.cycle(dev(f), du, u_all_zeros=True)
     den = gmax(float(np.max(np.abs(uref))))
     e = gmax(relerr(du.cpu().numpy(), uref, den))
-    expect(e <= 1e-11, f"V(1,1)-cycle, zero initial guess (err {e:.2e})")
+    expect(e <= 1e-12, f"V(1,1)-cycle, zero initial guess (err {e:.2e})")
 
     # ---- PCG
     ref = pb.pcg(precond="amg", tol=1e-8, max_iter=100, two_norm=1)

@@ -110,6 +110,7 @@ def _load() -> C.CDLL:
         "hb200_amg_set_level": ([vp, C.c_int, vp, vp, vp, vp, C.c_double, C.c_double], C.c_int),
         "hb200_amg_set_level_cheby": ([vp, C.c_int, vp, vp, C.c_int], C.c_int),
         "hb200_amg_set_cycle": ([vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+        "hb200_amg_set_level_weights": ([vp, C.c_int, C.c_double, C.c_double], C.c_int),
         "hb200_amg_set_solve": ([vp, C.c_double, C.c_int, C.c_int, C.c_int], C.c_int),
         "hb200_amg_set_coarse_ge": ([vp, vp, C.c_int, C.c_int, C.c_int], C.c_int),
         "hb200_amg_set_use_graph": ([vp, C.c_int], C.c_int),

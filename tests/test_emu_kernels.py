@@ -120,6 +120,16 @@ def test_multi_rank_parity_on_the_host_emulation(nproc, halo, fuse_wait):
     assert r.returncode == 0 and "MULTI-RANK PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_peer_halo_watchdog_on_the_host_emulation():
+    """a polling halo kernel whose peer never shows up gives up after HB200_HALO_TIMEOUT_S and the
+    library reports it (hb_peer.cuh, halo_check_error) — no unbounded spin on the device"""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bridge_mpi.so")):
+        pytest.skip("oracle/_ref/libref_bridge_mpi.so not built (needs /root/reference)")
+    build_emu_mpi()
+    r = run_ranks(2, "emu_halo_timeout_worker.py", timeout=300, extra_env={"HB200_HALO_TIMEOUT_S": "1"})
+    assert r.returncode == 0 and "WATCHDOG OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_bench_code_path_on_the_host_emulation():
     """bench.py itself, unchanged, on 2 emulated ranks: stages and watchdog, halo choice (auto -> peer
     puts at N = 2), per-level kernel timing, the JSON contract.  Its numbers mean nothing here."""

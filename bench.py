@@ -400,13 +400,14 @@ def main():
         """algorithmic bytes of one y = A x on the diag block in the format it is stored in"""
         fi = M.format_info()
         n, nnz = M.num_rows, M.diag_nnz
-        if fi["kernel"] == 7:
+        if fi["kernel"] in (7, 9):
             by = 1.0 * n + 8.0 * M.num_cols + 8.0 * n + 12.0 * fi["pattern_entries"] \
                 + 12.0 * fi["pattern_irregular_nnz"] + 8.0 * fi["pattern_irregular_rows"]
             if M.num_rows != M.num_cols:
                 by += 4.0 * n                       # first column of every row (rectangular blocks: P, P^T)
             irr = fi["pattern_irregular_rows"]
-            name = "spmv_pat<EPI_AXPBY> (row-pattern format, 1 B/row + x + y" \
+            name = ("spmv_box<EPI_AXPBY> (row-pattern format, compact-stencil kernel, 1 B/row + x + y" if fi["kernel"] == 9
+                    else "spmv_pat<EPI_AXPBY> (row-pattern format, 1 B/row + x + y") \
                 + (f"; {irr} irregular rows in CSR)" if irr else ")")
         elif fi["kernel"] == 6:
             by = float(fi["sell_entries"]) * fi["sell_bytes_per_entry"] + 8.0 * (n / 32.0) + 4.0 * n \

@@ -156,7 +156,8 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7, SPMV_VECTOR16 = 8 };
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7, SPMV_VECTOR16 = 8,
+                SPMV_BOX = 9 };   // row-pattern format whose patterns are compact 3 x 3 x 3 stencils: register-window kernel
 
 struct DCsr {
    int        nrows = 0, ncols = 0;
@@ -199,6 +200,13 @@ struct DCsr {
    int       *pat_irr = nullptr;       // rows outside the table (code 255), swept by the CSR kernel
    int        pat_nirr = 0;
    long long  pat_irr_nnz = 0;
+   // box view of the row-pattern table (kernels_pat.cu, spmv_box): every pattern is a subset of the
+   // 27 offsets {dz*sz + dy*sy + dx}, stored diagonal first and then in ascending order
+   bool       has_box = false;
+   int        box_sy = 0, box_sz = 0, box_p0 = -1;   // strides; the full (27-entry) pattern, -1 = none
+   unsigned int *box_mask = nullptr;   // pat_npat presence masks (bit t = slot (dz+1)*9 + (dy+1)*3 + (dx+1))
+   double    *box_val = nullptr;       // pat_npat x 27 slot values
+   double     box_p0_val[27] = {0};    // the full pattern's values (kernel argument: constant bank)
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
    // formats the automatic choice cannot pick for this block are built on first request
@@ -226,6 +234,7 @@ struct PatHost {
 };
 int  pat_analyze_host(int nrows, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out, bool wide);
 int  dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha);    // kernels_pat.cu
+
 int  dcsr_free_pat(DCsr &M);
 // host-side transpose (stable: entries of each output row in ascending source-row order,
 // the order hypre_CSRMatrixMatvecTHost accumulates in, csr_matvec.c:1095-1110)
@@ -268,6 +277,8 @@ int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
                 bool use_rownnz, cudaStream_t st);
 int spmv_sell_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
+int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st);
+bool spmv_box_supports(int epi_kind);
 bool spmv_can_fuse_dot(const DCsr &M, int epi_kind);   // row-pattern format, no rows outside the table
 bool fused_dots_enabled();                              // HB200_FUSED_DOTS=1 turns them on
 

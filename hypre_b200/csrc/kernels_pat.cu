@@ -227,15 +227,16 @@ static int pat_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 
 bool fused_dots_enabled()
 {
-   // opt-in until the DOT kernel variants have run on hardware (logic verified in the host emulation)
-   static const bool on = env_flag("HB200_FUSED_DOTS", false);
+   // on by default (B200, 27-pt 256^3: 49.97 -> 48.18 ms per solve, same iterations and residual;
+   // profiles/r2_session_log.md); HB200_FUSED_DOTS=0 keeps the separate dot kernels
+   static const bool on = env_flag("HB200_FUSED_DOTS", true);
    return on;
 }
 
 bool spmv_can_fuse_dot(const DCsr &M, int epi_kind)
 {
-   return fused_dots_enabled() && (epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7) && M.kind == SPMV_PAT &&
-          M.has_pat && !M.pat_wide && !M.pat_base && M.pat_nirr == 0;
+   return fused_dots_enabled() && (epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7) &&
+          (M.kind == SPMV_PAT || M.kind == SPMV_BOX) && M.has_pat && !M.pat_wide && !M.pat_base && M.pat_nirr == 0;
 }
 
 // the fused-dot instantiations exist for the two epilogues that produce a Krylov dot operand
@@ -301,6 +302,261 @@ int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
    }
 }
 
+// =======================================================================================
+// Box view of the row-pattern format: compact 3 x 3 x 3 stencils (spmv_box)
+// =======================================================================================
+// When every pattern of the table is a subset of the 27 offsets {dz*sz + dy*sy + dx : d in {-1,0,1}}
+// for one pair of strides (sy, sz), stored diagonal first and then in ascending order — the 7-point
+// and 27-point operators of `ij` on a box, with every boundary variant — a row is the 27-slot list
+// (presence bit, value) and the SpMV is a stencil sweep:
+//   * a thread owns one in-plane position q (< sz) and walks a run of planes z: its rows are
+//     q + z*sz.  The 27 x values of row z are 9 in-plane neighbours (dy, dx) on the planes z-1, z,
+//     z+1; moving to z+1 keeps 18 of them in registers and loads 9.  One row costs 9 coalesced
+//     loads of x instead of 27 gathers (the L1 wavefronts that bounded spmv_pat), no table read in
+//     the interior (the full pattern's 27 values are a kernel argument: constant bank operands);
+//   * a warp whose 32 rows all carry the full pattern takes that path; any other row (the faces,
+//     edges and corners of the box: 2 % at 256^3) reads its mask and values from shared memory and
+//     runs the same 27 slots predicated;
+//   * products are added in CSR order — diagonal, then ascending offsets — with separate multiply
+//     and add: bit-identical to spmv_pat and to the 1-thread CPU reference (csr_matvec.c:683-721).
+// Bound: HBM (17 B per row + the epilogue vectors: x is read once, the z-halo of a run comes
+// from L2) and the FP64 pipe (54 instructions per row), no longer L1.
+struct BoxP0 { double a[27]; };
+
+constexpr int kBoxThreads = 256;
+
+template <int EPI, bool DOT>
+__global__ void __launch_bounds__(kBoxThreads, 2)
+spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
+         const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
+         const double *__restrict__ x, EpiArgs ea)
+{
+   HB_DYN_SHARED(double, s_mem);
+   double       *s_val = s_mem;                                          // npat x 27
+   unsigned int *s_mask = reinterpret_cast<unsigned int *>(s_val + npat * 27);
+   const int tid = threadIdx.x;
+   for (int k = tid; k < npat * 27; k += kBoxThreads) s_val[k] = vals[k];
+   for (int k = tid; k < npat; k += kBoxThreads) s_mask[k] = masks[k];
+   __syncthreads();
+   // blocks are numbered in-plane first: neighbours in q run the same planes at the same time (L2)
+   const int q = (int) (blockIdx.x % (unsigned) gx) * kBoxThreads + tid;   // in-plane position
+   const int z0 = (int) (blockIdx.x / (unsigned) gx) * zrun;
+   const int z1 = min(z0 + zrun, nplanes);
+   const bool qok = q < sz;
+   const int skip_c = (EPI == EPI_JACOBI_CORE && ea.skip_diag) ? 1 : 0;   // leave the diagonal out
+   // in-plane neighbour offsets, class c = (dy+1)*3 + (dx+1)
+   int offc[9];
+#pragma unroll
+   for (int c = 0; c < 9; c++) offc[c] = (c / 3 - 1) * sy + (c % 3 - 1);
+   auto ldx = [&](long long idx) -> double {
+      return (idx >= 0 && idx < (long long) nrows) ? __ldg(x + idx) : 0.0;
+   };
+   double W[3][9];                                                        // planes z-1, z, z+1 (rotating)
+   {
+      const long long rm = (long long) (z0 - 1) * sz + q, rc = (long long) z0 * sz + q;
+#pragma unroll
+      for (int c = 0; c < 9; c++) { W[0][c] = ldx(rm + offc[c]); W[1][c] = ldx(rc + offc[c]); }
+   }
+   double dacc = 0.0;
+   for (int zb = z0; zb < z1; zb += 3) {
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+         const int z = zb + u;
+         // (compile-time) roles of the three register planes in this step
+         double (&Wm)[9] = W[u % 3];
+         double (&Wc)[9] = W[(u + 1) % 3];
+         double (&Wp)[9] = W[(u + 2) % 3];
+         const long long row = (long long) z * sz + q;
+         const bool live = qok && z < z1 && row < (long long) nrows;
+         {
+            const long long rp = row + sz;
+#pragma unroll
+            for (int c = 0; c < 9; c++) Wp[c] = (z < z1) ? ldx(rp + offc[c]) : 0.0;
+         }
+         int code = 255;
+         if (live) code = (int) pat[row];
+         const bool full = (code == p0);
+         double s = 0.0;
+         if (__all_sync(0xffffffffu, full)) {
+            // interior warp: all 27 slots, values from the constant bank
+            if (!skip_c) s = __dadd_rn(s, __dmul_rn(P0.a[13], Wc[4]));
+#pragma unroll
+            for (int t = 0; t < 27; t++) {
+               if (t == 13) continue;
+               const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+               s = __dadd_rn(s, __dmul_rn(P0.a[t], w));
+            }
+         } else if (code != 255) {
+            const unsigned int m = s_mask[code];
+            const double *a = s_val + code * 27;
+            if (!skip_c && (m & (1u << 13))) s = __dadd_rn(s, __dmul_rn(a[13], Wc[4]));
+#pragma unroll
+            for (int t = 0; t < 27; t++) {
+               if (t == 13) continue;
+               const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+               if (m & (1u << t)) s = __dadd_rn(s, __dmul_rn(a[t], w));
+            }
+         }
+         if (live && code != 255) {
+            const int r = (int) row;
+            if (DOT) dacc += epi_apply_ret<EPI>(ea, r, s) * __ldg(ea.dotw + r);
+            else     epi_apply<EPI>(ea, r, s, full ? P0.a[13] : s_val[code * 27 + 13]);
+         }
+      }
+   }
+   if (DOT) pat_dot_finish<kBoxThreads>(dacc, ea.dot_slot);
+}
+
+bool spmv_box_supports(int epi_kind) { return epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7 || epi_kind == EPI_JACOBI_CORE; }
+
+static int box_zrun()
+{
+   static int z = 0;
+   if (z == 0) {
+      const char *e = getenv("HB200_BOX_ZRUN");
+      z = e ? atoi(e) : 0;
+      if (z < 3) z = 0; else z = (z + 2) / 3 * 3;
+      if (z == 0) z = -1;
+   }
+   return z;
+}
+
+template <int EPI, bool DOT>
+static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   const size_t smem = (size_t) M.pat_npat * 27 * sizeof(double) + (size_t) M.pat_npat * sizeof(unsigned int) + 8;
+   static bool opted = false;
+   if (!opted) {
+      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPatMaxPatterns * 27 * 8 + kPatMaxPatterns * 4 + 8));
+      opted = true;
+   }
+   if (DOT) {
+      static bool bound = false;
+      if (!bound) {
+         Ctx &c = ctx();
+         HB_CUDA(cudaMemcpyToSymbol(g_pd_partials, &c.d_partials, sizeof(double *)));
+         HB_CUDA(cudaMemcpyToSymbol(g_pd_counter, &c.d_counter, sizeof(unsigned int *)));
+         HB_CUDA(cudaMemcpyToSymbol(g_pd_scalars, &c.d_scalars, sizeof(double *)));
+         bound = true;
+      }
+   }
+   const int nplanes = (int) (((long long) M.nrows + M.box_sz - 1) / M.box_sz);
+   const int gx = (M.box_sz + kBoxThreads - 1) / kBoxThreads;
+   // planes per thread: long runs amortise the two halo planes, short ones fill the GPU; aim at >= 4
+   // waves of 2 blocks per SM
+   int zrun = box_zrun();
+   if (zrun < 0) {
+      zrun = 48;
+      while (zrun > 6 && (long long) gx * ((nplanes + zrun - 1) / zrun) < 4LL * 2 * kNumSMs) zrun -= 6;
+   }
+   int gy = (nplanes + zrun - 1) / zrun;
+   if (DOT && (long long) gx * gy > kRedBlocksMax) {
+      // the fused dot keeps one partial per block: fewer, longer runs
+      gy = kRedBlocksMax / gx; if (gy < 1) gy = 1;
+      zrun = ((nplanes + gy - 1) / gy + 2) / 3 * 3;
+      gy = (nplanes + zrun - 1) / zrun;
+      if ((long long) gx * gy > kRedBlocksMax) return set_error(HB200_ERROR_GENERIC, "spmv_box: fused dot on a plane of more than %d blocks", kRedBlocksMax);
+   }
+   BoxP0 P0;
+   for (int t = 0; t < 27; t++) P0.a[t] = M.box_p0_val[t];
+   HB_LAUNCH((spmv_box<EPI, DOT>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
+             M.pat_npat, M.box_p0, M.box_mask, M.box_val, P0, x, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)
+{
+   if (ea.dot_slot >= 0 && ea.dotw != nullptr) {
+      if (!spmv_can_fuse_dot(M, epi_kind)) return set_error(HB200_ERROR_GENERIC, "fused dot requested on a block that cannot fuse it");
+      return epi_kind == EPI_AXPBY ? box_launch_t<EPI_AXPBY, true>(M, x, ea, st) : box_launch_t<EPI_JACOBI7, true>(M, x, ea, st);
+   }
+   switch (epi_kind) {
+      case EPI_AXPBY:       return box_launch_t<EPI_AXPBY, false>(M, x, ea, st);
+      case EPI_JACOBI7:     return box_launch_t<EPI_JACOBI7, false>(M, x, ea, st);
+      case EPI_JACOBI_CORE: return box_launch_t<EPI_JACOBI_CORE, false>(M, x, ea, st);
+      default: return set_error(HB200_ERROR_ARG, "spmv_box_launch: epilogue %d has no box kernel", epi_kind);
+   }
+}
+
+// Host side: does the pattern table describe compact stencils?  Finds the strides (sy, sz) for which
+// every offset of every pattern is dz*sz + dy*sy + dx with d in {-1,0,1} (the decomposition has to
+// be unique: sy >= 3, sz >= 2*sy + 3), checks the storage order (diagonal first, then ascending
+// slots: the order `ij`'s generators and hypre's IJ assembly produce), and lays every pattern out
+// as 27 (presence, value) slots.  Pure host code.
+struct BoxHost {
+   bool ok = false;
+   int sy = 0, sz = 0, p0 = -1;
+   std::vector<unsigned int> mask;
+   std::vector<double> val;
+};
+
+static bool box_slot_of(int off, int sy, int sz, int *slot)
+{
+   for (int dz = -1; dz <= 1; dz++) {
+      for (int dy = -1; dy <= 1; dy++) {
+         const int dx = off - dz * sz - dy * sy;
+         if (dx >= -1 && dx <= 1) { *slot = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1); return true; }
+      }
+   }
+   return false;
+}
+
+static void box_analyze_host(const PatHost &ph, int nrows, BoxHost &out)
+{
+   out = BoxHost();
+   if (!ph.ok || !ph.square || ph.wide) return;
+   const int npat = (int) ph.ptr.size() - 1;
+   if (npat < 1) return;
+   // candidate strides from the positive offsets of the table
+   std::vector<int> pos;
+   for (int o : ph.off) if (o > 1) pos.push_back(o);
+   std::sort(pos.begin(), pos.end());
+   pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+   if (pos.empty() || pos.size() > 16) return;
+   std::vector<int> cand;
+   for (int o : pos) { for (int d = -1; d <= 1; d++) if (o + d >= 3) cand.push_back(o + d); }
+   std::sort(cand.begin(), cand.end());
+   cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+   int best_sy = 0, best_sz = 0;
+   for (size_t i = 0; i < cand.size() && !best_sy; i++) {
+      for (size_t j = 0; j < cand.size() && !best_sy; j++) {
+         const int sy = cand[i], sz = cand[j];
+         if (sz < 2 * sy + 3) continue;
+         bool all = true;
+         int slot;
+         for (int o : ph.off) { if (!box_slot_of(o, sy, sz, &slot)) { all = false; break; } }
+         if (all) { best_sy = sy; best_sz = sz; }
+      }
+   }
+   // a one- or two-dimensional operator (no offset beyond the row / the plane) is a box with a
+   // stride nobody reaches
+   if (!best_sy) return;
+   if ((long long) best_sz > (long long) nrows) return;
+   out.sy = best_sy; out.sz = best_sz;
+   out.mask.assign((size_t) npat, 0u);
+   out.val.assign((size_t) npat * 27, 0.0);
+   for (int p = 0; p < npat; p++) {
+      int prev = -1;
+      for (int k = ph.ptr[p]; k < ph.ptr[p + 1]; k++) {
+         int slot = -1;
+         if (!box_slot_of(ph.off[k], best_sy, best_sz, &slot)) return;
+         if (k == ph.ptr[p]) {
+            if (slot != 13) return;                       // the diagonal comes first (par_relax.c:274)
+         } else {
+            if (slot == 13 || slot <= prev) return;       // then ascending
+            prev = slot;
+         }
+         if (out.mask[(size_t) p] & (1u << slot)) return;
+         out.mask[(size_t) p] |= 1u << slot;
+         out.val[(size_t) p * 27 + slot] = ph.val[(size_t) k];
+      }
+      if (out.mask[(size_t) p] == 0x7ffffffu && out.p0 < 0) out.p0 = p;   // patterns are sorted by frequency
+   }
+   out.ok = true;
+}
+
 int dcsr_free_pat(DCsr &M)
 {
    if (M.pat_code) cudaFree(M.pat_code);
@@ -309,6 +565,9 @@ int dcsr_free_pat(DCsr &M)
    if (M.pat_val) cudaFree(M.pat_val);
    if (M.pat_base) cudaFree(M.pat_base);
    if (M.pat_irr) cudaFree(M.pat_irr);
+   if (M.box_mask) cudaFree(M.box_mask);
+   if (M.box_val) cudaFree(M.box_val);
+   M.box_mask = nullptr; M.box_val = nullptr; M.has_box = false;
    M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr; M.pat_irr = nullptr;
    M.pat_nirr = 0;
    M.pat_wide = false;
@@ -464,6 +723,20 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
    M.pat_npat = npat;
    M.pat_nent = nent;
    M.has_pat = true;
+   // compact stencils: the register-window kernel (spmv_box) takes the block
+   if (!env_flag("HB200_NO_BOX", false)) {
+      BoxHost bh;
+      box_analyze_host(ph, n, bh);
+      if (bh.ok) {
+         HB_CUDA(cudaMalloc(&M.box_mask, sizeof(unsigned int) * (size_t) npat));
+         HB_CUDA(cudaMemcpy(M.box_mask, bh.mask.data(), sizeof(unsigned int) * (size_t) npat, cudaMemcpyHostToDevice));
+         HB_CUDA(cudaMalloc(&M.box_val, sizeof(double) * (size_t) npat * 27));
+         HB_CUDA(cudaMemcpy(M.box_val, bh.val.data(), sizeof(double) * (size_t) npat * 27, cudaMemcpyHostToDevice));
+         M.box_sy = bh.sy; M.box_sz = bh.sz; M.box_p0 = bh.p0;
+         for (int t = 0; t < 27; t++) M.box_p0_val[t] = bh.p0 >= 0 ? bh.val[(size_t) bh.p0 * 27 + t] : 0.0;
+         M.has_box = true;
+      }
+   }
    return 0;
 }
 

@@ -353,8 +353,9 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
 {
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
-   if (!use_rownnz && M.kind == SPMV_PAT && M.has_pat) {
-      HB_CHECK(spmv_pat_launch(M, x, EPI, ea, st));
+   if (!use_rownnz && (M.kind == SPMV_PAT || M.kind == SPMV_BOX) && M.has_pat) {
+      if (M.kind == SPMV_BOX && M.has_box && spmv_box_supports(EPI)) HB_CHECK(spmv_box_launch(M, x, EPI, ea, st));
+      else HB_CHECK(spmv_pat_launch(M, x, EPI, ea, st));
       if (M.pat_nirr == 0) return 0;
       // rows outside the pattern table: CSR sweep over the row list (disjoint rows, same epilogue)
       const double avg = (double) M.pat_irr_nnz / (double) M.pat_nirr;
@@ -425,7 +426,8 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
    // the sub-warp vector kernel beat the shared-memory stream kernel on every level measured
    // (profiles/r1_level_sweep.md): the stream kernel is L1-wavefront bound by its smem round trip
    const int csr = M.j16 ? SPMV_VECTOR16 : SPMV_VECTOR;
-   if (kind == SPMV_AUTO) kind = M.has_pat ? SPMV_PAT : M.has_sell ? SPMV_SELL : csr;
+   if (kind == SPMV_AUTO) kind = M.has_box ? SPMV_BOX : M.has_pat ? SPMV_PAT : M.has_sell ? SPMV_SELL : csr;
+   if (kind == SPMV_BOX && !M.has_box) kind = SPMV_PAT;
    if (kind == SPMV_PAT && !M.has_pat) kind = M.has_sell ? SPMV_SELL : csr;
    if (kind == SPMV_SELL && !M.has_sell) kind = csr;
    if (kind == SPMV_VECTOR16 && !M.j16) kind = SPMV_VECTOR;

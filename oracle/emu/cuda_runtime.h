@@ -49,6 +49,7 @@ struct ThreadCtx { hb_emu_dim3 tid, bid, bdim, gdim; };
 extern ThreadCtx *g_cur;             // the running fiber's coordinates
 void  syncthreads();
 unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int width);
+int   vote_all(int pred);
 void *dyn_smem();
 void  launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
 long long launches();
@@ -84,6 +85,8 @@ inline T __shfl_down_sync(unsigned, T v, unsigned delta, int width = 32)
    memcpy(&out, &bits, sizeof(T));
    return out;
 }
+
+inline int __all_sync(unsigned, int pred) { return hb_emu::vote_all(pred); }
 
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcs(const T *p) { return *p; }

@@ -38,6 +38,7 @@ struct Block {
    int      warrived[kMaxThreads / 32];
    int      wlive[kMaxThreads / 32];
    unsigned long long wslot[kMaxThreads / 32][32];
+   unsigned char      wvalid[kMaxThreads / 32][32];   // lanes taking part in the vote in flight
 };
 
 ucontext_t               g_sched;
@@ -110,6 +111,20 @@ unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int w
    return out;
 }
 
+// warp vote: every lane of the warp publishes its predicate; all = AND over the lanes that are still in the kernel
+int vote_all(int pred)
+{
+   const int t = g_running, w = t / 32, lane = t % 32;
+   g_blk.wslot[w][lane] = pred ? 1ull : 0ull;
+   g_blk.wvalid[w][lane] = 1;
+   warp_barrier(w);
+   int all = 1;
+   for (int l = 0; l < 32; l++) { if (g_blk.wvalid[w][l] && !g_blk.wslot[w][l]) all = 0; }
+   warp_barrier(w);
+   g_blk.wvalid[w][lane] = 0;
+   return all;
+}
+
 void *dyn_smem() { return g_dyn.data(); }
 long long launches() { return g_launches; }
 
@@ -133,7 +148,7 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
       Block &b = g_blk;
       b.nthreads = b.live = (int) block;
       b.bar_gen = 0; b.bar_arrived = 0;
-      for (unsigned w = 0; w < block / 32; w++) { b.wgen[w] = 0; b.warrived[w] = 0; b.wlive[w] = 32; }
+      for (unsigned w = 0; w < block / 32; w++) { b.wgen[w] = 0; b.warrived[w] = 0; b.wlive[w] = 32; memset(b.wvalid[w], 0, 32); }
       for (unsigned t = 0; t < block; t++) {
          Fiber &f = g_fibers[t];
          f.done = false;

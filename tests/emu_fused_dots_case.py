@@ -30,7 +30,7 @@ def test_pcg_solve_report():
     pb.setup_amg(relax_type=18)
     mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), use_graph=True)    # the bench's configuration: captured V-cycle
     A = mats[0][0]
-    assert A.format_info()["kernel"] == 7
+    assert A.format_info()["kernel"] in (7, 9)
     ref = pb.pcg(precond="amg", tol=1e-8, max_iter=100, two_norm=1)
     pcg = hb.ParCSRPCG(tol=1e-8, max_iter=100, two_norm=1, logging=1)
     pcg.set_precond(amg)

@@ -57,7 +57,7 @@ def test_fused_dots_on_the_host_emulation(tmp_path):
         pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
     build_emu()
     reports = {}
-    for name, env in (("fused", {"HB200_FUSED_DOTS": "1"}), ("separate", {})):
+    for name, env in (("fused", {"HB200_FUSED_DOTS": "1"}), ("separate", {"HB200_FUSED_DOTS": "0"})):
         path = str(tmp_path / f"{name}.json")
         r = run_child(dict(env, HB200_EMU_REPORT=path), os.path.join("tests", "emu_fused_dots_case.py"))
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -121,8 +121,9 @@ def test_matvec_bit_exact_fine_level(request, torch, case_name):
     # stream kernel with one lane per row, the packed SELL kernel and the row-pattern kernel (one
     # thread per row): all add the products in CSR order with separate multiply / add
     fi = A.format_info()
-    assert fi["pattern"] and fi["kernel"] == 7, fi   # constant-coefficient stencil
-    for kind, lanes in ((2, 1), (6, 0), (7, 0)):
+    assert fi["pattern"] and fi["kernel"] == 9, fi   # constant-coefficient compact stencil: the box kernel
+    # (kind 9: the register-window stencil sweep over the same table, kind 7: the generic row-pattern kernel)
+    for kind, lanes in ((2, 1), (6, 0), (7, 0), (9, 0)):
         A.set_spmv_kernel(kind, lanes)
         # the packed SELL copy of a block stored as row patterns is built by this request, not at upload
         assert A.format_info()["kernel"] == kind and (kind != 6 or A.format_info()["sell"]), (kind, A.format_info())
@@ -134,7 +135,7 @@ def test_matvec_bit_exact_fine_level(request, torch, case_name):
     A.set_spmv_kernel(0, 0)
 
 
-@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32), (6, 0), (7, 0), (8, 0), (8, 4)])
+@pytest.mark.parametrize("kind,lanes", [(1, 0), (1, 1), (1, 4), (1, 32), (2, 1), (2, 4), (2, 32), (3, 1), (3, 8), (4, 2), (4, 8), (5, 1), (5, 4), (5, 32), (6, 0), (7, 0), (8, 0), (8, 4), (9, 0)])
 def test_matvec_kernel_variants(lap27, torch, kind, lanes):
     rng = np.random.default_rng(5)
     for l in (0, 2):
@@ -223,7 +224,7 @@ def test_pattern_format_with_irregular_rows(lap27, hb, torch):
     M = hb.ParCSRMatrix(n, n, di, dj, data)
     fi = M.format_info()
     # the perturbed rows are irregular, and so are the 8 corner patterns of the box (one row each)
-    assert fi["pattern"] and fi["kernel"] == 7, fi
+    assert fi["pattern"] and fi["kernel"] in (7, 9), fi
     assert len(odd) <= fi["pattern_irregular_rows"] <= len(odd) + 8, fi
     x = rng.standard_normal(n)
     b = rng.standard_normal(n)

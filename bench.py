@@ -60,6 +60,9 @@ def parse():
                          "-vardifconv -n 256^3 -P 2 2 2)")
     ap.add_argument("--no-e2e-ij", action="store_true",
                     help="skip the `oracle/_ref/ij_b200` leg (the solve time the unmodified ij driver prints)")
+    ap.add_argument("--coarsen-type", type=int, default=-1,
+                    help="BoomerAMG coarsening of the reference setup (-1: ij's CPU default, HMIS = 10; 8: PMIS, "
+                         "the only one hypre's own device setup has — used to compare with baseline/_ref/ij_hypre_cuda)")
     ap.add_argument("--mpi-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
@@ -77,6 +80,8 @@ def workload_string(args, gn, P):
     """the ij command line this run stands for — the same text on both arms (hb200 / reference)"""
     solver = -1 if args.spmv_only else (1 if args.solver == "pcg" else 3)
     tail = f" -nmv {args.nmv} -x0rand" if args.spmv_only else " -rlx 18"
+    if args.coarsen_type == 8 and not args.spmv_only:
+        tail += " -pmis"
     return f"ij -{args.problem} -n {gn[0]} {gn[1]} {gn[2]} -P {P[0]} {P[1]} {P[2]} -solver {solver}{tail}"
 
 
@@ -142,7 +147,7 @@ def build_problem(args, rank, world):
     t0 = time.time()
     pb = rb.Problem(args.problem, gn, P=P, mpi=mpi, x0rand=args.spmv_only)
     gen_s = time.time() - t0
-    setup_s = 0.0 if args.spmv_only else pb.setup_amg(relax_type=18)
+    setup_s = 0.0 if args.spmv_only else pb.setup_amg(relax_type=18, coarsen_type=args.coarsen_type)
     return rb, pb, gn, gen_s, setup_s
 
 
@@ -170,7 +175,7 @@ def run_reference(args):
         cmd = [mpirun, "-np", str(N), sys.executable, os.path.abspath(__file__), "--impl", "reference",
                "--mpi-worker", "--gpus", str(N), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--n", str(args.n), "--problem", args.problem, "--tol", str(args.tol), "--solver", args.solver,
-               "--cpu-iters", str(args.cpu_iters), "--nmv", str(args.nmv)]
+               "--cpu-iters", str(args.cpu_iters), "--nmv", str(args.nmv), "--coarsen-type", str(args.coarsen_type)]
         cmd += ["--spmv-only"] if args.spmv_only else []
         cmd += ["--global-size"] if args.global_size else []
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
@@ -215,7 +220,7 @@ def run_reference(args):
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
-    setup_s = pb.setup_amg(relax_type=18)
+    setup_s = pb.setup_amg(relax_type=18, coarsen_type=args.coarsen_type)
     if args.solver == "gmres":
         solve = lambda mi: pb.gmres(precond="amg", tol=args.tol, max_iter=mi, k_dim=5)
     else:

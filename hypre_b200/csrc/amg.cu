@@ -113,10 +113,12 @@ static int do_relax(hb200_amg *amg, int level, int relax_type, int relax_order, 
    const double *f = L.F;
    if (relax_type == 9 || relax_type == 19) {
       HB_REQUIRE(amg->has_ge, HB200_ERROR_GENERIC, "coarse relax type 9 but no GE data was set");
+      ProfRange pr("Coarse solve");
       HB_CHECK(ge_solve(amg->ge, f, L.u_cur));
       L.u_zero = false;
       return 0;
    }
+   ProfRange pr_relax("Relaxation");
    if (relax_type == 16) {
       HB_REQUIRE(!L.cheby_coefs.empty(), HB200_ERROR_GENERIC, "Chebyshev relaxation but no coefficients set");
       if (!L.cheby_work) HB_CUDA(cudaMalloc(&L.cheby_work, sizeof(double) * 4 * (size_t) (L.n ? L.n : 1)));
@@ -184,6 +186,8 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
    }
    for (int l = 1; l < nl; l++) { amg->lev[l].u_cur = amg->lev[l].U; amg->lev[l].u_zero = false; }
 
+   ProfRange pr_cycle("AMGCycle");
+   char lvl_name[32];
    // ---- the reference's cycling state machine (par_cycle.c:225-243, 300-865) ----
    std::vector<int> lev_counter(nl);
    lev_counter[0] = 1;
@@ -194,6 +198,8 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
    while (not_finished) {
       int num_sweep, relax_type;
       bool one_level = false;
+      snprintf(lvl_name, sizeof(lvl_name), "AMG Level-%d", level);
+      ProfRange pr_level(lvl_name);
       if (nl > 1) {
          num_sweep = amg->num_grid_sweeps[cycle_param];
          relax_type = amg->grid_relax_type[cycle_param];
@@ -214,13 +220,19 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
          hb200_amg_level &Lc = amg->lev[level + 1];
          Lc.u_cur = Lc.U;
          Lc.u_zero = true;                     // hypre_ParVectorSetZeros(U_array[coarse])
-         if (Lf.u_zero) {
-            // r = f - A*0 : no relaxation happened on this level (num_sweeps == 0)
-            HB_CHECK(vec_copy(Lf.F, Lf.Vtemp, (size_t) Lf.n, c.s_comp));
-         } else {
-            HB_CHECK(parcsr_matvec(Lf.A, -1.0, Lf.u_cur, 1.0, Lf.F, Lf.Vtemp));
+         {
+            ProfRange pr("Residual");
+            if (Lf.u_zero) {
+               // r = f - A*0 : no relaxation happened on this level (num_sweeps == 0)
+               HB_CHECK(vec_copy(Lf.F, Lf.Vtemp, (size_t) Lf.n, c.s_comp));
+            } else {
+               HB_CHECK(parcsr_matvec(Lf.A, -1.0, Lf.u_cur, 1.0, Lf.F, Lf.Vtemp));
+            }
          }
-         HB_CHECK(parcsr_matvecT(Lf.P, 1.0, Lf.Vtemp, 0.0, Lc.F));
+         {
+            ProfRange pr("Restriction");
+            HB_CHECK(parcsr_matvecT(Lf.P, 1.0, Lf.Vtemp, 0.0, Lc.F));
+         }
          ++level;
          lev_counter[level] = lev_counter[level] > amg->cycle_type ? lev_counter[level] : amg->cycle_type;
          cycle_param = (level == nl - 1) ? 3 : 1;
@@ -228,6 +240,7 @@ static int cycle_body(hb200_amg *amg, const double *f_dev, double *u_dev, bool u
          // go up: interpolation u_f += P u_c (par_cycle.c:815-843)
          hb200_amg_level &Lf = amg->lev[level - 1];
          hb200_amg_level &Lc = amg->lev[level];
+         ProfRange pr("Interpolation");
          if (Lc.u_zero) HB_CHECK(vec_set(Lc.u_cur, 0.0, (size_t) Lc.n, c.s_comp));
          if (Lf.u_zero) { HB_CHECK(vec_set(Lf.u_cur, 0.0, (size_t) Lf.n, c.s_comp)); }
          HB_CHECK(parcsr_matvec(Lf.P, 1.0, Lc.u_cur, 1.0, Lf.u_cur, Lf.u_cur));

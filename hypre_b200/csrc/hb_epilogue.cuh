@@ -9,15 +9,28 @@ namespace hb {
 // ---------------------------------------------------------------------------------------
 // The epilogue vectors (b/f, l1 norms, cf marker) are read once per sweep and y is written once:
 // streaming (evict-first) accesses keep them from displacing the gathered x lines in L1/L2.
+// the arithmetic of the two epilogues that also exist with their per-row inputs staged by the caller
+// (spmv_box reads b / f / l1 through its shared-memory ring): one definition, identical rounding
+__device__ __forceinline__ double epi_axpby_value(const EpiArgs &ea, double b, double sum)
+{
+   // reference: y = (beta/alpha)*b; y += sum; y *= alpha  ==  beta*b + alpha*sum
+   // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
+   return ea.beta * b + ea.alpha * sum;
+}
+__device__ __forceinline__ double epi_jacobi7_value(const EpiArgs &ea, double uo, double f, double d, double sum)
+{
+   // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
+   const double vt = (ea.w == 1.0) ? (f - sum) : (ea.w * f - ea.w * sum);
+   return uo + vt / d;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum, double diag)
 {
    if (EPI == EPI_AXPBY) {
-      // reference: y = (beta/alpha)*b; y += sum; y *= alpha  ==  beta*b + alpha*sum
-      // (csr_matvec.c:836-845); for alpha = +-1 the specialised branches are exact copies.
       double v;
       if (ea.beta == 0.0) { v = ea.alpha * sum; }
-      else                { v = ea.beta * __ldcs(ea.b + row) + ea.alpha * sum; }
+      else                { v = epi_axpby_value(ea, __ldcs(ea.b + row), sum); }
       __stcs(ea.y + row, v);
    }
    else if (EPI == EPI_ACC) {
@@ -27,9 +40,7 @@ __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum
       // Vtemp = w*f - w*A*u ; u += Vtemp ./ l1   (par_relax.c:1216-1244)
       const double uo = ea.u[row];
       if (ea.cf == nullptr || __ldcs(ea.cf + row) == ea.relax_points) {
-         const double f = __ldcs(ea.b + row);
-         const double vt = (ea.w == 1.0) ? (f - sum) : (ea.w * f - ea.w * sum);
-         __stcs(ea.y + row, uo + vt / __ldcs(ea.d + row));
+         __stcs(ea.y + row, epi_jacobi7_value(ea, uo, __ldcs(ea.b + row), __ldcs(ea.d + row), sum));
       } else {
          __stcs(ea.y + row, uo);
       }
@@ -67,13 +78,11 @@ __device__ __forceinline__ double epi_apply_ret(const EpiArgs &ea, int row, doub
    double v;
    if (EPI == EPI_AXPBY) {
       if (ea.beta == 0.0) { v = ea.alpha * sum; }
-      else                { v = ea.beta * __ldcs(ea.b + row) + ea.alpha * sum; }
+      else                { v = epi_axpby_value(ea, __ldcs(ea.b + row), sum); }
    } else {   // EPI_JACOBI7
       const double uo = ea.u[row];
       if (ea.cf == nullptr || __ldcs(ea.cf + row) == ea.relax_points) {
-         const double f = __ldcs(ea.b + row);
-         const double vt = (ea.w == 1.0) ? (f - sum) : (ea.w * f - ea.w * sum);
-         v = uo + vt / __ldcs(ea.d + row);
+         v = epi_jacobi7_value(ea, uo, __ldcs(ea.b + row), __ldcs(ea.d + row), sum);
       } else {
          v = uo;
       }

@@ -116,6 +116,13 @@ void timer_tick_impl(int cat);
 inline void timer_tick(int cat) { if (g_timers_on) timer_tick_impl(cat); }
 void timers_begin();
 void timers_report(const char *what);
+// profiler ranges with the reference's own names (hypre_GpuProfilingPushRange, src/utilities/
+// device_markers.c:70-123; "AMGCycle", "AMG Level-k", "Relaxation", "Residual", "Restriction",
+// "Interpolation", "Coarse solve" in par_cycle.c:119-869, "PCG-Solve" in pcg.c:379): NVTX v3, header-only,
+// a no-op unless a tool is attached.  Ranges around captured launches mark the capture, not the replays.
+void prof_push(const char *name);
+void prof_pop();
+struct ProfRange { explicit ProfRange(const char *n) { prof_push(n); } ~ProfRange() { prof_pop(); } };
 int arena_setup();                                         // collective, after the NCCL communicator exists
 int arena_alloc(size_t bytes, size_t *offset);             // 256-byte aligned carve-out
 void arena_release(size_t offset, size_t bytes);           // give a carve-out back (plan destruction)
@@ -156,7 +163,8 @@ int  require_ready();
 // ---------------------------------------------------------------------------------------
 // device CSR block
 // ---------------------------------------------------------------------------------------
-enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_STREAM_V4 = 3, SPMV_VECTOR_U2 = 4, SPMV_VECTOR_U4 = 5, SPMV_SELL = 6, SPMV_PAT = 7, SPMV_VECTOR16 = 8,
+// (3, 4, 5 were the stream-v4 / unrolled vector variants of round 1: removed, they lost on every level measured)
+enum SpmvKind { SPMV_AUTO = 0, SPMV_VECTOR = 1, SPMV_STREAM = 2, SPMV_SELL = 6, SPMV_PAT = 7, SPMV_VECTOR16 = 8,
                 SPMV_BOX = 9 };   // row-pattern format whose patterns are compact 3 x 3 x 3 stencils: register-window kernel
 
 struct DCsr {

@@ -323,58 +323,134 @@ int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
 // from L2) and the FP64 pipe (54 instructions per row), no longer L1.
 struct BoxP0 { double a[27]; };
 
-constexpr int kBoxThreads = 256;
+constexpr int kBoxThreads = 512;   // in-plane positions per block (one per thread)
+constexpr int kBoxStages  = 4;     // planes in flight per block (cp.async ring)
 
-template <int EPI, bool DOT>
-__global__ void __launch_bounds__(kBoxThreads, 2)
+// asynchronous 8-byte copy global -> shared (cp.async, LDGSTS): the x slab of the planes ahead is
+// in flight while the block computes, whatever the occupancy
+__device__ __forceinline__ void box_cp_async8(double *smem_dst, const double *gsrc)
+{
+#ifndef HB200_EMU
+   const unsigned int d = (unsigned int) __cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+   *smem_dst = *gsrc;
+#endif
+}
+__device__ __forceinline__ void box_cp_commit()
+{
+#ifndef HB200_EMU
+   asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void box_cp_wait()
+{
+#ifndef HB200_EMU
+   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// The kernel.  A block owns kBoxThreads consecutive in-plane positions [q0, q0 + NT) and a run of
+// planes; plane p of its x slab is the contiguous segment x[p*sz + q0 - sy - 1 .. p*sz + q0 + NT + sy + 1),
+// copied into a ring of shared-memory stages by cp.async kBoxStages - 1 planes ahead of the compute
+// (the same stage carries the per-row inputs of the epilogue: b, or f and l1).  Per plane a thread
+// reads its 9 in-plane neighbours of the NEW plane from shared memory into the register window
+// (the other 18 values are already there) and runs the 27 slots.
+//   STREAMS = number of epilogue vectors staged with the slab (0: none, 1: b, 2: f and l1)
+template <int EPI, bool DOT, int STREAMS>
+__global__ void __launch_bounds__(kBoxThreads, 1)
 spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
          const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
          const double *__restrict__ x, EpiArgs ea)
 {
+   constexpr int NT = kBoxThreads, NS = kBoxStages;
    HB_DYN_SHARED(double, s_mem);
-   double       *s_val = s_mem;                                          // npat x 27
+   const int seg = NT + 2 * sy + 2;                    // doubles of one plane segment
+   const int stage_len = seg + STREAMS * NT;           // + the staged epilogue vectors
+   double       *s_ring = s_mem;                                          // NS stages
+   double       *s_val = s_ring + (size_t) NS * stage_len;               // npat x 27
    unsigned int *s_mask = reinterpret_cast<unsigned int *>(s_val + npat * 27);
    const int tid = threadIdx.x;
-   for (int k = tid; k < npat * 27; k += kBoxThreads) s_val[k] = vals[k];
-   for (int k = tid; k < npat; k += kBoxThreads) s_mask[k] = masks[k];
-   __syncthreads();
+   for (int k = tid; k < npat * 27; k += NT) s_val[k] = vals[k];
+   for (int k = tid; k < npat; k += NT) s_mask[k] = masks[k];
    // blocks are numbered in-plane first: neighbours in q run the same planes at the same time (L2)
-   const int q = (int) (blockIdx.x % (unsigned) gx) * kBoxThreads + tid;   // in-plane position
+   const int q0 = (int) (blockIdx.x % (unsigned) gx) * NT;
+   const int q = q0 + tid;                                                // in-plane position
    const int z0 = (int) (blockIdx.x / (unsigned) gx) * zrun;
    const int z1 = min(z0 + zrun, nplanes);
    const bool qok = q < sz;
    const int skip_c = (EPI == EPI_JACOBI_CORE && ea.skip_diag) ? 1 : 0;   // leave the diagonal out
-   // in-plane neighbour offsets, class c = (dy+1)*3 + (dx+1)
+   const double *st0 = (STREAMS >= 1) ? ea.b : nullptr;                   // AXPBY: b ; JACOBI7: f
+   const double *st1 = (STREAMS >= 2) ? ea.d : nullptr;                   // JACOBI7: l1 norms
+
+   // issue the copies of plane p (x segment) and of the epilogue inputs of plane p - 1's rows...
+   // stage (p - z0 + 1) % NS holds: x of plane p, epilogue vectors of the rows of plane p - 1
+   auto issue = [&](int p) {
+      double *dst = s_ring + (size_t) ((p - z0 + 1) % NS) * stage_len;
+      {
+         const long long g0 = (long long) p * sz + q0 - sy - 1;           // global index of dst[0]
+         for (int k = tid; k < seg; k += NT) {
+            const long long gi = g0 + k;
+            if (gi >= 0 && gi < (long long) nrows) box_cp_async8(dst + k, x + gi);
+         }
+      }
+      if (STREAMS >= 1) {
+         const long long r = (long long) (p - 1) * sz + q;
+         if (p - 1 >= z0 && p - 1 < z1 && qok && r < (long long) nrows) {
+            box_cp_async8(dst + seg + tid, st0 + r);
+            if (STREAMS >= 2) box_cp_async8(dst + seg + NT + tid, st1 + r);
+         }
+      }
+      box_cp_commit();
+   };
+   // prologue: planes z0 - 1 .. z0 + NS - 2 (NS groups in flight)
+#pragma unroll
+   for (int k = 0; k < NS; k++) issue(z0 - 1 + k);
+   // in-plane neighbour offsets inside a segment, class c = (dy+1)*3 + (dx+1)
    int offc[9];
 #pragma unroll
-   for (int c = 0; c < 9; c++) offc[c] = (c / 3 - 1) * sy + (c % 3 - 1);
-   auto ldx = [&](long long idx) -> double {
-      return (idx >= 0 && idx < (long long) nrows) ? __ldg(x + idx) : 0.0;
-   };
+   for (int c = 0; c < 9; c++) offc[c] = tid + sy + 1 + (c / 3 - 1) * sy + (c % 3 - 1);
    double W[3][9];                                                        // planes z-1, z, z+1 (rotating)
+   // planes z0 - 1 and z0 into the window
+   box_cp_wait<NS - 2>();
+   __syncthreads();
    {
-      const long long rm = (long long) (z0 - 1) * sz + q, rc = (long long) z0 * sz + q;
+      const double *sm = s_ring + (size_t) 0 * stage_len, *sc = s_ring + (size_t) 1 * stage_len;
 #pragma unroll
-      for (int c = 0; c < 9; c++) { W[0][c] = ldx(rm + offc[c]); W[1][c] = ldx(rc + offc[c]); }
+      for (int c = 0; c < 9; c++) { W[0][c] = sm[offc[c]]; W[1][c] = sc[offc[c]]; }
    }
+   // row codes are prefetched two planes ahead in registers
+   auto ldcode = [&](int z) -> int {
+      const long long r = (long long) z * sz + q;
+      return (qok && z < z1 && r < (long long) nrows) ? (int) __ldg(pat + r) : 255;
+   };
+   int code_a = ldcode(z0), code_b = ldcode(z0 + 1);
    double dacc = 0.0;
    for (int zb = z0; zb < z1; zb += 3) {
 #pragma unroll
       for (int u = 0; u < 3; u++) {
          const int z = zb + u;
+         if (z >= z1) break;                              // block-uniform
          // (compile-time) roles of the three register planes in this step
          double (&Wm)[9] = W[u % 3];
          double (&Wc)[9] = W[(u + 1) % 3];
          double (&Wp)[9] = W[(u + 2) % 3];
-         const long long row = (long long) z * sz + q;
-         const bool live = qok && z < z1 && row < (long long) nrows;
-         {
-            const long long rp = row + sz;
+         // plane z + 1 has landed (all but the NS - 3 youngest groups are complete); the barrier also
+         // tells that every thread is done with the stage read one step ago, which is refilled now
+         box_cp_wait<NS - 3>();
+         __syncthreads();
+         const double *sp = s_ring + (size_t) ((z + 1 - z0 + 1) % NS) * stage_len;
 #pragma unroll
-            for (int c = 0; c < 9; c++) Wp[c] = (z < z1) ? ldx(rp + offc[c]) : 0.0;
-         }
-         int code = 255;
-         if (live) code = (int) pat[row];
+         for (int c = 0; c < 9; c++) Wp[c] = sp[offc[c]];
+         double e0 = 0.0, e1 = 0.0;
+         if (STREAMS >= 1) e0 = sp[seg + tid];
+         if (STREAMS >= 2) e1 = sp[seg + NT + tid];
+         issue(z + NS - 1);                               // refills the stage of plane z - 1 (read at step z - 2)
+         const int code = code_a;
+         code_a = code_b;
+         code_b = ldcode(z + 2);
+         const long long row = (long long) z * sz + q;
          const bool full = (code == p0);
          double s = 0.0;
          if (__all_sync(0xffffffffu, full)) {
@@ -397,14 +473,28 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
                if (m & (1u << t)) s = __dadd_rn(s, __dmul_rn(a[t], w));
             }
          }
-         if (live && code != 255) {
+         if (code != 255) {                               // (255: past the end, or a row of the CSR pass)
             const int r = (int) row;
-            if (DOT) dacc += epi_apply_ret<EPI>(ea, r, s) * __ldg(ea.dotw + r);
-            else     epi_apply<EPI>(ea, r, s, full ? P0.a[13] : s_val[code * 27 + 13]);
+            double v;
+            // the epilogues of hb_epilogue.cuh with their per-row inputs already at hand
+            if (EPI == EPI_AXPBY) {
+               v = (STREAMS == 0) ? ea.alpha * s : epi_axpby_value(ea, e0, s);
+               __stcs(ea.y + r, v);
+            } else if (EPI == EPI_JACOBI7) {
+               const double uo = Wc[4];                   // u_in is the vector the sweep multiplies
+               if (ea.cf == nullptr || __ldcs(ea.cf + r) == ea.relax_points) v = epi_jacobi7_value(ea, uo, e0, e1, s);
+               else v = uo;
+               __stcs(ea.y + r, v);
+            } else {
+               epi_apply<EPI>(ea, r, s, full ? P0.a[13] : s_val[code * 27 + 13]);
+               v = 0.0;
+            }
+            if (DOT) dacc += v * __ldg(ea.dotw + r);
          }
       }
    }
-   if (DOT) pat_dot_finish<kBoxThreads>(dacc, ea.dot_slot);
+   box_cp_wait<0>();
+   if (DOT) pat_dot_finish<NT>(dacc, ea.dot_slot);
 }
 
 bool spmv_box_supports(int epi_kind) { return epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7 || epi_kind == EPI_JACOBI_CORE; }
@@ -421,15 +511,24 @@ static int box_zrun()
    return z;
 }
 
-template <int EPI, bool DOT>
+static size_t box_smem_bytes(const DCsr &M, int streams)
+{
+   const size_t seg = (size_t) kBoxThreads + 2 * (size_t) M.box_sy + 2;
+   return sizeof(double) * ((size_t) kBoxStages * (seg + (size_t) streams * kBoxThreads) + (size_t) M.pat_npat * 27) +
+          sizeof(unsigned int) * (size_t) M.pat_npat + 16;
+}
+
+// the slab ring has to fit one block's shared memory: in-plane strides up to ~4000 (a 4000-wide grid)
+static bool box_fits(const DCsr &M) { return box_smem_bytes(M, 2) <= 200 * 1024; }
+
+template <int EPI, bool DOT, int STREAMS>
 static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
-   const size_t smem = (size_t) M.pat_npat * 27 * sizeof(double) + (size_t) M.pat_npat * sizeof(unsigned int) + 8;
-   static bool opted = false;
-   if (!opted) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kPatMaxPatterns * 27 * 8 + kPatMaxPatterns * 4 + 8));
-      opted = true;
+   const size_t smem = box_smem_bytes(M, STREAMS);
+   static size_t opted = 0;
+   if (opted < smem) {
+      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      opted = smem;
    }
    if (DOT) {
       static bool bound = false;
@@ -443,12 +542,12 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    const int nplanes = (int) (((long long) M.nrows + M.box_sz - 1) / M.box_sz);
    const int gx = (M.box_sz + kBoxThreads - 1) / kBoxThreads;
-   // planes per thread: long runs amortise the two halo planes, short ones fill the GPU; aim at >= 4
-   // waves of 2 blocks per SM
+   // planes per block: long runs amortise the pipeline fill (3 planes), short ones fill the GPU:
+   // aim at >= 3 waves of one block per SM
    int zrun = box_zrun();
    if (zrun < 0) {
       zrun = 48;
-      while (zrun > 6 && (long long) gx * ((nplanes + zrun - 1) / zrun) < 4LL * 2 * kNumSMs) zrun -= 6;
+      while (zrun > 6 && (long long) gx * ((nplanes + zrun - 1) / zrun) < 3LL * kNumSMs) zrun -= 6;
    }
    int gy = (nplanes + zrun - 1) / zrun;
    if (DOT && (long long) gx * gy > kRedBlocksMax) {
@@ -460,7 +559,7 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    BoxP0 P0;
    for (int t = 0; t < 27; t++) P0.a[t] = M.box_p0_val[t];
-   HB_LAUNCH((spmv_box<EPI, DOT>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
+   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
              M.pat_npat, M.box_p0, M.box_mask, M.box_val, P0, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
@@ -468,14 +567,16 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
 
 int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)
 {
-   if (ea.dot_slot >= 0 && ea.dotw != nullptr) {
-      if (!spmv_can_fuse_dot(M, epi_kind)) return set_error(HB200_ERROR_GENERIC, "fused dot requested on a block that cannot fuse it");
-      return epi_kind == EPI_AXPBY ? box_launch_t<EPI_AXPBY, true>(M, x, ea, st) : box_launch_t<EPI_JACOBI7, true>(M, x, ea, st);
-   }
+   const bool dot = ea.dot_slot >= 0 && ea.dotw != nullptr;
+   if (dot && !spmv_can_fuse_dot(M, epi_kind)) return set_error(HB200_ERROR_GENERIC, "fused dot requested on a block that cannot fuse it");
    switch (epi_kind) {
-      case EPI_AXPBY:       return box_launch_t<EPI_AXPBY, false>(M, x, ea, st);
-      case EPI_JACOBI7:     return box_launch_t<EPI_JACOBI7, false>(M, x, ea, st);
-      case EPI_JACOBI_CORE: return box_launch_t<EPI_JACOBI_CORE, false>(M, x, ea, st);
+      case EPI_AXPBY:
+         if (ea.beta == 0.0) return dot ? box_launch_t<EPI_AXPBY, true, 0>(M, x, ea, st) : box_launch_t<EPI_AXPBY, false, 0>(M, x, ea, st);
+         return dot ? box_launch_t<EPI_AXPBY, true, 1>(M, x, ea, st) : box_launch_t<EPI_AXPBY, false, 1>(M, x, ea, st);
+      case EPI_JACOBI7:
+         if (ea.u != x) return spmv_pat_launch(M, x, epi_kind, ea, st);   // (the sweep always multiplies the vector it updates)
+         return dot ? box_launch_t<EPI_JACOBI7, true, 2>(M, x, ea, st) : box_launch_t<EPI_JACOBI7, false, 2>(M, x, ea, st);
+      case EPI_JACOBI_CORE: return box_launch_t<EPI_JACOBI_CORE, false, 0>(M, x, ea, st);
       default: return set_error(HB200_ERROR_ARG, "spmv_box_launch: epilogue %d has no box kernel", epi_kind);
    }
 }
@@ -734,7 +835,7 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
          HB_CUDA(cudaMemcpy(M.box_val, bh.val.data(), sizeof(double) * (size_t) npat * 27, cudaMemcpyHostToDevice));
          M.box_sy = bh.sy; M.box_sz = bh.sz; M.box_p0 = bh.p0;
          for (int t = 0; t < 27; t++) M.box_p0_val[t] = bh.p0 >= 0 ? bh.val[(size_t) bh.p0 * 27 + t] : 0.0;
-         M.has_box = true;
+         M.has_box = box_fits(M);
       }
    }
    return 0;

@@ -25,103 +25,17 @@
 namespace hb {
 
 // ---------------------------------------------------------------------------------------
-// stream kernel
+// stream kernel (nnz-balanced CTA windows, products parked in shared memory, then ONE thread per
+// row adds them in CSR order with separate multiply / add: bit-identical to the 1-thread CPU
+// reference).  It lost to the sub-warp vector kernel on every level measured (0.59 against 0.87 of
+// the HBM peak on A_0: the shared-memory round trip is L1-wavefront bound, profiles/r1_level_sweep_*.txt)
+// and is kept, in this one variant, as the order-preserving cross-check of the parity tests.
+// Lane l of a warp takes nonzero p+l, so the x gathers of one load instruction fall on neighbouring
+// columns; col_ind / values are read with scalar, perfectly coalesced loads, 4 in flight per thread.
 // ---------------------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;
+constexpr int kStreamCap = 2048;
 
-template <int EPI, int L, int CAP>
-__global__ void __launch_bounds__(kStreamThreads)
-spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind,
-            const double *__restrict__ val, const double *__restrict__ x,
-            const int *__restrict__ blk_row, EpiArgs ea)
-{
-   __shared__ double prod[CAP + 4];
-   const int tid = threadIdx.x;
-   const int r0  = blk_row[blockIdx.x];
-   const int r1  = blk_row[blockIdx.x + 1];
-   const int p0  = rowptr[r0];
-   const int p1  = rowptr[r1];
-   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
-
-   if (p1 - p0 + 3 > CAP) {
-      // a single row longer than the shared-memory window: whole CTA on one row
-      double s = 0.0;
-      for (int p = p0 + skip + tid; p < p1; p += kStreamThreads) {
-         s += val[p] * __ldg(x + colind[p]);
-      }
-      __shared__ double red[kStreamThreads / 32];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if ((tid & 31) == 0) red[tid >> 5] = s;
-      __syncthreads();
-      if (tid == 0) {
-         double t = 0.0;
-#pragma unroll
-         for (int w = 0; w < kStreamThreads / 32; w++) t += red[w];
-         epi_apply<EPI>(ea, r0, t, epi_needs_diag<EPI>() ? val[p0] : 0.0);
-      }
-      return;
-   }
-
-   // ---- phase 1: coalesced 128-bit streaming of (col, val), gather x, products -> smem
-   const int base = p0 & ~3;
-   for (int q = base + 4 * tid; q < p1; q += 4 * kStreamThreads) {
-      const int4    c  = *reinterpret_cast<const int4 *>(colind + q);
-      const double2 v0 = *reinterpret_cast<const double2 *>(val + q);
-      const double2 v1 = *reinterpret_cast<const double2 *>(val + q + 2);
-      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y);
-      const double x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
-      double *dst = prod + (q - base);
-      // separate multiply (rounded) then ordered adds in phase 2 == the reference's
-      // tempx += A_data[jj] * x_data[A_j[jj]] without FMA contraction
-      dst[0] = __dmul_rn(v0.x, x0);
-      dst[1] = __dmul_rn(v0.y, x1);
-      dst[2] = __dmul_rn(v1.x, x2);
-      dst[3] = __dmul_rn(v1.y, x3);
-   }
-   __syncthreads();
-
-   // ---- phase 2: L lanes per row
-   const int nrows = r1 - r0;
-   if (L == 1) {
-      for (int r = tid; r < nrows; r += kStreamThreads) {
-         const int row = r0 + r;
-         const int a = rowptr[row] - base, b = rowptr[row + 1] - base;
-         double s = 0.0;
-         for (int k = a + skip; k < b; k++) s = __dadd_rn(s, prod[k]);
-         epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
-      }
-   } else {
-      const int lane = tid % L;
-      const int grp  = tid / L;
-      constexpr int NG = kStreamThreads / L;
-      // all lanes of a warp run the same trip count so that the shuffles stay converged
-      const int trips = (nrows + NG - 1) / NG;
-      for (int t = 0; t < trips; t++) {
-         const int r = grp + t * NG;
-         double s = 0.0;
-         int row = r0 + r;
-         int a = 0;
-         if (r < nrows) {
-            a = rowptr[row] - base;
-            const int b = rowptr[row + 1] - base;
-            for (int k = a + skip + lane; k < b; k += L) s += prod[k];
-         }
-#pragma unroll
-         for (int o = L / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, L);
-         if (r < nrows && lane == 0) {
-            epi_apply<EPI>(ea, row, s, epi_needs_diag<EPI>() ? val[rowptr[row]] : 0.0);
-         }
-      }
-   }
-}
-
-// ---------------------------------------------------------------------------------------
-// stream kernel, lane-consecutive variant: lane l of a warp takes nonzero p+l, so the x gathers
-// of one load instruction fall on neighbouring columns (a 27-point row is 9 runs of 3
-// consecutive columns) and coalesce into few L1 sectors; col_ind / values are read with
-// scalar but perfectly coalesced loads, UNROLL of them in flight per thread.
-// ---------------------------------------------------------------------------------------
 template <int EPI, int L, int CAP, int NT>
 __global__ void __launch_bounds__(NT)
 spmv_stream_lc(const int *__restrict__ rowptr, const int *__restrict__ colind,
@@ -230,20 +144,6 @@ spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ 
       p0 = rowptr[row];
       const int p1 = rowptr[row + 1];
       int p = p0 + skip + lane;
-      if (U > 1) {
-         // U independent (index, value) loads in flight per lane before the dependent x gathers:
-         // the kernel is latency-bound on bytes in flight, not on issue slots
-         for (; p + (U - 1) * K < p1; p += U * K) {
-            int c[U];
-            double v[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) c[u] = colind[p + u * K];
-#pragma unroll
-            for (int u = 0; u < U; u++) v[u] = val[p + u * K];
-#pragma unroll
-            for (int u = 0; u < U; u++) s += v[u] * __ldg(x + c[u]);
-         }
-      }
       if (I16) {
          const double *xr = x + row;
          for (; p < p1; p += K) s += val[p] * __ldg(xr + col16[p]);
@@ -261,38 +161,19 @@ spmv_vector(int nlist, const int *__restrict__ rowlist, const int *__restrict__ 
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-constexpr int kStreamCap = 2048;
-
-template <int EPI, int L>
-static int launch_stream_L(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
-{
-   if (M.kind == SPMV_STREAM_V4) {
-      HB_LAUNCH((spmv_stream<EPI, L, kStreamCap>), M.nblks, kStreamThreads, 0, st, M.i, M.j, M.a, x,
-                M.blk_row, ea);
-   } else {
-      HB_LAUNCH((spmv_stream_lc<EPI, L, kStreamCap, kStreamThreads>), M.nblks, kStreamThreads, 0, st,
-                M.i, M.j, M.a, x, M.blk_row, ea);
-   }
-   HB_LAUNCH_CHECK();
-   return 0;
-}
 
 template <int EPI>
 static int launch_stream(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
-   switch (M.lanes) {
-      case 1:  return launch_stream_L<EPI, 1>(M, x, ea, st);
-      case 2:  return launch_stream_L<EPI, 2>(M, x, ea, st);
-      case 4:  return launch_stream_L<EPI, 4>(M, x, ea, st);
-      case 8:  return launch_stream_L<EPI, 8>(M, x, ea, st);
-      case 16: return launch_stream_L<EPI, 16>(M, x, ea, st);
-      default: return launch_stream_L<EPI, 32>(M, x, ea, st);
-   }
+   HB_LAUNCH((spmv_stream_lc<EPI, 1, kStreamCap, kStreamThreads>), M.nblks, kStreamThreads, 0, st,
+             M.i, M.j, M.a, x, M.blk_row, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
 }
 
 template <int EPI, int K>
 static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, const int *rowlist, int nlist,
-                           int unroll, cudaStream_t st)
+                           cudaStream_t st)
 {
    const long long threads = (long long) nlist * K;
    const int grid = (int) ((threads + kVecThreads - 1) / kVecThreads);
@@ -303,24 +184,22 @@ static int launch_vector_K(const DCsr &M, const double *x, const EpiArgs &ea, co
       HB_LAUNCH_CHECK();
       return 0;
    }
-   if (unroll >= 4)      HB_LAUNCH((spmv_vector<EPI, K, 4>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
-   else if (unroll >= 2) HB_LAUNCH((spmv_vector<EPI, K, 2>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
-   else                  HB_LAUNCH((spmv_vector<EPI, K, 1>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
+   HB_LAUNCH((spmv_vector<EPI, K, 1>), grid, kVecThreads, 0, st, nlist, rl, M.i, M.j, M.a, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
 }
 
 template <int EPI>
 static int launch_vector(const DCsr &M, const double *x, const EpiArgs &ea, const int *rowlist, int nlist,
-                         int lanes, int unroll, cudaStream_t st)
+                         int lanes, cudaStream_t st)
 {
    switch (lanes) {
-      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, rowlist, nlist, unroll, st);
-      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, rowlist, nlist, unroll, st);
-      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, rowlist, nlist, unroll, st);
-      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, rowlist, nlist, unroll, st);
-      case 16: return launch_vector_K<EPI, 16>(M, x, ea, rowlist, nlist, unroll, st);
-      default: return launch_vector_K<EPI, 32>(M, x, ea, rowlist, nlist, unroll, st);
+      case 1:  return launch_vector_K<EPI, 1>(M, x, ea, rowlist, nlist, st);
+      case 2:  return launch_vector_K<EPI, 2>(M, x, ea, rowlist, nlist, st);
+      case 4:  return launch_vector_K<EPI, 4>(M, x, ea, rowlist, nlist, st);
+      case 8:  return launch_vector_K<EPI, 8>(M, x, ea, rowlist, nlist, st);
+      case 16: return launch_vector_K<EPI, 16>(M, x, ea, rowlist, nlist, st);
+      default: return launch_vector_K<EPI, 32>(M, x, ea, rowlist, nlist, st);
    }
 }
 
@@ -359,22 +238,18 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
       if (M.pat_nirr == 0) return 0;
       // rows outside the pattern table: CSR sweep over the row list (disjoint rows, same epilogue)
       const double avg = (double) M.pat_irr_nnz / (double) M.pat_nirr;
-      return launch_vector<EPI>(M, x, ea, M.pat_irr, M.pat_nirr, widen_lanes(vector_lanes_for(avg), M.pat_nirr, avg), 1, st);
+      return launch_vector<EPI>(M, x, ea, M.pat_irr, M.pat_nirr, widen_lanes(vector_lanes_for(avg), M.pat_nirr, avg), st);
    }
    if (!use_rownnz && M.kind == SPMV_SELL && M.has_sell) return spmv_sell_launch(M, x, EPI, ea, st);
-   if (!use_rownnz && (M.kind == SPMV_STREAM || M.kind == SPMV_STREAM_V4) && M.nblks > 0) {
-      return launch_stream<EPI>(M, x, ea, st);
-   }
-   const bool vec = (M.kind == SPMV_VECTOR || M.kind == SPMV_VECTOR_U2 || M.kind == SPMV_VECTOR_U4 ||
-                     M.kind == SPMV_VECTOR16);
+   if (!use_rownnz && M.kind == SPMV_STREAM && M.nblks > 0) return launch_stream<EPI>(M, x, ea, st);
+   const bool vec = (M.kind == SPMV_VECTOR || M.kind == SPMV_VECTOR16);
    int lanes = (vec && M.lanes > 0 && !use_rownnz) ? M.lanes : 0;
-   const int unroll = M.kind == SPMV_VECTOR_U4 ? 4 : M.kind == SPMV_VECTOR_U2 ? 2 : 1;
    if (lanes == 0) {
       const double avg = use_rownnz ? (double) M.nnz / (double) (M.num_rownnz ? M.num_rownnz : 1)
                                     : M.avg_row_nnz;
       lanes = widen_lanes(vector_lanes_for(avg), nlist, avg);
    }
-   return launch_vector<EPI>(M, x, ea, use_rownnz ? M.rownnz : (const int *) nullptr, nlist, lanes, unroll, st);
+   return launch_vector<EPI>(M, x, ea, use_rownnz ? M.rownnz : (const int *) nullptr, nlist, lanes, st);
 }
 
 int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, bool use_rownnz,
@@ -433,10 +308,8 @@ void dcsr_choose_kernel(DCsr &M, int kind, int lanes)
    if (kind == SPMV_VECTOR16 && !M.j16) kind = SPMV_VECTOR;
    M.kind = kind;
    if (lanes > 0) { M.lanes = lanes; return; }
-   if (kind == SPMV_STREAM || kind == SPMV_STREAM_V4) {
-      // phase-2 lanes per row: keep the per-thread serial chain short on the dense coarse levels
-      const double a = M.avg_row_nnz;
-      M.lanes = a <= 40 ? 1 : a <= 80 ? 2 : a <= 160 ? 4 : a <= 320 ? 8 : 16;
+   if (kind == SPMV_STREAM) {
+      M.lanes = 1;   // the one variant kept: one thread per row, CSR order
    } else {
       M.lanes = widen_lanes(vector_lanes_for(M.avg_row_nnz, M.nrows), M.nrows, M.avg_row_nnz);
    }

@@ -114,6 +114,7 @@ static int pcg_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_pc
    const int my_id = c.rank;
    const bool log = (P->logging > 0 || P->print_level > 0) && norms;
    int eflag = 0;
+   ProfRange pr_solve("PCG-Solve");
    HB_TRACE("pcg_solve: %zu local rows, halo mode %d", n, c.halo_mode);
 
    // work vectors p, s, r [, r_old, v] (hypre_PCGSetup, pcg.c:233-250) from the persistent workspace
@@ -451,6 +452,7 @@ static int gmres_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_
    const bool log = (P->logging > 0 || P->print_level > 0) && norms;
    HB_REQUIRE(k_dim >= 1 && k_dim <= 100, HB200_ERROR_ARG, "k_dim out of range (1..100)");
    int eflag = 0;
+   ProfRange pr_solve("GMRES-Solve");
 
    // basis p[0..k_dim] as one slab (par_krylov_func.c:66-104), plus r, w [, w_2]
    double *slab = nullptr;

@@ -471,7 +471,7 @@ int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10)
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row)
 {
    HB_REQUIRE(A != nullptr, HB200_ERROR_ARG, "null matrix");
-   HB_REQUIRE(kind >= 0 && kind <= 9, HB200_ERROR_ARG, "kind must be 0..9");
+   HB_REQUIRE(kind >= 0 && kind <= 9 && !(kind >= 3 && kind <= 5), HB200_ERROR_ARG, "kind must be 0, 1, 2, 6, 7, 8 or 9");
    HB_REQUIRE(lanes_per_row == 0 || (lanes_per_row <= 32 && (lanes_per_row & (lanes_per_row - 1)) == 0),
               HB200_ERROR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
    HB_CHECK(dcsr_ensure_formats(A->diag, kind));

@@ -8,6 +8,9 @@
 #include <strings.h>
 #include <mutex>
 #include <dlfcn.h>
+#ifndef HB200_EMU
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 namespace hb {
 
@@ -26,6 +29,21 @@ int set_error(int flag, const char *fmt, ...)
    g_err = buf;
    if (getenv("HB200_VERBOSE")) fprintf(stderr, "[hb200] error %d: %s\n", flag, buf);
    return flag;
+}
+
+void prof_push(const char *name)
+{
+#ifndef HB200_EMU
+   nvtxRangePushA(name);
+#else
+   (void) name;
+#endif
+}
+void prof_pop()
+{
+#ifndef HB200_EMU
+   nvtxRangePop();
+#endif
 }
 
 bool env_flag(const char *name, bool dflt)

@@ -139,13 +139,15 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
  * info[7] = the kernel kind in force (numbering of hb200_parcsr_set_spmv_kernel);
  * info[8] = rows outside the pattern table (swept in CSR), info[9] = their nonzeros. */
 int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10);
-/* Selects the SpMV kernel for this matrix: 0 = auto (row-pattern, else packed SELL, else vector
- * with lanes from nnz/row; default), 1 = vector-per-row (sub-warp of K lanes), 2 = nnz-balanced
- * stream (merge-style), 3 = stream with 128-bit index/value loads (kept for comparison), 4/5 =
- * vector with 2x/4x unrolled loads, 6 = packed SELL, 7 = row-pattern, 8 = vector-per-row over
- * 16-bit column offsets from the row (10 B per nonzero; square blocks whose entries stay within
- * +-32767 of the diagonal).  6, 7 and 8 fall back to the next format when the block does not
- * qualify; auto prefers 7, 6, 8, 1 in that order. */
+/* Selects the SpMV kernel for this matrix: 0 = auto (compact-stencil, else row-pattern, else packed
+ * SELL, else vector with lanes from nnz/row; default), 1 = vector-per-row (sub-warp of K lanes: the
+ * general CSR kernel), 2 = nnz-balanced stream, one thread per row adding in CSR order (the
+ * order-preserving cross-check of the parity tests; lanes_per_row is ignored), 6 = packed SELL,
+ * 7 = row-pattern, 8 = vector-per-row over 16-bit column offsets from the row (10 B per nonzero;
+ * square blocks whose entries stay within +-32767 of the diagonal), 9 = the compact-stencil
+ * (3 x 3 x 3 box) kernel over the row-pattern table.  6 - 9 fall back to the next format when the
+ * block does not qualify; auto prefers 9, 7, 6, 8, 1 in that order.  (3, 4, 5 — the stream / unrolled
+ * variants of the first release, slower on every level measured — are gone: argument error.) */
 int hb200_parcsr_set_spmv_kernel(hb200_parcsr *A, int kind, int lanes_per_row);
 /* Host-side half of the upload, no GPU needed: the row-pattern analysis of one CSR
  * block (a hypre_CSRMatrix: i / j / data, src/seq_mv/csr_matrix.h:33-62) exactly as

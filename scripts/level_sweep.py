@@ -21,7 +21,7 @@ def timeit(fn, reps=20, warm=3):
     for _ in range(reps): fn()
     e1.record(stream); hb.sync()
     return e0.elapsed_time(e1) / reps
-cfgs = [(0, 0), (7, 0), (6, 0), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (8, 1), (8, 2), (8, 4), (8, 8), (8, 16), (8, 32)]
+cfgs = [(0, 0), (9, 0), (7, 0), (6, 0), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (8, 1), (8, 2), (8, 4), (8, 8), (8, 16), (8, 32)]
 if len(sys.argv) > 3: cfgs = [(0, 0), (1, 0), (8, 0)]
 print(f"# {kind} n={n}")
 for l, (A, P) in enumerate(mats):

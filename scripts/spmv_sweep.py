@@ -39,9 +39,9 @@ rows = []
 spmv_bytes = 12.0 * nnz + 4.0 * N + 8.0 * N + 8.0 * N
 def spmv(): check(lib.hb200_parcsr_matvec(A.handle, 1.0, x.data_ptr(), 0.0, y.data_ptr(), y.data_ptr()))
 if variants == "one":
-    cfgs = [(7, 1), (6, 1)]
+    cfgs = [(9, 0), (7, 0), (6, 0)]
 else:
-    cfgs = [(7, 1), (6, 1), (1, 2), (1, 4), (4, 4), (2, 1)]
+    cfgs = [(9, 0), (7, 0), (6, 0), (1, 2), (1, 4), (2, 0)]
 for k, L in cfgs:
     A.set_spmv_kernel(k, L)
     ms = timeit(spmv)

@@ -120,6 +120,7 @@ def _load() -> C.CDLL:
         "hb200_pcg_default_params": ([C.POINTER(PCGParams)], None),
         "hb200_pcg_solve": ([vp, C.c_int, vp, C.POINTER(PCGParams), vp, vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_pcg_solve_host": ([vp, C.c_int, vp, C.POINTER(PCGParams), vp, vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_krylov_warmup": ([vp, C.c_int, vp, C.c_int, C.c_int], C.c_int),
         "hb200_gmres_default_params": ([C.POINTER(GMRESParams)], None),
         "hb200_gmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_gmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),

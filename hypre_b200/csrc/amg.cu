@@ -299,7 +299,7 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    long long &runs = amg->dot_req_slot >= 0 ? amg->cycles_run_dot : amg->cycles_run;
    if (runs++ == 0) return cycle_body(amg, f_dev, u_dev, u_all_zeros);
    for (int l = 0; l + 1 < amg->num_levels; l++) HB_CHECK(parcsr_ensure_T(amg->lev[l].P));
-   if (amg->graphs.size() >= 8) {
+   if (amg->graphs.size() >= 128) {   // (GMRES(k) presents k + 1 different (f, u) pairs)
       cudaGraphExecDestroy(amg->graphs.front().exec);
       amg->graphs.erase(amg->graphs.begin());
    }

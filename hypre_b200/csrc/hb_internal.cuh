@@ -223,6 +223,7 @@ struct DCsr {
 };
 
 int  dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha);
+int  dcsr_analyze(DCsr &M, const int *hi, const int *hj, const double *ha);   // formats + kernel choice of a block whose CSR is on the device
 int  dcsr_free(DCsr &M);
 void dcsr_choose_kernel(DCsr &M, int kind, int lanes);
 int  dcsr_ensure_formats(DCsr &M, int kind);

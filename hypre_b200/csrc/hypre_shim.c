@@ -42,6 +42,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "_hypre_utilities.h"
 #include "HYPRE.h"
@@ -56,6 +57,13 @@
 
 static int g_ready = 0, g_failed = 0, g_verbose = 0, g_strict = 0;
 static int g_nprocs = 1, g_myid = 0;   /* the communicator the library was bound on (first matrix seen) */
+
+static double wall_now(void)
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
 
 static void *next_sym(const char *name)
 {
@@ -594,13 +602,27 @@ HYPRE_Int hypre_BoomerAMGSetup(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
 
 /* Krylov setup: the operator itself goes to the device here (diagonal scaling / no preconditioner:
  * nothing else would upload it before the first Solve) */
-static void krylov_setup_upload(void *matvec_fn, void *A)
+static int precond_kind(void *precond_fn, void *precond_data, hypre_ParCSRMatrix *A, hb200_amg **amg, const char **why);
+
+static void krylov_setup_upload(void *matvec_fn, void *A, void *precond_fn, void *precond_data, void *precond_Mat,
+                                int is_gmres, int k_dim)
 {
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   hb200_parcsr *dA;
+   hb200_amg *amg = NULL;
+   const char *why = NULL;
+   int kind;
    if (!A || matvec_fn != (void *) hypre_ParKrylovMatvec || lazy_upload() || g_failed) { return; }
    if (shim_init(hypre_ParCSRMatrixComm(pA))) { return; }
    if (comm_off_path(hypre_ParCSRMatrixComm(pA))) { return; }
-   mirror_matrix_checked(pA, 1);
+   dA = mirror_matrix_checked(pA, 1);
+   if (!dA || (precond_Mat && precond_Mat != A) || k_dim > 100) { return; }
+   /* the solve this setup prepares: work vectors, lazily built scratch, captured cycles (a hand-back
+    * decided at Solve time - multivectors, printing - just leaves the warm-up unused) */
+   kind = precond_kind(precond_fn, precond_data, pA, &amg, &why);
+   if (kind < 0 || why) { return; }
+   if (getenv("HYPRE_B200_NO_WARMUP")) { return; }
+   if (hb200_krylov_warmup(dA, kind, amg, is_gmres, k_dim)) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); }
 }
 
 HYPRE_Int hypre_PCGSetup(void *pcg_vdata, void *A, void *b, void *x)
@@ -609,7 +631,11 @@ HYPRE_Int hypre_PCGSetup(void *pcg_vdata, void *A, void *b, void *x)
    HYPRE_Int ierr;
    if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_PCGSetup"); }
    ierr = orig(pcg_vdata, A, b, x);   /* calls precond_setup -> hypre_BoomerAMGSetup above */
-   if (!ierr) { krylov_setup_upload((void *) ((hypre_PCGData *) pcg_vdata)->functions->Matvec, A); }
+   if (!ierr)
+   {
+      hypre_PCGData *pd = (hypre_PCGData *) pcg_vdata;
+      krylov_setup_upload((void *) pd->functions->Matvec, A, (void *) pd->functions->precond, pd->precond_data, pd->precond_Mat, 0, 0);
+   }
    return hypre_error_flag;
 }
 
@@ -619,7 +645,11 @@ HYPRE_Int hypre_GMRESSetup(void *gmres_vdata, void *A, void *b, void *x)
    HYPRE_Int ierr;
    if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_GMRESSetup"); }
    ierr = orig(gmres_vdata, A, b, x);
-   if (!ierr) { krylov_setup_upload((void *) ((hypre_GMRESData *) gmres_vdata)->functions->Matvec, A); }
+   if (!ierr)
+   {
+      hypre_GMRESData *gd = (hypre_GMRESData *) gmres_vdata;
+      krylov_setup_upload((void *) gd->functions->Matvec, A, (void *) gd->functions->precond, gd->precond_data, gd->precond_Mat, 1, gd->k_dim);
+   }
    return hypre_error_flag;
 }
 
@@ -740,6 +770,7 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    hb200_krylov_result R;
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
    int kind = 0, flag;
+   double t_call;
    if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_PCGSolve"); }
    /* only the ParCSR function table (HYPRE_ParCSRPCGCreate) is on the accelerated path */
    if (fn->Matvec != hypre_ParKrylovMatvec) { return orig(pcg_vdata, A, b, x); }
@@ -768,6 +799,7 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    P.logging = pd->logging; P.print_level = pd->print_level;
    pd->converged = 0;
    memset(&R, 0, sizeof(R));
+   t_call = wall_now();
    flag = hb200_pcg_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
                                hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)),
                                pd->norms, pd->rel_norms, &R);
@@ -782,7 +814,7 @@ HYPRE_Int hypre_PCGSolve(void *pcg_vdata, void *A, void *b, void *x)
    pd->converged = R.converged;
    hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
    if (flag & HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_CONV, hb200_last_error()); }
-   if (g_verbose) { fprintf(stderr, "[hypre_b200] PCG on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] PCG on device: %d its, %.3f ms, %lld kernel launches; %.3f ms host wall clock of the call (H2D of b, x; solve; D2H of x)\n", R.num_iterations, R.solve_ms, R.kernel_launches, 1e3 * (wall_now() - t_call)); }
    return hypre_error_flag;
 }
 

@@ -324,15 +324,25 @@ int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
 struct BoxP0 { double a[27]; };
 
 constexpr int kBoxThreads = 512;   // in-plane positions per block (one per thread)
-constexpr int kBoxStages  = 4;     // planes in flight per block (cp.async ring)
+constexpr int kBoxStages  = 4;     // planes in flight per block (shared-memory ring)
 
-// asynchronous 8-byte copy global -> shared (cp.async, LDGSTS): the x slab of the planes ahead is
-// in flight while the block computes, whatever the occupancy
+__device__ __forceinline__ unsigned int box_smem_u32(const void *p)
+{
+#ifndef HB200_EMU
+   return (unsigned int) __cvta_generic_to_shared(p);
+#else
+   return 0u;
+#endif
+}
+// ---- the two ways a plane reaches shared memory ----------------------------------------------
+// (a) TMA bulk copy (cp.async.bulk, SASS UBLKCP): ONE thread issues one instruction per contiguous
+//     piece, the copy engine moves it and signals an mbarrier with the byte count; needs 16-byte
+//     aligned addresses and sizes (the launcher checks the pointers, the kernel pads the segment);
+// (b) per-thread 8-byte cp.async (LDGSTS): no alignment demand, ~3 instructions per thread and plane
 __device__ __forceinline__ void box_cp_async8(double *smem_dst, const double *gsrc)
 {
 #ifndef HB200_EMU
-   const unsigned int d = (unsigned int) __cvta_generic_to_shared(smem_dst);
-   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(box_smem_u32(smem_dst)), "l"(gsrc) : "memory");
 #else
    *smem_dst = *gsrc;
 #endif
@@ -350,15 +360,58 @@ __device__ __forceinline__ void box_cp_wait()
    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 #endif
 }
+__device__ __forceinline__ void box_mbar_init(unsigned long long *bar, int count)
+{
+#ifndef HB200_EMU
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(box_smem_u32(bar)), "r"(count) : "memory");
+#else
+   *bar = 0;
+#endif
+}
+__device__ __forceinline__ void box_mbar_fence_init()
+{
+#ifndef HB200_EMU
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void box_mbar_expect(unsigned long long *bar, unsigned int bytes)
+{
+#ifndef HB200_EMU
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(box_smem_u32(bar)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void box_bulk_copy(void *smem_dst, const void *gsrc, unsigned int bytes, unsigned long long *bar)
+{
+#ifndef HB200_EMU
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(box_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(box_smem_u32(bar)) : "memory");
+#else
+   memcpy(smem_dst, gsrc, bytes);
+#endif
+}
+__device__ __forceinline__ void box_mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+#ifndef HB200_EMU
+   unsigned int done = 0;
+   const unsigned int a = box_smem_u32(bar);
+   while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(a), "r"(parity) : "memory");
+   }
+#endif
+}
 
 // The kernel.  A block owns kBoxThreads consecutive in-plane positions [q0, q0 + NT) and a run of
 // planes; plane p of its x slab is the contiguous segment x[p*sz + q0 - sy - 1 .. p*sz + q0 + NT + sy + 1),
-// copied into a ring of shared-memory stages by cp.async kBoxStages - 1 planes ahead of the compute
-// (the same stage carries the per-row inputs of the epilogue: b, or f and l1).  Per plane a thread
-// reads its 9 in-plane neighbours of the NEW plane from shared memory into the register window
-// (the other 18 values are already there) and runs the 27 slots.
+// brought into a ring of shared-memory stages kBoxStages - 1 planes ahead of the compute (the same
+// stage carries the per-row inputs of the epilogue: b, or f and l1).  Per plane a thread reads its 9
+// in-plane neighbours of the NEW plane from shared memory into the register window (the other 18
+// values are already there) and runs the 27 slots.
 //   STREAMS = number of epilogue vectors staged with the slab (0: none, 1: b, 2: f and l1)
-template <int EPI, bool DOT, int STREAMS>
+//   BULK    = planes arrive by TMA bulk copies on an mbarrier per stage, else by per-thread cp.async
+//   NEG1    = every off-diagonal coefficient of the full pattern is exactly -1.0 (the Laplacians):
+//             a * x is -x, bit for bit, so the interior rows add -x instead of multiplying
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1>
 __global__ void __launch_bounds__(kBoxThreads, 1)
 spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
          const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
@@ -367,13 +420,20 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    constexpr int NT = kBoxThreads, NS = kBoxStages;
    HB_DYN_SHARED(double, s_mem);
    const int seg = NT + 2 * sy + 2;                    // doubles of one plane segment
-   const int stage_len = seg + STREAMS * NT;           // + the staged epilogue vectors
-   double       *s_ring = s_mem;                                          // NS stages
-   double       *s_val = s_ring + (size_t) NS * stage_len;               // npat x 27
-   unsigned int *s_mask = reinterpret_cast<unsigned int *>(s_val + npat * 27);
+   const int segpad = (seg + 2) & ~1;                  // + the parity shift of an aligned copy, even
+   const int stage_len = segpad + STREAMS * NT;        // + the staged epilogue vectors
+   double             *s_ring = s_mem;                                          // NS stages
+   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_ring + (size_t) NS * stage_len);   // NS mbarriers
+   double             *s_val = reinterpret_cast<double *>(s_bar + NS);          // npat x 27
+   unsigned int       *s_mask = reinterpret_cast<unsigned int *>(s_val + npat * 27);
    const int tid = threadIdx.x;
    for (int k = tid; k < npat * 27; k += NT) s_val[k] = vals[k];
    for (int k = tid; k < npat; k += NT) s_mask[k] = masks[k];
+   if (BULK && tid == 0) {
+      for (int k = 0; k < NS; k++) box_mbar_init(s_bar + k, 1);
+      box_mbar_fence_init();
+   }
+   __syncthreads();
    // blocks are numbered in-plane first: neighbours in q run the same planes at the same time (L2)
    const int q0 = (int) (blockIdx.x % (unsigned) gx) * NT;
    const int q = q0 + tid;                                                // in-plane position
@@ -383,49 +443,102 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    const int skip_c = (EPI == EPI_JACOBI_CORE && ea.skip_diag) ? 1 : 0;   // leave the diagonal out
    const double *st0 = (STREAMS >= 1) ? ea.b : nullptr;                   // AXPBY: b ; JACOBI7: f
    const double *st1 = (STREAMS >= 2) ? ea.d : nullptr;                   // JACOBI7: l1 norms
+   // global index of xs[0] of plane p is p*sz + q0 - sy - 1 - dpar: dpar = parity of the segment start,
+   // so that an aligned (even) global index lands on an even shared-memory index (BULK: sz is even,
+   // the parity is the same for every plane)
+   const int dpar = BULK ? ((q0 - sy - 1) & 1) : 0;
+   const int nq = min(NT, sz - q0);                                       // in-plane positions of this block
 
-   // issue the copies of plane p (x segment) and of the epilogue inputs of plane p - 1's rows...
-   // stage (p - z0 + 1) % NS holds: x of plane p, epilogue vectors of the rows of plane p - 1
-   auto issue = [&](int p) {
-      double *dst = s_ring + (size_t) ((p - z0 + 1) % NS) * stage_len;
-      {
-         const long long g0 = (long long) p * sz + q0 - sy - 1;           // global index of dst[0]
+   // ---- producer: plane p (x segment) and the epilogue inputs of the rows of plane p - 1 go to stage
+   //      (p - z0 + 1) % NS
+   auto issue = [&](int p, int stage) {
+      double *dst = s_ring + (size_t) stage * stage_len;
+      const long long gstart = (long long) p * sz + q0 - sy - 1;          // global index of the segment start
+      if (BULK) {
+         if (tid == 0) {
+            unsigned long long *bar = s_bar + stage;
+            // clamp to the vector, align to 16 bytes (pairs of doubles)
+            long long cs = gstart < 0 ? 0 : gstart;
+            long long ce = gstart + seg;
+            if (ce > (long long) nrows) ce = nrows;
+            long long as = cs & ~1LL, ae = (ce + 1) & ~1LL;
+            bool tail = false;
+            if (ae > (long long) nrows) { ae = ce - 1; tail = true; }     // odd vector length: last element by hand
+            const long long r0 = (long long) (p - 1) * sz + q0;           // first row of the staged epilogue inputs
+            long long rcnt = 0;
+            if (STREAMS >= 1 && p - 1 >= z0 && p - 1 < z1) {
+               rcnt = nq;
+               if (r0 + rcnt > (long long) nrows) rcnt = (long long) nrows - r0;
+               if (rcnt < 0) rcnt = 0;
+            }
+            const long long rev = rcnt & ~1LL;                            // even part by bulk copy
+            unsigned int bytes = 0;
+            if (ae > as) bytes += (unsigned int) ((ae - as) * 8);
+            bytes += (unsigned int) (rev * 8 * STREAMS);
+            box_mbar_expect(bar, bytes);
+            if (ae > as) box_bulk_copy(dst + (as - gstart + dpar), x + as, (unsigned int) ((ae - as) * 8), bar);
+            if (tail && ce - 1 >= cs) dst[ce - 1 - gstart + dpar] = x[ce - 1];
+            if (STREAMS >= 1 && rev > 0) {
+               box_bulk_copy(dst + segpad, st0 + r0, (unsigned int) (rev * 8), bar);
+               if (STREAMS >= 2) box_bulk_copy(dst + segpad + NT, st1 + r0, (unsigned int) (rev * 8), bar);
+            }
+            if (STREAMS >= 1 && rcnt > rev) {
+               dst[segpad + rev] = st0[r0 + rev];
+               if (STREAMS >= 2) dst[segpad + NT + rev] = st1[r0 + rev];
+            }
+         }
+      } else {
          for (int k = tid; k < seg; k += NT) {
-            const long long gi = g0 + k;
+            const long long gi = gstart + k;
             if (gi >= 0 && gi < (long long) nrows) box_cp_async8(dst + k, x + gi);
          }
-      }
-      if (STREAMS >= 1) {
-         const long long r = (long long) (p - 1) * sz + q;
-         if (p - 1 >= z0 && p - 1 < z1 && qok && r < (long long) nrows) {
-            box_cp_async8(dst + seg + tid, st0 + r);
-            if (STREAMS >= 2) box_cp_async8(dst + seg + NT + tid, st1 + r);
+         if (STREAMS >= 1) {
+            const long long r = (long long) (p - 1) * sz + q;
+            if (p - 1 >= z0 && p - 1 < z1 && qok && r < (long long) nrows) {
+               box_cp_async8(dst + segpad + tid, st0 + r);
+               if (STREAMS >= 2) box_cp_async8(dst + segpad + NT + tid, st1 + r);
+            }
          }
+         box_cp_commit();
       }
-      box_cp_commit();
    };
-   // prologue: planes z0 - 1 .. z0 + NS - 2 (NS groups in flight)
+   // ---- consumer: plane p has landed in its stage (use number `use` of that stage)
+   auto landed = [&](int stage, int use, bool first) {
+      if (BULK) {
+         box_mbar_wait(s_bar + stage, (unsigned int) (use & 1));
+      } else {
+         if (first) box_cp_wait<NS - 2>(); else box_cp_wait<NS - 3>();
+      }
+   };
+   // prologue: planes z0 - 1 .. z0 + NS - 2 into stages 0 .. NS - 1
 #pragma unroll
-   for (int k = 0; k < NS; k++) issue(z0 - 1 + k);
+   for (int k = 0; k < NS; k++) issue(z0 - 1 + k, k);
+#ifdef HB200_EMU
+   __syncthreads();   // (the emulated copies are synchronous, made by thread 0: let it run first)
+#endif
    // in-plane neighbour offsets inside a segment, class c = (dy+1)*3 + (dx+1)
    int offc[9];
 #pragma unroll
-   for (int c = 0; c < 9; c++) offc[c] = tid + sy + 1 + (c / 3 - 1) * sy + (c % 3 - 1);
+   for (int c = 0; c < 9; c++) offc[c] = tid + sy + 1 + dpar + (c / 3 - 1) * sy + (c % 3 - 1);
    double W[3][9];                                                        // planes z-1, z, z+1 (rotating)
    // planes z0 - 1 and z0 into the window
-   box_cp_wait<NS - 2>();
-   __syncthreads();
+   landed(0, 0, true);
+   landed(1, 0, true);
+   __syncthreads();   // (cp.async data of the other threads; the hand-copied tail elements of thread 0)
    {
-      const double *sm = s_ring + (size_t) 0 * stage_len, *sc = s_ring + (size_t) 1 * stage_len;
+      const double *sm = s_ring, *sc = s_ring + stage_len;
 #pragma unroll
       for (int c = 0; c < 9; c++) { W[0][c] = sm[offc[c]]; W[1][c] = sc[offc[c]]; }
    }
-   // row codes are prefetched two planes ahead in registers
-   auto ldcode = [&](int z) -> int {
-      const long long r = (long long) z * sz + q;
-      return (qok && z < z1 && r < (long long) nrows) ? (int) __ldg(pat + r) : 255;
+   // row codes are prefetched two planes ahead in registers (32-bit row arithmetic: rows are ints)
+   const unsigned int urows = (unsigned int) nrows, usz = (unsigned int) sz;
+   unsigned int rowq = (unsigned int) z0 * usz + (unsigned int) q;        // this thread's row in plane z
+   auto ldcode = [&](unsigned int r, int z) -> int {
+      return (qok && z < z1 && r < urows) ? (int) __ldg(pat + r) : 255;
    };
-   int code_a = ldcode(z0), code_b = ldcode(z0 + 1);
+   int code_a = ldcode(rowq, z0), code_b = ldcode(rowq + usz, z0 + 1);
+   int st_new = 2, use_new = 0;          // stage / use count of plane z + 1
+   int st_old = 0, use_old = 0;          // stage of plane z - 1: the one refilled in step z
    double dacc = 0.0;
    for (int zb = z0; zb < z1; zb += 3) {
 #pragma unroll
@@ -436,21 +549,24 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
          double (&Wm)[9] = W[u % 3];
          double (&Wc)[9] = W[(u + 1) % 3];
          double (&Wp)[9] = W[(u + 2) % 3];
-         // plane z + 1 has landed (all but the NS - 3 youngest groups are complete); the barrier also
-         // tells that every thread is done with the stage read one step ago, which is refilled now
-         box_cp_wait<NS - 3>();
+         // the barrier tells that every thread is done with the stage read one step ago (plane z - 1's:
+         // its x part was read in step z - 2, its epilogue inputs in step z - 1), which is refilled now
+         // with plane z + NS - 1; then wait for plane z + 1
+         if (!BULK) landed(st_new, use_new, false);
          __syncthreads();
-         const double *sp = s_ring + (size_t) ((z + 1 - z0 + 1) % NS) * stage_len;
+         issue(z + NS - 1, st_old);
+         if (BULK) landed(st_new, use_new, false);
+         const double *sp = s_ring + (size_t) st_new * stage_len;
 #pragma unroll
          for (int c = 0; c < 9; c++) Wp[c] = sp[offc[c]];
          double e0 = 0.0, e1 = 0.0;
-         if (STREAMS >= 1) e0 = sp[seg + tid];
-         if (STREAMS >= 2) e1 = sp[seg + NT + tid];
-         issue(z + NS - 1);                               // refills the stage of plane z - 1 (read at step z - 2)
+         if (STREAMS >= 1) e0 = sp[segpad + tid];
+         if (STREAMS >= 2) e1 = sp[segpad + NT + tid];
+         if (++st_new == NS) { st_new = 0; use_new++; }
+         if (++st_old == NS) { st_old = 0; use_old++; }
          const int code = code_a;
          code_a = code_b;
-         code_b = ldcode(z + 2);
-         const long long row = (long long) z * sz + q;
+         code_b = ldcode(rowq + 2u * usz, z + 2);
          const bool full = (code == p0);
          double s = 0.0;
          if (__all_sync(0xffffffffu, full)) {
@@ -460,7 +576,8 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
             for (int t = 0; t < 27; t++) {
                if (t == 13) continue;
                const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-               s = __dadd_rn(s, __dmul_rn(P0.a[t], w));
+               if (NEG1) s = __dadd_rn(s, -w);            // (-1.0) * w == -w exactly
+               else      s = __dadd_rn(s, __dmul_rn(P0.a[t], w));
             }
          } else if (code != 255) {
             const unsigned int m = s_mask[code];
@@ -474,7 +591,7 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
             }
          }
          if (code != 255) {                               // (255: past the end, or a row of the CSR pass)
-            const int r = (int) row;
+            const int r = (int) rowq;
             double v;
             // the epilogues of hb_epilogue.cuh with their per-row inputs already at hand
             if (EPI == EPI_AXPBY) {
@@ -491,9 +608,20 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
             }
             if (DOT) dacc += v * __ldg(ea.dotw + r);
          }
+         rowq += usz;
       }
    }
-   box_cp_wait<0>();
+   if (BULK) {
+      // the planes issued beyond the run are still in flight: let them land before the block leaves
+      __syncthreads();
+      for (int k = 0; k < NS - 2; k++) {                  // planes z1 + 1 .. z1 + NS - 2
+         landed(st_new, use_new, false);
+         if (++st_new == NS) { st_new = 0; use_new++; }
+      }
+   } else {
+      box_cp_wait<0>();
+   }
+   (void) use_old;
    if (DOT) pat_dot_finish<NT>(dacc, ea.dot_slot);
 }
 
@@ -514,20 +642,21 @@ static int box_zrun()
 static size_t box_smem_bytes(const DCsr &M, int streams)
 {
    const size_t seg = (size_t) kBoxThreads + 2 * (size_t) M.box_sy + 2;
-   return sizeof(double) * ((size_t) kBoxStages * (seg + (size_t) streams * kBoxThreads) + (size_t) M.pat_npat * 27) +
+   const size_t segpad = (seg + 2) & ~(size_t) 1;
+   return sizeof(double) * ((size_t) kBoxStages * (segpad + (size_t) streams * kBoxThreads) + kBoxStages + (size_t) M.pat_npat * 27) +
           sizeof(unsigned int) * (size_t) M.pat_npat + 16;
 }
 
 // the slab ring has to fit one block's shared memory: in-plane strides up to ~4000 (a 4000-wide grid)
 static bool box_fits(const DCsr &M) { return box_smem_bytes(M, 2) <= 200 * 1024; }
 
-template <int EPI, bool DOT, int STREAMS>
-static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1>
+static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
    const size_t smem = box_smem_bytes(M, STREAMS);
    static size_t opted = 0;
    if (opted < smem) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS, BULK, NEG1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       opted = smem;
    }
    if (DOT) {
@@ -559,10 +688,27 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    BoxP0 P0;
    for (int t = 0; t < 27; t++) P0.a[t] = M.box_p0_val[t];
-   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
+   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS, BULK, NEG1>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
              M.pat_npat, M.box_p0, M.box_mask, M.box_val, P0, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
+}
+
+template <int EPI, bool DOT, int STREAMS>
+static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
+{
+   // TMA bulk copies need 16-byte aligned pieces: an even plane size and aligned vectors (every cudaMalloc'ed
+   // vector is; a GMRES basis vector inside a slab of odd-length vectors is not)
+   auto al16 = [](const void *p) { return (((uintptr_t) p) & 15u) == 0; };
+   static const bool no_bulk = env_flag("HB200_BOX_NO_BULK", false);
+   const bool bulk = !no_bulk && (M.box_sz % 2 == 0) && al16(x) && (STREAMS < 1 || al16(ea.b)) && (STREAMS < 2 || al16(ea.d));
+   // the Laplacians: every off-diagonal coefficient of the full pattern is exactly -1
+   bool neg1 = M.box_p0 >= 0;
+   for (int t = 0; t < 27 && neg1; t++) if (t != 13 && M.box_p0_val[t] != -1.0) neg1 = false;
+   static const bool no_neg1 = env_flag("HB200_BOX_NO_NEG1", false);
+   if (no_neg1) neg1 = false;
+   if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false>(M, x, ea, st);
+   return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false>(M, x, ea, st);
 }
 
 int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)

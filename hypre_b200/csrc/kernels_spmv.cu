@@ -347,10 +347,14 @@ int dcsr_ensure_formats(DCsr &M, int kind)
 {
    const bool want_j16 = (kind == SPMV_VECTOR16) && M.defer_j16;
    const bool want_sell = (kind == SPMV_SELL) && M.defer_sell;
-   if (!want_j16 && !want_sell) return 0;
-   std::vector<int> hi((size_t) M.nrows + 1), hj((size_t) M.nnz);
+   const bool want_part = (kind == SPMV_STREAM) && M.nblks == 0 && M.nrows > 0;
+   if (!want_j16 && !want_sell && !want_part) return 0;
+   std::vector<int> hi((size_t) M.nrows + 1), hj;
    std::vector<double> ha;
    HB_CUDA(cudaMemcpy(hi.data(), M.i, sizeof(int) * hi.size(), cudaMemcpyDeviceToHost));
+   if (want_part) HB_CHECK(dcsr_build_partition(M, hi.data()));
+   if (!want_j16 && !want_sell) { HB_CUDA(cudaDeviceSynchronize()); return 0; }
+   hj.resize((size_t) M.nnz);
    HB_CUDA(cudaMemcpy(hj.data(), M.j, sizeof(int) * hj.size(), cudaMemcpyDeviceToHost));
    if (want_j16) {
       M.defer_j16 = false;
@@ -373,28 +377,12 @@ static double upload_now()
    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha)
+// second half of an upload: everything derived from the CSR arrays (non-empty row list, row statistics,
+// the structured formats, the kernel choice).  M.i / M.j / M.a are already on the device; hi / hj / ha
+// are the same arrays in host memory.
+int dcsr_analyze(DCsr &M, const int *hi, const int *hj, const double *ha)
 {
-   const double t_start = upload_now();
-   M.nrows = nrows;
-   M.ncols = ncols;
-   M.nnz = nrows > 0 ? hi[nrows] : 0;
-   const size_t nnz_pad = (size_t) M.nnz + 8;   // the stream kernel reads up to 3 entries past the end
-   HB_CUDA(cudaMalloc(&M.i, sizeof(int) * ((size_t) nrows + 1)));
-   HB_CUDA(cudaMalloc(&M.j, sizeof(int) * nnz_pad));
-   HB_CUDA(cudaMalloc(&M.a, sizeof(double) * nnz_pad));
-   HB_CUDA(cudaMemset(M.j + M.nnz, 0, sizeof(int) * (nnz_pad - (size_t) M.nnz)));       // the pad only
-   HB_CUDA(cudaMemset(M.a + M.nnz, 0, sizeof(double) * (nnz_pad - (size_t) M.nnz)));
-   if (nrows > 0) {
-      HB_CUDA(cudaMemcpy(M.i, hi, sizeof(int) * ((size_t) nrows + 1), cudaMemcpyHostToDevice));
-   } else {
-      int z = 0;
-      HB_CUDA(cudaMemcpy(M.i, &z, sizeof(int), cudaMemcpyHostToDevice));
-   }
-   if (M.nnz > 0) {
-      HB_CUDA(cudaMemcpy(M.j, hj, sizeof(int) * (size_t) M.nnz, cudaMemcpyHostToDevice));
-      HB_CUDA(cudaMemcpy(M.a, ha, sizeof(double) * (size_t) M.nnz, cudaMemcpyHostToDevice));
-   }
+   const int nrows = M.nrows, ncols = M.ncols;
    const double t_copied = upload_now();
    // non-empty row list + row statistics
    std::vector<int> rn;
@@ -411,7 +399,8 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
       HB_CUDA(cudaMalloc(&M.rownnz, sizeof(int) * rn.size()));
       HB_CUDA(cudaMemcpy(M.rownnz, rn.data(), sizeof(int) * rn.size(), cudaMemcpyHostToDevice));
    }
-   if (nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
+   // (the nnz-balanced partition of the stream kernel is built when that kernel is asked for:
+   //  dcsr_ensure_formats)
    const double t_rows = upload_now();
    if (nrows > 0) HB_CHECK(dcsr_build_pat(M, hi, hj, ha));
    const double t_pat = upload_now();
@@ -423,16 +412,77 @@ int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, con
    const double t_csr = upload_now();
    if (square && (eager || !M.has_pat)) HB_CHECK(dcsr_build_sell(M, hi, hj, ha)); else M.defer_sell = square;   // square (A_l) blocks only
    const double t_sell = upload_now();
+   if (eager && nrows > 0) HB_CHECK(dcsr_build_partition(M, hi));
    dcsr_choose_kernel(M, SPMV_AUTO, 0);
    // uploads use the legacy default stream, kernels the non-blocking compute stream (see dcsr_ensure_formats)
    HB_CUDA(cudaDeviceSynchronize());
    if (nrows >= 1024) {
-      HB_TRACE("upload %d x %d block, %lld nnz: CSR copy %.3f s, row lists %.3f s, row patterns %.3f s, 16-bit offsets %.3f s%s, "
-               "packed SELL %.3f s%s -> kernel kind %d", nrows, ncols, M.nnz, t_copied - t_start, t_rows - t_copied,
+      HB_TRACE("analysis of a %d x %d block, %lld nnz: row lists %.3f s, row patterns %.3f s, 16-bit offsets %.3f s%s, "
+               "packed SELL %.3f s%s -> kernel kind %d", nrows, ncols, M.nnz, t_rows - t_copied,
                t_pat - t_rows, t_csr - t_pat, M.defer_j16 ? " (deferred)" : "", t_sell - t_csr,
                M.defer_sell ? " (deferred)" : "", M.kind);
    }
    return 0;
+}
+
+// host -> device copy of one big array through two pinned staging buffers: the CPU fills one while
+// the DMA engine drains the other (a pageable cudaMemcpy stages through one small driver buffer)
+static int upload_array(void *dst, const void *src, size_t bytes)
+{
+   static char *stage[2] = {nullptr, nullptr};
+   static cudaEvent_t done[2];
+   static cudaStream_t st = nullptr;
+   constexpr size_t kChunk = (size_t) 32 << 20;
+   if (bytes == 0) return 0;
+   if (bytes < ((size_t) 1 << 20) || env_flag("HB200_PAGEABLE_UPLOAD", false)) {
+      HB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+      return 0;
+   }
+   if (!st) {
+      HB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; k++) {
+         HB_CUDA(cudaMallocHost((void **) &stage[k], kChunk));
+         HB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+      }
+   }
+   int k = 0;
+   bool used[2] = {false, false};
+   for (size_t off = 0; off < bytes; off += kChunk, k ^= 1) {
+      const size_t len = bytes - off < kChunk ? bytes - off : kChunk;
+      if (used[k]) HB_CUDA(cudaEventSynchronize(done[k]));
+      memcpy(stage[k], (const char *) src + off, len);
+      HB_CUDA(cudaMemcpyAsync((char *) dst + off, stage[k], len, cudaMemcpyHostToDevice, st));
+      HB_CUDA(cudaEventRecord(done[k], st));
+      used[k] = true;
+   }
+   HB_CUDA(cudaStreamSynchronize(st));
+   return 0;
+}
+
+int dcsr_upload(DCsr &M, int nrows, int ncols, const int *hi, const int *hj, const double *ha)
+{
+   const double t_start = upload_now();
+   M.nrows = nrows;
+   M.ncols = ncols;
+   M.nnz = nrows > 0 ? hi[nrows] : 0;
+   const size_t nnz_pad = (size_t) M.nnz + 8;   // the stream kernel reads up to 3 entries past the end
+   HB_CUDA(cudaMalloc(&M.i, sizeof(int) * ((size_t) nrows + 1)));
+   HB_CUDA(cudaMalloc(&M.j, sizeof(int) * nnz_pad));
+   HB_CUDA(cudaMalloc(&M.a, sizeof(double) * nnz_pad));
+   HB_CUDA(cudaMemset(M.j + M.nnz, 0, sizeof(int) * (nnz_pad - (size_t) M.nnz)));       // the pad only
+   HB_CUDA(cudaMemset(M.a + M.nnz, 0, sizeof(double) * (nnz_pad - (size_t) M.nnz)));
+   if (nrows > 0) {
+      HB_CHECK(upload_array(M.i, hi, sizeof(int) * ((size_t) nrows + 1)));
+   } else {
+      int z = 0;
+      HB_CUDA(cudaMemcpy(M.i, &z, sizeof(int), cudaMemcpyHostToDevice));
+   }
+   if (M.nnz > 0) {
+      HB_CHECK(upload_array(M.j, hj, sizeof(int) * (size_t) M.nnz));
+      HB_CHECK(upload_array(M.a, ha, sizeof(double) * (size_t) M.nnz));
+   }
+   if (nrows >= 1024) HB_TRACE("upload %d x %d block, %lld nnz: CSR copy %.3f s", nrows, ncols, M.nnz, upload_now() - t_start);
+   return dcsr_analyze(M, hi, hj, ha);
 }
 
 int dcsr_free(DCsr &M)

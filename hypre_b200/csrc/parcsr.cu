@@ -10,10 +10,14 @@
 //   comp stream : diag block SpMV (all rows, epilogue y = beta*b + alpha*sum)   [overlapped]
 //   comp stream : wait(halo) ; offd block SpMV over the non-empty-row list, y += alpha*sum
 #include "hb_internal.cuh"
+#ifndef HB200_EMU
+#include <cub/device/device_radix_sort.cuh>
+#endif
 #include <chrono>
 #include <algorithm>
 #include <numeric>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hb {
 
@@ -217,26 +221,124 @@ static int dcsr_download(const DCsr &M, std::vector<int> &hi, std::vector<int> &
    return 0;
 }
 
+#ifndef HB200_EMU
+// ---- stored transpose on the device (hypre_CSRMatrixTranspose / hypre_ParCSRMatrixLocalTranspose,
+// src/parcsr_mv/par_csr_matop.c:2200): a STABLE sort of the entries by column — entries of one output
+// row keep their ascending source-row order, the order hypre_CSRMatrixMatvecTHost accumulates in
+// (csr_matvec.c:1095-1110) — so the result is the same array the host transpose produces.
+__global__ void tr_entry_rows_kernel(int nrows, const int *__restrict__ ai, int *__restrict__ rows, int *__restrict__ idx)
+{
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r < nrows) {
+      for (int p = ai[r]; p < ai[r + 1]; p++) { rows[p] = r; idx[p] = p; }
+   }
+}
+__global__ void tr_gather_kernel(long long nnz, const int *__restrict__ perm, const int *__restrict__ rows,
+                                 const double *__restrict__ a, int *__restrict__ tj, double *__restrict__ ta)
+{
+   const long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+   if (q < nnz) { const int p = perm[q]; tj[q] = rows[p]; ta[q] = a[p]; }
+}
+// row pointer of the transpose from the sorted column keys: ti[c] = first position whose key >= c
+__global__ void tr_rowptr_kernel(long long nnz, int ncols, const int *__restrict__ keys, int *__restrict__ ti)
+{
+   const long long q = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+   if (q > nnz) return;
+   const int lo = q == 0 ? -1 : keys[q - 1];
+   const int hi = q == nnz ? ncols : keys[q];
+   for (int c = lo + 1; c <= hi; c++) ti[c] = (int) q;
+}
+
+static int dcsr_transpose_device(const DCsr &M, int **ti_out, int **tj_out, double **ta_out)
+{
+   Ctx &c = ctx();
+   const long long nnz = M.nnz;
+   const int n = M.nrows, m = M.ncols;
+   int *rows = nullptr, *idx = nullptr, *keys = nullptr, *perm = nullptr, *ti = nullptr, *tj = nullptr;
+   double *ta = nullptr;
+   void *tmp = nullptr;
+   size_t tmp_bytes = 0;
+   auto cleanup = [&]() { cudaFree(rows); cudaFree(idx); cudaFree(keys); cudaFree(perm); cudaFree(tmp); };
+   HB_CUDA(cudaMalloc(&rows, sizeof(int) * (size_t) nnz));
+   HB_CUDA(cudaMalloc(&idx, sizeof(int) * (size_t) nnz));
+   HB_CUDA(cudaMalloc(&keys, sizeof(int) * (size_t) nnz));
+   HB_CUDA(cudaMalloc(&perm, sizeof(int) * (size_t) nnz));
+   HB_CUDA(cudaMalloc(&ti, sizeof(int) * ((size_t) m + 1)));
+   HB_CUDA(cudaMalloc(&tj, sizeof(int) * ((size_t) nnz + 8)));
+   HB_CUDA(cudaMalloc(&ta, sizeof(double) * ((size_t) nnz + 8)));
+   HB_CUDA(cudaMemsetAsync(tj + nnz, 0, sizeof(int) * 8, c.s_comp));
+   HB_CUDA(cudaMemsetAsync(ta + nnz, 0, sizeof(double) * 8, c.s_comp));
+   HB_LAUNCH(tr_entry_rows_kernel, (n + 255) / 256, 256, 0, c.s_comp, n, M.i, rows, idx);
+   int bits = 1;
+   while (bits < 31 && (1LL << bits) < (long long) m) bits++;
+   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, M.j, keys, idx, perm, (int) nnz, 0, bits, c.s_comp);
+   if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 8);
+   if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, M.j, keys, idx, perm, (int) nnz, 0, bits, c.s_comp);
+   if (e != cudaSuccess) {
+      cleanup(); cudaFree(ti); cudaFree(tj); cudaFree(ta);
+      return set_error(HB200_ERROR_GENERIC, "device transpose: radix sort failed: %s", cudaGetErrorString(e));
+   }
+   HB_LAUNCH(tr_gather_kernel, (int) ((nnz + 255) / 256), 256, 0, c.s_comp, nnz, perm, rows, M.a, tj, ta);
+   HB_LAUNCH(tr_rowptr_kernel, (int) ((nnz + 1 + 255) / 256), 256, 0, c.s_comp, nnz, m, keys, ti);
+   HB_LAUNCH_CHECK();
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   cleanup();
+   *ti_out = ti; *tj_out = tj; *ta_out = ta;
+   return 0;
+}
+#endif
+
+// stored transpose of one block: on the device when the block is big enough to matter (the host
+// transpose of P_0 at 256^3 took ~2 s: a random scatter over 60 M entries), on the host otherwise
+static int dcsr_build_transpose(const DCsr &M, DCsr &T)
+{
+   std::vector<int> hi, hj, ti, tj;
+   std::vector<double> ha, ta;
+   const auto t0 = std::chrono::steady_clock::now();
+#ifndef HB200_EMU
+   const char *thr = getenv("HB200_DEVICE_TRANSPOSE_MIN");   // (tests lower it to run small blocks through the device path)
+   const long long min_nnz = thr ? atoll(thr) : 65536;
+   if (M.nnz >= min_nnz && M.nnz > 0 && M.nnz < 0x7fffffffLL && !env_flag("HB200_HOST_TRANSPOSE", false)) {
+      int *d_ti = nullptr, *d_tj = nullptr;
+      double *d_ta = nullptr;
+      HB_CHECK(dcsr_transpose_device(M, &d_ti, &d_tj, &d_ta));
+      const auto t1 = std::chrono::steady_clock::now();
+      T.nrows = M.ncols; T.ncols = M.nrows; T.nnz = M.nnz;
+      T.i = d_ti; T.j = d_tj; T.a = d_ta;
+      // the format analysis reads the arrays on the host
+      ti.resize((size_t) T.nrows + 1); tj.resize((size_t) T.nnz); ta.resize((size_t) T.nnz);
+      HB_CUDA(cudaMemcpy(ti.data(), T.i, sizeof(int) * ti.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(tj.data(), T.j, sizeof(int) * tj.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(ta.data(), T.a, sizeof(double) * ta.size(), cudaMemcpyDeviceToHost));
+      const auto t2 = std::chrono::steady_clock::now();
+      HB_CHECK(dcsr_analyze(T, ti.data(), tj.data(), ta.data()));
+      HB_TRACE("stored transpose of a %d x %d block (%lld nnz): device sort %.3f s, download %.3f s, analysis %.3f s", M.nrows,
+               M.ncols, M.nnz, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
+      return 0;
+   }
+#endif
+   HB_CHECK(dcsr_download(M, hi, hj, ha));
+   const auto t1 = std::chrono::steady_clock::now();
+   host_csr_transpose(M.nrows, M.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
+   const auto t2 = std::chrono::steady_clock::now();
+   HB_CHECK(dcsr_upload(T, M.ncols, M.nrows, ti.data(), tj.data(), ta.data()));
+   if (M.nrows >= 1024) {
+      HB_TRACE("stored transpose of a %d x %d block: download %.3f s, host transpose %.3f s, upload %.3f s", M.nrows,
+               M.ncols, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
+   }
+   return 0;
+}
+
 int parcsr_ensure_T(hb200_parcsr *A)
 {
    if (A->has_T) return 0;
    // stored transposes, as the reference does under keepTranspose (par_csr_matvec.c:298-299,
    // 430-468): restriction stays a row-parallel, atomics-free, deterministic SpMV
-   std::vector<int> hi, hj, ti, tj;
-   std::vector<double> ha, ta;
-   const auto t0 = std::chrono::steady_clock::now();
-   HB_CHECK(dcsr_download(A->diag, hi, hj, ha));
-   const auto t1 = std::chrono::steady_clock::now();
-   host_csr_transpose(A->diag.nrows, A->diag.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
-   const auto t2 = std::chrono::steady_clock::now();
-   HB_CHECK(dcsr_upload(A->diagT, A->diag.ncols, A->diag.nrows, ti.data(), tj.data(), ta.data()));
-   HB_TRACE("stored transpose of a %d x %d block: download %.3f s, host transpose %.3f s, upload %.3f s", A->diag.nrows,
-            A->diag.ncols, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
+   HB_CHECK(dcsr_build_transpose(A->diag, A->diagT));
    if (A->num_cols_offd > 0) {
-      HB_CHECK(dcsr_download(A->offd, hi, hj, ha));
-      host_csr_transpose(A->offd.nrows, A->offd.ncols, hi.data(), hj.data(), ha.data(), ti, tj, ta);
-      HB_CHECK(dcsr_upload(A->offdT, A->offd.ncols, A->offd.nrows, ti.data(), tj.data(), ta.data()));
+      HB_CHECK(dcsr_build_transpose(A->offd, A->offdT));
       HB_CUDA(cudaMalloc(&A->d_ytmp, sizeof(double) * (size_t) A->num_cols_offd));
    }
    A->has_T = true;

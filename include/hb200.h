@@ -316,6 +316,13 @@ void hb200_pcg_default_params(hb200_pcg_params *p);   /* hypre_PCGCreate default
 int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                     const hb200_pcg_params *params, const double *b_dev, double *x_dev,
                     double *norms, double *rel_norms, hb200_krylov_result *result);
+/* Setup-time warm-up (hypre_PCGSetup / hypre_GMRESSetup, src/krylov/pcg.c:198-283, gmres.c:185-283,
+ * allocate the work vectors there): allocates the persistent Krylov workspace and runs a few
+ * iterations on b = 1, x = 0 inside it so that halo plans, smoother scratch and the captured V-cycle
+ * graphs of the solve exist before the application times its Solve call.  is_gmres: 0 = PCG, 1 =
+ * GMRES(k_dim).  Collective. */
+int hb200_krylov_warmup(hb200_parcsr *A, int precond_kind, hb200_amg *amg, int is_gmres, int k_dim);
+
 /* Same call with HOST b and x (what HYPRE_PCGSolve sees in a CPU-memory application):
  * H2D of b and x0, solve, D2H of x, all inside. */
 int hb200_pcg_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,

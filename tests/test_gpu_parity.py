@@ -275,6 +275,33 @@ def test_matvecT_restriction(request, torch, case_name):
 # ----------------------------------------------------------------------------------------
 # BLAS-1 (a14)
 # ----------------------------------------------------------------------------------------
+def test_device_transpose_is_the_host_transpose(lap27, lap7, hb, torch):
+    """the stored transpose built on the device (stable radix sort by column, parcsr.cu) gives the same
+    arrays as the host transpose: restriction results are bit-identical between the two"""
+    import os
+    if os.environ.get("HB200_EMU_TEST"):
+        pytest.skip("the host emulation has no device transpose (cub)")
+    rng = np.random.default_rng(99)
+    for case in (lap27, lap7):
+        a = case.h["levels"][0]["P"].arrays()
+        P0 = case.mats[0][1]
+        out = []
+        for env in ({"HB200_HOST_TRANSPOSE": "1"}, {"HB200_DEVICE_TRANSPOSE_MIN": "1"}):
+            for k in ("HB200_HOST_TRANSPOSE", "HB200_DEVICE_TRANSPOSE_MIN"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            M = hb.ParCSRMatrix(P0.num_rows, P0.num_cols, a["diag_i"], a["diag_j"], a["diag_data"])
+            x = np.random.default_rng(5).standard_normal(P0.num_rows)
+            y = torch.zeros(P0.num_cols, dtype=torch.float64, device="cuda")
+            M.matvecT(1.0, dev(torch, x), 0.0, y)
+            out.append(y.cpu().numpy().copy())
+            M.destroy()
+        for k in ("HB200_HOST_TRANSPOSE", "HB200_DEVICE_TRANSPOSE_MIN"):
+            os.environ.pop(k, None)
+        assert np.array_equal(out[0], out[1])
+        assert np.max(np.abs(out[0])) > 0
+
+
 def test_blas1(lap7, hb, torch):
     rng = np.random.default_rng(3)
     n = lap7.mats[0][0].num_rows

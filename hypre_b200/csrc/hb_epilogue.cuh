@@ -62,6 +62,28 @@ __device__ __forceinline__ void epi_apply(const EpiArgs &ea, int row, double sum
          ea.y[row] = uo;
       }
    }
+   else if (EPI == EPI_CHEBY_FIRST || EPI == EPI_CHEBY_STEP) {
+      // hypre_ParCSRRelax_Cheby_SolveHost (par_cheby_solve.c:284-341), one row: d = ds (NULL: unscaled
+      // variant), w = the coefficient of this step, b = f, u = orig_u; same operations, same order
+      const double ds = ea.d ? __ldcs(ea.d + row) : 1.0;
+      double un;
+      if (EPI == EPI_CHEBY_FIRST) {
+         double rr = __dadd_rn(__ldcs(ea.b + row), -sum);          // f + (-A u)
+         if (ea.d) rr = __dmul_rn(ds, rr);
+         __stcs(ea.r_out + row, rr);
+         un = __dmul_rn(rr, ea.w);
+      } else {
+         const double t = ea.d ? __dmul_rn(ds, sum) : sum;
+         un = __dadd_rn(__dmul_rn(ea.w, __ldcs(ea.r + row)), t);
+      }
+      if (ea.cheby_last) {
+         const double t = ea.d ? __dmul_rn(ds, un) : un;
+         ea.y[row] = __dadd_rn(ea.u[row], t);                      // u = orig_u + ds*u
+      } else {
+         ea.y[row] = un;
+         if (ea.d) ea.y2[row] = __dmul_rn(ds, un);                 // the next SpMV multiplies ds*u
+      }
+   }
    else if (EPI == EPI_JACOBI_CORE_ACC) {
       const double di = ea.d ? ea.d[row] : diag;
       if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {

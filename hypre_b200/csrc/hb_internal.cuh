@@ -260,9 +260,9 @@ enum EpiKind {
    EPI_JACOBI7_ACC,   // y -= (w*sum)/d           [marked]  (offd pass)
    EPI_JACOBI_CORE,   // y = (1-w*skip)*u + w*(f - sum)/d, only if d != 0 [marked] (par_relax.c:258-295)
    EPI_JACOBI_CORE_ACC,
-   EPI_CHEBY_SCALED_R,// r = ds*(f - sum); y(orig_u)=u; u = r*c   (par_cheby_solve.c:284-305)
-   EPI_CHEBY_STEP,    // u = mult*r + ds*sum                       (par_cheby_solve.c:324-331)
-   EPI_CHEBY_LAST     // u = orig_u + ds*(mult*r + ds*sum)         (last step fused with :338-341)
+   // Chebyshev smoothing fused into its SpMVs (par_cheby_solve.c:284-341; blocks without an offd part):
+   EPI_CHEBY_FIRST,   // r = [ds*](f - sum); u1 = r*c; [t = ds*u1]; last: y = orig_u + [ds*]u1
+   EPI_CHEBY_STEP     // u' = mult*r + [ds*]sum; [t = ds*u']; last: y = orig_u + [ds*]u'
 };
 
 struct EpiArgs {
@@ -275,7 +275,9 @@ struct EpiArgs {
    int           skip_diag = 0;
    double       *y = nullptr;      // output
    double       *y2 = nullptr;     // second output (Chebyshev)
-   const double *r = nullptr;      // Chebyshev r
+   const double *r = nullptr;      // Chebyshev: r (read by the steps)
+   double       *r_out = nullptr;  // Chebyshev first step: r is written here
+   int           cheby_last = 0;   // this SpMV is the last of the sweep: y = orig_u (ea.u) + [ds*]u'
    // optional fused dot: partial[block] = sum_rows y[row]*dotw[row] (deterministic 2-stage)
    const double *dotw = nullptr;
    int           dot_slot = -1;

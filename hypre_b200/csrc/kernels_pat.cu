@@ -298,6 +298,8 @@ int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
       case EPI_JACOBI7_ACC:     return pat_dispatch<EPI_JACOBI7_ACC>(M, x, ea, st);
       case EPI_JACOBI_CORE:     return pat_dispatch<EPI_JACOBI_CORE>(M, x, ea, st);
       case EPI_JACOBI_CORE_ACC: return pat_dispatch<EPI_JACOBI_CORE_ACC>(M, x, ea, st);
+      case EPI_CHEBY_FIRST:     return pat_dispatch<EPI_CHEBY_FIRST>(M, x, ea, st);
+      case EPI_CHEBY_STEP:      return pat_dispatch<EPI_CHEBY_STEP>(M, x, ea, st);
       default: return set_error(HB200_ERROR_ARG, "spmv_pat_launch: unknown epilogue %d", epi_kind);
    }
 }
@@ -323,8 +325,9 @@ int spmv_pat_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
 // from L2) and the FP64 pipe (54 instructions per row), no longer L1.
 struct BoxP0 { double a[27]; };
 
-constexpr int kBoxThreads = 512;   // in-plane positions per block (one per thread)
-constexpr int kBoxStages  = 4;     // planes in flight per block (shared-memory ring)
+constexpr int kBoxThreads = 256;   // in-plane positions per block (one per thread)
+constexpr int kBoxRows    = 2;     // U: planes (rows per thread) computed per step — independent summation chains
+constexpr int kBoxStages  = 3 * kBoxRows + 1;   // planes in the shared-memory ring per block (two steps of look-ahead)
 
 __device__ __forceinline__ unsigned int box_smem_u32(const void *p)
 {
@@ -403,21 +406,24 @@ __device__ __forceinline__ void box_mbar_wait(unsigned long long *bar, unsigned 
 
 // The kernel.  A block owns kBoxThreads consecutive in-plane positions [q0, q0 + NT) and a run of
 // planes; plane p of its x slab is the contiguous segment x[p*sz + q0 - sy - 1 .. p*sz + q0 + NT + sy + 1),
-// brought into a ring of shared-memory stages kBoxStages - 1 planes ahead of the compute (the same
-// stage carries the per-row inputs of the epilogue: b, or f and l1).  Per plane a thread reads its 9
-// in-plane neighbours of the NEW plane from shared memory into the register window (the other 18
-// values are already there) and runs the 27 slots.
+// brought into a ring of shared-memory stages up to two steps ahead of the compute (the same stage
+// carries the per-row inputs of the epilogue: b, or f and l1).  A step computes the rows of U
+// consecutive planes: a thread reads its 9 in-plane neighbours of the U NEW planes from shared memory
+// into the register window (U + 2 planes; 2 stay from the step before) and runs the 27 slots of its U
+// rows — U independent summation chains per thread.  The chain (27 dependent FP64 adds, in CSR order
+// for bit-identity with the reference) is what one row costs in latency: with 2 blocks x 8 warps x U
+// chains per SM the FP64 pipe and the memory system stay busy while every chain waits for itself.
 //   STREAMS = number of epilogue vectors staged with the slab (0: none, 1: b, 2: f and l1)
 //   BULK    = planes arrive by TMA bulk copies on an mbarrier per stage, else by per-thread cp.async
 //   NEG1    = every off-diagonal coefficient of the full pattern is exactly -1.0 (the Laplacians):
 //             a * x is -x, bit for bit, so the interior rows add -x instead of multiplying
 template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1>
-__global__ void __launch_bounds__(kBoxThreads, 1)
+__global__ void __launch_bounds__(kBoxThreads, 2)
 spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
          const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
          const double *__restrict__ x, EpiArgs ea)
 {
-   constexpr int NT = kBoxThreads, NS = kBoxStages;
+   constexpr int NT = kBoxThreads, NS = kBoxStages, U = kBoxRows, NW = U + 2;
    HB_DYN_SHARED(double, s_mem);
    const int seg = NT + 2 * sy + 2;                    // doubles of one plane segment
    const int segpad = (seg + 2) & ~1;                  // + the parity shift of an aligned copy, even
@@ -502,126 +508,148 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
          box_cp_commit();
       }
    };
-   // ---- consumer: plane p has landed in its stage (use number `use` of that stage)
-   auto landed = [&](int stage, int use, bool first) {
-      if (BULK) {
-         box_mbar_wait(s_bar + stage, (unsigned int) (use & 1));
-      } else {
-         if (first) box_cp_wait<NS - 2>(); else box_cp_wait<NS - 3>();
+   // planes are issued in order, one cp.async group / one mbarrier phase each
+   int next_plane = z0 - 1, next_stage = 0;          // the next plane to issue and its stage
+   auto issue_upto = [&](int last) {
+      for (; next_plane <= last; next_plane++) {
+         issue(next_plane, next_stage);
+         if (++next_stage == NS) next_stage = 0;
       }
    };
-   // prologue: planes z0 - 1 .. z0 + NS - 2 into stages 0 .. NS - 1
-#pragma unroll
-   for (int k = 0; k < NS; k++) issue(z0 - 1 + k, k);
+   // prologue: planes z0 - 1 .. z0 + NS - 2 fill the ring
+   issue_upto(z0 + NS - 2);
 #ifdef HB200_EMU
    __syncthreads();   // (the emulated copies are synchronous, made by thread 0: let it run first)
 #endif
+   // consumer side: stage / use count of the next plane to take out of the ring (planes leave in order)
+   int rd_stage = 0, rd_use = 0;
+   auto landed_bulk = [&]() { box_mbar_wait(s_bar + rd_stage, (unsigned int) (rd_use & 1)); };
+   auto advance = [&]() { if (++rd_stage == NS) { rd_stage = 0; rd_use++; } };
    // in-plane neighbour offsets inside a segment, class c = (dy+1)*3 + (dx+1)
    int offc[9];
 #pragma unroll
    for (int c = 0; c < 9; c++) offc[c] = tid + sy + 1 + dpar + (c / 3 - 1) * sy + (c % 3 - 1);
-   double W[3][9];                                                        // planes z-1, z, z+1 (rotating)
-   // planes z0 - 1 and z0 into the window
-   landed(0, 0, true);
-   landed(1, 0, true);
+   double W[NW][9];                                                       // planes z-1 .. z+U (rotating roles)
+   // planes z0 - 1 and z0 into the window (cp.async groups complete in order: the NS - 2 planes issued
+   // after them may still be in flight)
+   if (BULK) { landed_bulk(); advance(); landed_bulk(); advance(); }
+   else      { box_cp_wait<NS - 2>(); advance(); advance(); }
    __syncthreads();   // (cp.async data of the other threads; the hand-copied tail elements of thread 0)
    {
       const double *sm = s_ring, *sc = s_ring + stage_len;
 #pragma unroll
       for (int c = 0; c < 9; c++) { W[0][c] = sm[offc[c]]; W[1][c] = sc[offc[c]]; }
    }
-   // row codes are prefetched two planes ahead in registers (32-bit row arithmetic: rows are ints)
+   // row codes are prefetched one step ahead in registers (32-bit row arithmetic: rows are ints)
    const unsigned int urows = (unsigned int) nrows, usz = (unsigned int) sz;
    unsigned int rowq = (unsigned int) z0 * usz + (unsigned int) q;        // this thread's row in plane z
    auto ldcode = [&](unsigned int r, int z) -> int {
       return (qok && z < z1 && r < urows) ? (int) __ldg(pat + r) : 255;
    };
-   int code_a = ldcode(rowq, z0), code_b = ldcode(rowq + usz, z0 + 1);
-   int st_new = 2, use_new = 0;          // stage / use count of plane z + 1
-   int st_old = 0, use_old = 0;          // stage of plane z - 1: the one refilled in step z
+   int code_nx[U];
+#pragma unroll
+   for (int i = 0; i < U; i++) code_nx[i] = ldcode(rowq + (unsigned int) i * usz, z0 + i);
    double dacc = 0.0;
-   for (int zb = z0; zb < z1; zb += 3) {
+   // the window rotates by U planes per step: its roles repeat every NW / gcd(U, NW) steps
+   constexpr int PERIOD = (NW % U == 0) ? NW / U : NW;
+   for (int zb = z0; zb < z1; zb += PERIOD * U) {
 #pragma unroll
-      for (int u = 0; u < 3; u++) {
-         const int z = zb + u;
+      for (int ph = 0; ph < PERIOD; ph++) {
+         const int z = zb + ph * U;
          if (z >= z1) break;                              // block-uniform
-         // (compile-time) roles of the three register planes in this step
-         double (&Wm)[9] = W[u % 3];
-         double (&Wc)[9] = W[(u + 1) % 3];
-         double (&Wp)[9] = W[(u + 2) % 3];
-         // the barrier tells that every thread is done with the stage read one step ago (plane z - 1's:
-         // its x part was read in step z - 2, its epilogue inputs in step z - 1), which is refilled now
-         // with plane z + NS - 1; then wait for plane z + 1
-         if (!BULK) landed(st_new, use_new, false);
+         // the barrier tells that every thread has the planes <= z of the ring in its registers (or is
+         // done with them): their stages are refilled now, up to plane z + NS; then the U new planes
          __syncthreads();
-         issue(z + NS - 1, st_old);
-         if (BULK) landed(st_new, use_new, false);
-         const double *sp = s_ring + (size_t) st_new * stage_len;
+         issue_upto(z + NS);
+         int code[U];
 #pragma unroll
-         for (int c = 0; c < 9; c++) Wp[c] = sp[offc[c]];
-         double e0 = 0.0, e1 = 0.0;
-         if (STREAMS >= 1) e0 = sp[segpad + tid];
-         if (STREAMS >= 2) e1 = sp[segpad + NT + tid];
-         if (++st_new == NS) { st_new = 0; use_new++; }
-         if (++st_old == NS) { st_old = 0; use_old++; }
-         const int code = code_a;
-         code_a = code_b;
-         code_b = ldcode(rowq + 2u * usz, z + 2);
-         const bool full = (code == p0);
-         double s = 0.0;
-         if (__all_sync(0xffffffffu, full)) {
-            // interior warp: all 27 slots, values from the constant bank
-            if (!skip_c) s = __dadd_rn(s, __dmul_rn(P0.a[13], Wc[4]));
+         for (int i = 0; i < U; i++) code[i] = code_nx[i];
 #pragma unroll
-            for (int t = 0; t < 27; t++) {
-               if (t == 13) continue;
-               const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-               if (NEG1) s = __dadd_rn(s, -w);            // (-1.0) * w == -w exactly
-               else      s = __dadd_rn(s, __dmul_rn(P0.a[t], w));
+         for (int i = 0; i < U; i++) code_nx[i] = ldcode(rowq + (unsigned int) (U + i) * usz, z + U + i);
+         double e0[U], e1[U];
+         if (!BULK) {
+            // planes z + 1 .. z + U have landed when only the NS - U planes issued after them are pending
+            box_cp_wait<NS - U>();
+            __syncthreads();                              // (everybody's part of them)
+         }
+#pragma unroll
+         for (int i = 0; i < U; i++) {
+            // plane z + 1 + i: role (ph*U + 2 + i) % NW of the window
+            double (&Wn)[9] = W[(ph * U + 2 + i) % NW];
+            if (BULK) landed_bulk();
+            const double *sp = s_ring + (size_t) rd_stage * stage_len;
+#pragma unroll
+            for (int c = 0; c < 9; c++) Wn[c] = sp[offc[c]];
+            e0[i] = (STREAMS >= 1) ? sp[segpad + tid] : 0.0;
+            e1[i] = (STREAMS >= 2) ? sp[segpad + NT + tid] : 0.0;
+            advance();
+         }
+         // ---- the U rows of this step: independent chains, interleaved by the compiler
+         double s[U];
+         bool fullw[U];
+#pragma unroll
+         for (int i = 0; i < U; i++) fullw[i] = __all_sync(0xffffffffu, code[i] == p0);
+#pragma unroll
+         for (int i = 0; i < U; i++) {
+            double (&Wm)[9] = W[(ph * U + i) % NW];
+            double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+            double (&Wp)[9] = W[(ph * U + i + 2) % NW];
+            double acc = 0.0;
+            if (fullw[i]) {
+               // interior warp: all 27 slots, values from the constant bank
+               if (!skip_c) acc = __dadd_rn(acc, __dmul_rn(P0.a[13], Wc[4]));
+#pragma unroll
+               for (int t = 0; t < 27; t++) {
+                  if (t == 13) continue;
+                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+                  if (NEG1) acc = __dadd_rn(acc, -w);       // (-1.0) * w == -w exactly
+                  else      acc = __dadd_rn(acc, __dmul_rn(P0.a[t], w));
+               }
+            } else if (code[i] != 255) {
+               const unsigned int m = s_mask[code[i]];
+               const double *a = s_val + code[i] * 27;
+               if (!skip_c && (m & (1u << 13))) acc = __dadd_rn(acc, __dmul_rn(a[13], Wc[4]));
+#pragma unroll
+               for (int t = 0; t < 27; t++) {
+                  if (t == 13) continue;
+                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+                  if (m & (1u << t)) acc = __dadd_rn(acc, __dmul_rn(a[t], w));
+               }
             }
-         } else if (code != 255) {
-            const unsigned int m = s_mask[code];
-            const double *a = s_val + code * 27;
-            if (!skip_c && (m & (1u << 13))) s = __dadd_rn(s, __dmul_rn(a[13], Wc[4]));
+            s[i] = acc;
+         }
 #pragma unroll
-            for (int t = 0; t < 27; t++) {
-               if (t == 13) continue;
-               const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-               if (m & (1u << t)) s = __dadd_rn(s, __dmul_rn(a[t], w));
+         for (int i = 0; i < U; i++) {
+            if (code[i] != 255) {                         // (255: past the end, or a row of the CSR pass)
+               const int r = (int) (rowq + (unsigned int) i * usz);
+               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+               double v;
+               // the epilogues of hb_epilogue.cuh with their per-row inputs already at hand
+               if (EPI == EPI_AXPBY) {
+                  v = (STREAMS == 0) ? ea.alpha * s[i] : epi_axpby_value(ea, e0[i], s[i]);
+                  __stcs(ea.y + r, v);
+               } else if (EPI == EPI_JACOBI7) {
+                  const double uo = Wc[4];                // u_in is the vector the sweep multiplies
+                  if (ea.cf == nullptr || __ldcs(ea.cf + r) == ea.relax_points) v = epi_jacobi7_value(ea, uo, e0[i], e1[i], s[i]);
+                  else v = uo;
+                  __stcs(ea.y + r, v);
+               } else {
+                  epi_apply<EPI>(ea, r, s[i], code[i] == p0 ? P0.a[13] : s_val[code[i] * 27 + 13]);
+                  v = 0.0;
+               }
+               if (DOT) dacc += v * __ldg(ea.dotw + r);
             }
          }
-         if (code != 255) {                               // (255: past the end, or a row of the CSR pass)
-            const int r = (int) rowq;
-            double v;
-            // the epilogues of hb_epilogue.cuh with their per-row inputs already at hand
-            if (EPI == EPI_AXPBY) {
-               v = (STREAMS == 0) ? ea.alpha * s : epi_axpby_value(ea, e0, s);
-               __stcs(ea.y + r, v);
-            } else if (EPI == EPI_JACOBI7) {
-               const double uo = Wc[4];                   // u_in is the vector the sweep multiplies
-               if (ea.cf == nullptr || __ldcs(ea.cf + r) == ea.relax_points) v = epi_jacobi7_value(ea, uo, e0, e1, s);
-               else v = uo;
-               __stcs(ea.y + r, v);
-            } else {
-               epi_apply<EPI>(ea, r, s, full ? P0.a[13] : s_val[code * 27 + 13]);
-               v = 0.0;
-            }
-            if (DOT) dacc += v * __ldg(ea.dotw + r);
-         }
-         rowq += usz;
+         rowq += (unsigned int) U * usz;
       }
    }
+   // the planes issued beyond the run are still in flight: let them land before the block leaves
+   __syncthreads();
    if (BULK) {
-      // the planes issued beyond the run are still in flight: let them land before the block leaves
-      __syncthreads();
-      for (int k = 0; k < NS - 2; k++) {                  // planes z1 + 1 .. z1 + NS - 2
-         landed(st_new, use_new, false);
-         if (++st_new == NS) { st_new = 0; use_new++; }
-      }
+      for (int k = rd_use * NS + rd_stage; k < next_plane - (z0 - 1); k++) { landed_bulk(); advance(); }
    } else {
       box_cp_wait<0>();
    }
-   (void) use_old;
    if (DOT) pat_dot_finish<NT>(dacc, ea.dot_slot);
 }
 
@@ -633,7 +661,7 @@ static int box_zrun()
    if (z == 0) {
       const char *e = getenv("HB200_BOX_ZRUN");
       z = e ? atoi(e) : 0;
-      if (z < 3) z = 0; else z = (z + 2) / 3 * 3;
+      if (z < 2) z = 0; else z = (z + 3) / 4 * 4;
       if (z == 0) z = -1;
    }
    return z;
@@ -671,18 +699,18 @@ static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    const int nplanes = (int) (((long long) M.nrows + M.box_sz - 1) / M.box_sz);
    const int gx = (M.box_sz + kBoxThreads - 1) / kBoxThreads;
-   // planes per block: long runs amortise the pipeline fill (3 planes), short ones fill the GPU:
-   // aim at >= 3 waves of one block per SM
+   // planes per block: long runs amortise the pipeline fill, short ones fill the GPU: aim at >= 3
+   // waves of two blocks per SM
    int zrun = box_zrun();
    if (zrun < 0) {
       zrun = 48;
-      while (zrun > 6 && (long long) gx * ((nplanes + zrun - 1) / zrun) < 3LL * kNumSMs) zrun -= 6;
+      while (zrun > 8 && (long long) gx * ((nplanes + zrun - 1) / zrun) < 3LL * 2 * kNumSMs) zrun -= 8;
    }
    int gy = (nplanes + zrun - 1) / zrun;
    if (DOT && (long long) gx * gy > kRedBlocksMax) {
       // the fused dot keeps one partial per block: fewer, longer runs
       gy = kRedBlocksMax / gx; if (gy < 1) gy = 1;
-      zrun = ((nplanes + gy - 1) / gy + 2) / 3 * 3;
+      zrun = ((nplanes + gy - 1) / gy + 3) / 4 * 4;
       gy = (nplanes + zrun - 1) / zrun;
       if ((long long) gx * gy > kRedBlocksMax) return set_error(HB200_ERROR_GENERIC, "spmv_box: fused dot on a plane of more than %d blocks", kRedBlocksMax);
    }

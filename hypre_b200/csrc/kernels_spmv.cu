@@ -262,6 +262,8 @@ int spmv_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea,
       case EPI_JACOBI7_ACC:     return spmv_dispatch<EPI_JACOBI7_ACC>(M, x, ea, use_rownnz, st);
       case EPI_JACOBI_CORE:     return spmv_dispatch<EPI_JACOBI_CORE>(M, x, ea, use_rownnz, st);
       case EPI_JACOBI_CORE_ACC: return spmv_dispatch<EPI_JACOBI_CORE_ACC>(M, x, ea, use_rownnz, st);
+      case EPI_CHEBY_FIRST:     return spmv_dispatch<EPI_CHEBY_FIRST>(M, x, ea, use_rownnz, st);
+      case EPI_CHEBY_STEP:      return spmv_dispatch<EPI_CHEBY_STEP>(M, x, ea, use_rownnz, st);
       default: return set_error(HB200_ERROR_ARG, "spmv_launch: unknown epilogue %d", epi_kind);
    }
 }

@@ -133,6 +133,38 @@ int cheby_solve(hb200_parcsr *A, const double *f, const double *ds, const double
    if (order < 1) order = 1;
    const int cheby_order = order - 1;
    HB_REQUIRE(!scale || ds != nullptr || n == 0, HB200_ERROR_ARG, "scaled Chebyshev needs ds");
+   // ---- fused form: every element-wise step rides in the epilogue of the SpMV that produces its input
+   // (`order` launches per sweep instead of 3*order + 2).  Blocks with an offd part keep the unfused form:
+   // the epilogue needs the complete row sum, which the offd pass adds later.
+   const bool fuse = env_flag("HB200_FUSED_CHEBY", true);
+   const int kd = A->diag.kind;
+   if (fuse && n > 0 && A->num_cols_offd == 0 && c.nranks == 1 &&
+       (kd == SPMV_VECTOR || kd == SPMV_VECTOR16 || kd == SPMV_PAT || kd == SPMV_BOX)) {
+      const double *dsv = scale ? ds : nullptr;
+      // SpMV inputs ping-pong between two scratch vectors; orig_u is u itself, untouched until the last step
+      double *in_a = scale ? tmp : v, *in_b = orig_u;    // scaled: t = ds*u' ; unscaled: u' itself
+      EpiArgs e1;
+      e1.b = f; e1.d = dsv; e1.w = coefs[cheby_order]; e1.r_out = r; e1.u = u;
+      e1.cheby_last = (cheby_order == 0);
+      // (order 1: the only SpMV multiplies u itself, so the result cannot land in u directly)
+      e1.y = v; e1.y2 = in_a;
+      if (!scale && !e1.cheby_last) e1.y = in_a;
+      HB_CHECK(spmv_launch(A->diag, u, EPI_CHEBY_FIRST, e1, false, c.s_comp));
+      if (e1.cheby_last) return vec_copy(v, u, n, c.s_comp);
+      const double *xin = in_a;
+      for (int i = cheby_order - 1; i >= 0; i--) {
+         EpiArgs es;
+         es.d = dsv; es.w = coefs[i]; es.r = r; es.u = u;
+         es.cheby_last = (i == 0);
+         double *next_in = (xin == in_a) ? in_b : in_a;
+         if (es.cheby_last) { es.y = u; }
+         else if (scale)    { es.y = v; es.y2 = next_in; }
+         else               { es.y = next_in; }
+         HB_CHECK(spmv_launch(A->diag, xin, EPI_CHEBY_STEP, es, false, c.s_comp));
+         xin = next_in;
+      }
+      return 0;
+   }
    if (!scale) {
       HB_CHECK(parcsr_matvec(A, -1.0, u, 1.0, f, r));
       FChebyStart fs{f, nullptr, nullptr, r, orig_u, u, coefs[cheby_order], 0};

@@ -365,9 +365,11 @@ def test_relax_hybrid_gs(lap27, hb, torch, relax_type, weights, points):
         assert err <= RTOL, (relax_type, weights, points, l, err)
 
 
-def test_chebyshev(rb, hb, torch):
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_chebyshev(rb, hb, torch, order):
+    """fused form (every element-wise step in the epilogue of the SpMV before it) on one rank"""
     for scale in (1, 0):
-        case = Case(rb, hb, "laplacian", (16, 15, 14), relax_type=16, cheby_scale=scale, cheby_order=3)
+        case = Case(rb, hb, "laplacian", (16, 15, 14), relax_type=16, cheby_scale=scale, cheby_order=order)
         rng = np.random.default_rng(41)
         for l in range(min(case.nl - 1, 3)):
             A = case.mats[l][0]
@@ -379,6 +381,19 @@ def test_chebyshev(rb, hb, torch):
             hb.cheby_solve(A, dev(torch, f), du, L["cheby_coefs"], case.h["params"]["cheby_order"],
                            scale, ds=dev(torch, L["cheby_ds"]) if L["cheby_ds"] is not None else None)
             assert relerr(du.cpu().numpy(), uref) <= RTOL, (scale, l)
+            # the unfused form (separate element-wise kernels, the reference's own sequence): same bits
+            import os
+            os.environ["HB200_FUSED_CHEBY"] = "0"
+            try:
+                du2 = dev(torch, u)
+                hb.cheby_solve(A, dev(torch, f), du2, L["cheby_coefs"], case.h["params"]["cheby_order"],
+                               scale, ds=dev(torch, L["cheby_ds"]) if L["cheby_ds"] is not None else None)
+            finally:
+                os.environ.pop("HB200_FUSED_CHEBY", None)
+            if A.format_info()["kernel"] in (7, 9):      # row sums in CSR order in both forms
+                assert np.array_equal(du.cpu().numpy(), du2.cpu().numpy()), (scale, l, order)
+            else:
+                assert relerr(du.cpu().numpy(), du2.cpu().numpy()) <= 1e-14, (scale, l, order)
 
 
 # ----------------------------------------------------------------------------------------

@@ -25,6 +25,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the reference library's OpenMP threads must not spin on the host cores after its setup returns
+# (they would compete with the upload's host-side work)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 import numpy as np  # noqa: E402
 

@@ -540,15 +540,18 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
 #pragma unroll
       for (int c = 0; c < 9; c++) { W[0][c] = sm[offc[c]]; W[1][c] = sc[offc[c]]; }
    }
-   // row codes are prefetched one step ahead in registers (32-bit row arithmetic: rows are ints)
+   // row codes are prefetched two steps ahead in registers (32-bit row arithmetic: rows are ints)
    const unsigned int urows = (unsigned int) nrows, usz = (unsigned int) sz;
    unsigned int rowq = (unsigned int) z0 * usz + (unsigned int) q;        // this thread's row in plane z
    auto ldcode = [&](unsigned int r, int z) -> int {
       return (qok && z < z1 && r < urows) ? (int) __ldg(pat + r) : 255;
    };
-   int code_nx[U];
+   int code_n1[U], code_n2[U];
 #pragma unroll
-   for (int i = 0; i < U; i++) code_nx[i] = ldcode(rowq + (unsigned int) i * usz, z0 + i);
+   for (int i = 0; i < U; i++) {
+      code_n1[i] = ldcode(rowq + (unsigned int) i * usz, z0 + i);
+      code_n2[i] = ldcode(rowq + (unsigned int) (U + i) * usz, z0 + U + i);
+   }
    double dacc = 0.0;
    // the window rotates by U planes per step: its roles repeat every NW / gcd(U, NW) steps
    constexpr int PERIOD = (NW % U == 0) ? NW / U : NW;
@@ -557,25 +560,21 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
       for (int ph = 0; ph < PERIOD; ph++) {
          const int z = zb + ph * U;
          if (z >= z1) break;                              // block-uniform
-         // the barrier tells that every thread has the planes <= z of the ring in its registers (or is
-         // done with them): their stages are refilled now, up to plane z + NS; then the U new planes
-         __syncthreads();
-         issue_upto(z + NS);
          int code[U];
 #pragma unroll
-         for (int i = 0; i < U; i++) code[i] = code_nx[i];
+         for (int i = 0; i < U; i++) { code[i] = code_n1[i]; code_n1[i] = code_n2[i]; }
 #pragma unroll
-         for (int i = 0; i < U; i++) code_nx[i] = ldcode(rowq + (unsigned int) (U + i) * usz, z + U + i);
+         for (int i = 0; i < U; i++) code_n2[i] = ldcode(rowq + (unsigned int) (2 * U + i) * usz, z + 2 * U + i);
+         // ---- the U new planes z + 1 .. z + U: shared memory -> register window
          double e0[U], e1[U];
          if (!BULK) {
-            // planes z + 1 .. z + U have landed when only the NS - U planes issued after them are pending
+            // they have landed when only the NS - U planes issued after them are pending
             box_cp_wait<NS - U>();
             __syncthreads();                              // (everybody's part of them)
          }
 #pragma unroll
          for (int i = 0; i < U; i++) {
-            // plane z + 1 + i: role (ph*U + 2 + i) % NW of the window
-            double (&Wn)[9] = W[(ph * U + 2 + i) % NW];
+            double (&Wn)[9] = W[(ph * U + 2 + i) % NW];   // plane z + 1 + i: role (ph*U + 2 + i) % NW
             if (BULK) landed_bulk();
             const double *sp = s_ring + (size_t) rd_stage * stage_len;
 #pragma unroll
@@ -584,39 +583,56 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
             e1[i] = (STREAMS >= 2) ? sp[segpad + NT + tid] : 0.0;
             advance();
          }
-         // ---- the U rows of this step: independent chains, interleaved by the compiler
+         // every thread has the planes <= z + U of the ring in its registers: their stages are refilled
+         // (thread 0; it overlaps with the other warps' arithmetic below) up to plane z + U + NS
+         __syncthreads();
+         issue_upto(z + U + NS);
+         // ---- the U rows of this step.  Interior warps: U independent chains in ONE basic block, so that the
+         // compiler interleaves them (a chain is 27 dependent FP64 adds: latency, not throughput)
          double s[U];
-         bool fullw[U];
+         bool all_full = true;
 #pragma unroll
-         for (int i = 0; i < U; i++) fullw[i] = __all_sync(0xffffffffu, code[i] == p0);
+         for (int i = 0; i < U; i++) all_full = all_full && (code[i] == p0);
+         if (__all_sync(0xffffffffu, all_full)) {
 #pragma unroll
-         for (int i = 0; i < U; i++) {
-            double (&Wm)[9] = W[(ph * U + i) % NW];
-            double (&Wc)[9] = W[(ph * U + i + 1) % NW];
-            double (&Wp)[9] = W[(ph * U + i + 2) % NW];
-            double acc = 0.0;
-            if (fullw[i]) {
-               // interior warp: all 27 slots, values from the constant bank
-               if (!skip_c) acc = __dadd_rn(acc, __dmul_rn(P0.a[13], Wc[4]));
+            for (int i = 0; i < U; i++) {
+               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+               s[i] = 0.0;
+               if (!skip_c) s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[13], Wc[4]));
+            }
 #pragma unroll
-               for (int t = 0; t < 27; t++) {
-                  if (t == 13) continue;
+            for (int t = 0; t < 27; t++) {
+               if (t == 13) continue;
+#pragma unroll
+               for (int i = 0; i < U; i++) {
+                  double (&Wm)[9] = W[(ph * U + i) % NW];
+                  double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+                  double (&Wp)[9] = W[(ph * U + i + 2) % NW];
                   const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-                  if (NEG1) acc = __dadd_rn(acc, -w);       // (-1.0) * w == -w exactly
-                  else      acc = __dadd_rn(acc, __dmul_rn(P0.a[t], w));
-               }
-            } else if (code[i] != 255) {
-               const unsigned int m = s_mask[code[i]];
-               const double *a = s_val + code[i] * 27;
-               if (!skip_c && (m & (1u << 13))) acc = __dadd_rn(acc, __dmul_rn(a[13], Wc[4]));
-#pragma unroll
-               for (int t = 0; t < 27; t++) {
-                  if (t == 13) continue;
-                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-                  if (m & (1u << t)) acc = __dadd_rn(acc, __dmul_rn(a[t], w));
+                  if (NEG1) s[i] = __dadd_rn(s[i], -w);     // (-1.0) * w == -w exactly
+                  else      s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[t], w));
                }
             }
-            s[i] = acc;
+         } else {
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+               double (&Wm)[9] = W[(ph * U + i) % NW];
+               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+               double (&Wp)[9] = W[(ph * U + i + 2) % NW];
+               double acc = 0.0;
+               if (code[i] != 255) {
+                  const unsigned int m = s_mask[code[i]];
+                  const double *a = s_val + code[i] * 27;
+                  if (!skip_c && (m & (1u << 13))) acc = __dadd_rn(acc, __dmul_rn(a[13], Wc[4]));
+#pragma unroll
+                  for (int t = 0; t < 27; t++) {
+                     if (t == 13) continue;
+                     const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+                     if (m & (1u << t)) acc = __dadd_rn(acc, __dmul_rn(a[t], w));
+                  }
+               }
+               s[i] = acc;
+            }
          }
 #pragma unroll
          for (int i = 0; i < U; i++) {

@@ -254,6 +254,7 @@ static int dcsr_transpose_device(const DCsr &M, int **ti_out, int **tj_out, doub
    Ctx &c = ctx();
    const long long nnz = M.nnz;
    const int n = M.nrows, m = M.ncols;
+   const auto t0 = std::chrono::steady_clock::now();
    int *rows = nullptr, *idx = nullptr, *keys = nullptr, *perm = nullptr, *ti = nullptr, *tj = nullptr;
    double *ta = nullptr;
    void *tmp = nullptr;
@@ -268,6 +269,7 @@ static int dcsr_transpose_device(const DCsr &M, int **ti_out, int **tj_out, doub
    HB_CUDA(cudaMalloc(&ta, sizeof(double) * ((size_t) nnz + 8)));
    HB_CUDA(cudaMemsetAsync(tj + nnz, 0, sizeof(int) * 8, c.s_comp));
    HB_CUDA(cudaMemsetAsync(ta + nnz, 0, sizeof(double) * 8, c.s_comp));
+   const auto t1 = std::chrono::steady_clock::now();
    HB_LAUNCH(tr_entry_rows_kernel, (n + 255) / 256, 256, 0, c.s_comp, n, M.i, rows, idx);
    int bits = 1;
    while (bits < 31 && (1LL << bits) < (long long) m) bits++;
@@ -282,7 +284,13 @@ static int dcsr_transpose_device(const DCsr &M, int **ti_out, int **tj_out, doub
    HB_LAUNCH(tr_rowptr_kernel, (int) ((nnz + 1 + 255) / 256), 256, 0, c.s_comp, nnz, m, keys, ti);
    HB_LAUNCH_CHECK();
    HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   const auto t2 = std::chrono::steady_clock::now();
    cleanup();
+   if (nnz >= 1000000) {
+      HB_TRACE("device transpose of %lld entries: allocations %.3f s, kernels + sort %.3f s, frees %.3f s", nnz,
+               std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
+   }
    *ti_out = ti; *tj_out = tj; *ta_out = ta;
    return 0;
 }

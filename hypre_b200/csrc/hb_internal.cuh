@@ -214,7 +214,9 @@ struct DCsr {
    int        box_sy = 0, box_sz = 0, box_p0 = -1;   // strides; the full (27-entry) pattern, -1 = none
    unsigned int *box_mask = nullptr;   // pat_npat presence masks (bit t = slot (dz+1)*9 + (dy+1)*3 + (dx+1))
    double    *box_val = nullptr;       // pat_npat x 27 slot values
-   double     box_p0_val[27] = {0};    // the full pattern's values (kernel argument: constant bank)
+   double     box_p0_val[27] = {0};    // the reference pattern's values (kernel argument: constant bank)
+   bool       box_uniform = false;     // every pattern = the reference pattern with slots missing
+   unsigned int box_ref_mask = 0;      // slots of the reference pattern
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
    // formats the automatic choice cannot pick for this block are built on first request

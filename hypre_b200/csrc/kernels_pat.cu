@@ -415,9 +415,14 @@ __device__ __forceinline__ void box_mbar_wait(unsigned long long *bar, unsigned 
 // chains per SM the FP64 pipe and the memory system stay busy while every chain waits for itself.
 //   STREAMS = number of epilogue vectors staged with the slab (0: none, 1: b, 2: f and l1)
 //   BULK    = planes arrive by TMA bulk copies on an mbarrier per stage, else by per-thread cp.async
-//   NEG1    = every off-diagonal coefficient of the full pattern is exactly -1.0 (the Laplacians):
-//             a * x is -x, bit for bit, so the interior rows add -x instead of multiplying
-template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1>
+//   NEG1    = every off-diagonal coefficient of the reference pattern is exactly -1.0 (the Laplacians):
+//             a * x is -x, bit for bit, so the rows add -x instead of multiplying
+//   UNI     = every pattern of the table is the reference pattern with some slots missing (a constant-
+//             coefficient stencil: the boundary rows only LOSE entries): one branch-free path for all rows,
+//             the row's presence mask predicates the 27 slots, the values are kernel arguments.  Without it
+//             a warp with one boundary lane reads masks and values from shared memory for all its rows, and
+//             the per-step barrier makes the whole block as slow as that warp.
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI>
 __global__ void __launch_bounds__(kBoxThreads, 2)
 spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
          const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
@@ -593,7 +598,31 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
          bool all_full = true;
 #pragma unroll
          for (int i = 0; i < U; i++) all_full = all_full && (code[i] == p0);
-         if (__all_sync(0xffffffffu, all_full)) {
+         if (UNI) {
+            unsigned int m[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+               m[i] = code[i] != 255 ? s_mask[code[i]] : 0u;
+               s[i] = 0.0;
+               if (!skip_c && (m[i] & (1u << 13))) s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[13], Wc[4]));
+            }
+#pragma unroll
+            for (int t = 0; t < 27; t++) {
+               if (t == 13) continue;
+#pragma unroll
+               for (int i = 0; i < U; i++) {
+                  double (&Wm)[9] = W[(ph * U + i) % NW];
+                  double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+                  double (&Wp)[9] = W[(ph * U + i + 2) % NW];
+                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+                  if (m[i] & (1u << t)) {
+                     if (NEG1) s[i] = __dadd_rn(s[i], -w);  // (-1.0) * w == -w exactly
+                     else      s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[t], w));
+                  }
+               }
+            }
+         } else if (__all_sync(0xffffffffu, all_full)) {
 #pragma unroll
             for (int i = 0; i < U; i++) {
                double (&Wc)[9] = W[(ph * U + i + 1) % NW];
@@ -650,7 +679,7 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
                   else v = uo;
                   __stcs(ea.y + r, v);
                } else {
-                  epi_apply<EPI>(ea, r, s[i], code[i] == p0 ? P0.a[13] : s_val[code[i] * 27 + 13]);
+                  epi_apply<EPI>(ea, r, s[i], (UNI || code[i] == p0) ? P0.a[13] : s_val[code[i] * 27 + 13]);
                   v = 0.0;
                }
                if (DOT) dacc += v * __ldg(ea.dotw + r);
@@ -694,13 +723,13 @@ static size_t box_smem_bytes(const DCsr &M, int streams)
 // the slab ring has to fit one block's shared memory: in-plane strides up to ~4000 (a 4000-wide grid)
 static bool box_fits(const DCsr &M) { return box_smem_bytes(M, 2) <= 200 * 1024; }
 
-template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1>
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI>
 static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
    const size_t smem = box_smem_bytes(M, STREAMS);
    static size_t opted = 0;
    if (opted < smem) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS, BULK, NEG1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       opted = smem;
    }
    if (DOT) {
@@ -732,7 +761,7 @@ static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    BoxP0 P0;
    for (int t = 0; t < 27; t++) P0.a[t] = M.box_p0_val[t];
-   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS, BULK, NEG1>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
+   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
              M.pat_npat, M.box_p0, M.box_mask, M.box_val, P0, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
@@ -746,13 +775,20 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    auto al16 = [](const void *p) { return (((uintptr_t) p) & 15u) == 0; };
    static const bool no_bulk = env_flag("HB200_BOX_NO_BULK", false);
    const bool bulk = !no_bulk && (M.box_sz % 2 == 0) && al16(x) && (STREAMS < 1 || al16(ea.b)) && (STREAMS < 2 || al16(ea.d));
-   // the Laplacians: every off-diagonal coefficient of the full pattern is exactly -1
-   bool neg1 = M.box_p0 >= 0;
-   for (int t = 0; t < 27 && neg1; t++) if (t != 13 && M.box_p0_val[t] != -1.0) neg1 = false;
+   // the Laplacians: every off-diagonal coefficient of the reference pattern is exactly -1
+   bool neg1 = M.box_p0 >= 0 || M.box_uniform;
+   for (int t = 0; t < 27 && neg1; t++) if (t != 13 && (M.box_ref_mask & (1u << t)) && M.box_p0_val[t] != -1.0) neg1 = false;
    static const bool no_neg1 = env_flag("HB200_BOX_NO_NEG1", false);
    if (no_neg1) neg1 = false;
-   if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false>(M, x, ea, st);
-   return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false>(M, x, ea, st);
+   static const bool no_uni = env_flag("HB200_BOX_NO_UNI", false);
+   const bool uni = M.box_uniform && !no_uni;
+   if (uni) {
+      if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false, true>(M, x, ea, st);
+      return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false, true>(M, x, ea, st);
+   }
+   if (M.box_p0 < 0) return spmv_pat_launch(M, x, EPI, ea, st);   // no full pattern and no uniform table: the generic kernel
+   if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true, false>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false, false>(M, x, ea, st);
+   return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true, false>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false, false>(M, x, ea, st);
 }
 
 int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs &ea, cudaStream_t st)
@@ -777,8 +813,9 @@ int spmv_box_launch(const DCsr &M, const double *x, int epi_kind, const EpiArgs 
 // slots: the order `ij`'s generators and hypre's IJ assembly produce), and lays every pattern out
 // as 27 (presence, value) slots.  Pure host code.
 struct BoxHost {
-   bool ok = false;
-   int sy = 0, sz = 0, p0 = -1;
+   bool ok = false, uniform = false;
+   int sy = 0, sz = 0, p0 = -1, pref = -1;    // p0: the full (27-slot) pattern; pref: the reference pattern (most slots)
+   unsigned int ref_mask = 0;
    std::vector<unsigned int> mask;
    std::vector<double> val;
 };
@@ -844,6 +881,19 @@ static void box_analyze_host(const PatHost &ph, int nrows, BoxHost &out)
          out.val[(size_t) p * 27 + slot] = ph.val[(size_t) k];
       }
       if (out.mask[(size_t) p] == 0x7ffffffu && out.p0 < 0) out.p0 = p;   // patterns are sorted by frequency
+   }
+   // uniform table: every pattern is the reference pattern (the one with the most slots) minus some slots
+   int best = 0;
+   for (int p = 1; p < npat; p++) if (__builtin_popcount(out.mask[(size_t) p]) > __builtin_popcount(out.mask[(size_t) best])) best = p;
+   out.pref = best;
+   out.ref_mask = out.mask[(size_t) best];
+   out.uniform = true;
+   for (int p = 0; p < npat && out.uniform; p++) {
+      if (out.mask[(size_t) p] & ~out.ref_mask) { out.uniform = false; break; }
+      for (int t = 0; t < 27; t++) {
+         if ((out.mask[(size_t) p] & (1u << t)) &&
+             memcmp(&out.val[(size_t) p * 27 + t], &out.val[(size_t) best * 27 + t], sizeof(double)) != 0) { out.uniform = false; break; }
+      }
    }
    out.ok = true;
 }
@@ -1024,8 +1074,11 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
          HB_CUDA(cudaMalloc(&M.box_val, sizeof(double) * (size_t) npat * 27));
          HB_CUDA(cudaMemcpy(M.box_val, bh.val.data(), sizeof(double) * (size_t) npat * 27, cudaMemcpyHostToDevice));
          M.box_sy = bh.sy; M.box_sz = bh.sz; M.box_p0 = bh.p0;
-         for (int t = 0; t < 27; t++) M.box_p0_val[t] = bh.p0 >= 0 ? bh.val[(size_t) bh.p0 * 27 + t] : 0.0;
-         M.has_box = box_fits(M);
+         M.box_uniform = bh.uniform; M.box_ref_mask = bh.ref_mask;
+         // the kernel-argument values: the reference pattern's when the table is uniform, else the full pattern's
+         const int pv = bh.uniform ? bh.pref : bh.p0;
+         for (int t = 0; t < 27; t++) M.box_p0_val[t] = pv >= 0 ? bh.val[(size_t) pv * 27 + t] : 0.0;
+         M.has_box = box_fits(M) && (bh.uniform || bh.p0 >= 0);
       }
    }
    return 0;

@@ -22,11 +22,13 @@ P
 }
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "bit_exact or kernel_variants or relax_jacobi or pcg_amg or vcycle" 2>&1 | tail -2
 for n in 128 192 256 384; do one spmv_box_$n X=1 -- --spmv-only --n $n --steps 2 --warmup 2 --no-cpu-baseline; done
+one spmv_box_256_nouni HB200_BOX_NO_UNI=1 -- --spmv-only --n 256 --steps 2 --warmup 2 --no-cpu-baseline
+one spmv_lap7_256 X=1 -- --spmv-only --problem laplacian --n 256 --steps 2 --warmup 2 --no-cpu-baseline
 one spmv_box_256_nobulk HB200_BOX_NO_BULK=1 -- --spmv-only --n 256 --steps 2 --warmup 2 --no-cpu-baseline
 for z in 16 32 64; do one spmv_box_z$z HB200_BOX_ZRUN=$z -- --spmv-only --n 256 --steps 2 --warmup 2 --no-cpu-baseline; done
 one bench_default X=1 -- --steps 10 --warmup 3 --no-e2e-ij --no-cpu-baseline
 one bench_nobox HB200_NO_BOX=1 -- --steps 10 --warmup 3 --no-cpu-baseline --no-e2e-ij
-timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "bit_exact_fine_level or relax_jacobi" 2>&1 | tail -2
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "bit_exact_fine_level or relax_jacobi" > $OUT/racecheck.log 2>&1; grep -m 12 "hazard\|Hazard\|at hb::\|RACECHECK" $OUT/racecheck.log; tail -2 $OUT/racecheck.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_box -s 60 -c 4 -o $OUT/ncu_box_solve \
    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e-ij --no-graph > $OUT/ncu_box_solve.log 2>&1
 HB200_TRACE=1 timeout 400 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e-ij 2>&1 | grep "transpose" > $OUT/upload_trace.log; cat $OUT/upload_trace.log

@@ -573,8 +573,9 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
          // ---- the U new planes z + 1 .. z + U: shared memory -> register window
          double e0[U], e1[U];
          if (!BULK) {
-            // they have landed when only the NS - U planes issued after them are pending
-            box_cp_wait<NS - U>();
+            // they have landed when only the planes issued after them are pending (cp.async groups complete in
+            // order): the first step sees the prologue's planes up to z0 + NS - 2, the others up to z + NS
+            if (z == z0) box_cp_wait<NS - 2 - U>(); else box_cp_wait<NS - U>();
             __syncthreads();                              // (everybody's part of them)
          }
 #pragma unroll
@@ -1078,7 +1079,10 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
          // the kernel-argument values: the reference pattern's when the table is uniform, else the full pattern's
          const int pv = bh.uniform ? bh.pref : bh.p0;
          for (int t = 0; t < 27; t++) M.box_p0_val[t] = pv >= 0 ? bh.val[(size_t) pv * 27 + t] : 0.0;
-         M.has_box = box_fits(M) && (bh.uniform || bh.p0 >= 0);
+         // the stencil sweep pays its fixed cost per row (9 shared-memory reads, 27 predicated slots) back only on
+         // dense stencils: a 7-point operator stays with the generic row-pattern kernel (7 gathers per row;
+         // B200, 256^3: 0.071 ms against 0.19 ms)
+         M.has_box = box_fits(M) && (bh.uniform || bh.p0 >= 0) && __builtin_popcount(bh.ref_mask) >= 15;
       }
    }
    return 0;

@@ -125,6 +125,8 @@ def test_matvec_bit_exact_fine_level(request, torch, case_name):
     assert fi["pattern"] and fi["kernel"] == (9 if case_name == "lap27" else 7), fi
     # (kind 9: the register-window stencil sweep over the same table, kind 7: the generic row-pattern kernel)
     for kind, lanes in ((2, 1), (6, 0), (7, 0), (9, 0)):
+        if kind == 9 and case_name != "lap27":
+            continue                                    # (a 7-point operator has no stencil-sweep view)
         A.set_spmv_kernel(kind, lanes)
         # the packed SELL copy of a block stored as row patterns is built by this request, not at upload
         assert A.format_info()["kernel"] == kind and (kind != 6 or A.format_info()["sell"]), (kind, A.format_info())

@@ -51,6 +51,6 @@ HB200_TIMERS=1 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-pe
 grep -A12 "hb200 timers rank 0\] hb200_pcg_solve" $OUT/timers_peer.log | tail -13
 echo "#### other configs at N=$NG"
 run lap7 X=1 -- $S --problem laplacian
-run vdc_gmres_strong X=1 -- $S --problem vardifconv --solver gmres --n 256 --global-size
-run spmv_256 X=1 -- --spmv-only --n 256 --steps 2 --warmup 2
-run strong_27pt_256 X=1 -- $S --n 256 --global-size
+run vdc_gmres_strong X=1 -- $S --problem vardifconv --solver gmres --size 256 --global-size
+run spmv_256 X=1 -- --spmv-only --size 256 --steps 2 --warmup 2
+run strong_27pt_256 X=1 -- $S --size 256 --global-size

@@ -358,6 +358,7 @@ struct hb200_parcsr {
    int64_t *d_col_map_offd = nullptr;
    hb::CommPkgD pkg;
    double  *d_ytmp = nullptr;        // MatvecT: offd^T x (num_cols_offd)
+   int     *d_unpack_slot = nullptr; // MatvecT, fused kernel: coarse row -> position in the unpack plan, -1 = none
    double  *d_diaginv = nullptr;     // lazily extracted diagonal (DIAGSCALE precond, Jacobi type 0)
    // kept host copies of the CSR (needed to build transposes / level schedules lazily)
    std::vector<int> h_diag_i, h_diag_j, h_offd_i, h_offd_j;
@@ -395,6 +396,22 @@ struct PeerWaitArgs {
    unsigned long long timeout_ns = 0;
 };
 bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out);   // false when the plan receives nothing
+// everything one kernel needs to run a complete halo exchange itself (kernels_offd.cu, parcsr_fused):
+// the put half (gather map, remote buffers and arrival flags, consumed-flags of the receivers) and
+// the wait half (PeerWaitArgs)
+struct PeerFusedArgs {
+   PeerWaitArgs w;
+   int n_out = 0, total_out = 0;
+   const int *out_starts = nullptr, *gather = nullptr;
+   double *const *dst2 = nullptr;
+   unsigned long long *const *flag2 = nullptr;
+   const unsigned long long *acks = nullptr;
+};
+void peer_fused_args(const PeerPlan *pl, PeerFusedArgs *out);
+// one launch = put + diag pass + wait + offd pass + epilogue of a ParCSR operation on a latency-bound
+// level; *done = false when the block does not qualify (the caller then runs the separate kernels)
+int  parcsr_fused_try(hb200_parcsr *A, const double *x, int epi_kind, const EpiArgs &ea, bool *done);
+int  parcsr_fusedT_try(hb200_parcsr *A, double alpha, const double *x, double beta, double *y, bool *done);
 int  spmv_offd_wait_launch(const DCsr &M, const PeerWaitArgs &w, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 int  parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea);   // halo_end + offd SpMV (fused or not)
 void peer_plan_free(PeerPlan *pl);

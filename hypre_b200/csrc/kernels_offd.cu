@@ -92,6 +92,418 @@ static int offd_launch(const DCsr &M, const PeerWaitArgs &w, const EpiArgs &ea, 
    }
 }
 
+// =======================================================================================
+// parcsr_fused: ONE kernel = one complete ParCSR operation on a latency-bound level
+// =======================================================================================
+// On the coarse levels an operation y = epi(A x) is four dependent launches of a few microseconds each
+// (halo put, diag pass, halo wait, offd pass) plus the flag round trip between them: about 40 such
+// operations per V-cycle, and what keeps the N-GPU iteration above the single-GPU one.  Here the whole
+// operation is one launch over peer memory:
+//   put   : the first blocks gather x[send_map_elmts] and store it straight into the neighbours'
+//           receive buffers over NVLink, fence, and the last of them raises the arrival flags;
+//   diag  : every row group (K lanes per row) sums its diag-block row while the transfer is in flight;
+//   wait  : only blocks that own a row with offd entries poll their arrival flags;
+//   offd  : those rows add their offd part, read in place from the NVLink receive buffer;
+//   epi   : one store per row — the value of the diag epilogue, then the offd accumulation applied to it
+//           in registers (the same two roundings the two-kernel path makes through memory);
+//   ack   : the last block to finish tells the senders that the buffer has been read.
+// The protocol (double-buffered epochs, consumed-flags, bounded polling) is the one of parcsr_peer.cu;
+// the blocks that put never wait for anything of the current exchange and come first in the grid, so a
+// grid larger than the device still cannot starve the transfer.
+template <int EPI>
+__device__ __forceinline__ double fused_epi_value(const EpiArgs &ea, int row, double sd, double so, bool has_offd, double diag)
+{
+   if (EPI == EPI_AXPBY) {
+      double v = (ea.beta == 0.0) ? ea.alpha * sd : epi_axpby_value(ea, __ldcs(ea.b + row), sd);
+      if (has_offd) v += ea.alpha * so;
+      return v;
+   } else if (EPI == EPI_JACOBI7) {
+      const double uo = ea.u[row];
+      if (ea.cf == nullptr || __ldcs(ea.cf + row) == ea.relax_points) {
+         const double d = __ldcs(ea.d + row);
+         double v = epi_jacobi7_value(ea, uo, __ldcs(ea.b + row), d, sd);
+         if (has_offd) v -= (ea.w * so) / d;
+         return v;
+      }
+      return uo;
+   } else {   // EPI_JACOBI_CORE
+      const double uo = ea.u[row];
+      const double di = ea.d ? ea.d[row] : diag;
+      if ((ea.relax_points == 0 || ea.cf[row] == ea.relax_points) && di != 0.0) {
+         const double res = ea.b[row] - sd;
+         double v = ea.skip_diag ? uo * (1.0 - ea.w) + ea.w * res / di : uo + ea.w * res / di;
+         if (has_offd) v -= ea.w * so / di;
+         return v;
+      }
+      return uo;
+   }
+}
+
+constexpr int kFusedThreads = 256;
+
+template <int EPI, int K, bool I16>
+__global__ void __launch_bounds__(kFusedThreads)
+parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, const double *__restrict__ da,
+             const int *__restrict__ oi, const int *__restrict__ oj, const double *__restrict__ oa,
+             const double *__restrict__ x, PeerFusedArgs h, int gput, EpiArgs ea)
+{
+   __shared__ int s_flag;
+   const int tid = threadIdx.x;
+   SpinGuard guard;
+   guard.err = h.w.err; guard.timeout_ns = h.w.timeout_ns;
+   // ---- put: the first gput blocks
+   if (h.n_out > 0 && (int) blockIdx.x < gput) {
+      const unsigned long long epoch = h.w.epoch_ctr[0] + 1;
+      const int par = (int) (epoch & 1ull);
+      if (epoch > 2) {   // the receivers have read exchange (epoch - 2) out of this parity's buffers
+         for (int i = tid; i < h.n_out; i += kFusedThreads) spin_until_ge(h.acks + i, epoch - 2, guard, 1, i);
+         __syncthreads();
+      }
+      for (int k = blockIdx.x * kFusedThreads + tid; k < h.total_out; k += gput * kFusedThreads) {
+         int lo = 0, hi = h.n_out - 1;
+         while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (h.out_starts[mid] <= k) lo = mid; else hi = mid - 1;
+         }
+         h.dst2[par * h.n_out + lo][k - h.out_starts[lo]] = h.gather ? x[h.gather[k]] : x[k];
+      }
+      __syncthreads();
+      if (tid == 0) {
+         __threadfence_system();
+         int last = 1;
+         if (gput > 1) {
+            const unsigned int t = atomicInc(h.w.ticket, (unsigned int) gput - 1);
+            last = (t == (unsigned int) gput - 1);
+            if (last) __threadfence_system();
+         }
+         s_flag = last;
+      }
+      __syncthreads();
+      if (s_flag) {
+         for (int i = tid; i < h.n_out; i += kFusedThreads) st_release_sys(h.flag2[par * h.n_out + i], epoch);
+         if (tid == 0) h.w.epoch_ctr[0] = epoch;
+      }
+      __syncthreads();
+   }
+   // ---- diag pass: K lanes per row
+   const short *__restrict__ dj16 = reinterpret_cast<const short *>(dj);
+   const int gtid = blockIdx.x * kFusedThreads + tid;
+   const int row = gtid / K;
+   const int lane = tid % K;
+   const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
+   const bool active = row < nrows;
+   double sd = 0.0, so = 0.0;
+   int p0 = 0, q0 = 0, q1 = 0;
+   if (active) {
+      p0 = di[row];
+      const int p1 = di[row + 1];
+      if (I16) { const double *xr = x + row; for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
+      else     { for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
+      if (oi) { q0 = oi[row]; q1 = oi[row + 1]; }
+   }
+#pragma unroll
+   for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
+   const bool has_offd = q1 > q0;
+   // ---- wait + offd pass: only blocks with a boundary row look at the flags
+   unsigned long long epoch_in = 0;
+   if (h.w.n_in > 0) {
+      if (tid == 0) s_flag = 0;
+      __syncthreads();
+      if (has_offd) s_flag = 1;
+      __syncthreads();
+      epoch_in = h.w.epoch_ctr[1] + 1;
+      if (s_flag) {
+         const int par = (int) (epoch_in & 1ull);
+         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+         __syncthreads();
+         const double *xe = par ? h.w.buf1 : h.w.buf0;
+         if (has_offd) { for (int q = q0 + lane; q < q1; q += K) so += oa[q] * __ldcg(xe + oj[q]); }
+      }
+   }
+#pragma unroll
+   for (int o = K / 2; o > 0; o >>= 1) so += __shfl_down_sync(0xffffffffu, so, o, K);
+   if (active && lane == 0) {
+      ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, has_offd, epi_needs_diag<EPI>() ? da[p0] : 0.0);
+   }
+   // ---- ack: the receive buffer of this exchange has been read by everybody
+   if (h.w.n_in > 0) {
+      __syncthreads();
+      if (tid == 0) {
+         int last = 1;
+         if (gridDim.x > 1) {
+            __threadfence();
+            const unsigned int t = atomicInc(h.w.ticket + 1, gridDim.x - 1);
+            last = (t == gridDim.x - 1);
+         }
+         s_flag = last;
+      }
+      __syncthreads();
+      if (s_flag) {
+         for (int j = tid; j < h.w.n_in; j += kFusedThreads) st_release_sys(h.w.in_ack[j], epoch_in);
+         if (tid == 0) h.w.epoch_ctr[1] = epoch_in;
+      }
+   }
+}
+
+template <int EPI, int K>
+static int fused_launch_K(const hb200_parcsr *A, const double *x, const PeerFusedArgs &h, const EpiArgs &ea, cudaStream_t st)
+{
+   const DCsr &D = A->diag, &O = A->offd;
+   const long long threads = (long long) D.nrows * K;
+   int grid = (int) ((threads + kFusedThreads - 1) / kFusedThreads);
+   int gput = h.n_out > 0 ? (h.total_out + 2047) / 2048 : 0;
+   if (gput > 64) gput = 64;
+#ifdef HB200_EMU
+   if (gput > 1) gput = 1;   // (emulated blocks run one after the other: the put must be complete before a block waits)
+#endif
+   if (h.n_out > 0 && gput < 1) gput = 1;
+   if (grid < gput) grid = gput;
+   if (grid < 1) grid = 1;
+   const bool has_offd = A->num_cols_offd > 0;
+   if (D.kind == SPMV_VECTOR16 && D.j16) {
+      HB_LAUNCH((parcsr_fused<EPI, K, true>), grid, kFusedThreads, 0, st, D.nrows, D.i, reinterpret_cast<const int *>(D.j16), D.a,
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, x, h, gput, ea);
+   } else {
+      HB_LAUNCH((parcsr_fused<EPI, K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, x, h, gput, ea);
+   }
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+template <int EPI>
+static int fused_launch(const hb200_parcsr *A, const double *x, const PeerFusedArgs &h, const EpiArgs &ea, cudaStream_t st)
+{
+   switch (A->diag.lanes) {
+      case 1:  return fused_launch_K<EPI, 1>(A, x, h, ea, st);
+      case 2:  return fused_launch_K<EPI, 2>(A, x, h, ea, st);
+      case 4:  return fused_launch_K<EPI, 4>(A, x, h, ea, st);
+      case 8:  return fused_launch_K<EPI, 8>(A, x, h, ea, st);
+      case 16: return fused_launch_K<EPI, 16>(A, x, h, ea, st);
+      default: return fused_launch_K<EPI, 32>(A, x, h, ea, st);
+   }
+}
+
+// the operation qualifies when the halo goes by peer puts, the diag block runs the CSR vector kernel
+// and is small enough to be latency-bound (the fine levels hide the exchange behind a long diag pass
+// and keep their structured formats)
+int parcsr_fused_try(hb200_parcsr *A, const double *x, int epi_kind, const EpiArgs &ea, bool *done)
+{
+   *done = false;
+   Ctx &c = ctx();
+   static const bool on = env_flag("HB200_FUSED_HALO", true);
+   static const long long max_threads = []() { const char *e = getenv("HB200_FUSED_HALO_MAX"); return e ? atoll(e) : 148LL * 2048 * 2; }();
+   if (!on || c.halo_mode != 1 || c.nranks <= 1) return 0;
+   if (!(epi_kind == EPI_AXPBY || epi_kind == EPI_JACOBI7 || epi_kind == EPI_JACOBI_CORE)) return 0;
+   const DCsr &D = A->diag;
+   if (!(D.kind == SPMV_VECTOR || D.kind == SPMV_VECTOR16) || D.lanes < 1) return 0;
+   if ((long long) D.nrows * D.lanes > max_threads) return 0;
+   if (ea.dot_slot >= 0) return 0;
+   HB_CHECK(peer_plans_ensure(A, false));          // collective on first use, like the separate kernels
+   if (A->pkg.peer_off) return 0;
+   PeerFusedArgs h;
+   peer_fused_args(A->pkg.fwd, &h);
+   if (D.nrows == 0 && h.n_out == 0 && h.w.n_in == 0) { *done = true; return 0; }
+   timer_tick(T_MATVEC_DIAG);
+   int f;
+   switch (epi_kind) {
+      case EPI_AXPBY:   f = fused_launch<EPI_AXPBY>(A, x, h, ea, c.s_comp); break;
+      case EPI_JACOBI7: f = fused_launch<EPI_JACOBI7>(A, x, h, ea, c.s_comp); break;
+      default:          f = fused_launch<EPI_JACOBI_CORE>(A, x, h, ea, c.s_comp); break;
+   }
+   timer_tick(T_OTHER);
+   if (!f) *done = true;
+   return f;
+}
+
+// ---- the restriction y = alpha*A^T x + beta*y in one kernel (stored transposes diagT / offdT) -----------
+//   put   : the first blocks compute y_tmp = alpha * offdT x row by row and store every value straight into
+//           the owner's receive buffer (the reverse exchange, par_csr_matvec.c:402-470), then raise the flags;
+//   diag  : every row of diagT;
+//   wait  : blocks that own a row somebody contributes to poll the arrival flags;
+//   unpack: those rows add the received contributions in ascending send-entry order (the reference's
+//           sequential loop, par_csr_matvec.c:491-496), read in place from the NVLink receive buffer;
+//   ack.
+__global__ void unpack_slot_kernel(int n, const int *__restrict__ rows, int *__restrict__ slot)
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t < n) slot[rows[t]] = t;
+}
+
+template <int K, bool I16>
+__global__ void __launch_bounds__(kFusedThreads)
+parcsr_fusedT(int ncoarse, const int *__restrict__ di, const int *__restrict__ dj, const double *__restrict__ da,
+              int noffd, const int *__restrict__ oi, const int *__restrict__ oj, const double *__restrict__ oa,
+              const double *__restrict__ x, double alpha, double beta, double *__restrict__ y,
+              const int *__restrict__ unpack_slot, const int *__restrict__ unpack_ptr, const int *__restrict__ unpack_idx,
+              PeerFusedArgs h, int gput)
+{
+   __shared__ int s_flag;
+   const int tid = threadIdx.x;
+   const int lane = tid % K;
+   SpinGuard guard;
+   guard.err = h.w.err; guard.timeout_ns = h.w.timeout_ns;
+   // ---- put: y_tmp rows (the columns of the offd block), straight into the owners' buffers
+   if (h.n_out > 0 && (int) blockIdx.x < gput) {
+      const unsigned long long epoch = h.w.epoch_ctr[0] + 1;
+      const int par = (int) (epoch & 1ull);
+      if (epoch > 2) {
+         for (int i = tid; i < h.n_out; i += kFusedThreads) spin_until_ge(h.acks + i, epoch - 2, guard, 1, i);
+         __syncthreads();
+      }
+      constexpr int G = kFusedThreads / K;                       // rows per block and trip
+      const int trips = (noffd + gput * G - 1) / (gput * G);     // same trip count for every lane: shuffles stay converged
+      for (int t = 0; t < trips; t++) {
+         const int c = (t * gput + (int) blockIdx.x) * G + tid / K;
+         double s = 0.0;
+         if (c < noffd) { for (int q = oi[c] + lane; q < oi[c + 1]; q += K) s += oa[q] * __ldg(x + oj[q]); }
+#pragma unroll
+         for (int o = K / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, K);
+         if (c < noffd && lane == 0) {
+            int lo = 0, hi = h.n_out - 1;
+            while (lo < hi) {
+               const int mid = (lo + hi + 1) >> 1;
+               if (h.out_starts[mid] <= c) lo = mid; else hi = mid - 1;
+            }
+            h.dst2[par * h.n_out + lo][c - h.out_starts[lo]] = alpha * s;
+         }
+      }
+      __syncthreads();
+      if (tid == 0) {
+         __threadfence_system();
+         int last = 1;
+         if (gput > 1) {
+            const unsigned int t = atomicInc(h.w.ticket, (unsigned int) gput - 1);
+            last = (t == (unsigned int) gput - 1);
+            if (last) __threadfence_system();
+         }
+         s_flag = last;
+      }
+      __syncthreads();
+      if (s_flag) {
+         for (int i = tid; i < h.n_out; i += kFusedThreads) st_release_sys(h.flag2[par * h.n_out + i], epoch);
+         if (tid == 0) h.w.epoch_ctr[0] = epoch;
+      }
+      __syncthreads();
+   }
+   // ---- diagT rows
+   const short *__restrict__ dj16 = reinterpret_cast<const short *>(dj);
+   const int row = (blockIdx.x * kFusedThreads + tid) / K;
+   const bool active = row < ncoarse;
+   double sd = 0.0;
+   if (active) {
+      const int p0 = di[row], p1 = di[row + 1];
+      if (I16) { const double *xr = x + row; for (int p = p0 + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
+      else     { for (int p = p0 + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
+   }
+#pragma unroll
+   for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
+   double v = 0.0;
+   int slot = -1;
+   if (active && lane == 0) {
+      v = (beta == 0.0) ? alpha * sd : beta * y[row] + alpha * sd;
+      if (unpack_slot) slot = unpack_slot[row];
+   }
+   // ---- wait + unpack
+   unsigned long long epoch_in = 0;
+   if (h.w.n_in > 0) {
+      if (tid == 0) s_flag = 0;
+      __syncthreads();
+      if (slot >= 0) s_flag = 1;
+      __syncthreads();
+      epoch_in = h.w.epoch_ctr[1] + 1;
+      if (s_flag) {
+         const int par = (int) (epoch_in & 1ull);
+         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+         __syncthreads();
+         const double *buf = par ? h.w.buf1 : h.w.buf0;
+         if (slot >= 0) { for (int q = unpack_ptr[slot]; q < unpack_ptr[slot + 1]; q++) v = __dadd_rn(v, __ldcg(buf + unpack_idx[q])); }
+      }
+   }
+   if (active && lane == 0) y[row] = v;
+   if (h.w.n_in > 0) {
+      __syncthreads();
+      if (tid == 0) {
+         int last = 1;
+         if (gridDim.x > 1) {
+            __threadfence();
+            const unsigned int t = atomicInc(h.w.ticket + 1, gridDim.x - 1);
+            last = (t == gridDim.x - 1);
+         }
+         s_flag = last;
+      }
+      __syncthreads();
+      if (s_flag) {
+         for (int j = tid; j < h.w.n_in; j += kFusedThreads) st_release_sys(h.w.in_ack[j], epoch_in);
+         if (tid == 0) h.w.epoch_ctr[1] = epoch_in;
+      }
+   }
+}
+
+template <int K>
+static int fusedT_launch_K(hb200_parcsr *A, const double *x, double alpha, double beta, double *y, const PeerFusedArgs &h, cudaStream_t st)
+{
+   const DCsr &D = A->diagT, &O = A->offdT;
+   const CommPkgD &pk = A->pkg;
+   constexpr int G = kFusedThreads / K;
+   int grid = (D.nrows + G - 1) / G;
+   int gput = h.n_out > 0 ? (A->num_cols_offd + G - 1) / G : 0;
+   if (gput > 32) gput = 32;
+#ifdef HB200_EMU
+   if (gput > 1) gput = 1;   // (emulated blocks run one after the other: the put must be complete before a block waits)
+#endif
+   if (h.n_out > 0 && gput < 1) gput = 1;
+   if (grid < gput) grid = gput;
+   if (grid < 1) grid = 1;
+   const bool has_offd = A->num_cols_offd > 0;
+   if (D.kind == SPMV_VECTOR16 && D.j16) {
+      HB_LAUNCH((parcsr_fusedT<K, true>), grid, kFusedThreads, 0, st, D.nrows, D.i, reinterpret_cast<const int *>(D.j16), D.a,
+                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, A->d_unpack_slot, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput);
+   } else {
+      HB_LAUNCH((parcsr_fusedT<K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
+                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, A->d_unpack_slot, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput);
+   }
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+int parcsr_fusedT_try(hb200_parcsr *A, double alpha, const double *x, double beta, double *y, bool *done)
+{
+   *done = false;
+   Ctx &c = ctx();
+   static const bool on = env_flag("HB200_FUSED_HALO", true);
+   static const long long max_threads = []() { const char *e = getenv("HB200_FUSED_HALO_MAX"); return e ? atoll(e) : 148LL * 2048 * 2; }();
+   if (!on || c.halo_mode != 1 || c.nranks <= 1 || !A->has_T) return 0;
+   const DCsr &D = A->diagT;
+   if (!(D.kind == SPMV_VECTOR || D.kind == SPMV_VECTOR16) || D.lanes < 1) return 0;
+   if ((long long) D.nrows * D.lanes > max_threads || (long long) A->num_cols_offd * D.lanes > max_threads) return 0;
+   HB_CHECK(peer_plans_ensure(A, true));
+   if (A->pkg.peer_off_rev) return 0;
+   PeerFusedArgs h;
+   peer_fused_args(A->pkg.rev, &h);
+   if (D.nrows == 0 && h.n_out == 0 && h.w.n_in == 0) { *done = true; return 0; }
+   // row -> position in the unpack plan (built once)
+   if (!A->d_unpack_slot && A->pkg.n_unpack_rows > 0 && D.nrows > 0) {
+      HB_CUDA(cudaMalloc(&A->d_unpack_slot, sizeof(int) * (size_t) D.nrows));
+      HB_CUDA(cudaMemsetAsync(A->d_unpack_slot, 0xff, sizeof(int) * (size_t) D.nrows, c.s_comp));
+      HB_LAUNCH(unpack_slot_kernel, (A->pkg.n_unpack_rows + 255) / 256, 256, 0, c.s_comp, A->pkg.n_unpack_rows, A->pkg.d_unpack_rows, A->d_unpack_slot);
+      HB_LAUNCH_CHECK();
+   }
+   timer_tick(T_MATVEC_DIAG);
+   int f;
+   switch (D.lanes) {
+      case 1:  f = fusedT_launch_K<1>(A, x, alpha, beta, y, h, c.s_comp); break;
+      case 2:  f = fusedT_launch_K<2>(A, x, alpha, beta, y, h, c.s_comp); break;
+      case 4:  f = fusedT_launch_K<4>(A, x, alpha, beta, y, h, c.s_comp); break;
+      case 8:  f = fusedT_launch_K<8>(A, x, alpha, beta, y, h, c.s_comp); break;
+      case 16: f = fusedT_launch_K<16>(A, x, alpha, beta, y, h, c.s_comp); break;
+      default: f = fusedT_launch_K<32>(A, x, alpha, beta, y, h, c.s_comp); break;
+   }
+   timer_tick(T_OTHER);
+   if (!f) *done = true;
+   return f;
+}
+
 int spmv_offd_wait_launch(const DCsr &M, const PeerWaitArgs &w, int epi_kind, const EpiArgs &ea, cudaStream_t st)
 {
    switch (epi_kind) {

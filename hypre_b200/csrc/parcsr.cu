@@ -161,11 +161,17 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
       if (beta == 0.0) return vec_set(y, 0.0, A->num_rows, c.s_comp);
       return vec_axpby_out(beta, b, 0.0, b, y, A->num_rows, c.s_comp);
    }
+   EpiArgs ea;
+   ea.alpha = alpha; ea.beta = beta; ea.b = b; ea.y = y;
+   if (!c.dot_req_armed) {
+      // latency-bound level over the peer halo: the whole operation is one kernel (kernels_offd.cu)
+      bool done = false;
+      HB_CHECK(parcsr_fused_try(A, x, EPI_AXPBY, ea, &done));
+      if (done) { c.last_dot_fused = false; return 0; }
+   }
    timer_tick(T_HALO_START);
    HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
    timer_tick(T_MATVEC_DIAG);
-   EpiArgs ea;
-   ea.alpha = alpha; ea.beta = beta; ea.b = b; ea.y = y;
    // an armed fused-dot request (<y, w>) is honoured when y is final after the diag pass
    const bool want_dot = c.dot_req_armed;
    c.dot_req_armed = false;
@@ -358,6 +364,11 @@ int parcsr_matvecT(hb200_parcsr *A, double alpha, const double *x, double beta, 
    Ctx &c = ctx();
    HB_CHECK(parcsr_ensure_T(A));
    CommPkgD &pk = A->pkg;
+   if (alpha != 0.0) {
+      bool done = false;
+      HB_CHECK(parcsr_fusedT_try(A, alpha, x, beta, y, &done));   // latency-bound level: one kernel
+      if (done) return 0;
+   }
    bool peer = (c.halo_mode == 1 && c.nranks > 1);
    const bool comm = (pk.num_sends || pk.num_recvs);
    if (peer) {
@@ -518,6 +529,7 @@ int hb200_parcsr_destroy(hb200_parcsr *A)
    peer_plan_free(pk.fwd);
    peer_plan_free(pk.rev);
    if (A->d_ytmp) cudaFree(A->d_ytmp);
+   if (A->d_unpack_slot) cudaFree(A->d_unpack_slot);
    if (A->d_diaginv) cudaFree(A->d_diaginv);
    if (A->gs_sched) gs_sched_free(A->gs_sched);
    delete A;

@@ -329,6 +329,21 @@ bool peer_wait_args(const PeerPlan *pl, PeerWaitArgs *out)
    return true;
 }
 
+void peer_fused_args(const PeerPlan *pl, PeerFusedArgs *out)
+{
+   *out = PeerFusedArgs();
+   out->w.err = ctx().d_halo_err;
+   out->w.timeout_ns = ctx().halo_timeout_ns;
+   if (!pl) return;
+   out->w.buf0 = pl->in_buf[0]; out->w.buf1 = pl->in_buf[1];
+   out->w.flags = pl->in_flags; out->w.in_ack = pl->d_in_ack;
+   out->w.epoch_ctr = pl->d_epoch; out->w.ticket = pl->d_ticket;
+   out->w.n_in = pl->n_in;
+   out->n_out = pl->n_out; out->total_out = pl->total_out;
+   out->out_starts = pl->d_out_starts; out->gather = pl->d_gather;
+   out->dst2 = pl->d_out_dst; out->flag2 = pl->d_out_flag; out->acks = pl->acks;
+}
+
 void peer_plan_free(PeerPlan *pl)
 {
    if (!pl) return;

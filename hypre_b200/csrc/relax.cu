@@ -50,12 +50,17 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
          timer_tick(T_OTHER);
          return fl;
       }
-      timer_tick(T_HALO_START);
-      HB_CHECK(parcsr_halo_begin(A, u_in, c.s_comp));
-      timer_tick(T_MATVEC_DIAG);
       EpiArgs ea;
       ea.w = w; ea.b = f; ea.u = u_in; ea.d = l1; ea.y = u_out;
       ea.cf = relax_points ? cf : nullptr; ea.relax_points = relax_points;
+      {
+         bool done = false;
+         HB_CHECK(parcsr_fused_try(A, u_in, EPI_JACOBI7, ea, &done));   // one kernel on a latency-bound level
+         if (done) return 0;
+      }
+      timer_tick(T_HALO_START);
+      HB_CHECK(parcsr_halo_begin(A, u_in, c.s_comp));
+      timer_tick(T_MATVEC_DIAG);
       if (want_dot && c.nranks == 1 && A->num_cols_offd == 0 && spmv_can_fuse_dot(A->diag, EPI_JACOBI7)) {
          ea.dotw = c.dot_req_w; ea.dot_slot = c.dot_req_slot;
          c.last_dot_fused = true;
@@ -73,7 +78,6 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       HB_CHECK(vec_set((double *) u_in, 0.0, (size_t) n, c.s_comp));
    }
    HB_REQUIRE(relax_points == 0 || cf != nullptr || n == 0, HB200_ERROR_ARG, "CF relaxation needs cf_marker");
-   HB_CHECK(parcsr_halo_begin(A, uin, c.s_comp));
    EpiArgs ea;
    ea.w = w; ea.b = f; ea.u = uin; ea.y = u_out;
    ea.cf = cf; ea.relax_points = relax_points;
@@ -84,6 +88,12 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       HB_CHECK(parcsr_diag(A, &dg));
       ea.d = dg; ea.skip_diag = 1;
    } else { ea.d = l1; ea.skip_diag = 0; }
+   {
+      bool done = false;
+      HB_CHECK(parcsr_fused_try(A, uin, EPI_JACOBI_CORE, ea, &done));
+      if (done) return 0;
+   }
+   HB_CHECK(parcsr_halo_begin(A, uin, c.s_comp));
    HB_CHECK(spmv_launch(A->diag, uin, EPI_JACOBI_CORE, ea, false, c.s_comp));
    HB_CHECK(parcsr_offd_pass(A, EPI_JACOBI_CORE_ACC, ea));
    timer_tick(T_OTHER);

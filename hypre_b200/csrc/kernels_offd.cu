@@ -141,131 +141,143 @@ __device__ __forceinline__ double fused_epi_value(const EpiArgs &ea, int row, do
 
 constexpr int kFusedThreads = 256;
 
+// the put half of an exchange, run by the first `gput` blocks of a fused kernel
+__device__ __forceinline__ void fused_put(const PeerFusedArgs &h, const double *__restrict__ src, int gput, const SpinGuard &guard, int *s_flag)
+{
+   const int tid = threadIdx.x;
+   const unsigned long long epoch = h.w.epoch_ctr[0] + 1;
+   const int par = (int) (epoch & 1ull);
+   if (epoch > 2) {   // the receivers have read exchange (epoch - 2) out of this parity's buffers
+      for (int i = tid; i < h.n_out; i += kFusedThreads) spin_until_ge(h.acks + i, epoch - 2, guard, 1, i);
+      __syncthreads();
+   }
+   for (int k = blockIdx.x * kFusedThreads + tid; k < h.total_out; k += gput * kFusedThreads) {
+      int lo = 0, hi = h.n_out - 1;
+      while (lo < hi) {
+         const int mid = (lo + hi + 1) >> 1;
+         if (h.out_starts[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      h.dst2[par * h.n_out + lo][k - h.out_starts[lo]] = h.gather ? src[h.gather[k]] : src[k];
+   }
+   __syncthreads();
+   if (tid == 0) {
+      __threadfence_system();
+      int last = 1;
+      if (gput > 1) {
+         const unsigned int t = atomicInc(h.w.ticket, (unsigned int) gput - 1);
+         last = (t == (unsigned int) gput - 1);
+         if (last) __threadfence_system();
+      }
+      *s_flag = last;
+   }
+   __syncthreads();
+   if (*s_flag) {
+      for (int i = tid; i < h.n_out; i += kFusedThreads) st_release_sys(h.flag2[par * h.n_out + i], epoch);
+      if (tid == 0) h.w.epoch_ctr[0] = epoch;
+   }
+}
+
+// the acknowledgement half: the last of the `nblocks` boundary blocks tells the senders
+__device__ __forceinline__ void fused_ack(const PeerFusedArgs &h, unsigned long long epoch_in, int nblocks, int *s_flag)
+{
+   const int tid = threadIdx.x;
+   __syncthreads();
+   if (tid == 0) {
+      int last = 1;
+      if (nblocks > 1) {
+         __threadfence();
+         const unsigned int t = atomicInc(h.w.ticket + 1, (unsigned int) nblocks - 1);
+         last = (t == (unsigned int) nblocks - 1);
+      }
+      *s_flag = last;
+   }
+   __syncthreads();
+   if (*s_flag) {
+      for (int j = tid; j < h.w.n_in; j += kFusedThreads) st_release_sys(h.w.in_ack[j], epoch_in);
+      if (tid == 0) h.w.epoch_ctr[1] = epoch_in;
+   }
+}
+
+// Block roles (by block index): [0, gput) put; [gput, gput + gint) the rows without offd entries — they
+// never look at a flag; [gput + gint, grid) the boundary rows (the non-empty-row list of the offd block):
+// diag part first, then the flags, then the offd part read in place from the NVLink receive buffer.  The
+// boundary blocks come last in the grid: the interior is never held up behind a poll.
 template <int EPI, int K, bool I16>
 __global__ void __launch_bounds__(kFusedThreads)
 parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, const double *__restrict__ da,
              const int *__restrict__ oi, const int *__restrict__ oj, const double *__restrict__ oa,
-             const double *__restrict__ x, PeerFusedArgs h, int gput, EpiArgs ea)
+             const int *__restrict__ bnd_rows, int nbnd, const double *__restrict__ x, PeerFusedArgs h,
+             int gput, int gint, EpiArgs ea)
 {
    __shared__ int s_flag;
    const int tid = threadIdx.x;
+   const int lane = tid % K;
+   constexpr int G = kFusedThreads / K;
    SpinGuard guard;
    guard.err = h.w.err; guard.timeout_ns = h.w.timeout_ns;
-   // ---- put: the first gput blocks
-   if (h.n_out > 0 && (int) blockIdx.x < gput) {
-      const unsigned long long epoch = h.w.epoch_ctr[0] + 1;
-      const int par = (int) (epoch & 1ull);
-      if (epoch > 2) {   // the receivers have read exchange (epoch - 2) out of this parity's buffers
-         for (int i = tid; i < h.n_out; i += kFusedThreads) spin_until_ge(h.acks + i, epoch - 2, guard, 1, i);
-         __syncthreads();
-      }
-      for (int k = blockIdx.x * kFusedThreads + tid; k < h.total_out; k += gput * kFusedThreads) {
-         int lo = 0, hi = h.n_out - 1;
-         while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (h.out_starts[mid] <= k) lo = mid; else hi = mid - 1;
-         }
-         h.dst2[par * h.n_out + lo][k - h.out_starts[lo]] = h.gather ? x[h.gather[k]] : x[k];
-      }
-      __syncthreads();
-      if (tid == 0) {
-         __threadfence_system();
-         int last = 1;
-         if (gput > 1) {
-            const unsigned int t = atomicInc(h.w.ticket, (unsigned int) gput - 1);
-            last = (t == (unsigned int) gput - 1);
-            if (last) __threadfence_system();
-         }
-         s_flag = last;
-      }
-      __syncthreads();
-      if (s_flag) {
-         for (int i = tid; i < h.n_out; i += kFusedThreads) st_release_sys(h.flag2[par * h.n_out + i], epoch);
-         if (tid == 0) h.w.epoch_ctr[0] = epoch;
-      }
-      __syncthreads();
-   }
-   // ---- diag pass: K lanes per row
    const short *__restrict__ dj16 = reinterpret_cast<const short *>(dj);
-   const int gtid = blockIdx.x * kFusedThreads + tid;
-   const int row = gtid / K;
-   const int lane = tid % K;
    const int skip = (EPI == EPI_JACOBI_CORE) ? ea.skip_diag : 0;
-   const bool active = row < nrows;
+   const int b = (int) blockIdx.x;
+   if (b < gput) { fused_put(h, x, gput, guard, &s_flag); return; }
+   const bool boundary = b >= gput + gint;
+   int row = -1;
+   if (!boundary) {
+      const int r = (b - gput) * G + tid / K;
+      if (r < nrows && !(oi && oi[r + 1] > oi[r])) row = r;          // rows with offd entries belong to the boundary blocks
+   } else {
+      const int t = (b - gput - gint) * G + tid / K;
+      if (t < nbnd) row = bnd_rows[t];
+   }
    double sd = 0.0, so = 0.0;
-   int p0 = 0, q0 = 0, q1 = 0;
-   if (active) {
+   int p0 = 0;
+   if (row >= 0) {
       p0 = di[row];
       const int p1 = di[row + 1];
       if (I16) { const double *xr = x + row; for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
       else     { for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
-      if (oi) { q0 = oi[row]; q1 = oi[row + 1]; }
    }
 #pragma unroll
    for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
-   const bool has_offd = q1 > q0;
-   // ---- wait + offd pass: only blocks with a boundary row look at the flags
    unsigned long long epoch_in = 0;
-   if (h.w.n_in > 0) {
-      if (tid == 0) s_flag = 0;
-      __syncthreads();
-      if (has_offd) s_flag = 1;
-      __syncthreads();
+   if (boundary) {
       epoch_in = h.w.epoch_ctr[1] + 1;
-      if (s_flag) {
-         const int par = (int) (epoch_in & 1ull);
-         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
-         __syncthreads();
-         const double *xe = par ? h.w.buf1 : h.w.buf0;
-         if (has_offd) { for (int q = q0 + lane; q < q1; q += K) so += oa[q] * __ldcg(xe + oj[q]); }
-      }
-   }
+      const int par = (int) (epoch_in & 1ull);
+      for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+      __syncthreads();
+      const double *xe = par ? h.w.buf1 : h.w.buf0;
+      if (row >= 0) { for (int q = oi[row] + lane; q < oi[row + 1]; q += K) so += oa[q] * __ldcg(xe + oj[q]); }
 #pragma unroll
-   for (int o = K / 2; o > 0; o >>= 1) so += __shfl_down_sync(0xffffffffu, so, o, K);
-   if (active && lane == 0) {
-      ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, has_offd, epi_needs_diag<EPI>() ? da[p0] : 0.0);
+      for (int o = K / 2; o > 0; o >>= 1) so += __shfl_down_sync(0xffffffffu, so, o, K);
    }
-   // ---- ack: the receive buffer of this exchange has been read by everybody
-   if (h.w.n_in > 0) {
-      __syncthreads();
-      if (tid == 0) {
-         int last = 1;
-         if (gridDim.x > 1) {
-            __threadfence();
-            const unsigned int t = atomicInc(h.w.ticket + 1, gridDim.x - 1);
-            last = (t == gridDim.x - 1);
-         }
-         s_flag = last;
-      }
-      __syncthreads();
-      if (s_flag) {
-         for (int j = tid; j < h.w.n_in; j += kFusedThreads) st_release_sys(h.w.in_ack[j], epoch_in);
-         if (tid == 0) h.w.epoch_ctr[1] = epoch_in;
-      }
+   if (row >= 0 && lane == 0) {
+      ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, boundary, epi_needs_diag<EPI>() ? da[p0] : 0.0);
    }
+   if (boundary) fused_ack(h, epoch_in, (int) gridDim.x - gput - gint, &s_flag);
 }
 
 template <int EPI, int K>
 static int fused_launch_K(const hb200_parcsr *A, const double *x, const PeerFusedArgs &h, const EpiArgs &ea, cudaStream_t st)
 {
    const DCsr &D = A->diag, &O = A->offd;
-   const long long threads = (long long) D.nrows * K;
-   int grid = (int) ((threads + kFusedThreads - 1) / kFusedThreads);
+   constexpr int G = kFusedThreads / K;
+   const bool has_offd = A->num_cols_offd > 0 && O.num_rownnz > 0 && h.w.n_in > 0;
    int gput = h.n_out > 0 ? (h.total_out + 2047) / 2048 : 0;
    if (gput > 64) gput = 64;
 #ifdef HB200_EMU
    if (gput > 1) gput = 1;   // (emulated blocks run one after the other: the put must be complete before a block waits)
 #endif
    if (h.n_out > 0 && gput < 1) gput = 1;
-   if (grid < gput) grid = gput;
-   if (grid < 1) grid = 1;
-   const bool has_offd = A->num_cols_offd > 0;
+   const int gint = (D.nrows + G - 1) / G;
+   int gbnd = has_offd ? (O.num_rownnz + G - 1) / G : 0;
+   if (h.w.n_in > 0 && gbnd < 1) gbnd = 1;              // (somebody sends to us: the exchange has to be consumed and acknowledged)
+   const int grid = gput + gint + gbnd;
+   if (grid < 1) return 0;
    if (D.kind == SPMV_VECTOR16 && D.j16) {
       HB_LAUNCH((parcsr_fused<EPI, K, true>), grid, kFusedThreads, 0, st, D.nrows, D.i, reinterpret_cast<const int *>(D.j16), D.a,
-                has_offd ? O.i : (const int *) nullptr, O.j, O.a, x, h, gput, ea);
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint, ea);
    } else {
       HB_LAUNCH((parcsr_fused<EPI, K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
-                has_offd ? O.i : (const int *) nullptr, O.j, O.a, x, h, gput, ea);
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint, ea);
    }
    HB_LAUNCH_CHECK();
    return 0;
@@ -330,31 +342,35 @@ __global__ void unpack_slot_kernel(int n, const int *__restrict__ rows, int *__r
    if (t < n) slot[rows[t]] = t;
 }
 
+// block roles: [0, gput) compute y_tmp = alpha * offdT x and put it; [gput, gput + gint) the coarse rows nobody
+// contributes to; [gput + gint, grid) the rows of the unpack plan: diagT part, flags, contributions in order
 template <int K, bool I16>
 __global__ void __launch_bounds__(kFusedThreads)
 parcsr_fusedT(int ncoarse, const int *__restrict__ di, const int *__restrict__ dj, const double *__restrict__ da,
               int noffd, const int *__restrict__ oi, const int *__restrict__ oj, const double *__restrict__ oa,
               const double *__restrict__ x, double alpha, double beta, double *__restrict__ y,
-              const int *__restrict__ unpack_slot, const int *__restrict__ unpack_ptr, const int *__restrict__ unpack_idx,
-              PeerFusedArgs h, int gput)
+              const int *__restrict__ unpack_slot, const int *__restrict__ unpack_rows, int nunpack,
+              const int *__restrict__ unpack_ptr, const int *__restrict__ unpack_idx,
+              PeerFusedArgs h, int gput, int gint)
 {
    __shared__ int s_flag;
    const int tid = threadIdx.x;
    const int lane = tid % K;
+   constexpr int G = kFusedThreads / K;
    SpinGuard guard;
    guard.err = h.w.err; guard.timeout_ns = h.w.timeout_ns;
-   // ---- put: y_tmp rows (the columns of the offd block), straight into the owners' buffers
-   if (h.n_out > 0 && (int) blockIdx.x < gput) {
+   const int b = (int) blockIdx.x;
+   if (b < gput) {
+      // ---- put: y_tmp rows (the columns of the offd block), straight into the owners' buffers
       const unsigned long long epoch = h.w.epoch_ctr[0] + 1;
       const int par = (int) (epoch & 1ull);
       if (epoch > 2) {
          for (int i = tid; i < h.n_out; i += kFusedThreads) spin_until_ge(h.acks + i, epoch - 2, guard, 1, i);
          __syncthreads();
       }
-      constexpr int G = kFusedThreads / K;                       // rows per block and trip
       const int trips = (noffd + gput * G - 1) / (gput * G);     // same trip count for every lane: shuffles stay converged
       for (int t = 0; t < trips; t++) {
-         const int c = (t * gput + (int) blockIdx.x) * G + tid / K;
+         const int c = (t * gput + b) * G + tid / K;
          double s = 0.0;
          if (c < noffd) { for (int q = oi[c] + lane; q < oi[c + 1]; q += K) s += oa[q] * __ldg(x + oj[q]); }
 #pragma unroll
@@ -384,14 +400,20 @@ parcsr_fusedT(int ncoarse, const int *__restrict__ di, const int *__restrict__ d
          for (int i = tid; i < h.n_out; i += kFusedThreads) st_release_sys(h.flag2[par * h.n_out + i], epoch);
          if (tid == 0) h.w.epoch_ctr[0] = epoch;
       }
-      __syncthreads();
+      return;
    }
-   // ---- diagT rows
+   const bool boundary = b >= gput + gint;
    const short *__restrict__ dj16 = reinterpret_cast<const short *>(dj);
-   const int row = (blockIdx.x * kFusedThreads + tid) / K;
-   const bool active = row < ncoarse;
+   int row = -1, slot = -1;
+   if (!boundary) {
+      const int r = (b - gput) * G + tid / K;
+      if (r < ncoarse && !(unpack_slot && unpack_slot[r] >= 0)) row = r;
+   } else {
+      const int t = (b - gput - gint) * G + tid / K;
+      if (t < nunpack) { row = unpack_rows[t]; slot = t; }
+   }
    double sd = 0.0;
-   if (active) {
+   if (row >= 0) {
       const int p0 = di[row], p1 = di[row + 1];
       if (I16) { const double *xr = x + row; for (int p = p0 + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
       else     { for (int p = p0 + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
@@ -399,45 +421,20 @@ parcsr_fusedT(int ncoarse, const int *__restrict__ di, const int *__restrict__ d
 #pragma unroll
    for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
    double v = 0.0;
-   int slot = -1;
-   if (active && lane == 0) {
-      v = (beta == 0.0) ? alpha * sd : beta * y[row] + alpha * sd;
-      if (unpack_slot) slot = unpack_slot[row];
-   }
-   // ---- wait + unpack
+   if (row >= 0 && lane == 0) v = (beta == 0.0) ? alpha * sd : beta * y[row] + alpha * sd;
    unsigned long long epoch_in = 0;
-   if (h.w.n_in > 0) {
-      if (tid == 0) s_flag = 0;
-      __syncthreads();
-      if (slot >= 0) s_flag = 1;
-      __syncthreads();
+   if (boundary) {
       epoch_in = h.w.epoch_ctr[1] + 1;
-      if (s_flag) {
-         const int par = (int) (epoch_in & 1ull);
-         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
-         __syncthreads();
-         const double *buf = par ? h.w.buf1 : h.w.buf0;
-         if (slot >= 0) { for (int q = unpack_ptr[slot]; q < unpack_ptr[slot + 1]; q++) v = __dadd_rn(v, __ldcg(buf + unpack_idx[q])); }
+      const int par = (int) (epoch_in & 1ull);
+      for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+      __syncthreads();
+      const double *buf = par ? h.w.buf1 : h.w.buf0;
+      if (row >= 0 && lane == 0) {
+         for (int q = unpack_ptr[slot]; q < unpack_ptr[slot + 1]; q++) v = __dadd_rn(v, __ldcg(buf + unpack_idx[q]));
       }
    }
-   if (active && lane == 0) y[row] = v;
-   if (h.w.n_in > 0) {
-      __syncthreads();
-      if (tid == 0) {
-         int last = 1;
-         if (gridDim.x > 1) {
-            __threadfence();
-            const unsigned int t = atomicInc(h.w.ticket + 1, gridDim.x - 1);
-            last = (t == gridDim.x - 1);
-         }
-         s_flag = last;
-      }
-      __syncthreads();
-      if (s_flag) {
-         for (int j = tid; j < h.w.n_in; j += kFusedThreads) st_release_sys(h.w.in_ack[j], epoch_in);
-         if (tid == 0) h.w.epoch_ctr[1] = epoch_in;
-      }
-   }
+   if (row >= 0 && lane == 0) y[row] = v;
+   if (boundary) fused_ack(h, epoch_in, (int) gridDim.x - gput - gint, &s_flag);
 }
 
 template <int K>
@@ -446,22 +443,27 @@ static int fusedT_launch_K(hb200_parcsr *A, const double *x, double alpha, doubl
    const DCsr &D = A->diagT, &O = A->offdT;
    const CommPkgD &pk = A->pkg;
    constexpr int G = kFusedThreads / K;
-   int grid = (D.nrows + G - 1) / G;
+   const bool has_offd = A->num_cols_offd > 0;
    int gput = h.n_out > 0 ? (A->num_cols_offd + G - 1) / G : 0;
    if (gput > 32) gput = 32;
 #ifdef HB200_EMU
    if (gput > 1) gput = 1;   // (emulated blocks run one after the other: the put must be complete before a block waits)
 #endif
    if (h.n_out > 0 && gput < 1) gput = 1;
-   if (grid < gput) grid = gput;
-   if (grid < 1) grid = 1;
-   const bool has_offd = A->num_cols_offd > 0;
+   const int gint = (D.nrows + G - 1) / G;
+   const int nunpack = h.w.n_in > 0 ? pk.n_unpack_rows : 0;
+   int gbnd = (nunpack + G - 1) / G;
+   if (h.w.n_in > 0 && gbnd < 1) gbnd = 1;
+   const int grid = gput + gint + gbnd;
+   if (grid < 1) return 0;
    if (D.kind == SPMV_VECTOR16 && D.j16) {
       HB_LAUNCH((parcsr_fusedT<K, true>), grid, kFusedThreads, 0, st, D.nrows, D.i, reinterpret_cast<const int *>(D.j16), D.a,
-                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, A->d_unpack_slot, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput);
+                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, nunpack ? A->d_unpack_slot : (int *) nullptr,
+                pk.d_unpack_rows, nunpack, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput, gint);
    } else {
       HB_LAUNCH((parcsr_fusedT<K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
-                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, A->d_unpack_slot, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput);
+                has_offd ? O.nrows : 0, O.i, O.j, O.a, x, alpha, beta, y, nunpack ? A->d_unpack_slot : (int *) nullptr,
+                pk.d_unpack_rows, nunpack, pk.d_unpack_ptr, pk.d_unpack_idx, h, gput, gint);
    }
    HB_LAUNCH_CHECK();
    return 0;

@@ -205,6 +205,7 @@ struct DCsr {
    double    *pat_val = nullptr;       // pat_nent
    int        pat_npat = 0, pat_nent = 0;
    bool       pat_wide = false;        // 16-bit codes in pat_code, table read from global memory
+   bool       pat_skips_boundary = false;   // the pattern kernels leave the rows with offd entries to the boundary kernel
    int       *pat_irr = nullptr;       // rows outside the table (code 255), swept by the CSR kernel
    int        pat_nirr = 0;
    long long  pat_irr_nnz = 0;
@@ -235,6 +236,7 @@ int  dcsr_free_sell(DCsr &M);
 // host-side result of the row-pattern analysis of one CSR block (kernels_pat.cu)
 struct PatHost {
    bool ok = false, square = true, wide = false;
+   bool skips_boundary = false;        // rows with offd entries carry the "outside" code and are in no list
    std::vector<unsigned char> code;    // per row: pattern id, 255 = outside the table
    std::vector<unsigned short> code16; // wide variant: 65535 = outside the table
    std::vector<int> base;              // per row first column (rectangular blocks only)
@@ -244,6 +246,7 @@ struct PatHost {
    long long irr_nnz = 0;
 };
 int  pat_analyze_host(int nrows, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out, bool wide);
+extern const int *g_pat_boundary_offd_i;   // set around the upload of a diag block whose ParCSR matrix has an offd block
 int  dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha);    // kernels_pat.cu
 
 int  dcsr_free_pat(DCsr &M);
@@ -412,6 +415,11 @@ void peer_fused_args(const PeerPlan *pl, PeerFusedArgs *out);
 // level; *done = false when the block does not qualify (the caller then runs the separate kernels)
 int  parcsr_fused_try(hb200_parcsr *A, const double *x, int epi_kind, const EpiArgs &ea, bool *done);
 int  parcsr_fusedT_try(hb200_parcsr *A, double alpha, const double *x, double beta, double *y, bool *done);
+// the boundary half of a split ParCSR operation: complete rows (diag part, offd part, one epilogue) over the
+// non-empty-row list of the offd block.  peer = true: with the put in front and the flag poll inside (side
+// stream, beside the main kernel); false: x_ext has already arrived in the matrix's receive buffer
+int  parcsr_boundary_launch(hb200_parcsr *A, const double *x, int epi_kind, const EpiArgs &ea, bool peer, cudaStream_t st);
+bool parcsr_main_skips_boundary(const hb200_parcsr *A);
 int  spmv_offd_wait_launch(const DCsr &M, const PeerWaitArgs &w, int epi_kind, const EpiArgs &ea, cudaStream_t st);
 int  parcsr_offd_pass(hb200_parcsr *A, int epi_kind, const EpiArgs &ea);   // halo_end + offd SpMV (fused or not)
 void peer_plan_free(PeerPlan *pl);

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kFusedThreads)
 parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, const double *__restrict__ da,
              const int *__restrict__ oi, const int *__restrict__ oj, const double *__restrict__ oa,
              const int *__restrict__ bnd_rows, int nbnd, const double *__restrict__ x, PeerFusedArgs h,
-             int gput, int gint, EpiArgs ea)
+             int gput, int gint, const double *__restrict__ xext_plain, EpiArgs ea)
 {
    __shared__ int s_flag;
    const int tid = threadIdx.x;
@@ -240,11 +240,14 @@ parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, 
    for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
    unsigned long long epoch_in = 0;
    if (boundary) {
-      epoch_in = h.w.epoch_ctr[1] + 1;
-      const int par = (int) (epoch_in & 1ull);
-      for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
-      __syncthreads();
-      const double *xe = par ? h.w.buf1 : h.w.buf0;
+      const double *xe = xext_plain;                    // (the halo already sits in the matrix's receive buffer)
+      if (!xext_plain) {
+         epoch_in = h.w.epoch_ctr[1] + 1;
+         const int par = (int) (epoch_in & 1ull);
+         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+         __syncthreads();
+         xe = par ? h.w.buf1 : h.w.buf0;
+      }
       if (row >= 0) { for (int q = oi[row] + lane; q < oi[row + 1]; q += K) so += oa[q] * __ldcg(xe + oj[q]); }
 #pragma unroll
       for (int o = K / 2; o > 0; o >>= 1) so += __shfl_down_sync(0xffffffffu, so, o, K);
@@ -252,7 +255,7 @@ parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, 
    if (row >= 0 && lane == 0) {
       ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, boundary, epi_needs_diag<EPI>() ? da[p0] : 0.0);
    }
-   if (boundary) fused_ack(h, epoch_in, (int) gridDim.x - gput - gint, &s_flag);
+   if (boundary && !xext_plain) fused_ack(h, epoch_in, (int) gridDim.x - gput - gint, &s_flag);
 }
 
 template <int EPI, int K>
@@ -274,13 +277,73 @@ static int fused_launch_K(const hb200_parcsr *A, const double *x, const PeerFuse
    if (grid < 1) return 0;
    if (D.kind == SPMV_VECTOR16 && D.j16) {
       HB_LAUNCH((parcsr_fused<EPI, K, true>), grid, kFusedThreads, 0, st, D.nrows, D.i, reinterpret_cast<const int *>(D.j16), D.a,
-                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint, ea);
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint,
+                (const double *) nullptr, ea);
    } else {
       HB_LAUNCH((parcsr_fused<EPI, K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
-                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint, ea);
+                has_offd ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, has_offd ? O.num_rownnz : 0, x, h, gput, gint,
+                (const double *) nullptr, ea);
    }
    HB_LAUNCH_CHECK();
    return 0;
+}
+
+// the boundary half alone (gint = 0): put + boundary rows over the peer halo, or boundary rows over a receive
+// buffer that has been filled already
+template <int EPI, int K>
+static int boundary_launch_K(const hb200_parcsr *A, const double *x, const PeerFusedArgs &h, const EpiArgs &ea, bool peer, cudaStream_t st)
+{
+   const DCsr &D = A->diag, &O = A->offd;
+   constexpr int G = kFusedThreads / K;
+   const int nb = A->num_cols_offd > 0 ? O.num_rownnz : 0;
+   int gput = 0, gbnd = (nb + G - 1) / G;
+   PeerFusedArgs hh = h;
+   const double *plain = nullptr;
+   if (peer) {
+      gput = h.n_out > 0 ? (h.total_out + 2047) / 2048 : 0;
+      if (gput > 64) gput = 64;
+#ifdef HB200_EMU
+      if (gput > 1) gput = 1;
+#endif
+      if (h.n_out > 0 && gput < 1) gput = 1;
+      if (h.w.n_in > 0 && gbnd < 1) gbnd = 1;
+   } else {
+      hh = PeerFusedArgs();
+      plain = A->pkg.d_recv_buf;
+      if (nb == 0) return 0;
+   }
+   const int grid = gput + gbnd;
+   if (grid < 1) return 0;
+   HB_LAUNCH((parcsr_fused<EPI, K, false>), grid, kFusedThreads, 0, st, D.nrows, D.i, D.j, D.a,
+             nb ? O.i : (const int *) nullptr, O.j, O.a, O.rownnz, nb, x, hh, gput, 0, plain, ea);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
+int parcsr_boundary_launch(hb200_parcsr *A, const double *x, int epi_kind, const EpiArgs &ea, bool peer, cudaStream_t st)
+{
+   PeerFusedArgs h;
+   if (peer) peer_fused_args(A->pkg.fwd, &h);
+   // lanes per boundary row from the length of its diag part (the offd part is a handful of entries)
+   const double avg = A->diag.avg_row_nnz;
+   int lanes = avg >= 150 ? 32 : avg >= 80 ? 16 : avg >= 36 ? 8 : avg >= 10 ? 4 : 2;
+   const long long nb = A->num_cols_offd > 0 ? A->offd.num_rownnz : 0;
+   while (lanes < 32 && nb * lanes < 148LL * 512 && lanes < avg) lanes *= 2;
+#define HB_BND(E) \
+   switch (lanes) { \
+      case 2:  return boundary_launch_K<E, 2>(A, x, h, ea, peer, st); \
+      case 4:  return boundary_launch_K<E, 4>(A, x, h, ea, peer, st); \
+      case 8:  return boundary_launch_K<E, 8>(A, x, h, ea, peer, st); \
+      case 16: return boundary_launch_K<E, 16>(A, x, h, ea, peer, st); \
+      default: return boundary_launch_K<E, 32>(A, x, h, ea, peer, st); \
+   }
+   switch (epi_kind) {
+      case EPI_AXPBY:       HB_BND(EPI_AXPBY)
+      case EPI_JACOBI7:     HB_BND(EPI_JACOBI7)
+      case EPI_JACOBI_CORE: HB_BND(EPI_JACOBI_CORE)
+      default: return set_error(HB200_ERROR_ARG, "parcsr_boundary_launch: epilogue %d", epi_kind);
+   }
+#undef HB_BND
 }
 
 template <int EPI>

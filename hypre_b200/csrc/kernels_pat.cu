@@ -913,6 +913,7 @@ int dcsr_free_pat(DCsr &M)
    M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr; M.pat_irr = nullptr;
    M.pat_nirr = 0;
    M.pat_wide = false;
+   M.pat_skips_boundary = false;
    M.has_pat = false;
    return 0;
 }
@@ -925,8 +926,14 @@ int dcsr_free_pat(DCsr &M)
 // swept by the CSR vector kernel over a row list (pat_irr).  The block qualifies when the table
 // covers at least 70% of the rows.  Irregular blocks leave after their first 64K rows.
 // Pure host code (no CUDA call): also reachable through hb200_host_pattern_analyze for CPU tests.
+// rows with entries in the offd block of the ParCSR matrix this diag block belongs to (set around the upload
+// of a diag block on N > 1 ranks, parcsr.cu): they are left out of the table AND of the irregular-row list —
+// the boundary kernel of the split ParCSR operation computes them completely (kernels_offd.cu)
+const int *g_pat_boundary_offd_i = nullptr;
+
 int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const double *ha, PatHost &out, bool wide)
 {
+   const int *bnd = g_pat_boundary_offd_i;
    // narrow: 1-byte codes, table in shared memory; wide: 2-byte codes, table in global memory
    const int max_pat = wide ? 65534 : kPatMaxPatterns - 1;
    const int max_ent = wide ? (1 << 20) : kPatMaxEntries;
@@ -960,8 +967,10 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
    };
    int prev = -1;
    long long misses = 0;
+   long long nbnd = 0;
    for (int r = 0; r < n; r++) {
       if ((r & 65535) == 0 && r > 0 && misses > r / 2) return 0;      // irregular block
+      if (bnd && bnd[r + 1] > bnd[r]) { rid[r] = -2; nbnd++; continue; }   // a boundary row: not this format's business
       if (prev >= 0 && same_rows(rep[prev], r)) { rid[r] = prev; count[prev]++; continue; }
       unsigned long long h = 1469598103934665603ull ^ (unsigned long long) (hi[r + 1] - hi[r]);
       for (int q = hi[r]; q < hi[r + 1]; q++) {
@@ -1011,15 +1020,16 @@ int pat_analyze_host(int n, int ncols, const int *hi, const int *hj, const doubl
       out.ptr.push_back((int) out.off.size());
       covered += count[c];
    }
-   if ((double) covered < 0.7 * (double) n) { out = PatHost(); return 0; }
+   if ((double) covered < 0.7 * (double) (n - nbnd)) { out = PatHost(); return 0; }
    if (wide) out.code16.resize((size_t) n); else out.code.resize((size_t) n);
    for (int r = 0; r < n; r++) {
       const int c = rid[r] >= 0 ? code_of[rid[r]] : -1;
-      if (c < 0) { out.irr.push_back(r); out.irr_nnz += hi[r + 1] - hi[r]; }
+      if (c < 0 && rid[r] != -2) { out.irr.push_back(r); out.irr_nnz += hi[r + 1] - hi[r]; }
       if (wide) out.code16[r] = (unsigned short) (c >= 0 ? c : 65535);
       else      out.code[r] = (unsigned char) (c >= 0 ? c : 255);
    }
    out.wide = wide;
+   out.skips_boundary = (bnd != nullptr);
    out.base.swap(basev);
    out.square = square;
    out.ok = true;
@@ -1062,6 +1072,7 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
    }
    M.pat_irr_nnz = ph.irr_nnz;
    M.pat_nirr = (int) ph.irr.size();
+   M.pat_skips_boundary = ph.skips_boundary;
    M.pat_npat = npat;
    M.pat_nent = nent;
    M.has_pat = true;

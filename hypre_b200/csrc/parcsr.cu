@@ -21,6 +21,12 @@
 
 namespace hb {
 
+bool parcsr_main_skips_boundary(const hb200_parcsr *A)
+{
+   const DCsr &D = A->diag;
+   return (D.kind == SPMV_PAT || D.kind == SPMV_BOX) && D.has_pat && D.pat_skips_boundary;
+}
+
 // ---------------------------------------------------------------------------------------
 // halo kernels
 // ---------------------------------------------------------------------------------------
@@ -168,6 +174,33 @@ int parcsr_matvec(hb200_parcsr *A, double alpha, const double *x, double beta, c
       bool done = false;
       HB_CHECK(parcsr_fused_try(A, x, EPI_AXPBY, ea, &done));
       if (done) { c.last_dot_fused = false; return 0; }
+   }
+   if (parcsr_main_skips_boundary(A)) {
+      // split operation: the main kernel computes the rows without offd entries, the boundary kernel the others
+      c.dot_req_armed = false; c.last_dot_fused = false;
+      const bool peer = (c.halo_mode == 1 && c.nranks > 1);
+      if (peer) HB_CHECK(peer_plans_ensure(A, false));
+      if (peer && !A->pkg.peer_off) {
+         timer_tick(T_HALO_START);
+         HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
+         HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+         HB_CHECK(parcsr_boundary_launch(A, x, EPI_AXPBY, ea, true, c.s_comm));   // put + flags + boundary rows, side stream
+         HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+         timer_tick(T_MATVEC_DIAG);
+         HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
+         HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
+      } else {
+         timer_tick(T_HALO_START);
+         HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
+         timer_tick(T_MATVEC_DIAG);
+         HB_CHECK(spmv_launch(A->diag, x, EPI_AXPBY, ea, false, c.s_comp));
+         timer_tick(T_HALO_WAIT);
+         HB_CHECK(parcsr_halo_end(A, c.s_comp));
+         timer_tick(T_MATVEC_OFFD);
+         HB_CHECK(parcsr_boundary_launch(A, x, EPI_AXPBY, ea, false, c.s_comp));
+      }
+      timer_tick(T_OTHER);
+      return 0;
    }
    timer_tick(T_HALO_START);
    HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
@@ -448,7 +481,11 @@ int hb200_parcsr_create(hb200_parcsr **Aout, int num_rows, int num_cols, int num
    A->global_rows = global_num_rows;
    A->global_cols = global_num_cols;
    int zero = 0;
+   // N > 1: the structured formats of the diag block leave the rows with offd entries to the boundary kernel
+   // (the split operation: main kernel beside put + boundary rows; HB200_NO_SPLIT=1 keeps every row)
+   if (ctx().nranks > 1 && num_cols_offd > 0 && num_rows > 0 && !env_flag("HB200_NO_SPLIT", false)) g_pat_boundary_offd_i = offd_i;
    int f = dcsr_upload(A->diag, num_rows, num_cols, num_rows ? diag_i : &zero, diag_j, diag_data);
+   g_pat_boundary_offd_i = nullptr;
    if (f) { hb200_parcsr_destroy(A); return f; }   // frees what the failed upload had already allocated
    if (num_cols_offd > 0) {
       f = dcsr_upload(A->offd, num_rows, num_cols_offd, offd_i, offd_j, offd_data);

@@ -21,6 +21,36 @@ bool relax_is_gs(int t)
    return t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14 || t == 88 || t == 89;
 }
 
+// split operation (parcsr.cu, parcsr_matvec): main kernel over the rows without offd entries, boundary kernel
+// (put + flags + complete boundary rows) beside it on the side stream
+static int relax_split(hb200_parcsr *A, const double *x, int epi, const EpiArgs &ea)
+{
+   Ctx &c = ctx();
+   const bool peer = (c.halo_mode == 1 && c.nranks > 1);
+   if (peer) HB_CHECK(peer_plans_ensure(A, false));
+   if (peer && !A->pkg.peer_off) {
+      timer_tick(T_HALO_START);
+      HB_CUDA(cudaEventRecord(c.ev_a, c.s_comp));
+      HB_CUDA(cudaStreamWaitEvent(c.s_comm, c.ev_a, 0));
+      HB_CHECK(parcsr_boundary_launch(A, x, epi, ea, true, c.s_comm));
+      HB_CUDA(cudaEventRecord(c.ev_b, c.s_comm));
+      timer_tick(T_MATVEC_DIAG);
+      HB_CHECK(spmv_launch(A->diag, x, epi, ea, false, c.s_comp));
+      HB_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_b, 0));
+   } else {
+      timer_tick(T_HALO_START);
+      HB_CHECK(parcsr_halo_begin(A, x, c.s_comp));
+      timer_tick(T_MATVEC_DIAG);
+      HB_CHECK(spmv_launch(A->diag, x, epi, ea, false, c.s_comp));
+      timer_tick(T_HALO_WAIT);
+      HB_CHECK(parcsr_halo_end(A, c.s_comp));
+      timer_tick(T_MATVEC_OFFD);
+      HB_CHECK(parcsr_boundary_launch(A, x, epi, ea, false, c.s_comp));
+   }
+   timer_tick(T_OTHER);
+   return 0;
+}
+
 // One out-of-place Jacobi-type sweep: u_out = sweep(u_in).  u_in may be NULL when
 // zero_guess (u == 0 by flag, memory content undefined).
 int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_type,
@@ -58,6 +88,7 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
          HB_CHECK(parcsr_fused_try(A, u_in, EPI_JACOBI7, ea, &done));   // one kernel on a latency-bound level
          if (done) return 0;
       }
+      if (parcsr_main_skips_boundary(A)) return relax_split(A, u_in, EPI_JACOBI7, ea);
       timer_tick(T_HALO_START);
       HB_CHECK(parcsr_halo_begin(A, u_in, c.s_comp));
       timer_tick(T_MATVEC_DIAG);
@@ -93,6 +124,7 @@ int relax_jacobi_oop(hb200_parcsr *A, const double *f, const int *cf, int relax_
       HB_CHECK(parcsr_fused_try(A, uin, EPI_JACOBI_CORE, ea, &done));
       if (done) return 0;
    }
+   if (parcsr_main_skips_boundary(A)) return relax_split(A, uin, EPI_JACOBI_CORE, ea);
    HB_CHECK(parcsr_halo_begin(A, uin, c.s_comp));
    HB_CHECK(spmv_launch(A->diag, uin, EPI_JACOBI_CORE, ea, false, c.s_comp));
    HB_CHECK(parcsr_offd_pass(A, EPI_JACOBI_CORE_ACC, ea));

@@ -67,6 +67,9 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned long long *p, unsig
    unsigned long long t0 = 0;
    unsigned int spins = 0;
    while (ld_acquire_sys(p) < target) {
+#ifndef HB200_EMU
+      __nanosleep(40);                       // a system-scope poll is not free for the memory system: back off
+#endif
       if ((++spins & 63u) != 0u) continue;
 #ifdef HB200_EMU
       sched_yield();                         // the peer is another host process
@@ -83,6 +86,47 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned long long *p, unsig
 #endif
          return false;
       }
+   }
+   return true;
+}
+
+// device-scope relay of an arrival: ONE block polls the system-scope flags the peers write over NVLink and
+// republishes the epoch in local memory; every other block of the kernel waits on that local word (a
+// thousand blocks polling system-scope flags slowed the whole device down by 5x: profiles/r2_session_log.md)
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+   unsigned long long v;
+#ifndef HB200_EMU
+   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else
+   v = *(const volatile unsigned long long *) p;
+#endif
+   return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+#ifndef HB200_EMU
+   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+   *(volatile unsigned long long *) p = v;
+#endif
+}
+__device__ __forceinline__ bool spin_local_until_ge(const unsigned long long *p, unsigned long long target, const SpinGuard &g)
+{
+   unsigned int spins = 0;
+   unsigned long long t0 = 0;
+   while (ld_acquire_gpu(p) < target) {
+#ifndef HB200_EMU
+      __nanosleep(100);
+#else
+      sched_yield();
+#endif
+      if ((++spins & 255u) != 0u || g.err == nullptr) continue;
+      if (*(volatile unsigned long long *) g.err != 0ull) return false;
+      if (g.timeout_ns == 0ull) continue;
+      const unsigned long long now = peer_now_ns();
+      if (t0 == 0ull) { t0 = now; continue; }
+      if (now - t0 > 2 * g.timeout_ns) return false;   // (the relay block reports the reason)
    }
    return true;
 }

@@ -220,42 +220,62 @@ parcsr_fused(int nrows, const int *__restrict__ di, const int *__restrict__ dj, 
    const int b = (int) blockIdx.x;
    if (b < gput) { fused_put(h, x, gput, guard, &s_flag); return; }
    const bool boundary = b >= gput + gint;
-   int row = -1;
    if (!boundary) {
+      // ---- interior rows: never look at a flag
       const int r = (b - gput) * G + tid / K;
-      if (r < nrows && !(oi && oi[r + 1] > oi[r])) row = r;          // rows with offd entries belong to the boundary blocks
-   } else {
-      const int t = (b - gput - gint) * G + tid / K;
-      if (t < nbnd) row = bnd_rows[t];
-   }
-   double sd = 0.0, so = 0.0;
-   int p0 = 0;
-   if (row >= 0) {
-      p0 = di[row];
-      const int p1 = di[row + 1];
-      if (I16) { const double *xr = x + row; for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
-      else     { for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
-   }
+      const int row = (r < nrows && !(oi && oi[r + 1] > oi[r])) ? r : -1;   // rows with offd entries belong to the boundary blocks
+      double sd = 0.0;
+      int p0 = 0;
+      if (row >= 0) {
+         p0 = di[row];
+         const int p1 = di[row + 1];
+         if (I16) { const double *xr = x + row; for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
+         else     { for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
+      }
 #pragma unroll
-   for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
+      for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
+      if (row >= 0 && lane == 0) ea.y[row] = fused_epi_value<EPI>(ea, row, sd, 0.0, false, epi_needs_diag<EPI>() ? da[p0] : 0.0);
+      return;
+   }
+   // ---- boundary rows: a bounded number of blocks walks the list; the diag part of a block's first rows is
+   // summed before anybody looks at a flag (the transfer is in flight meanwhile)
+   const int bb = b - gput - gint, gbnd = (int) gridDim.x - gput - gint;
+   const int trips = (nbnd + gbnd * G - 1) / (gbnd * G);        // the same for every lane: shuffles stay converged
    unsigned long long epoch_in = 0;
-   if (boundary) {
-      const double *xe = xext_plain;                    // (the halo already sits in the matrix's receive buffer)
-      if (!xext_plain) {
+   const double *xe = xext_plain;                                // (plain mode: the halo already sits in the receive buffer)
+   for (int t = 0; t < (trips > 0 ? trips : 1); t++) {
+      const int k = (t * gbnd + bb) * G + tid / K;
+      const int row = (k < nbnd) ? bnd_rows[k] : -1;
+      double sd = 0.0, so = 0.0;
+      int p0 = 0;
+      if (row >= 0) {
+         p0 = di[row];
+         const int p1 = di[row + 1];
+         if (I16) { const double *xr = x + row; for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(xr + dj16[p]); }
+         else     { for (int p = p0 + skip + lane; p < p1; p += K) sd += da[p] * __ldg(x + dj[p]); }
+      }
+#pragma unroll
+      for (int o = K / 2; o > 0; o >>= 1) sd += __shfl_down_sync(0xffffffffu, sd, o, K);
+      if (t == 0 && !xext_plain) {
+         // block 0 of the boundary group polls the peers' flags and republishes the epoch locally
          epoch_in = h.w.epoch_ctr[1] + 1;
          const int par = (int) (epoch_in & 1ull);
-         for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
-         __syncthreads();
+         if (bb == 0) {
+            for (int j = tid; j < h.w.n_in; j += kFusedThreads) spin_until_ge(h.w.flags + par * h.w.n_in + j, epoch_in, guard, 2, j);
+            __syncthreads();
+            if (tid == 0) st_release_gpu(h.w.epoch_ctr + 2, epoch_in);
+         } else {
+            if (tid == 0) spin_local_until_ge(h.w.epoch_ctr + 2, epoch_in, guard);
+            __syncthreads();
+         }
          xe = par ? h.w.buf1 : h.w.buf0;
       }
       if (row >= 0) { for (int q = oi[row] + lane; q < oi[row + 1]; q += K) so += oa[q] * __ldcg(xe + oj[q]); }
 #pragma unroll
       for (int o = K / 2; o > 0; o >>= 1) so += __shfl_down_sync(0xffffffffu, so, o, K);
+      if (row >= 0 && lane == 0) ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, true, epi_needs_diag<EPI>() ? da[p0] : 0.0);
    }
-   if (row >= 0 && lane == 0) {
-      ea.y[row] = fused_epi_value<EPI>(ea, row, sd, so, boundary, epi_needs_diag<EPI>() ? da[p0] : 0.0);
-   }
-   if (boundary && !xext_plain) fused_ack(h, epoch_in, (int) gridDim.x - gput - gint, &s_flag);
+   if (!xext_plain) fused_ack(h, epoch_in, gbnd, &s_flag);
 }
 
 template <int EPI, int K>
@@ -272,6 +292,7 @@ static int fused_launch_K(const hb200_parcsr *A, const double *x, const PeerFuse
    if (h.n_out > 0 && gput < 1) gput = 1;
    const int gint = (D.nrows + G - 1) / G;
    int gbnd = has_offd ? (O.num_rownnz + G - 1) / G : 0;
+   if (gbnd > 2 * kNumSMs) gbnd = 2 * kNumSMs;          // (they loop over the list)
    if (h.w.n_in > 0 && gbnd < 1) gbnd = 1;              // (somebody sends to us: the exchange has to be consumed and acknowledged)
    const int grid = gput + gint + gbnd;
    if (grid < 1) return 0;
@@ -297,6 +318,7 @@ static int boundary_launch_K(const hb200_parcsr *A, const double *x, const PeerF
    constexpr int G = kFusedThreads / K;
    const int nb = A->num_cols_offd > 0 ? O.num_rownnz : 0;
    int gput = 0, gbnd = (nb + G - 1) / G;
+   if (gbnd > 2 * kNumSMs) gbnd = 2 * kNumSMs;          // (they loop over the list)
    PeerFusedArgs hh = h;
    const double *plain = nullptr;
    if (peer) {

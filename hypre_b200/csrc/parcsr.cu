@@ -482,8 +482,8 @@ int hb200_parcsr_create(hb200_parcsr **Aout, int num_rows, int num_cols, int num
    A->global_cols = global_num_cols;
    int zero = 0;
    // N > 1: the structured formats of the diag block leave the rows with offd entries to the boundary kernel
-   // (the split operation: main kernel beside put + boundary rows; HB200_NO_SPLIT=1 keeps every row)
-   if (ctx().nranks > 1 && num_cols_offd > 0 && num_rows > 0 && !env_flag("HB200_NO_SPLIT", false)) g_pat_boundary_offd_i = offd_i;
+   // (the split operation: main kernel beside put + boundary rows; opt-in with HB200_SPLIT=1 until it wins on hardware)
+   if (ctx().nranks > 1 && num_cols_offd > 0 && num_rows > 0 && env_flag("HB200_SPLIT", false)) g_pat_boundary_offd_i = offd_i;
    int f = dcsr_upload(A->diag, num_rows, num_cols, num_rows ? diag_i : &zero, diag_j, diag_data);
    g_pat_boundary_offd_i = nullptr;
    if (f) { hb200_parcsr_destroy(A); return f; }   // frees what the failed upload had already allocated

@@ -41,7 +41,7 @@ struct PeerPlan {
    unsigned long long **d_in_ack = nullptr;       // [n_in] remote consumed flags (at the senders)
    double              *dst = nullptr;            // private destination buffer (borrowed)
    // device state
-   unsigned long long  *d_epoch = nullptr;        // [0] = out epoch, [1] = in epoch
+   unsigned long long  *d_epoch = nullptr;        // [0] = out epoch, [1] = in epoch, [2] = local relay of the arrival epoch
    unsigned int        *d_ticket = nullptr;       // [0] put, [1] wait
 };
 
@@ -457,8 +457,8 @@ static int build_plan(PeerPlan **out_plan, int n_out, const int *out_procs, cons
       ok = ok && cudaMemcpy(pl->d_out_flag, flag2.data(), sizeof(unsigned long long *) * flag2.size(), cudaMemcpyHostToDevice) == cudaSuccess;
       ok = ok && cudaMalloc((void **) &pl->d_in_ack, sizeof(unsigned long long *) * in_ack.size()) == cudaSuccess;
       ok = ok && cudaMemcpy(pl->d_in_ack, in_ack.data(), sizeof(unsigned long long *) * in_ack.size(), cudaMemcpyHostToDevice) == cudaSuccess;
-      ok = ok && cudaMalloc((void **) &pl->d_epoch, sizeof(unsigned long long) * 2) == cudaSuccess;
-      ok = ok && cudaMemset(pl->d_epoch, 0, sizeof(unsigned long long) * 2) == cudaSuccess;
+      ok = ok && cudaMalloc((void **) &pl->d_epoch, sizeof(unsigned long long) * 4) == cudaSuccess;
+      ok = ok && cudaMemset(pl->d_epoch, 0, sizeof(unsigned long long) * 4) == cudaSuccess;
       ok = ok && cudaMalloc((void **) &pl->d_ticket, sizeof(unsigned int) * 2) == cudaSuccess;
       ok = ok && cudaMemset(pl->d_ticket, 0, sizeof(unsigned int) * 2) == cudaSuccess;
       if (!ok) { cudaGetLastError(); bad = 1; }

@@ -25,9 +25,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# the reference library's OpenMP threads must not spin on the host cores after its setup returns
-# (they would compete with the upload's host-side work)
-os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 import numpy as np  # noqa: E402
 
@@ -243,7 +240,8 @@ def run_reference(args):
     if myrank != 0:
         return
     line = {
-        "impl": "reference", "metric": "amg_pcg_solve_mdof_per_s", "value": val, "unit": "MDOF/s",
+        "impl": "reference", "metric": "amg_pcg_solve_mdof_per_s" if args.solver == "pcg" else "amg_gmres_solve_mdof_per_s",
+        "value": val, "unit": "MDOF/s",
         "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_full * 1e3, "higher_is_better": True,
         "scaling": "strong" if args.global_size else "weak",

@@ -233,7 +233,12 @@ static int spmv_dispatch(const DCsr &M, const double *x, const EpiArgs &ea, bool
    const int nlist = use_rownnz ? M.num_rownnz : M.nrows;
    if (nlist == 0) return 0;
    if (!use_rownnz && (M.kind == SPMV_PAT || M.kind == SPMV_BOX) && M.has_pat) {
-      if (M.kind == SPMV_BOX && M.has_box && spmv_box_supports(EPI)) HB_CHECK(spmv_box_launch(M, x, EPI, ea, st));
+      // the fused l1-Jacobi sweep: the generic kernel's 4 rows per thread sit 256 rows apart, which makes them
+      // y-neighbours when the plane stride divides 256 — there it is the faster of the two (B200, 256^3: 0.238
+      // against 0.276 ms; the SpMV itself: 0.184 against 0.150 ms; profiles/r2_session_log.md)
+      static const bool box_jacobi = env_flag("HB200_BOX_JACOBI", false);
+      const bool pat_aligned = (EPI == EPI_JACOBI7) && M.box_sy > 0 && (256 % M.box_sy) == 0 && !box_jacobi;
+      if (M.kind == SPMV_BOX && M.has_box && spmv_box_supports(EPI) && !pat_aligned) HB_CHECK(spmv_box_launch(M, x, EPI, ea, st));
       else HB_CHECK(spmv_pat_launch(M, x, EPI, ea, st));
       if (M.pat_nirr == 0) return 0;
       // rows outside the pattern table: CSR sweep over the row list (disjoint rows, same epilogue)

@@ -40,6 +40,15 @@ class GMRESParams(C.Structure):
         ("k_dim", C.c_int), ("min_iter", C.c_int), ("max_iter", C.c_int),
         ("rel_change", C.c_int), ("skip_real_r_check", C.c_int), ("stop_crit", C.c_int),
         ("hybrid", C.c_int), ("logging", C.c_int), ("print_level", C.c_int),
+        ("cgs", C.c_int), ("unroll", C.c_int),
+    ]
+
+
+class BiCGSTABParams(C.Structure):
+    _fields_ = [
+        ("tol", C.c_double), ("a_tol", C.c_double), ("cf_tol", C.c_double),
+        ("min_iter", C.c_int), ("max_iter", C.c_int), ("stop_crit", C.c_int), ("hybrid", C.c_int),
+        ("logging", C.c_int), ("print_level", C.c_int),
     ]
 
 
@@ -124,6 +133,13 @@ def _load() -> C.CDLL:
         "hb200_gmres_default_params": ([C.POINTER(GMRESParams)], None),
         "hb200_gmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_gmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_flexgmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_flexgmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_cogmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_cogmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_bicgstab_default_params": ([C.POINTER(BiCGSTABParams)], None),
+        "hb200_bicgstab_solve": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_bicgstab_solve_host": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)   # AttributeError here = header/library mismatch

@@ -29,6 +29,7 @@ SOURCES = [
     "gs.cu",
     "amg.cu",
     "krylov.cu",
+    "krylov_ext.cu",
 ]
 
 NVCC_FLAGS = [

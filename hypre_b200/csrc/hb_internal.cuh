@@ -313,6 +313,10 @@ int vec_scale_div(double w, const double *f, const double *d, double *u, const i
 int vec_diag_scale(const double *diag, const double *x, double *y, size_t n, cudaStream_t st);
 // dot into device slot (local part only)
 int vec_dot_dev(const double *x, const double *y, size_t n, int slot, cudaStream_t st);
+// <Z_k, x> for k < nv <= kMassNV vectors of a slab in one pass (vector_batched.c); the reduction scratch holds 4 columns
+constexpr int kMassNV = 4;
+int vec_mass_dot_dev(const double *x, const double *Z, size_t zstride, int nv, size_t n, int slot0, int dump,
+                     cudaStream_t st);
 // two dots at once: slot0 = <x,y>, slot1 = <z,z2>
 int vec_dot2_dev(const double *x, const double *y, const double *z, const double *z2, size_t n,
                  int slot0, int slot1, cudaStream_t st);

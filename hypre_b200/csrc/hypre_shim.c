@@ -7,6 +7,9 @@
  *
  *   hypre_PCGSolve            (src/krylov/pcg.c:313)            -> hb200_pcg_solve_host
  *   hypre_GMRESSolve          (src/krylov/gmres.c:294)          -> hb200_gmres_solve_host
+ *   hypre_FlexGMRESSolve      (src/krylov/flexgmres.c:288)      -> hb200_flexgmres_solve_host
+ *   hypre_COGMRESSolve        (src/krylov/cogmres.c:270)        -> hb200_cogmres_solve_host
+ *   hypre_BiCGSTABSolve       (src/krylov/bicgstab.c:246)       -> hb200_bicgstab_solve_host
  *   hypre_BoomerAMGSolve      (src/parcsr_ls/par_amg_solve.c:22)-> hb200_amg_solve
  *   HYPRE_ParCSRMatrixMatvec  (src/parcsr_mv/HYPRE_parcsr_matrix.c:385) -> hb200_parcsr_matvec_host
  *   HYPRE_ParCSRMatrixMatvecT (:401)                            -> hb200_parcsr_matvecT
@@ -14,6 +17,7 @@
  *
  *   hypre_BoomerAMGSetup      (src/parcsr_ls/par_amg_setup.c)   -> the reference's setup, THEN the upload
  *   hypre_PCGSetup / hypre_GMRESSetup (src/krylov/pcg.c:198, gmres.c:185) -> the reference's, THEN upload A
+ *   hypre_FlexGMRESSetup / hypre_COGMRESSetup / hypre_BiCGSTABSetup (flexgmres.c:176, cogmres.c:178, bicgstab.c:150): same
  *   HYPRE_IJMatrixAssemble    (src/IJ_mv/HYPRE_IJMatrix.c)      -> the reference's, THEN drop the stale mirror
  *
  * Everything else (IJ assembly, BoomerAMGSetup, all other solvers) stays the reference's own
@@ -653,6 +657,52 @@ HYPRE_Int hypre_GMRESSetup(void *gmres_vdata, void *A, void *b, void *x)
    return hypre_error_flag;
 }
 
+/* the other drivers of the ParCSR function table (hb200.h, f4): same hook, warm-up kinds 2 / 3 / 4 */
+HYPRE_Int hypre_FlexGMRESSetup(void *fgmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_FlexGMRESSetup"); }
+   ierr = orig(fgmres_vdata, A, b, x);
+   if (!ierr)
+   {
+      hypre_FlexGMRESData *fd = (hypre_FlexGMRESData *) fgmres_vdata;
+      if (fd->functions->modify_pc == hypre_FlexGMRESModifyPCDefault)
+      {
+         krylov_setup_upload((void *) fd->functions->Matvec, A, (void *) fd->functions->precond, fd->precond_data, NULL, 2, fd->k_dim);
+      }
+   }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_COGMRESSetup(void *cogmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_COGMRESSetup"); }
+   ierr = orig(cogmres_vdata, A, b, x);
+   if (!ierr)
+   {
+      hypre_COGMRESData *cd = (hypre_COGMRESData *) cogmres_vdata;
+      krylov_setup_upload((void *) cd->functions->Matvec, A, (void *) cd->functions->precond, cd->precond_data, NULL, 3, cd->k_dim);
+   }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_BiCGSTABSetup(void *bicgstab_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_BiCGSTABSetup"); }
+   ierr = orig(bicgstab_vdata, A, b, x);
+   if (!ierr)
+   {
+      hypre_BiCGSTABData *bd = (hypre_BiCGSTABData *) bicgstab_vdata;
+      krylov_setup_upload((void *) bd->functions->Matvec, A, (void *) bd->functions->precond, bd->precond_data, bd->precond_Mat, 4, 0);
+   }
+   return hypre_error_flag;
+}
+
 /* values set through the IJ interface land in the ParCSR arrays at Assemble: the device copy of that
  * object is stale from here on (checked by checksum, so a re-assembly without changes costs no upload) */
 HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix)
@@ -872,6 +922,151 @@ HYPRE_Int hypre_GMRESSolve(void *gmres_vdata, void *A, void *b, void *x)
    hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
    if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
    if (g_verbose) { fprintf(stderr, "[hypre_b200] GMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+/* ---- FlexGMRES / COGMRES / BiCGSTAB (hb200.h, f4) -------------------------------------------------------- */
+
+/* what the three share with the two above: the on-path decision (collective), the device matrix, the
+ * preconditioner kind.  Returns 1 = run on the device, 0 = hand the call back to the reference (or, strict,
+ * an error was raised: *strict_err), -1 = error already raised */
+static int krylov_ext_on_path(void *matvec_fn, void *precond_fn, void *precond_data, void *precond_Mat, void *A, void *b,
+                              const char *why_in, int *noticed, hb200_parcsr **dA, hb200_amg **amg, int *kind, int *strict_err)
+{
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   const char *why = why_in;
+   *strict_err = 0; *kind = 0; *amg = NULL; *dA = NULL;
+   if (matvec_fn != (void *) hypre_ParKrylovMatvec) { return 0; }
+   if (!why && precond_Mat && precond_Mat != A) { why = "separate preconditioning matrix"; }
+   if (!why && hypre_ParVectorNumVectors((hypre_ParVector *) b) > 1) { why = "multi-vector Krylov solve"; }
+   if (!why)
+   {
+      if (shim_init(hypre_ParCSRMatrixComm(pA))) { return -1; }
+      why = comm_off_path(hypre_ParCSRMatrixComm(pA));
+      if (!why) { *kind = precond_kind(precond_fn, precond_data, pA, amg, &why); }
+      if (*kind == -2) { return -1; }
+   }
+   if (why)
+   {
+      if (g_strict) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, why); *strict_err = 1; return 0; }
+      notice_once(noticed, why);
+      return 0;
+   }
+   *dA = mirror_matrix(pA);
+   return *dA ? 1 : -1;
+}
+
+static void gmres_family_params(hb200_gmres_params *P, double tol, double a_tol, double cf_tol, int k_dim, int min_iter,
+                                int max_iter, int rel_change, int skip_real_r_check, int logging, int print_level)
+{
+   hb200_gmres_default_params(P);
+   P->tol = tol; P->a_tol = a_tol; P->cf_tol = cf_tol; P->k_dim = k_dim; P->min_iter = min_iter; P->max_iter = max_iter;
+   P->rel_change = rel_change; P->skip_real_r_check = skip_real_r_check; P->logging = logging; P->print_level = print_level;
+}
+
+HYPRE_Int hypre_FlexGMRESSolve(void *fgmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_FlexGMRESData *fd = (hypre_FlexGMRESData *) fgmres_vdata;
+   hypre_FlexGMRESFunctions *fn = fd->functions;
+   const char *why = NULL;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA = NULL;
+   hb200_gmres_params P;
+   hb200_krylov_result R;
+   int kind = 0, flag, on, strict_err = 0;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_FlexGMRESSolve"); }
+   if (fn->modify_pc != hypre_FlexGMRESModifyPCDefault) { why = "FlexGMRES with a user modify_pc callback"; }
+   if (!why && fd->print_level > 2) { why = "tagged residual printing (print_level > 2)"; }
+   if (!why && fd->k_dim > 100) { why = "FlexGMRES restart length above 100"; }
+   on = krylov_ext_on_path((void *) fn->Matvec, (void *) fn->precond, fd->precond_data, NULL, A, b, why, &noticed, &dA, &amg, &kind, &strict_err);
+   if (on < 0 || strict_err) { return hypre_error_flag; }
+   if (!on) { return orig(fgmres_vdata, A, b, x); }
+   gmres_family_params(&P, fd->tol, fd->a_tol, fd->cf_tol, fd->k_dim, fd->min_iter, fd->max_iter, 0, 0, fd->logging, fd->print_level);
+   fd->converged = 0;
+   memset(&R, 0, sizeof(R));
+   flag = hb200_flexgmres_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                                     hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), fd->norms, &R);
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); return hypre_error_flag; }
+   fd->num_iterations = R.num_iterations;
+   fd->rel_residual_norm = R.rel_residual_norm;
+   fd->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] FlexGMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_COGMRESSolve(void *cogmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_COGMRESData *cd = (hypre_COGMRESData *) cogmres_vdata;
+   hypre_COGMRESFunctions *fn = cd->functions;
+   const char *why = NULL;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA = NULL;
+   hb200_gmres_params P;
+   hb200_krylov_result R;
+   int kind = 0, flag, on, strict_err = 0;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_COGMRESSolve"); }
+   if (cd->k_dim > (cd->cgs > 1 ? 50 : 100)) { why = "COGMRES restart length above 100 (50 with re-orthogonalisation)"; }
+   on = krylov_ext_on_path((void *) fn->Matvec, (void *) fn->precond, cd->precond_data, NULL, A, b, why, &noticed, &dA, &amg, &kind, &strict_err);
+   if (on < 0 || strict_err) { return hypre_error_flag; }
+   if (!on) { return orig(cogmres_vdata, A, b, x); }
+   gmres_family_params(&P, cd->tol, cd->a_tol, cd->cf_tol, cd->k_dim, cd->min_iter, cd->max_iter, cd->rel_change,
+                       cd->skip_real_r_check, cd->logging, cd->print_level);
+   P.cgs = cd->cgs; P.unroll = cd->unroll;
+   cd->converged = 0;
+   memset(&R, 0, sizeof(R));
+   flag = hb200_cogmres_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                                   hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), cd->norms, &R);
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); return hypre_error_flag; }
+   cd->num_iterations = R.num_iterations;
+   cd->rel_residual_norm = R.rel_residual_norm;
+   cd->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] COGMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_BiCGSTABSolve(void *bicgstab_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_BiCGSTABData *bd = (hypre_BiCGSTABData *) bicgstab_vdata;
+   hypre_BiCGSTABFunctions *fn = bd->functions;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA = NULL;
+   hb200_bicgstab_params P;
+   hb200_krylov_result R;
+   int kind = 0, flag, on, strict_err = 0;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_BiCGSTABSolve"); }
+   on = krylov_ext_on_path((void *) fn->Matvec, (void *) fn->precond, bd->precond_data, bd->precond_Mat, A, b, NULL, &noticed, &dA, &amg, &kind, &strict_err);
+   if (on < 0 || strict_err) { return hypre_error_flag; }
+   if (!on) { return orig(bicgstab_vdata, A, b, x); }
+   hb200_bicgstab_default_params(&P);
+   P.tol = bd->tol; P.a_tol = bd->a_tol; P.cf_tol = bd->cf_tol; P.min_iter = bd->min_iter; P.max_iter = bd->max_iter;
+   P.stop_crit = bd->stop_crit; P.hybrid = bd->hybrid; P.logging = bd->logging; P.print_level = bd->print_level;
+   bd->converged = 0;
+   memset(&R, 0, sizeof(R));
+   flag = hb200_bicgstab_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                                    hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), bd->norms, &R);
+   if (flag & ~HB200_ERROR_CONV)
+   {
+      /* breakdown (the reference raises the same generic error, bicgstab.c:490, 571, 588) or a device failure */
+      hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error());
+      if (R.num_iterations > 0) { hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0; }
+      return hypre_error_flag;
+   }
+   bd->num_iterations = R.num_iterations;
+   bd->rel_residual_norm = R.rel_residual_norm;
+   bd->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] BiCGSTAB on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
    return hypre_error_flag;
 }
 

@@ -225,6 +225,42 @@ dot2_kernel(const double *__restrict__ x, const double *__restrict__ y,
    block_reduce_store<2>(s, partials, counter, scalars, slots);
 }
 
+// scalars[slot0 + k] = <Z_k, x> for k < nv <= kMassNV, Z_k = Z + k * zstride: the inner products of one
+// vector with a slab of basis vectors in ONE pass over x (hypre_SeqVectorMassInnerProd,
+// src/seq_mv/vector_batched.c:251-330; the device twin loops over cuBLAS dots).  Columns >= nv of the
+// reduction land in the scratch slot `dump`.
+__global__ void __launch_bounds__(kRedThreads)
+mass_dot_kernel(const double *__restrict__ x, const double *__restrict__ Z, size_t zstride, int nv, size_t n,
+                double *partials, unsigned int *counter, double *scalars, int slot0, int dump)
+{
+   const size_t stride = (size_t) gridDim.x * kRedThreads;
+   double s[kMassNV];
+#pragma unroll
+   for (int k = 0; k < kMassNV; k++) s[k] = 0.0;
+   for (size_t i = (size_t) blockIdx.x * kRedThreads + threadIdx.x; i < n; i += stride) {
+      const double xi = x[i];
+#pragma unroll
+      for (int k = 0; k < kMassNV; k++) {
+         if (k < nv) s[k] += Z[(size_t) k * zstride + i] * xi;
+      }
+   }
+   __shared__ int slots[kMassNV];
+   if (threadIdx.x < kMassNV) slots[threadIdx.x] = ((int) threadIdx.x < nv) ? slot0 + (int) threadIdx.x : dump;
+   __syncthreads();
+   block_reduce_store<kMassNV>(s, partials, counter, scalars, slots);
+}
+
+int vec_mass_dot_dev(const double *x, const double *Z, size_t zstride, int nv, size_t n, int slot0, int dump,
+                     cudaStream_t st)
+{
+   Ctx &c = ctx();
+   HB_REQUIRE(nv >= 1 && nv <= kMassNV, HB200_ERROR_ARG, "vec_mass_dot_dev: 1..4 vectors per pass");
+   HB_LAUNCH(mass_dot_kernel, red_grid(n), kRedThreads, 0, st, x, Z, zstride, nv, n, c.d_partials, c.d_counter,
+             c.d_scalars, slot0, dump);
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
 int vec_dot_dev(const double *x, const double *y, size_t n, int slot, cudaStream_t st)
 {
    Ctx &c = ctx();

@@ -10,95 +10,9 @@
 // formed on the device by the kernels that consume them, and the host reads ONE block of
 // scalars per iteration for the convergence / breakdown decisions (the reference blocks on
 // MPI_Allreduce three times per iteration).
-#include "hb_internal.cuh"
-#include "hb_ew.cuh"
-#include "relax.cuh"
-#include <float.h>
-#include <math.h>
-#include <string.h>
+#include "krylov.cuh"
 
 namespace hb {
-int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
-              int *num_iterations, double *rel_resid_norm);
-// fused-dot request for the next amg_solve (preconditioner use): slot >= 0 asks the cycle's last
-// level-0 sweep for <u, f>; amg_dot_fused tells whether it delivered (else the caller runs dot_kernel)
-void amg_set_dot_request(hb200_amg *amg, int slot);
-bool amg_dot_fused(const hb200_amg *amg);
-}
-
-namespace hb {
-
-// device scalar slots used by the Krylov drivers
-// PCG: the three dots that close an iteration (<r,s> = gamma, <r,r>, flexible <r_old,s>) sit in one
-// block of adjacent slots so that ONE all-reduce serves them; two blocks alternate between
-// iterations because the previous gamma is still needed (beta = gamma / gamma_old)
-enum {
-   S_BB = 0, S_SDOTP = 1, S_FLAG = 2, S_ALPHA = 3,   // S_ALPHA = S_FLAG + 1 (pcg_update_xr_kernel)
-   S_BLK0 = 4, S_BLK1 = 8,                           // {gamma, rr, delta} of even / odd iterations
-   B_GAMMA = 0, B_RR = 1, B_DELTA = 2,
-   S_T0 = 12, S_T1 = 13,
-   S_NFETCH = 12,                                    // slots the host reads once per iteration
-   S_H0 = 16   // GMRES: hh column (k_dim + 1 entries, k_dim <= 100)
-};
-
-// dot_slot >= 0: the caller wants <r, z> in that scalar slot next; *dot_done says whether the
-// preconditioner's last kernel already produced it (fused epilogue, single rank, row-pattern A_0)
-static int precond_apply(int kind, hb200_amg *amg, hb200_parcsr *A, const double *r, double *z,
-                         int dot_slot = -1, bool *dot_done = nullptr)
-{
-   // the Krylov solvers always ClearVector(z) first => zero initial guess
-   Ctx &c = ctx();
-   const size_t n = (size_t) A->num_rows;
-   if (dot_done) *dot_done = false;
-   switch (kind) {
-      case HB200_PRECOND_AMG: {
-         amg_set_dot_request(amg, (dot_done && fused_dots_enabled() && c.nranks == 1) ? dot_slot : -1);
-         const int fl = amg_solve(amg, A, r, z, true, nullptr, nullptr) & ~HB200_ERROR_CONV;
-         if (dot_done) *dot_done = (fl == 0) && amg_dot_fused(amg);
-         amg_set_dot_request(amg, -1);
-         return fl;
-      }
-      case HB200_PRECOND_DIAGSCALE: {
-         const double *dg = nullptr;
-         HB_CHECK(parcsr_diag(A, &dg));
-         return vec_diag_scale(dg, r, z, n, c.s_comp);
-      }
-      default:   // hypre_ParKrylovIdentity: copy
-         return vec_copy(r, z, n, c.s_comp);
-   }
-}
-
-struct FAxpyDev {   // y += sign*S[slot] * x
-   const double *x; double *y; const double *S; int slot; double sign;
-   __device__ void operator()(size_t i) const
-   {
-      const double a = sign * S[slot];
-      y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
-   }
-};
-struct FScaleInvSqrtDev {   // y *= 1/sqrt(S[slot]) unless S[slot] == 0
-   double *y; const double *S; int slot;
-   __device__ void operator()(size_t i) const
-   {
-      const double t = sqrt(S[slot]);
-      if (t != 0.0) y[i] = __dmul_rn(y[i], 1.0 / t);
-   }
-};
-
-static int dot_global(const double *x, const double *y, size_t n, int slot)
-{
-   Ctx &c = ctx();
-   timer_tick(T_BLAS1);
-   HB_CHECK(vec_dot_dev(x, y, n, slot, c.s_comp));
-   timer_tick(T_OTHER);
-   return scalars_allreduce(slot, 1, c.s_comp);
-}
-
-static int dot_global_host(const double *x, const double *y, size_t n, double *out)
-{
-   HB_CHECK(dot_global(x, y, n, S_T0));
-   return scalars_fetch(S_T0, 1, out, ctx().s_comp);
-}
 
 // =======================================================================================
 // PCG
@@ -721,6 +635,7 @@ void hb200_gmres_default_params(hb200_gmres_params *p)
 {
    memset(p, 0, sizeof(*p));
    p->k_dim = 5; p->tol = 1.0e-06; p->max_iter = 1000;   // gmres.c:60-75
+   p->cgs = 1;                                            // cogmres.c:97
 }
 
 static int check_precond(int kind, hb200_amg *amg, hb200_parcsr *A)
@@ -796,11 +711,18 @@ int hb200_krylov_warmup(hb200_parcsr *A, int precond_kind, hb200_amg *amg, int i
       HB_CHECK(vec_set(db, 1.0, n, c.s_comp));
       HB_CHECK(vec_set(dx, 0.0, n, c.s_comp));
       int f;
-      if (is_gmres) {
+      if (is_gmres == 4) {
+         hb200_bicgstab_params P;
+         hb200_bicgstab_default_params(&P);
+         P.tol = 0.0; P.max_iter = 2;
+         f = hb200_bicgstab_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
+      } else if (is_gmres) {
          hb200_gmres_params P;
          hb200_gmres_default_params(&P);
          P.k_dim = k_dim > 0 ? k_dim : 5; P.tol = 0.0; P.max_iter = P.k_dim + 1; P.skip_real_r_check = 1;
-         f = hb200_gmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
+         if (is_gmres == 2) f = hb200_flexgmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
+         else if (is_gmres == 3) f = hb200_cogmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
+         else f = hb200_gmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
       } else {
          hb200_pcg_params P;
          hb200_pcg_default_params(&P);

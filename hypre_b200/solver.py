@@ -20,7 +20,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from ._lib import (GMRESParams, HB200Error, KrylovResult, PCGParams, check, lib)
+from ._lib import (BiCGSTABParams, GMRESParams, HB200Error, KrylovResult, PCGParams, check, lib)
 
 _initialized = False
 
@@ -412,6 +412,73 @@ class ParCSRGMRES(_Krylov):
         return res
 
 
+class ParCSRFlexGMRES(ParCSRGMRES):
+    """HYPRE_ParCSRFlexGMRES: hypre_FlexGMRESSolve (src/krylov/flexgmres.c:288) over the ParCSR function
+    table, default modify_pc."""
+    _dev, _host = "hb200_flexgmres_solve", "hb200_flexgmres_solve_host"
+
+    def __init__(self, tol: float = 1e-6, max_iter: int = 1000, k_dim: int = 20, a_tol: float = 0.0,
+                 min_iter: int = 0, cf_tol: float = 0.0, logging: int = 1, print_level: int = 0):
+        # hypre_FlexGMRESCreate: k_dim 20 (flexgmres.c:88)
+        super().__init__(tol=tol, max_iter=max_iter, k_dim=k_dim, a_tol=a_tol, min_iter=min_iter,
+                         cf_tol=cf_tol, logging=logging, print_level=print_level)
+
+    def solve(self, A: ParCSRMatrix, b, x) -> KrylovResult:
+        self.norms = np.zeros(self.params.max_iter + 2)
+        res = KrylovResult()
+        amg = self.precond.handle if self.precond_kind == PRECOND_AMG else None
+        host = isinstance(b, np.ndarray)
+        fn = getattr(lib, self._host if host else self._dev)
+        if not host:
+            _torch_sync(b, x)
+        flag = fn(A.handle, self.precond_kind, amg, C.byref(self.params), _ptr(b), _ptr(x),
+                  _ptr(self.norms), C.byref(res))
+        check(flag, allow_conv=True)
+        self.result = res
+        return res
+
+
+class ParCSRCOGMRES(ParCSRFlexGMRES):
+    """HYPRE_ParCSRCOGMRES: hypre_COGMRESSolve (src/krylov/cogmres.c:270): classical Gram-Schmidt over the
+    batched inner products / updates; cgs = 2 re-orthogonalises."""
+    _dev, _host = "hb200_cogmres_solve", "hb200_cogmres_solve_host"
+
+    def __init__(self, tol: float = 1e-6, max_iter: int = 1000, k_dim: int = 5, a_tol: float = 0.0,
+                 min_iter: int = 0, rel_change: int = 0, skip_real_r_check: int = 0, cgs: int = 1,
+                 cf_tol: float = 0.0, logging: int = 1, print_level: int = 0):
+        ParCSRGMRES.__init__(self, tol=tol, max_iter=max_iter, k_dim=k_dim, a_tol=a_tol, min_iter=min_iter,
+                             rel_change=rel_change, skip_real_r_check=skip_real_r_check, cf_tol=cf_tol,
+                             logging=logging, print_level=print_level)
+        self.params.cgs = cgs
+
+
+class ParCSRBiCGSTAB(_Krylov):
+    """HYPRE_ParCSRBiCGSTAB: hypre_BiCGSTABSolve (src/krylov/bicgstab.c:246) over the ParCSR function table."""
+
+    def __init__(self, tol: float = 1e-6, max_iter: int = 1000, a_tol: float = 0.0, min_iter: int = 0,
+                 cf_tol: float = 0.0, stop_crit: int = 0, logging: int = 1, print_level: int = 0):
+        super().__init__()
+        p = BiCGSTABParams()
+        lib.hb200_bicgstab_default_params(C.byref(p))
+        p.tol, p.max_iter, p.a_tol, p.min_iter, p.cf_tol, p.stop_crit = tol, max_iter, a_tol, min_iter, cf_tol, stop_crit
+        p.logging, p.print_level = logging, print_level
+        self.params = p
+
+    def solve(self, A: ParCSRMatrix, b, x) -> KrylovResult:
+        self.norms = np.zeros(self.params.max_iter + 2)
+        res = KrylovResult()
+        amg = self.precond.handle if self.precond_kind == PRECOND_AMG else None
+        host = isinstance(b, np.ndarray)
+        fn = lib.hb200_bicgstab_solve_host if host else lib.hb200_bicgstab_solve
+        if not host:
+            _torch_sync(b, x)
+        flag = fn(A.handle, self.precond_kind, amg, C.byref(self.params), _ptr(b), _ptr(x),
+                  _ptr(self.norms), C.byref(res))
+        check(flag, allow_conv=True)
+        self.result = res
+        return res
+
+
 def relax(A: ParCSRMatrix, f, u, relax_type: int, relax_points: int = 0, relax_weight: float = 1.0,
           omega: float = 1.0, l1_norms=None, cf_marker=None, u_all_zeros: bool = False, vtemp=None):
     """hypre_BoomerAMGRelax on device vectors (l1_norms / cf_marker: torch CUDA tensors)."""
@@ -479,7 +546,8 @@ def amg_from_hierarchy(h, use_graph: bool = False):
 
 __all__ = [
     "init", "finalize", "comm_init", "comm_get_unique_id", "sync", "launch_count",
-    "ParCSRMatrix", "BoomerAMG", "ParCSRPCG", "ParCSRGMRES", "relax", "cheby_solve",
+    "ParCSRMatrix", "BoomerAMG", "ParCSRPCG", "ParCSRGMRES", "ParCSRFlexGMRES", "ParCSRCOGMRES",
+    "ParCSRBiCGSTAB", "relax", "cheby_solve",
     "inner_prod", "axpy", "amg_from_hierarchy", "HB200Error", "KrylovResult",
     "PRECOND_NONE", "PRECOND_AMG", "PRECOND_DIAGSCALE",
 ]

@@ -320,7 +320,7 @@ int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
  * allocate the work vectors there): allocates the persistent Krylov workspace and runs a few
  * iterations on b = 1, x = 0 inside it so that halo plans, smoother scratch and the captured V-cycle
  * graphs of the solve exist before the application times its Solve call.  is_gmres: 0 = PCG, 1 =
- * GMRES(k_dim).  Collective. */
+ * GMRES(k_dim), 2 = FlexGMRES(k_dim), 3 = COGMRES(k_dim), 4 = BiCGSTAB.  Collective. */
 int hb200_krylov_warmup(hb200_parcsr *A, int precond_kind, hb200_amg *amg, int is_gmres, int k_dim);
 
 /* Same call with HOST b and x (what HYPRE_PCGSolve sees in a CPU-memory application):
@@ -335,6 +335,7 @@ typedef struct {
    double tol, a_tol, cf_tol;
    int    k_dim, min_iter, max_iter, rel_change, skip_real_r_check, stop_crit, hybrid;
    int    logging, print_level;
+   int    cgs, unroll;    /* COGMRES only (cogmres.h: cgs = 2 re-orthogonalises; the device kernels have one unrolling) */
 } hb200_gmres_params;
 
 void hb200_gmres_default_params(hb200_gmres_params *p);   /* hypre_GMRESCreate, gmres.c:52-110 */
@@ -346,6 +347,48 @@ int hb200_gmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
 int hb200_gmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                            const hb200_gmres_params *params, const double *b_host,
                            double *x_host, double *norms, hb200_krylov_result *result);
+
+/* ------------------------------------------------------------------------------------ */
+/* (f4) the other Krylov drivers of the ParCSR function table                              */
+/* ------------------------------------------------------------------------------------ */
+
+/* hypre_FlexGMRESSolve (src/krylov/flexgmres.c:288-812), table of HYPRE_ParCSRFlexGMRESCreate
+ * (src/parcsr_ls/HYPRE_parcsr_flexgmres.c:15-45) with the default modify_pc (a no-op).  Reads k_dim, tol,
+ * a_tol, cf_tol, min_iter, max_iter, logging, print_level (<= 2). */
+int hb200_flexgmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                          const hb200_gmres_params *params, const double *b_dev, double *x_dev,
+                          double *norms, hb200_krylov_result *result);
+int hb200_flexgmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                               const hb200_gmres_params *params, const double *b_host,
+                               double *x_host, double *norms, hb200_krylov_result *result);
+
+/* hypre_COGMRESSolve (src/krylov/cogmres.c:270-896), table of HYPRE_ParCSRCOGMRESCreate
+ * (src/parcsr_ls/HYPRE_parcsr_cogmres.c:15-50): classical Gram-Schmidt through the batched vector
+ * operations hypre_ParVectorMassInnerProd / MassDotpTwo / MassAxpy (src/parcsr_mv/par_vector_batched.c:
+ * 17-135).  params->cgs = 2: the re-orthogonalising variant (k_dim <= 50). */
+int hb200_cogmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                        const hb200_gmres_params *params, const double *b_dev, double *x_dev,
+                        double *norms, hb200_krylov_result *result);
+int hb200_cogmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                             const hb200_gmres_params *params, const double *b_host,
+                             double *x_host, double *norms, hb200_krylov_result *result);
+
+/* user-settable part of hypre_BiCGSTABData (src/krylov/bicgstab.h:70-108) */
+typedef struct {
+   double tol, a_tol, cf_tol;
+   int    min_iter, max_iter, stop_crit, hybrid;
+   int    logging, print_level;
+} hb200_bicgstab_params;
+
+void hb200_bicgstab_default_params(hb200_bicgstab_params *p);   /* hypre_BiCGSTABCreate, bicgstab.c:64-106 */
+/* hypre_BiCGSTABSolve (src/krylov/bicgstab.c:246-606), table of HYPRE_ParCSRBiCGSTABCreate
+ * (src/parcsr_ls/HYPRE_parcsr_bicgstab.c:15-40). */
+int hb200_bicgstab_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                         const hb200_bicgstab_params *params, const double *b_dev, double *x_dev,
+                         double *norms, hb200_krylov_result *result);
+int hb200_bicgstab_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                              const hb200_bicgstab_params *params, const double *b_host,
+                              double *x_host, double *norms, hb200_krylov_result *result);
 
 #ifdef __cplusplus
 }

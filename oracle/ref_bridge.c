@@ -621,6 +621,97 @@ int rb_gmres_solve(rb_problem *pb, int precond, double tol, double atol, int max
    return k;
 }
 
+/* ij -solver 9 / 10 (BiCGSTAB, ij.c:8660-8690), 16 / 17 (COGMRES, ij.c:9088-9110), 61 / 60 (FlexGMRES,
+ * ij.c:8226-8245) over the same ParCSR table: which = 0 BiCGSTAB, 1 FlexGMRES, 2 COGMRES; cgs only COGMRES */
+int rb_krylov_ext_solve(rb_problem *pb, int which, int precond, double tol, double atol, int max_iter,
+                        int k_dim, int cgs, int rel_change, const double *b_in, double *x_io,
+                        int *num_iterations, double *final_res_norm, double *norms, double *solve_seconds)
+{
+   HYPRE_Solver ks;
+   hypre_ParCSRMatrix *M = (hypre_ParCSRMatrix *) pb->A;
+   HYPRE_BigInt g = hypre_ParCSRMatrixGlobalNumRows(M), *st = hypre_ParCSRMatrixRowStarts(M);
+   hypre_ParVector *vb = make_vec(pb, g, st, b_in ? b_in : rb_problem_b(pb));
+   hypre_ParVector *vx = make_vec(pb, g, st, x_io ? x_io : rb_problem_x(pb));
+   HYPRE_PtrToSolverFcn pc = NULL, pcs = (HYPRE_PtrToSolverFcn) HYPRE_ParCSRDiagScaleSetup;
+   HYPRE_Solver pcd = NULL;
+   HYPRE_Int its = 0;
+   HYPRE_Real fr = 0.0, *nr = NULL;
+   double t0;
+   int k;
+   if (precond == 1) { pc = (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSolve; pcd = pb->amg; }
+   else if (precond == 2) { pc = (HYPRE_PtrToSolverFcn) HYPRE_ParCSRDiagScale; }
+   if (which == 0)
+   {
+      HYPRE_ParCSRBiCGSTABCreate(pb->comm, &ks);
+      HYPRE_BiCGSTABSetMaxIter(ks, max_iter);
+      HYPRE_BiCGSTABSetTol(ks, tol);
+      HYPRE_BiCGSTABSetAbsoluteTol(ks, atol);
+      HYPRE_BiCGSTABSetLogging(ks, 1);
+      HYPRE_BiCGSTABSetPrintLevel(ks, 0);
+      if (pc) { HYPRE_BiCGSTABSetPrecond(ks, pc, pcs, pcd); }
+      HYPRE_BiCGSTABSetup(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      t0 = wall();
+      HYPRE_BiCGSTABSolve(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      if (solve_seconds) { *solve_seconds = wall() - t0; }
+      HYPRE_BiCGSTABGetNumIterations(ks, &its);
+      HYPRE_BiCGSTABGetFinalRelativeResidualNorm(ks, &fr);
+      nr = ((hypre_BiCGSTABData *) ks)->norms;
+   }
+   else if (which == 1)
+   {
+      HYPRE_ParCSRFlexGMRESCreate(pb->comm, &ks);
+      HYPRE_FlexGMRESSetKDim(ks, k_dim);
+      HYPRE_FlexGMRESSetMaxIter(ks, max_iter);
+      HYPRE_FlexGMRESSetTol(ks, tol);
+      HYPRE_FlexGMRESSetAbsoluteTol(ks, atol);
+      HYPRE_FlexGMRESSetLogging(ks, 1);
+      HYPRE_FlexGMRESSetPrintLevel(ks, 0);
+      if (pc) { HYPRE_FlexGMRESSetPrecond(ks, pc, pcs, pcd); }
+      HYPRE_FlexGMRESSetup(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      t0 = wall();
+      HYPRE_FlexGMRESSolve(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      if (solve_seconds) { *solve_seconds = wall() - t0; }
+      HYPRE_FlexGMRESGetNumIterations(ks, &its);
+      HYPRE_FlexGMRESGetFinalRelativeResidualNorm(ks, &fr);
+      nr = ((hypre_FlexGMRESData *) ks)->norms;
+   }
+   else
+   {
+      HYPRE_ParCSRCOGMRESCreate(pb->comm, &ks);
+      HYPRE_COGMRESSetKDim(ks, k_dim);
+      HYPRE_COGMRESSetCGS(ks, cgs);
+      HYPRE_COGMRESSetMaxIter(ks, max_iter);
+      HYPRE_COGMRESSetTol(ks, tol);
+      HYPRE_COGMRESSetAbsoluteTol(ks, atol);
+      HYPRE_COGMRESSetLogging(ks, 1);
+      HYPRE_COGMRESSetPrintLevel(ks, 0);
+      ((hypre_COGMRESData *) ks)->rel_change = rel_change;   /* no public setter in 3.1.0 */
+      if (pc) { HYPRE_COGMRESSetPrecond(ks, pc, pcs, pcd); }
+      HYPRE_COGMRESSetup(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      t0 = wall();
+      HYPRE_COGMRESSolve(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      if (solve_seconds) { *solve_seconds = wall() - t0; }
+      HYPRE_COGMRESGetNumIterations(ks, &its);
+      HYPRE_COGMRESGetFinalRelativeResidualNorm(ks, &fr);
+      nr = ((hypre_COGMRESData *) ks)->norms;
+   }
+   if (norms && nr)
+   {
+      /* BiCGSTAB logs every iteration; the GMRES family keeps norms[iter] only when printing (norms[0] always) */
+      for (k = 0; k <= its && k <= max_iter; k++) { norms[k] = nr[k]; }
+   }
+   if (num_iterations) { *num_iterations = (int) its; }
+   if (final_res_norm) { *final_res_norm = fr; }
+   if (x_io) { take_vec(vx, x_io); }
+   if (which == 0) { HYPRE_ParCSRBiCGSTABDestroy(ks); }
+   else if (which == 1) { HYPRE_ParCSRFlexGMRESDestroy(ks); }
+   else { HYPRE_ParCSRCOGMRESDestroy(ks); }
+   hypre_ParVectorDestroy(vb); hypre_ParVectorDestroy(vx);
+   k = (int) HYPRE_GetError();
+   HYPRE_ClearAllErrors();
+   return k;
+}
+
 /* reference BLAS-1 (hypre_ParVectorInnerProd / Axpy) on raw arrays of the fine-level size */
 double rb_inner_prod(rb_problem *pb, const double *x, const double *y)
 {

@@ -114,6 +114,7 @@ def load(mpi=None) -> C.CDLL:
         "rb_level_vector": ([vp, C.c_int, C.c_int, vp], C.c_int),
         "rb_pcg_solve": ([vp, C.c_int, C.c_double, C.c_double] + [C.c_int] * 5 + [vp, vp, c_int_p, dp, vp, dp], C.c_int),
         "rb_gmres_solve": ([vp, C.c_int, C.c_double, C.c_double] + [C.c_int] * 3 + [vp, vp, c_int_p, dp, vp, dp], C.c_int),
+        "rb_krylov_ext_solve": ([vp, C.c_int, C.c_int, C.c_double, C.c_double] + [C.c_int] * 4 + [vp, vp, c_int_p, dp, vp, dp], C.c_int),
         "rb_inner_prod": ([vp, vp, vp], C.c_double),
         "rb_axpy": ([vp, C.c_double, vp, vp], C.c_int),
     }
@@ -319,6 +320,20 @@ class Problem:
         bb = None if b is None else np.ascontiguousarray(b, np.float64)
         flag = self.lib.rb_gmres_solve(self.h, pk, tol, atol, max_iter, k_dim, rel_change, _p(bb),
                                        _p(x), C.byref(its), C.byref(fr), _p(norms), C.byref(t))
+        return {"iterations": its.value, "final_rel_res": fr.value, "norms": norms[: its.value + 1],
+                "x": x, "seconds": t.value, "error_flag": flag}
+
+    def krylov_ext(self, which, precond="amg", tol=1e-8, atol=0.0, max_iter=100, k_dim=5, cgs=1, rel_change=0,
+                   b=None, x0=None) -> dict:
+        """ij -solver 9/10 (which="bicgstab"), 61/60 ("flexgmres"), 16/17 ("cogmres") with BoomerAMG / diagonal scaling"""
+        wk = {"bicgstab": 0, "flexgmres": 1, "cogmres": 2}[which]
+        pk = {"none": 0, "amg": 1, "diagscale": 2}[precond]
+        its, fr, t = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+        norms = np.zeros(max_iter + 2)
+        x = np.array(self.x0 if x0 is None else x0, dtype=np.float64, copy=True)
+        bb = None if b is None else np.ascontiguousarray(b, np.float64)
+        flag = self.lib.rb_krylov_ext_solve(self.h, wk, pk, tol, atol, max_iter, k_dim, cgs, rel_change, _p(bb),
+                                            _p(x), C.byref(its), C.byref(fr), _p(norms), C.byref(t))
         return {"iterations": its.value, "final_rel_res": fr.value, "norms": norms[: its.value + 1],
                 "x": x, "seconds": t.value, "error_flag": flag}
 

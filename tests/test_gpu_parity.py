@@ -522,6 +522,65 @@ def test_gmres_amg_nonsymmetric(vdc, hb, torch):
     assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-7
 
 
+# the other Krylov drivers of the ParCSR function table: BiCGSTAB, FlexGMRES, COGMRES
+def _ext_solver(hb, which, **kw):
+    return {"bicgstab": hb.ParCSRBiCGSTAB, "flexgmres": hb.ParCSRFlexGMRES, "cogmres": hb.ParCSRCOGMRES}[which](**kw)
+
+
+@pytest.mark.parametrize("which,kw", [("bicgstab", {}), ("flexgmres", dict(k_dim=5)), ("cogmres", dict(k_dim=5)),
+                                      ("cogmres", dict(k_dim=5, cgs=2)), ("cogmres", dict(k_dim=3, rel_change=1))])
+def test_krylov_ext_amg_nonsymmetric(vdc, hb, torch, which, kw):
+    ref = vdc.pb.krylov_ext(which, precond="amg", tol=1e-8, max_iter=100, **kw)
+    assert ref["error_flag"] == 0
+    A = vdc.mats[0][0]
+    ks = _ext_solver(hb, which, tol=1e-8, max_iter=100, **kw)
+    ks.set_precond(vdc.amg)
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    ks.solve(A, dev(torch, vdc.pb.b), x)
+    assert ks.num_iterations == ref["iterations"]
+    assert abs(ks.norms[0] - ref["norms"][0]) <= 1e-12 * ref["norms"][0]
+    if which == "bicgstab":   # logs every iteration (bicgstab.c:519-522)
+        assert relerr(ks.norms[: ref["iterations"] + 1], ref["norms"]) <= 1e-8
+    assert abs(ks.final_relative_residual_norm - ref["final_rel_res"]) <= 1e-3 * ref["final_rel_res"]
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-7
+    # host-buffer entry point gives the same answer
+    xh = np.zeros(A.num_rows)
+    ks.solve(A, np.array(vdc.pb.b), xh)
+    assert np.array_equal(xh, x.cpu().numpy())
+
+
+@pytest.mark.parametrize("which,kw", [("bicgstab", {}), ("flexgmres", dict(k_dim=10)), ("cogmres", dict(k_dim=10)),
+                                      ("cogmres", dict(k_dim=7, cgs=2))])
+def test_krylov_ext_diagscale_restarts(lap7, hb, torch, which, kw):
+    # diagonal scaling: many iterations, many restarts of the short bases
+    ref = lap7.pb.krylov_ext(which, precond="diagscale", tol=1e-8, max_iter=500, **kw)
+    A = lap7.mats[0][0]
+    ks = _ext_solver(hb, which, tol=1e-8, max_iter=500, **kw)
+    ks.set_precond("diagscale")
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    ks.solve(A, dev(torch, lap7.pb.b), x)
+    if which == "bicgstab":
+        # unpreconditioned BiCGSTAB amplifies rounding differences of the dots by ~10x every three iterations
+        # (1e-14 at iteration 3, 1e-9 at 15 on this problem): the histories agree while that is small, both runs
+        # reach the tolerance within a few iterations of each other
+        assert relerr(ks.norms[:13], ref["norms"][:13]) <= 1e-8
+        assert abs(ks.num_iterations - ref["iterations"]) <= 6
+    else:
+        assert abs(ks.num_iterations - ref["iterations"]) <= 1
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-6
+
+
+def test_mass_inner_products_match_single_dots(lap7, hb, torch):
+    # COGMRES with a long basis drives the batched dots through every chunk size (1..4 vectors per pass)
+    ref = lap7.pb.krylov_ext("cogmres", precond="none", tol=1e-6, max_iter=30, k_dim=11)
+    A = lap7.mats[0][0]
+    ks = hb.ParCSRCOGMRES(tol=1e-6, max_iter=30, k_dim=11)
+    x = torch.zeros(A.num_rows, dtype=torch.float64, device="cuda")
+    ks.solve(A, dev(torch, lap7.pb.b), x)
+    assert ks.num_iterations == ref["iterations"]
+    assert relerr(x.cpu().numpy(), ref["x"]) <= 1e-9
+
+
 def test_zero_rhs_and_errors(lap7, hb, torch):
     A = lap7.mats[0][0]
     pcg = hb.ParCSRPCG(tol=1e-8, max_iter=10, two_norm=1)
@@ -678,7 +737,7 @@ def _ij(binary, args, nprocs=1, env_extra=None):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ref, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     its = re.findall(r"Iterations = (\d+)", r.stdout)
-    res = re.findall(r"Final (?:GMRES )?Relative Residual Norm = ([0-9.eE+-]+)", r.stdout)
+    res = re.findall(r"Final (?:\w+ )?Relative Residual Norm = ([0-9.eE+-]+)", r.stdout)
     return (int(its[-1]) if its else None, float(res[-1]) if res else None, r.stdout, r.stderr)
 
 
@@ -688,7 +747,11 @@ def _ij(binary, args, nprocs=1, env_extra=None):
                                   "-vardifconv -n 30 30 30 -solver 3 -rlx 18",
                                   "-laplacian -n 30 30 30 -solver 2",
                                   "-laplacian -n 30 30 30 -solver 1 -rlx 16",
-                                  "-laplacian -n 30 30 30 -solver 1 -rlx 18 -CF 1 -mu 2"])
+                                  "-laplacian -n 30 30 30 -solver 1 -rlx 18 -CF 1 -mu 2",
+                                  "-vardifconv -n 30 30 30 -solver 9 -rlx 18",     # AMG-BiCGSTAB
+                                  "-vardifconv -n 30 30 30 -solver 16 -rlx 18",    # AMG-COGMRES
+                                  "-vardifconv -n 30 30 30 -solver 61 -rlx 18",    # AMG-FlexGMRES
+                                  "-27pt -n 20 20 20 -solver 17"])                 # DS-COGMRES: 11 restarts
 def test_ij_dropin_matches_reference(args):
     its_ref, res_ref, _, _ = _ij("ij_ref", args)
     its_dev, res_dev, out, err = _ij("ij_b200", args)
@@ -696,7 +759,9 @@ def test_ij_dropin_matches_reference(args):
     assert its_dev == its_ref, (args, its_dev, its_ref)
     # PCG: final residual to the 7 digits the reference's regression suite compares; GMRES: the
     # Givens-recurrence residual estimate is only reproducible to a few per cent at 1e-9
-    rtol = 5e-2 if "-solver 3" in args else 2e-6
+    # (the same holds for COGMRES / FlexGMRES; BiCGSTAB's closing true residual sits at the cancellation level)
+    solver_id = int(args.split("-solver")[1].split()[0])
+    rtol = 2e-6 if solver_id in (1, 2) else 5e-2
     assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
 
 

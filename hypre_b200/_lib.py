@@ -116,6 +116,8 @@ def _load() -> C.CDLL:
         "hb200_cheby_solve": ([vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "hb200_amg_create": ([C.POINTER(vp), C.c_int], C.c_int),
         "hb200_amg_destroy": ([vp], C.c_int),
+        "hb200_parcsr_set_gs_chunks": ([vp, C.c_int], C.c_int),
+        "hb200_gs_auto_chunks": ([C.c_int], C.c_int),
         "hb200_amg_set_level": ([vp, C.c_int, vp, vp, vp, vp, C.c_double, C.c_double], C.c_int),
         "hb200_amg_set_level_cheby": ([vp, C.c_int, vp, vp, C.c_int], C.c_int),
         "hb200_amg_set_cycle": ([vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),

@@ -6,7 +6,20 @@
 // (src/parcsr_ls/par_relax.h:12-110, 238-330), single-thread semantics (the reference's
 // OpenMP variant changes the result with the thread count).
 //
-// GPU formulation: the sequential sweep is a sparse triangular dependency graph.  At first
+// Two device formulations, selected per matrix by hb200_parcsr_set_gs_chunks (the reference's
+// hypre_NumThreads(), par_relax.c:727):
+//
+//  * chunks <= 1: the 1-thread reference, exactly (below: wavefronts);
+//  * chunks = T > 1: the reference's OpenMP semantics with T threads (par_relax.c:868-896 over
+//    hypre_HybridGaussSeidelNSThreads / hypre_HybridGaussSeidelThreads, par_relax.h:107-218, 332-440): rows are
+//    cut into T contiguous chunks by hypre_partition1D, Gauss-Seidel inside a chunk, the values of all other
+//    chunks frozen at their state before the call (Vtemp).  One group of K lanes walks one chunk row after
+//    row, 32 / K chunks per warp in lock step, ONE launch per call whatever the matrix: with a few thousand
+//    chunks the sweep is bound by the HBM stream of the CSR block like the Jacobi sweep, not by launches.
+//    The result is the reference's at OMP_NUM_THREADS = T (tests run both at the same T); the l1 norms of
+//    the l1 variants belong to the same T (hypre_ParCSRComputeL1NormsThreads, ams.c:4523).
+//
+// Wavefront formulation: the sequential sweep is a sparse triangular dependency graph.  At first
 // use the rows are grouped into wavefronts (level schedule) of the *symmetrised* pattern, so
 // that every row in a wavefront (a) has all its lower-index neighbours finished and (b) is
 // not read by any row of the same wavefront; the sweep is then one launch per wavefront over
@@ -194,19 +207,116 @@ static int gs_sweep(hb200_parcsr *A, const GsSched *s, bool forward, const GsArg
    return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// T chunks (the reference with T OpenMP threads)
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+gs_chunk_kernel(int n, int T, int nsweeps, int gs_order, GsArgs g)
+{
+   constexpr int G = 32 / K;   // chunks per warp
+   const int warp   = (int) ((blockIdx.x * 256u + threadIdx.x) >> 5);
+   const int lane32 = threadIdx.x & 31;
+   const int lane   = lane32 % K;
+   const int chunk  = warp * G + lane32 / K;
+   // hypre_partition1D (utilities/general.c): the first `rest` chunks hold one row more
+   const int size = n / T, rest = n - size * T;
+   int ns = 0, ne = 0;
+   if (chunk < T) {
+      if (chunk < rest) { ns = chunk * (size + 1); ne = ns + size + 1; }
+      else              { ns = chunk * size + rest; ne = ns + size; }
+   }
+   const int cnt = ne - ns;
+   const int maxrows = size + (rest ? 1 : 0);   // the same for every lane: the loops below stay warp-uniform
+   for (int sw = 0; sw < nsweeps; sw++) {
+      const int iorder = nsweeps == 1 ? gs_order : (sw == 0 ? 1 : -1);
+      for (int step = 0; step < maxrows; step++) {
+         const bool have = step < cnt;
+         const int i = iorder > 0 ? ns + step : ne - 1 - step;
+         bool relax = false;
+         double d = 0.0;
+         double res = 0.0, res0 = 0.0, res2 = 0.0;   // frozen part (other chunks + offd), own chunk (current), own chunk (old)
+         if (have) {
+            d = g.l1 ? g.l1[i] : g.da[g.di[i]];
+            relax = (g.relax_points == 0 || g.cf[i] == g.relax_points) && d != 0.0;
+         }
+         if (relax) {
+            const int p1 = g.di[i + 1];
+            for (int p = g.di[i] + g.skip_diag + lane; p < p1; p += K) {
+               const int ii = g.dj[p];
+               const double a = g.da[p];
+               if (ii >= ns && ii < ne) {
+                  res0 -= a * g.u[ii];                       // rows of this chunk: written by lane 0 of this group only
+                  if (!g.non_scale) res2 += a * g.vtmp[ii];
+               } else {
+                  res -= a * g.vtmp[ii];
+               }
+            }
+            if (g.oi) {
+               const int q1 = g.oi[i + 1];
+               for (int q = g.oi[i] + lane; q < q1; q += K) res -= g.oa[q] * g.vext[g.oj[q]];
+            }
+         }
+#pragma unroll
+         for (int o = K / 2; o > 0; o >>= 1) {
+            res  += __shfl_down_sync(0xffffffffu, res, o, K);
+            res0 += __shfl_down_sync(0xffffffffu, res0, o, K);
+            res2 += __shfl_down_sync(0xffffffffu, res2, o, K);
+         }
+         if (relax && lane == 0) {
+            if (g.non_scale) {
+               // par_relax.h:150-176: res = f - sum ; u = res/d  or  u += res/d
+               const double r = g.f[i] + res + res0;
+               if (g.skip_diag) g.u[i] = r / d;
+               else             g.u[i] = g.u[i] + r / d;
+            } else {
+               // par_relax.h:376-400
+               const double r = g.f[i] + res;
+               double ui = g.u[i];
+               if (g.skip_diag) ui *= g.prod;
+               ui += g.w * (g.omega * r + res0 + g.one_minus_omega * res2) / d;
+               g.u[i] = ui;
+            }
+         }
+         __syncwarp();   // the next row of the chunk reads what lane 0 just wrote
+      }
+   }
+}
+
+static int gs_chunks_launch(hb200_parcsr *A, int nsweeps, int gs_order, const GsArgs &g)
+{
+   Ctx &c = ctx();
+   const int n = A->num_rows, T = A->gs_chunks;
+   if (n == 0) return 0;
+   const double avg = A->diag.avg_row_nnz;
+   const int K = avg >= 40 ? 32 : avg >= 20 ? 16 : avg >= 6 ? 8 : 4;
+   const int G = 32 / K;
+   const long long warps = ((long long) T + G - 1) / G;
+   const int grid = (int) ((warps + 7) / 8);
+   switch (K) {
+      case 4:  HB_LAUNCH((gs_chunk_kernel<4>),  grid, 256, 0, c.s_comp, n, T, nsweeps, gs_order, g); break;
+      case 8:  HB_LAUNCH((gs_chunk_kernel<8>),  grid, 256, 0, c.s_comp, n, T, nsweeps, gs_order, g); break;
+      case 16: HB_LAUNCH((gs_chunk_kernel<16>), grid, 256, 0, c.s_comp, n, T, nsweeps, gs_order, g); break;
+      default: HB_LAUNCH((gs_chunk_kernel<32>), grid, 256, 0, c.s_comp, n, T, nsweeps, gs_order, g); break;
+   }
+   HB_LAUNCH_CHECK();
+   return 0;
+}
+
 static int gs_core(hb200_parcsr *A, const double *f, const int *cf, int relax_points, double w,
                    double omega, const double *l1, double *u, double *vtemp, int gs_order,
                    int symm, int skip_diag)
 {
    // hypre_BoomerAMGRelaxHybridGaussSeidel_core, num_threads == 1 branch (par_relax.c:905-936)
    Ctx &c = ctx();
+   const bool chunked = A->gs_chunks > 1 && A->num_rows > 0;
    GsSched *s = nullptr;
-   HB_CHECK(gs_get_sched(A, &s));
+   if (!chunked) HB_CHECK(gs_get_sched(A, &s));
    const int non_scale = (w == 1.0 && omega == 1.0);
    // halo exchange of u, once per call (par_relax.c:806-835), frozen during the sweep(s)
    HB_CHECK(parcsr_halo_begin(A, u, c.s_comp));
-   if (!non_scale) {
-      HB_REQUIRE(vtemp != nullptr || A->num_rows == 0, HB200_ERROR_ARG, "scaled hybrid GS needs vtemp");
+   if (!non_scale || chunked) {
+      HB_REQUIRE(vtemp != nullptr || A->num_rows == 0, HB200_ERROR_ARG, "scaled / chunked hybrid GS needs vtemp");
       HB_CHECK(vec_copy(u, vtemp, (size_t) A->num_rows, c.s_comp));   // par_relax.c:857-866
    }
    HB_CHECK(parcsr_halo_end(A, c.s_comp));
@@ -221,6 +331,9 @@ static int gs_core(hb200_parcsr *A, const double *f, const int *cf, int relax_po
    const double avg = A->diag.avg_row_nnz;
    const int K = avg >= 48 ? 16 : avg >= 20 ? 8 : avg >= 8 ? 4 : avg >= 3 ? 2 : 1;
    const int nsweeps = symm ? 2 : 1;
+   // T chunks: both sweeps of a symmetric call stay inside the chunk, against the same frozen copy
+   // (par_relax.c:876-895)
+   if (chunked) return gs_chunks_launch(A, nsweeps, gs_order > 0 ? 1 : -1, g);
    for (int sw = 0; sw < nsweeps; sw++) {
       const int iorder = nsweeps == 1 ? (gs_order > 0 ? 1 : -1) : (sw == 0 ? 1 : -1);
       HB_CHECK(gs_sweep(A, s, iorder > 0, g, K));
@@ -252,6 +365,25 @@ int relax_hybrid_gs(hb200_parcsr *A, const double *f, const int *cf, int relax_t
 }
 
 }  // namespace hb
+
+// hypre_NumThreads() of the hybrid Gauss-Seidel sweeps on this matrix (see the header of this file)
+extern "C" int hb200_parcsr_set_gs_chunks(hb200_parcsr *A, int num_chunks)
+{
+   using namespace hb;
+   HB_REQUIRE(A != nullptr && num_chunks >= 0, HB200_ERROR_ARG, "hb200_parcsr_set_gs_chunks: bad argument");
+   A->gs_chunks = (num_chunks > A->num_rows) ? A->num_rows : num_chunks;
+   return 0;
+}
+
+// the chunk count the device prefers for a block of num_rows rows: enough chunks to keep every SM's
+// warps busy (148 SMs x 32 warps x 4 chunks), at least 32 rows per chunk
+extern "C" int hb200_gs_auto_chunks(int num_rows)
+{
+   const long long cap = (long long) hb::kNumSMs * 32 * 4;
+   long long t = num_rows / 32;
+   if (t > cap) t = cap;
+   return t < 1 ? 1 : (int) t;
+}
 
 // host half of the hybrid-GS path, reachable without a GPU (CPU tests of the schedule)
 extern "C" int hb200_host_gs_schedule(int num_rows, const int *row_ptr, const int *col_ind, int forward,

@@ -373,6 +373,7 @@ struct hb200_parcsr {
    bool     keep_host = true;
    // level schedule of the diag block for hybrid Gauss-Seidel (relax.cu), built lazily
    void    *gs_sched = nullptr;
+   int      gs_chunks = 0;            // hybrid GS: the reference's thread count (0 / 1: sequential sweep)
 };
 
 namespace hb {

@@ -446,6 +446,41 @@ static const char *amg_unsupported(hypre_ParAMGData *amg, MPI_Comm comm)
    return g_reasons[v->code];
 }
 
+/* Hybrid Gauss-Seidel smoothers (3, 4, 6, 8, 13, 14, 88, 89): the reference's sweep depends on its thread count
+ * (par_relax.c:727, 868-896).  Default: the sequential sweep (one thread), as before.  HYPRE_B200_GS_CHUNKS =
+ * host: hypre_NumThreads() chunks (the numbers of the OpenMP run this library replaces); = auto: the chunk
+ * count the device prefers (one launch per sweep, HBM-bound); = N: N chunks.  The l1 norms of the l1 variants
+ * depend on the same partition: when it differs from the one the setup ran with they are recomputed by the
+ * reference's own routine (hypre_ParCSRComputeL1NormsThreads, ams.c:4523; options as par_amg_setup.c:3296-3349). */
+static int gs_chunks_wanted(int num_rows)
+{
+   const char *e = getenv("HYPRE_B200_GS_CHUNKS");
+   if (!e || !*e) { return 0; }
+   if (!strcmp(e, "auto")) { return hb200_gs_auto_chunks(num_rows); }
+   if (!strcmp(e, "host")) { return hypre_NumThreads(); }
+   return atoi(e);
+}
+
+static int gs_l1_option(hypre_ParAMGData *amg, int level, int num_levels)
+{
+   const HYPRE_Int *t = hypre_ParAMGDataGridRelaxType(amg);
+   int opt = 0, k, k0 = (level < num_levels - 1) ? 1 : 3, k1 = (level < num_levels - 1) ? 2 : 3;
+   for (k = k0; k <= k1; k++) { if (t[k] == 8 || t[k] == 89 || t[k] == 13 || t[k] == 14) { opt = 4; } }
+   for (k = k0; k <= k1; k++) { if (t[k] == 88) { opt = 6; } }
+   return opt;
+}
+
+static int level_uses_gs(hypre_ParAMGData *amg, int level, int num_levels)
+{
+   const HYPRE_Int *t = hypre_ParAMGDataGridRelaxType(amg);
+   int k, k0 = (level < num_levels - 1) ? 1 : 3, k1 = (level < num_levels - 1) ? 2 : 3;
+   for (k = k0; k <= k1; k++)
+   {
+      if (t[k] == 3 || t[k] == 4 || t[k] == 6 || t[k] == 8 || t[k] == 13 || t[k] == 14 || t[k] == 88 || t[k] == 89) { return 1; }
+   }
+   return 0;
+}
+
 static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
 {
    hypre_ParAMGData *amg = (hypre_ParAMGData *) amg_vdata;
@@ -493,8 +528,15 @@ static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
       /* level 0 is the caller's matrix (par_amg_solve.c:108), mirrored once and shared with the Krylov solver */
       hb200_parcsr *dA = (l == 0) ? mirror_matrix(A0) : upload_matrix(A_array[l]);
       hb200_parcsr *dP = NULL;
-      int uses_cheby = 0, k;
+      int uses_cheby = 0, k, chunks = 0;
+      HYPRE_Real *l1_alt = NULL;
       if (!dA) { goto fail; }
+      if (level_uses_gs(amg, l, nl)) { chunks = gs_chunks_wanted(hypre_ParCSRMatrixNumRows(A_array[l])); }
+      if (chunks > 1 && chunks != hypre_NumThreads() && gs_l1_option(amg, l, nl))
+      {
+         HYPRE_Int *cfl = (hypre_ParAMGDataRelaxOrder(amg) && l < nl - 1 && cf && cf[l]) ? hypre_IntArrayData(cf[l]) : NULL;
+         hypre_ParCSRComputeL1NormsThreads(A_array[l], gs_l1_option(amg, l, nl), chunks, cfl, &l1_alt);
+      }
       if (l > 0) { m->owned[m->num_owned++] = dA; }
       if (l < nl - 1)
       {
@@ -502,10 +544,13 @@ static hb200_amg *mirror_amg(void *amg_vdata, hypre_ParCSRMatrix *A0)
          if (!dP) { goto fail; }
          m->owned[m->num_owned++] = dP;
       }
-      if (hb200_amg_set_level(m->dev, l, dA, dP,
-                              (l1 && l1[l]) ? hypre_VectorData(l1[l]) : NULL,
+      k = hb200_amg_set_level(m->dev, l, dA, dP,
+                              l1_alt ? l1_alt : ((l1 && l1[l]) ? hypre_VectorData(l1[l]) : NULL),
                               (cf && cf[l]) ? hypre_IntArrayData(cf[l]) : NULL,
-                              hypre_ParAMGDataRelaxWeight(amg)[l], hypre_ParAMGDataOmega(amg)[l])) { goto fail; }
+                              hypre_ParAMGDataRelaxWeight(amg)[l], hypre_ParAMGDataOmega(amg)[l]);
+      hypre_TFree(l1_alt, HYPRE_MEMORY_HOST);
+      if (k) { goto fail; }
+      if (chunks > 1 && hb200_parcsr_set_gs_chunks(dA, chunks)) { goto fail; }
       for (k = 1; k <= 3; k++) { if (hypre_ParAMGDataGridRelaxType(amg)[k] == 16) { uses_cheby = 1; } }
       if (uses_cheby && coefs && coefs[l])
       {

@@ -174,6 +174,11 @@ class ParCSRMatrix:
     def set_spmv_kernel(self, kind: int = 0, lanes_per_row: int = 0) -> None:
         check(lib.hb200_parcsr_set_spmv_kernel(self.handle, kind, lanes_per_row))
 
+    def set_gs_chunks(self, num_chunks: int) -> None:
+        """hybrid Gauss-Seidel on this matrix: the reference's thread count (hypre_NumThreads(), par_relax.c:727);
+        0 / 1 = the sequential sweep, T > 1 = the reference's result at OMP_NUM_THREADS = T in one launch"""
+        check(lib.hb200_parcsr_set_gs_chunks(self.handle, num_chunks))
+
     def format_info(self) -> dict:
         """storage formats of the diag block (hb200_parcsr_format_info)"""
         info = (C.c_longlong * 10)()
@@ -518,17 +523,20 @@ def axpy(alpha: float, x, y):
     return y
 
 
-def amg_from_hierarchy(h, use_graph: bool = False):
+def amg_from_hierarchy(h, use_graph: bool = False, gs_chunks: int = 0):
     """Upload a hierarchy description (any object with the fields below, e.g. the reference
     bridge's view of hypre_ParAMGData after the reference's own BoomerAMGSetup) and return
     (list of level matrices, BoomerAMG).  Fields: levels = [dict(A=view, P=view|None,
     l1_norms, cf_marker, relax_weight, omega, cheby_ds, cheby_coefs)], params dict,
-    coarse_ge dict|None."""
+    coarse_ge dict|None.  gs_chunks: the thread count the reference's setup ran with when the smoothers are
+    hybrid Gauss-Seidel (its sweeps and its l1 norms depend on it, ParCSRMatrix.set_gs_chunks)."""
     levels = []
     mats = []
     for L in h["levels"]:
         A = ParCSRMatrix.from_view(L["A"])
         P = ParCSRMatrix.from_view(L["P"]) if L.get("P") is not None else None
+        if gs_chunks > 1:
+            A.set_gs_chunks(gs_chunks)
         mats.append((A, P))
         d = dict(L)
         d["A"], d["P"] = A, P

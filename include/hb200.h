@@ -175,6 +175,15 @@ int hb200_host_pattern_analyze_wide(int num_rows, int num_cols, const int *row_p
  * t_row_ptr[num_cols + 1], t_col_ind / t_values[nnz].  Host only, no GPU needed. */
 int hb200_host_csr_transpose(int num_rows, int num_cols, const int *row_ptr, const int *col_ind,
                              const double *values, int *t_row_ptr, int *t_col_ind, double *t_values);
+/* Hybrid Gauss-Seidel (relax types 3, 4, 6, 8, 13, 14, 88, 89): the reference's result depends on its thread
+ * count (hypre_NumThreads(), src/parcsr_ls/par_relax.c:727, 868-896): rows are cut into that many chunks
+ * (hypre_partition1D), Gauss-Seidel inside a chunk, Jacobi between chunks.  num_chunks <= 1 (default): the
+ * 1-thread sweep, exactly (wavefront schedule, one launch per wavefront); num_chunks = T > 1: the sweep of the
+ * reference at OMP_NUM_THREADS = T, one launch per call.  The l1 norms of the l1 variants must be the ones of
+ * the same T (hypre_ParCSRComputeL1NormsThreads, src/parcsr_ls/ams.c:4523). */
+int hb200_parcsr_set_gs_chunks(hb200_parcsr *A, int num_chunks);
+/* the chunk count the device prefers for a block of num_rows rows (no GPU needed) */
+int hb200_gs_auto_chunks(int num_rows);
 /* Wavefront schedule of the hybrid Gauss-Seidel sweeps (src/parcsr_ls/par_relax.h:12-330 run with
  * one thread): rows of one level are mutually uncoupled and every row comes after the rows it
  * reads updated values from, so sweeping the levels in order reproduces the sequential sweep.

@@ -48,6 +48,7 @@ namespace hb_emu {
 struct ThreadCtx { hb_emu_dim3 tid, bid, bdim, gdim; };
 extern ThreadCtx *g_cur;             // the running fiber's coordinates
 void  syncthreads();
+void  syncwarp();
 unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int width);
 int   vote_all(int pred);
 void *dyn_smem();
@@ -71,6 +72,7 @@ inline void launch_bound(unsigned grid, unsigned block, size_t smem, std::functi
 #define gridDim   (hb_emu::g_cur->gdim)
 
 inline void __syncthreads() { hb_emu::syncthreads(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { hb_emu::syncwarp(); }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 

@@ -98,6 +98,9 @@ void syncthreads()
    while (b.bar_gen == gen) yield_to_scheduler();
 }
 
+// __syncwarp: every live lane of the warp arrives before any of them goes on
+void syncwarp() { warp_barrier(g_running / 32); }
+
 unsigned long long shfl_down_bits(unsigned long long bits, unsigned delta, int width)
 {
    const int t = g_running, w = t / 32, lane = t % 32;

@@ -167,7 +167,7 @@ def test_smoke_entry_point_on_the_host_emulation():
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-def _ij_run(binary, args, nprocs=1):
+def _ij_run(binary, args, nprocs=1, env_extra=None):
     import re
     ref = os.path.join(ROOT, "oracle", "_ref")
     exe = os.path.join(ref, binary)
@@ -175,6 +175,7 @@ def _ij_run(binary, args, nprocs=1):
     if nprocs > 1:
         cmd = [os.path.join(ref, "mpirun"), "-np", str(nprocs)] + cmd
     env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
+    env.update(env_extra or {})
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ref, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     its = re.findall(r"Iterations = (\d+)", r.stdout)
@@ -205,6 +206,26 @@ def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     solver_id = int(args.split("-solver")[1].split()[0])
     rtol = 2e-6 if solver_id in (1, 2) else 5e-2
     assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
+
+
+def test_hybrid_gs_chunks_through_the_shim_on_the_host_emulation():
+    """the reference's default smoother (hybrid l1-GS 13 / 14) depends on its thread count: with
+    HYPRE_B200_GS_CHUNKS=host the drop-in reproduces the 3-thread reference digit for digit (one launch per sweep);
+    with a chunk count of its own (5) it reproduces the 5-thread reference, l1 norms of that partition included,
+    whatever the host's thread count is"""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs /root/reference to build the ij driver")
+    for target in ("ij", "emu_shim"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", target], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    args = "-27pt -n 9 9 9 -solver 1"
+    its3, res3, _ = _ij_run("ij_ref", args, env_extra={"OMP_NUM_THREADS": "3"})
+    its5, res5, _ = _ij_run("ij_ref", args, env_extra={"OMP_NUM_THREADS": "5"})
+    assert abs(res3 - res5) > 1e-6 * res3          # the thread count does change the reference's numbers
+    its, res, err = _ij_run("ij_b200_emu", args, env_extra={"OMP_NUM_THREADS": "3", "HYPRE_B200_GS_CHUNKS": "host"})
+    assert "on device" in err and its == its3 and abs(res - res3) <= 2e-6 * res3, (its, its3, res, res3)
+    its, res, err = _ij_run("ij_b200_emu", args, env_extra={"OMP_NUM_THREADS": "2", "HYPRE_B200_GS_CHUNKS": "5"})
+    assert "on device" in err and its == its5 and abs(res - res5) <= 2e-6 * res5, (its, its5, res, res5)
 
 
 def test_random_krylov_options_on_the_host_emulation():

@@ -368,6 +368,41 @@ def test_relax_hybrid_gs(lap27, hb, torch, relax_type, weights, points):
         assert err <= RTOL, (relax_type, weights, points, l, err)
 
 
+@pytest.mark.parametrize("relax_type", [3, 4, 6, 8, 13, 14, 88, 89])
+@pytest.mark.parametrize("weights", [(1.0, 1.0), (0.9, 1.1)])
+@pytest.mark.parametrize("points,chunks", [(0, 3), (1, 7), (0, 40)])
+def test_relax_hybrid_gs_chunks(lap27, rb, hb, torch, relax_type, weights, points, chunks):
+    """hybrid GS with T chunks = the reference at OMP_NUM_THREADS = T (par_relax.c:868-896): Gauss-Seidel inside
+    a chunk of hypre_partition1D, the other chunks frozen; one launch per call"""
+    rng = np.random.default_rng(37)
+    w, om = weights
+    rb.set_num_threads(chunks)
+    try:
+        for l in range(min(lap27.nl - 1, 3)):
+            A = lap27.mats[l][0]
+            L = lap27.h["levels"][l]
+            n = A.num_rows
+            if n < chunks:
+                continue
+            f = rng.standard_normal(n)
+            u = rng.standard_normal(n)
+            use_l1 = relax_type in (8, 13, 14, 88, 89)
+            uref = lap27.pb.relax(l, relax_type, f, u, relax_points=points, relax_weight=w, omega=om,
+                                  use_l1=use_l1)
+            du = dev(torch, u)
+            A.set_gs_chunks(chunks)
+            try:
+                hb.relax(A, dev(torch, f), du, relax_type, relax_points=points, relax_weight=w, omega=om,
+                         l1_norms=dev(torch, L["l1_norms"]) if use_l1 else None,
+                         cf_marker=torch.from_numpy(np.ascontiguousarray(L["cf_marker"])).cuda())
+            finally:
+                A.set_gs_chunks(0)
+            err = relerr(du.cpu().numpy(), uref)
+            assert err <= RTOL, (relax_type, weights, points, chunks, l, err)
+    finally:
+        rb.set_num_threads(1)
+
+
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_chebyshev(rb, hb, torch, order):
     """fused form (every element-wise step in the epilogue of the SpMV before it) on one rank"""
@@ -456,6 +491,27 @@ def test_vcycle_smoother_variants(rb, hb, torch, smoother):
     du = torch.zeros(n, dtype=torch.float64, device="cuda")
     case.amg.cycle(dev(torch, f), du, u_all_zeros=True)
     assert relerr(du.cpu().numpy(), uref) <= RTOL, smoother
+
+
+@pytest.mark.parametrize("smoother,threads", [(dict(relax_type=-1), 3), (dict(relax_type=8, relax_order=1), 6),
+                                              (dict(relax_type=6), 4)])
+def test_vcycle_hybrid_gs_with_the_reference_thread_count(rb, hb, torch, smoother, threads):
+    """the V-cycle with hybrid GS smoothers against the reference run with `threads` OpenMP threads: setup (l1
+    norms of that partition) and cycle on the reference side, chunked sweeps (one launch each) on the device"""
+    rb.set_num_threads(threads)
+    try:
+        pb = rb.Problem("27pt", (13, 12, 11))
+        pb.setup_amg(**smoother)
+        mats, amg = hb.amg_from_hierarchy(pb.hierarchy(), gs_chunks=threads)
+        rng = np.random.default_rng(59)
+        n = mats[0][0].num_rows
+        f = rng.standard_normal(n)
+        uref = pb.amg_solve(f, np.zeros(n), u_all_zeros=True)
+        du = torch.zeros(n, dtype=torch.float64, device="cuda")
+        amg.cycle(dev(torch, f), du, u_all_zeros=True)
+        assert relerr(du.cpu().numpy(), uref) <= RTOL, (smoother, threads)
+    finally:
+        rb.set_num_threads(1)
 
 
 # ----------------------------------------------------------------------------------------
@@ -763,6 +819,22 @@ def test_ij_dropin_matches_reference(args):
     solver_id = int(args.split("-solver")[1].split()[0])
     rtol = 2e-6 if solver_id in (1, 2) else 5e-2
     assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
+
+
+def test_ij_dropin_hybrid_gs_chunks():
+    """hypre's default smoother (hybrid l1-GS 13 / 14) with the reference's OpenMP semantics on the device:
+    HYPRE_B200_GS_CHUNKS=host reproduces the 4-thread reference, =5 the 5-thread one (l1 norms of that partition
+    recomputed by the reference's own routine), one launch per sweep instead of one per wavefront"""
+    args = "-27pt -n 24 24 24 -solver 1"
+    its4, res4, _, _ = _ij("ij_ref", args, env_extra={"OMP_NUM_THREADS": "4"})
+    its5, res5, _, _ = _ij("ij_ref", args, env_extra={"OMP_NUM_THREADS": "5"})
+    its, res, _, err = _ij("ij_b200", args, env_extra={"OMP_NUM_THREADS": "4", "HYPRE_B200_GS_CHUNKS": "host"})
+    assert "on device" in err and its == its4 and abs(res - res4) <= 2e-6 * res4, (its, its4, res, res4)
+    its, res, _, err = _ij("ij_b200", args, env_extra={"OMP_NUM_THREADS": "2", "HYPRE_B200_GS_CHUNKS": "5"})
+    assert "on device" in err and its == its5 and abs(res - res5) <= 2e-6 * res5, (its, its5, res, res5)
+    # the device's own chunk counts: converges to the same tolerance
+    its, res, _, err = _ij("ij_b200", args, env_extra={"HYPRE_B200_GS_CHUNKS": "auto"})
+    assert "on device" in err and its <= its4 + 3 and res < 1e-8, (its, res)
 
 
 def test_ij_dropin_two_ranks(torch):

@@ -412,7 +412,11 @@ def main():
             if M.num_rows != M.num_cols:
                 by += 4.0 * n                       # first column of every row (rectangular blocks: P, P^T)
             irr = fi["pattern_irregular_rows"]
-            name = ("spmv_box<EPI_AXPBY> (row-pattern format, compact-stencil kernel, 1 B/row + x + y" if fi["kernel"] == 9
+            geo = fi["kernel"] == 9 and fi.get("box_geo") and os.environ.get("HB200_BOX_NO_GEO", "0") in ("", "0")
+            if geo:
+                by -= 1.0 * n                       # the grid-box kernel reads no row codes: x + y only
+            name = ("spmv_box<EPI_AXPBY,GEO> (row-pattern format, compact-stencil kernel on a grid box, x + y only" if geo
+                    else "spmv_box<EPI_AXPBY> (row-pattern format, compact-stencil kernel, 1 B/row + x + y" if fi["kernel"] == 9
                     else "spmv_pat<EPI_AXPBY> (row-pattern format, 1 B/row + x + y") \
                 + (f"; {irr} irregular rows in CSR)" if irr else ")")
         elif fi["kernel"] == 6:

@@ -218,6 +218,8 @@ struct DCsr {
    double     box_p0_val[27] = {0};    // the reference pattern's values (kernel argument: constant bank)
    bool       box_uniform = false;     // every pattern = the reference pattern with slots missing
    unsigned int box_ref_mask = 0;      // slots of the reference pattern
+   bool       box_geo = false;         // full 27-slot reference pattern and every row misses exactly the neighbours
+                                       // outside the box sy x (sz / sy) x (nrows / sz): no row codes needed
    int        max_row_nnz = 0;
    double     avg_row_nnz = 0.0;
    // formats the automatic choice cannot pick for this block are built on first request

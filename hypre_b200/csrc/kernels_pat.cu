@@ -422,7 +422,14 @@ __device__ __forceinline__ void box_mbar_wait(unsigned long long *bar, unsigned 
 //             the row's presence mask predicates the 27 slots, the values are kernel arguments.  Without it
 //             a warp with one boundary lane reads masks and values from shared memory for all its rows, and
 //             the per-step barrier makes the whole block as slow as that warp.
-template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI>
+//   GEO     = (with UNI) the reference pattern is the full 27-point stencil and a row misses exactly the neighbours
+//             that lie outside the box sy x (sz / sy) x nplanes (checked row by row at upload): the missing
+//             operands are ZERO instead of the additions being predicated — an in-plane neighbour outside the
+//             box reads a zero word of the stage (its offset is fixed per thread), a plane outside the box
+//             loads zeros — so every row runs the 27 unconditional slots of the interior and no row code is
+//             read at all.  s + a * 0 == s: same values as the predicated form (a partial sum of -0.0 may
+//             become +0.0).  One instruction per slot instead of three.
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI, bool GEO = false>
 __global__ void __launch_bounds__(kBoxThreads, 2)
 spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigned char *__restrict__ pat, int npat, int p0,
          const unsigned int *__restrict__ masks, const double *__restrict__ vals, BoxP0 P0,
@@ -432,7 +439,8 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    HB_DYN_SHARED(double, s_mem);
    const int seg = NT + 2 * sy + 2;                    // doubles of one plane segment
    const int segpad = (seg + 2) & ~1;                  // + the parity shift of an aligned copy, even
-   const int stage_len = segpad + STREAMS * NT;        // + the staged epilogue vectors
+   const int zslot = segpad + STREAMS * NT;            // GEO: a zero word behind the staged data of every stage
+   const int stage_len = zslot + (GEO ? 2 : 0);        // + the staged epilogue vectors (+ the zero pair)
    double             *s_ring = s_mem;                                          // NS stages
    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_ring + (size_t) NS * stage_len);   // NS mbarriers
    double             *s_val = reinterpret_cast<double *>(s_bar + NS);          // npat x 27
@@ -440,6 +448,7 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    const int tid = threadIdx.x;
    for (int k = tid; k < npat * 27; k += NT) s_val[k] = vals[k];
    for (int k = tid; k < npat; k += NT) s_mask[k] = masks[k];
+   if (GEO && tid < NS) { s_ring[(size_t) tid * stage_len + zslot] = 0.0; s_ring[(size_t) tid * stage_len + zslot + 1] = 0.0; }
    if (BULK && tid == 0) {
       for (int k = 0; k < NS; k++) box_mbar_init(s_bar + k, 1);
       box_mbar_fence_init();
@@ -534,6 +543,15 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    int offc[9];
 #pragma unroll
    for (int c = 0; c < 9; c++) offc[c] = tid + sy + 1 + dpar + (c / 3 - 1) * sy + (c % 3 - 1);
+   if (GEO) {
+      // in-plane neighbours outside the box: the same for every plane of this thread
+      const int ny = sz / sy, xq = q % sy, yq = q / sy;
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+         const bool in = qok && (unsigned int) (xq + c % 3 - 1) < (unsigned int) sy && (unsigned int) (yq + c / 3 - 1) < (unsigned int) ny;
+         if (!in) offc[c] = zslot;
+      }
+   }
    double W[NW][9];                                                       // planes z-1 .. z+U (rotating roles)
    // planes z0 - 1 and z0 into the window (cp.async groups complete in order: the NS - 2 planes issued
    // after them may still be in flight)
@@ -543,12 +561,13 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
    {
       const double *sm = s_ring, *sc = s_ring + stage_len;
 #pragma unroll
-      for (int c = 0; c < 9; c++) { W[0][c] = sm[offc[c]]; W[1][c] = sc[offc[c]]; }
+      for (int c = 0; c < 9; c++) { W[0][c] = (GEO && z0 == 0) ? 0.0 : sm[offc[c]]; W[1][c] = sc[offc[c]]; }
    }
    // row codes are prefetched two steps ahead in registers (32-bit row arithmetic: rows are ints)
    const unsigned int urows = (unsigned int) nrows, usz = (unsigned int) sz;
    unsigned int rowq = (unsigned int) z0 * usz + (unsigned int) q;        // this thread's row in plane z
    auto ldcode = [&](unsigned int r, int z) -> int {
+      if (GEO) return (qok && z < z1 && r < urows) ? 0 : 255;   // every row of the box is a table row: nothing to read
       return (qok && z < z1 && r < urows) ? (int) __ldg(pat + r) : 255;
    };
    int code_n1[U], code_n2[U];
@@ -584,7 +603,7 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
             if (BULK) landed_bulk();
             const double *sp = s_ring + (size_t) rd_stage * stage_len;
 #pragma unroll
-            for (int c = 0; c < 9; c++) Wn[c] = sp[offc[c]];
+            for (int c = 0; c < 9; c++) Wn[c] = (GEO && z + 1 + i >= nplanes) ? 0.0 : sp[offc[c]];   // (block-uniform)
             e0[i] = (STREAMS >= 1) ? sp[segpad + tid] : 0.0;
             e1[i] = (STREAMS >= 2) ? sp[segpad + NT + tid] : 0.0;
             advance();
@@ -599,7 +618,27 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
          bool all_full = true;
 #pragma unroll
          for (int i = 0; i < U; i++) all_full = all_full && (code[i] == p0);
-         if (UNI) {
+         if (GEO || (!UNI && __all_sync(0xffffffffu, all_full))) {
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+               s[i] = 0.0;
+               if (!skip_c) s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[13], Wc[4]));
+            }
+#pragma unroll
+            for (int t = 0; t < 27; t++) {
+               if (t == 13) continue;
+#pragma unroll
+               for (int i = 0; i < U; i++) {
+                  double (&Wm)[9] = W[(ph * U + i) % NW];
+                  double (&Wc)[9] = W[(ph * U + i + 1) % NW];
+                  double (&Wp)[9] = W[(ph * U + i + 2) % NW];
+                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
+                  if (NEG1) s[i] = __dadd_rn(s[i], -w);     // (-1.0) * w == -w exactly
+                  else      s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[t], w));
+               }
+            }
+         } else if (UNI) {
             unsigned int m[U];
 #pragma unroll
             for (int i = 0; i < U; i++) {
@@ -621,26 +660,6 @@ spmv_box(int nrows, int sy, int sz, int zrun, int nplanes, int gx, const unsigne
                      if (NEG1) s[i] = __dadd_rn(s[i], -w);  // (-1.0) * w == -w exactly
                      else      s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[t], w));
                   }
-               }
-            }
-         } else if (__all_sync(0xffffffffu, all_full)) {
-#pragma unroll
-            for (int i = 0; i < U; i++) {
-               double (&Wc)[9] = W[(ph * U + i + 1) % NW];
-               s[i] = 0.0;
-               if (!skip_c) s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[13], Wc[4]));
-            }
-#pragma unroll
-            for (int t = 0; t < 27; t++) {
-               if (t == 13) continue;
-#pragma unroll
-               for (int i = 0; i < U; i++) {
-                  double (&Wm)[9] = W[(ph * U + i) % NW];
-                  double (&Wc)[9] = W[(ph * U + i + 1) % NW];
-                  double (&Wp)[9] = W[(ph * U + i + 2) % NW];
-                  const double w = t < 9 ? Wm[t] : t < 18 ? Wc[t - 9] : Wp[t - 18];
-                  if (NEG1) s[i] = __dadd_rn(s[i], -w);     // (-1.0) * w == -w exactly
-                  else      s[i] = __dadd_rn(s[i], __dmul_rn(P0.a[t], w));
                }
             }
          } else {
@@ -717,20 +736,20 @@ static size_t box_smem_bytes(const DCsr &M, int streams)
 {
    const size_t seg = (size_t) kBoxThreads + 2 * (size_t) M.box_sy + 2;
    const size_t segpad = (seg + 2) & ~(size_t) 1;
-   return sizeof(double) * ((size_t) kBoxStages * (segpad + (size_t) streams * kBoxThreads) + kBoxStages + (size_t) M.pat_npat * 27) +
+   return sizeof(double) * ((size_t) kBoxStages * (segpad + (size_t) streams * kBoxThreads + 2) + kBoxStages + (size_t) M.pat_npat * 27) +
           sizeof(unsigned int) * (size_t) M.pat_npat + 16;
 }
 
 // the slab ring has to fit one block's shared memory: in-plane strides up to ~4000 (a 4000-wide grid)
 static bool box_fits(const DCsr &M) { return box_smem_bytes(M, 2) <= 200 * 1024; }
 
-template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI>
+template <int EPI, bool DOT, int STREAMS, bool BULK, bool NEG1, bool UNI, bool GEO = false>
 static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaStream_t st)
 {
    const size_t smem = box_smem_bytes(M, STREAMS);
    static size_t opted = 0;
    if (opted < smem) {
-      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      HB_CUDA(cudaFuncSetAttribute(spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       opted = smem;
    }
    if (DOT) {
@@ -762,7 +781,7 @@ static int box_launch_v(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    }
    BoxP0 P0;
    for (int t = 0; t < 27; t++) P0.a[t] = M.box_p0_val[t];
-   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
+   HB_LAUNCH((spmv_box<EPI, DOT, STREAMS, BULK, NEG1, UNI, GEO>), gx * gy, kBoxThreads, smem, st, M.nrows, M.box_sy, M.box_sz, zrun, nplanes, gx, M.pat_code,
              M.pat_npat, M.box_p0, M.box_mask, M.box_val, P0, x, ea);
    HB_LAUNCH_CHECK();
    return 0;
@@ -783,6 +802,11 @@ static int box_launch_t(const DCsr &M, const double *x, const EpiArgs &ea, cudaS
    if (no_neg1) neg1 = false;
    static const bool no_uni = env_flag("HB200_BOX_NO_UNI", false);
    const bool uni = M.box_uniform && !no_uni;
+   static const bool no_geo = env_flag("HB200_BOX_NO_GEO", false);
+   if (uni && M.box_geo && !no_geo) {
+      if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false, true, true>(M, x, ea, st);
+      return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false, true, true>(M, x, ea, st);
+   }
    if (uni) {
       if (bulk) return neg1 ? box_launch_v<EPI, DOT, STREAMS, true, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, true, false, true>(M, x, ea, st);
       return neg1 ? box_launch_v<EPI, DOT, STREAMS, false, true, true>(M, x, ea, st) : box_launch_v<EPI, DOT, STREAMS, false, false, true>(M, x, ea, st);
@@ -899,6 +923,44 @@ static void box_analyze_host(const PatHost &ph, int nrows, BoxHost &out)
    out.ok = true;
 }
 
+// GEO (spmv_box): the table is uniform with the full 27-point reference pattern, the rows fill the box
+// sy x (sz / sy) x (nrows / sz) exactly, and the pattern of every row is the reference pattern minus the
+// neighbours outside that box.  One pass over the row codes.
+static bool box_geo_check(const PatHost &ph, const BoxHost &bh, int n)
+{
+   if (!bh.ok || !bh.uniform || bh.ref_mask != 0x7ffffffu || !ph.irr.empty() || ph.skips_boundary) return false;
+   const int sy = bh.sy, sz = bh.sz;
+   if (sy < 1 || sz % sy != 0 || n % sz != 0 || (int) ph.code.size() != n) return false;
+   const int ny = sz / sy, nz = n / sz;
+   // masks of the 64 combinations of "first / last" along x, y, z
+   unsigned int tab[64];
+   for (int f = 0; f < 64; f++) {
+      unsigned int m = 0;
+      for (int t = 0; t < 27; t++) {
+         const int dx = t % 3 - 1, dy = (t / 3) % 3 - 1, dz = t / 9 - 1;
+         const bool out = (dx < 0 && (f & 1)) || (dx > 0 && (f & 2)) || (dy < 0 && (f & 4)) || (dy > 0 && (f & 8)) ||
+                          (dz < 0 && (f & 16)) || (dz > 0 && (f & 32));
+         if (!out) m |= 1u << t;
+      }
+      tab[f] = m;
+   }
+   const unsigned char *code = ph.code.data();
+   const int npat = (int) bh.mask.size();
+   size_t r = 0;
+   for (int z = 0; z < nz; z++) {
+      const int fz = (z == 0 ? 16 : 0) | (z == nz - 1 ? 32 : 0);
+      for (int y = 0; y < ny; y++) {
+         const int fy = fz | (y == 0 ? 4 : 0) | (y == ny - 1 ? 8 : 0);
+         for (int x = 0; x < sy; x++, r++) {
+            const int f = fy | (x == 0 ? 1 : 0) | (x == sy - 1 ? 2 : 0);
+            const int c = code[r];
+            if (c >= npat || bh.mask[(size_t) c] != tab[f]) return false;
+         }
+      }
+   }
+   return true;
+}
+
 int dcsr_free_pat(DCsr &M)
 {
    if (M.pat_code) cudaFree(M.pat_code);
@@ -909,7 +971,7 @@ int dcsr_free_pat(DCsr &M)
    if (M.pat_irr) cudaFree(M.pat_irr);
    if (M.box_mask) cudaFree(M.box_mask);
    if (M.box_val) cudaFree(M.box_val);
-   M.box_mask = nullptr; M.box_val = nullptr; M.has_box = false;
+   M.box_mask = nullptr; M.box_val = nullptr; M.has_box = false; M.box_geo = false;
    M.pat_code = nullptr; M.pat_ptr = nullptr; M.pat_off = nullptr; M.pat_val = nullptr; M.pat_base = nullptr; M.pat_irr = nullptr;
    M.pat_nirr = 0;
    M.pat_wide = false;
@@ -1094,6 +1156,7 @@ int dcsr_build_pat(DCsr &M, const int *hi, const int *hj, const double *ha)
          // dense stencils: a 7-point operator stays with the generic row-pattern kernel (7 gathers per row;
          // B200, 256^3: 0.071 ms against 0.19 ms)
          M.has_box = box_fits(M) && (bh.uniform || bh.p0 >= 0) && __builtin_popcount(bh.ref_mask) >= 15;
+         M.box_geo = M.has_box && box_geo_check(ph, bh, n);
       }
    }
    return 0;

@@ -618,7 +618,7 @@ int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10)
       info10[2] = A->diag.sell_vidx ? 2 : 9;
       info10[3] = A->diag.sell_nv;
    }
-   info10[4] = A->diag.has_pat ? 1 : 0;
+   info10[4] = (A->diag.has_pat ? 1 : 0) | (A->diag.has_box ? 2 : 0) | (A->diag.box_uniform ? 4 : 0) | (A->diag.box_geo ? 8 : 0);
    info10[5] = A->diag.pat_npat;
    info10[6] = A->diag.pat_nent;
    info10[7] = A->diag.kind;

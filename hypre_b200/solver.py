@@ -184,7 +184,8 @@ class ParCSRMatrix:
         info = (C.c_longlong * 10)()
         check(lib.hb200_parcsr_format_info(self.handle, info))
         return {"sell": bool(info[0]), "sell_entries": int(info[1]), "sell_bytes_per_entry": int(info[2]),
-                "sell_values": int(info[3]), "pattern": bool(info[4]), "patterns": int(info[5]),
+                "sell_values": int(info[3]), "pattern": bool(info[4] & 1), "box": bool(info[4] & 2),
+                "box_uniform": bool(info[4] & 4), "box_geo": bool(info[4] & 8), "patterns": int(info[5]),
                 "pattern_entries": int(info[6]), "kernel": int(info[7]),
                 "pattern_irregular_rows": int(info[8]), "pattern_irregular_nnz": int(info[9])}
 

@@ -133,9 +133,12 @@ int hb200_parcsr_download_maps(const hb200_parcsr *A, int *diag_i, int *diag_j,
  * copy exists (structured operators: <= 256 distinct column offsets), info[1] = its stored
  * entries incl. padding, info[2] = bytes per stored entry (2 = offset + value codes, 9 = offset
  * code + fp64 value), info[3] = number of distinct values (0 when values are stored raw);
- * info[4] = 1 when a row-pattern copy exists (>= 70% of the rows fall into <= 255 distinct rows
+ * info[4] bit 0 = a row-pattern copy exists (>= 70% of the rows fall into <= 255 distinct rows
  * as lists of (column - base, value): constant-coefficient stencils and the regular part of
- * their first coarse level; 1 byte per row), info[5] = patterns, info[6] = table entries;
+ * their first coarse level; 1 byte per row), bit 1 = its patterns are compact 3 x 3 x 3 stencils (the
+ * stencil-sweep kernel applies), bit 2 = all patterns are one reference pattern with slots missing,
+ * bit 3 = the missing slots are exactly the neighbours outside the grid box (no row codes are read);
+ * info[5] = patterns, info[6] = table entries;
  * info[7] = the kernel kind in force (numbering of hb200_parcsr_set_spmv_kernel);
  * info[8] = rows outside the pattern table (swept in CSR), info[9] = their nonzeros. */
 int hb200_parcsr_format_info(const hb200_parcsr *A, long long *info10);

@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="hb200", choices=["hb200", "reference"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="brick edge per GPU")
     ap.add_argument("--problem", default="27pt", choices=["27pt", "laplacian", "vardifconv"])
-    ap.add_argument("--solver", default="pcg", choices=["pcg", "gmres"])
+    ap.add_argument("--solver", default="pcg", choices=sorted(SOLVERS))
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer"],
@@ -67,6 +67,37 @@ def parse():
     return ap.parse_args()
 
 
+# --solver: ij's solver id, metric name, label, reference-side runner, device-side class
+SOLVERS = {
+    "pcg": (1, "amg_pcg_solve_mdof_per_s", "BoomerAMG-PCG"),
+    "gmres": (3, "amg_gmres_solve_mdof_per_s", "BoomerAMG-GMRES(5)"),
+    "bicgstab": (9, "amg_bicgstab_solve_mdof_per_s", "BoomerAMG-BiCGSTAB"),
+    "cogmres": (16, "amg_cogmres_solve_mdof_per_s", "BoomerAMG-COGMRES(5)"),
+    "flexgmres": (61, "amg_flexgmres_solve_mdof_per_s", "BoomerAMG-FlexGMRES(5)"),
+}
+
+
+def reference_solve(pb, args, max_iter):
+    """the reference's own solve of the configured Krylov driver (oracle/ref_bridge.c: ij's settings)"""
+    if args.solver == "pcg":
+        return pb.pcg(precond="amg", tol=args.tol, max_iter=max_iter, two_norm=1)
+    if args.solver == "gmres":
+        return pb.gmres(precond="amg", tol=args.tol, max_iter=max_iter, k_dim=5)
+    return pb.krylov_ext(args.solver, precond="amg", tol=args.tol, max_iter=max_iter, k_dim=5)
+
+
+def device_solver(hb, args):
+    if args.solver == "pcg":
+        return hb.ParCSRPCG(tol=args.tol, max_iter=100, two_norm=1, logging=1)
+    if args.solver == "gmres":
+        return hb.ParCSRGMRES(tol=args.tol, max_iter=100, k_dim=5, logging=1)
+    if args.solver == "bicgstab":
+        return hb.ParCSRBiCGSTAB(tol=args.tol, max_iter=100, logging=1)
+    if args.solver == "cogmres":
+        return hb.ParCSRCOGMRES(tol=args.tol, max_iter=100, k_dim=5, logging=1)
+    return hb.ParCSRFlexGMRES(tol=args.tol, max_iter=100, k_dim=5, logging=1)
+
+
 def grid_of(args, world):
     """global grid and process grid of a run: weak scaling (one n^3 brick per GPU) unless --global-size"""
     P = PGRID[world]
@@ -78,7 +109,7 @@ def grid_of(args, world):
 
 def workload_string(args, gn, P):
     """the ij command line this run stands for — the same text on both arms (hb200 / reference)"""
-    solver = -1 if args.spmv_only else (1 if args.solver == "pcg" else 3)
+    solver = -1 if args.spmv_only else SOLVERS[args.solver][0]
     tail = f" -nmv {args.nmv} -x0rand" if args.spmv_only else " -rlx 18"
     if args.coarsen_type == 8 and not args.spmv_only:
         tail += " -pmis"
@@ -221,10 +252,7 @@ def run_reference(args):
         print(json.dumps(line), flush=True)
         return
     setup_s = pb.setup_amg(relax_type=18, coarsen_type=args.coarsen_type)
-    if args.solver == "gmres":
-        solve = lambda mi: pb.gmres(precond="amg", tol=args.tol, max_iter=mi, k_dim=5)
-    else:
-        solve = lambda mi: pb.pcg(precond="amg", tol=args.tol, max_iter=mi, two_norm=1)
+    solve = lambda mi: reference_solve(pb, args, mi)
     full = solve(100)
     its_full = full["iterations"]
     k = args.cpu_iters if args.cpu_iters > 0 else 3
@@ -240,7 +268,7 @@ def run_reference(args):
     if myrank != 0:
         return
     line = {
-        "impl": "reference", "metric": "amg_pcg_solve_mdof_per_s" if args.solver == "pcg" else "amg_gmres_solve_mdof_per_s",
+        "impl": "reference", "metric": SOLVERS[args.solver][1],
         "value": val, "unit": "MDOF/s",
         "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_full * 1e3, "higher_is_better": True,
@@ -269,7 +297,7 @@ def run_ij_dropin(args, gn, P):
     exe = os.path.join(ROOT, "oracle", "_ref", "ij_b200")
     if not os.path.exists(exe):
         return {"unavailable": "oracle/_ref/ij_b200 not built (needs /root/reference at build time)"}
-    solver = 1 if args.solver == "pcg" else 3
+    solver = SOLVERS[args.solver][0]
     cmd = [exe, f"-{args.problem}", "-n", str(gn[0]), str(gn[1]), str(gn[2]), "-solver", str(solver), "-rlx", "18",
            "-tol", str(args.tol)]
     env = dict(os.environ, HYPRE_B200_VERBOSE="1")
@@ -582,10 +610,7 @@ def main():
     b = b_host.cuda()
     x = torch.zeros(nloc, dtype=torch.float64, device="cuda")
 
-    if args.solver == "pcg":
-        solver = hb.ParCSRPCG(tol=args.tol, max_iter=100, two_norm=1, logging=1)
-    else:
-        solver = hb.ParCSRGMRES(tol=args.tol, max_iter=100, k_dim=5, logging=1)
+    solver = device_solver(hb, args)
     solver.set_precond(amg)
 
     def step_dev():
@@ -695,8 +720,7 @@ def main():
     cpu = None
     ref_parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref_solve = (lambda mi: pb.pcg(precond="amg", tol=args.tol, max_iter=mi, two_norm=1)) if args.solver == "pcg" \
-            else (lambda mi: pb.gmres(precond="amg", tol=args.tol, max_iter=mi, k_dim=5))
+        ref_solve = lambda mi: reference_solve(pb, args, mi)
         if args.cpu_iters <= 0 or args.n <= 256:
             # the whole reference solve on the host cores (~10-20 s at 256^3): also the full-size
             # parity evidence (iteration count, final residual)
@@ -723,14 +747,14 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "amg_pcg_solve_mdof_per_s" if args.solver == "pcg" else "amg_gmres_solve_mdof_per_s",
+            "metric": SOLVERS[args.solver][1],
             "value": value, "unit": "MDOF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if args.global_size else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_string(args, gn, P),
-                "solver": ("BoomerAMG-PCG" if args.solver == "pcg" else "BoomerAMG-GMRES(5)")
+                "solver": SOLVERS[args.solver][2]
                           + ", HMIS + ext+i, l1-Jacobi V(1,1); hierarchy from the reference's BoomerAMGSetup, "
                             "uploaded once (not timed)",
                 "rows": rows, "rows_per_gpu": nloc, "nnz_A0_per_gpu": nnz0, "levels": pb.num_levels,

@@ -142,6 +142,14 @@ def _load() -> C.CDLL:
         "hb200_bicgstab_default_params": ([C.POINTER(BiCGSTABParams)], None),
         "hb200_bicgstab_solve": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_bicgstab_solve_host": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_parcsr_from_ij": ([C.POINTER(vp)] + [C.c_int64] * 5 + [vp, vp, vp, C.c_int], C.c_int),
+        "hb200_parcsr_read_ij": ([C.POINTER(vp), C.c_char_p, C.c_int], C.c_int),
+        "hb200_parcsr_info": ([vp, vp], C.c_int),
+        "hb200_parcsr_print_ij": ([vp, C.c_char_p], C.c_int),
+        "hb200_vector_print_ij": ([vp, C.c_int64, C.c_int, C.c_char_p], C.c_int),
+        "hb200_vector_read_ij": ([C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int], C.c_int),
+        "hb200_host_ij_assemble": ([C.c_int64] * 5 + [vp, vp, vp, C.c_int, c_int_p, c_int_p, c_int_p] + [vp] * 7, C.c_int),
+        "hb200_host_ij_commpkg": ([C.c_int, C.c_int, vp, vp, C.c_int64, c_int_p, vp, vp, vp, C.c_int, c_int_p, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)   # AttributeError here = header/library mismatch

@@ -30,6 +30,7 @@ SOURCES = [
     "amg.cu",
     "krylov.cu",
     "krylov_ext.cu",
+    "ij.cu",
 ]
 
 NVCC_FLAGS = [

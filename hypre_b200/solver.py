@@ -124,6 +124,44 @@ class ParCSRMatrix:
         self.handle = h
 
     @classmethod
+    def _adopt(cls, handle) -> "ParCSRMatrix":
+        """wrap a matrix the library assembled itself (from_ij / read_ij): sizes from hb200_parcsr_info"""
+        info = (C.c_int64 * 12)()
+        check(lib.hb200_parcsr_info(handle, info))
+        m = cls.__new__(cls)
+        m.handle = handle
+        m.num_rows, m.num_cols, m.num_cols_offd = int(info[0]), int(info[1]), int(info[2])
+        m.diag_nnz, m.offd_nnz = int(info[3]), int(info[4])
+        m.num_sends, m.num_recvs, m.n_send_elmts = int(info[5]), int(info[6]), int(info[7])
+        m.first_row, m.first_col, m.global_rows, m.global_cols = (int(info[k]) for k in range(8, 12))
+        return m
+
+    @classmethod
+    def from_ij(cls, ilower: int, iupper: int, jlower: int, jupper: int, rows, cols, values,
+                add_duplicates: bool = False) -> "ParCSRMatrix":
+        """HYPRE_IJMatrixCreate + SetValues / AddToValues + Assemble: this rank's coordinate triplets (global
+        indices) become its rows of a device-resident ParCSR matrix.  Collective."""
+        init_required()
+        r, c_, v = _np(rows, np.int64), _np(cols, np.int64), _np(values, np.float64)
+        n = 0 if r is None else int(r.shape[0])
+        h = C.c_void_p()
+        check(lib.hb200_parcsr_from_ij(C.byref(h), int(ilower), int(iupper), int(jlower), int(jupper), n,
+                                       _ptr(r), _ptr(c_), _ptr(v), 1 if add_duplicates else 0))
+        return cls._adopt(h)
+
+    @classmethod
+    def read_ij(cls, filename: str, matrix_market: bool = False) -> "ParCSRMatrix":
+        """HYPRE_IJMatrixRead / HYPRE_IJMatrixReadMM: `<filename>.<5-digit rank>` per rank, or one Matrix Market file"""
+        init_required()
+        h = C.c_void_p()
+        check(lib.hb200_parcsr_read_ij(C.byref(h), filename.encode(), 1 if matrix_market else 0))
+        return cls._adopt(h)
+
+    def print_ij(self, filename: str) -> None:
+        """HYPRE_IJMatrixPrint: the reference's text format, one file per rank"""
+        check(lib.hb200_parcsr_print_ij(self.handle, filename.encode()))
+
+    @classmethod
     def from_view(cls, v) -> "ParCSRMatrix":
         """Build from any object exposing the hypre_ParCSRMatrix fields as arrays/pointers
         (e.g. the reference bridge's view of A_array[l] / P_array[l])."""
@@ -485,6 +523,24 @@ class ParCSRBiCGSTAB(_Krylov):
         return res
 
 
+def vector_print_ij(x, jlower: int, filename: str) -> None:
+    """HYPRE_IJVectorPrint of a device vector: `<filename>.<5-digit rank>`"""
+    _torch_sync(x)
+    check(lib.hb200_vector_print_ij(_ptr(x), int(jlower), int(x.shape[0]), filename.encode()))
+
+
+def vector_read_ij(filename: str):
+    """HYPRE_IJVectorRead into a new device vector; returns (jlower, tensor)"""
+    import torch
+    lo, hi = C.c_int64(0), C.c_int64(-1)
+    check(lib.hb200_vector_read_ij(filename.encode(), C.byref(lo), C.byref(hi), None, 0))
+    n = int(hi.value - lo.value + 1)
+    x = torch.zeros(max(n, 0), dtype=torch.float64, device="cuda")
+    check(lib.hb200_vector_read_ij(filename.encode(), C.byref(lo), C.byref(hi), _ptr(x), n))
+    sync()
+    return int(lo.value), x
+
+
 def relax(A: ParCSRMatrix, f, u, relax_type: int, relax_points: int = 0, relax_weight: float = 1.0,
           omega: float = 1.0, l1_norms=None, cf_marker=None, u_all_zeros: bool = False, vtemp=None):
     """hypre_BoomerAMGRelax on device vectors (l1_norms / cf_marker: torch CUDA tensors)."""
@@ -556,7 +612,7 @@ def amg_from_hierarchy(h, use_graph: bool = False, gs_chunks: int = 0):
 __all__ = [
     "init", "finalize", "comm_init", "comm_get_unique_id", "sync", "launch_count",
     "ParCSRMatrix", "BoomerAMG", "ParCSRPCG", "ParCSRGMRES", "ParCSRFlexGMRES", "ParCSRCOGMRES",
-    "ParCSRBiCGSTAB", "relax", "cheby_solve",
+    "ParCSRBiCGSTAB", "relax", "cheby_solve", "vector_print_ij", "vector_read_ij",
     "inner_prod", "axpy", "amg_from_hierarchy", "HB200Error", "KrylovResult",
     "PRECOND_NONE", "PRECOND_AMG", "PRECOND_DIAGSCALE",
 ]

@@ -402,6 +402,49 @@ int hb200_bicgstab_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                               const hb200_bicgstab_params *params, const double *b_host,
                               double *x_host, double *norms, hb200_krylov_result *result);
 
+/* ------------------------------------------------------------------------------------ */
+/* (f3) IJ interface and on-disk formats: matrices and vectors enter without hypre        */
+/* ------------------------------------------------------------------------------------ */
+
+/* HYPRE_IJMatrixCreate(ilower, iupper, jlower, jupper) + SetValues / AddToValues + Assemble
+ * (src/IJ_mv/HYPRE_IJMatrix.c:45, 539, 731, 869; hypre_IJMatrixAssembleParCSR, src/IJ_mv/IJMatrix_parcsr.c:2641)
+ * in one collective call: this rank's coordinate triplets (global indices, rows inside [ilower, iupper]; HOST
+ * arrays) become its rows of a ParCSR matrix on the device.  A row keeps the order its entries were given in,
+ * a repeated (i, j) lands on its first occurrence (add_duplicates: summed, else the last value wins), the
+ * diagonal entry of a square block comes first (the relaxation sweeps rely on it, par_relax.c:274),
+ * col_map_offd ascends.  On N ranks the CommPkg (hypre_MatvecCommPkgCreate, src/parcsr_mv/
+ * par_csr_communication.c) is built from two NCCL all-gathers.  Values for rows of other ranks
+ * (HYPRE_IJMatrixAddToValues off-processor) are not supported. */
+int hb200_parcsr_from_ij(hb200_parcsr **A, int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper,
+                         int64_t num_entries, const int64_t *rows, const int64_t *cols,
+                         const double *values, int add_duplicates);
+/* HYPRE_IJMatrixRead (src/IJ_mv/IJMatrix.c:110-249): every rank reads `<filename>.<5-digit rank>` (header
+ * `ilower iupper jlower jupper`, then `i j value` lines); is_matrix_market: HYPRE_IJMatrixReadMM, the whole
+ * file on one rank (coordinate, real / integer, general / symmetric).  Collective. */
+int hb200_parcsr_read_ij(hb200_parcsr **A, const char *filename, int is_matrix_market);
+/* sizes of a matrix (what the caller of hb200_parcsr_create passed; needed after from_ij / read_ij): info[0..11]
+ * = num_rows, num_cols, num_cols_offd, diag nonzeros, offd nonzeros, num_sends, num_recvs, send_map_starts[num_sends],
+ * first_row_index, first_col_diag, global_num_rows, global_num_cols (hypre_ParCSRMatrix, par_csr_matrix.h:27-92) */
+int hb200_parcsr_info(const hb200_parcsr *A, int64_t *info12);
+/* HYPRE_IJMatrixPrint -> hypre_ParCSRMatrixPrintIJ (src/parcsr_mv/par_csr_matrix.c): the same text the
+ * reference writes for the same matrix (diag entries, then offd entries of a row; `%.14e`). */
+int hb200_parcsr_print_ij(const hb200_parcsr *A, const char *filename);
+/* HYPRE_IJVectorPrint / HYPRE_IJVectorRead (hypre_ParVectorPrintIJ, src/parcsr_mv/par_vector.c): `jlower
+ * jupper`, then `j value` lines, per rank file.  read with x_dev == NULL only returns the range. */
+int hb200_vector_print_ij(const double *x_dev, int64_t jlower, int num_values, const char *filename);
+int hb200_vector_read_ij(const char *filename, int64_t *jlower, int64_t *jupper, double *x_dev, int capacity);
+/* The host halves (no GPU): the assembly of one rank's rows (call with NULL arrays for the sizes first) and
+ * the CommPkg of rank `me` from the all-gathered ownership (own5[5 q ..] = ilower, iupper, jlower, jupper,
+ * number of off-range columns of rank q) and need lists (need[q * max_offd ..] = rank q's col_map_offd). */
+int hb200_host_ij_assemble(int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper, int64_t num_entries,
+                           const int64_t *rows, const int64_t *cols, const double *values, int add_duplicates,
+                           int *diag_nnz, int *offd_nnz, int *num_cols_offd, int *diag_i, int *diag_j,
+                           double *diag_data, int *offd_i, int *offd_j, double *offd_data,
+                           int64_t *col_map_offd);
+int hb200_host_ij_commpkg(int num_ranks, int me, const int64_t *own5, const int64_t *need, int64_t max_offd,
+                          int *num_sends, int *send_procs, int *send_map_starts, int *send_map_elmts,
+                          int send_capacity, int *num_recvs, int *recv_procs, int *recv_vec_starts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,7 @@ typedef struct
    HYPRE_ParVector     b, x;
    int                 b_from_generator;
    HYPRE_Solver        amg;
+   HYPRE_IJMatrix      ij;                /* the owner of A when the problem was read from an IJ file */
    int64_t            *colmap64[64][2];   /* widened col_map_offd per level / matrix kind */
 } rb_problem;
 
@@ -182,12 +183,58 @@ rb_problem *rb_problem_create(int type, int nx, int ny, int nz, int P, int Q, in
    return pb;
 }
 
+/* ij -fromfile <name> (ij.c:3174: HYPRE_IJMatrixRead) / a Matrix Market file (HYPRE_IJMatrixReadMM): the matrix the
+ * reference assembles from `<name>.<5-digit rank>`; b = ones, x = 0 */
+rb_problem *rb_problem_from_ij_file(const char *filename, int is_mm)
+{
+   rb_problem *pb = (rb_problem *) calloc(1, sizeof(rb_problem));
+   hypre_ParCSRMatrix *A;
+   void *obj = NULL;
+   rb_init();
+   pb->comm = hypre_MPI_COMM_WORLD;
+   hypre_MPI_Comm_rank(pb->comm, &pb->myid);
+   hypre_MPI_Comm_size(pb->comm, &pb->nprocs);
+   if (is_mm) { HYPRE_IJMatrixReadMM(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
+   else { HYPRE_IJMatrixRead(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
+   if (HYPRE_GetError() || !pb->ij) { HYPRE_ClearAllErrors(); free(pb); return NULL; }
+   HYPRE_IJMatrixGetObject(pb->ij, &obj);
+   pb->A = (HYPRE_ParCSRMatrix) obj;
+   A = (hypre_ParCSRMatrix *) pb->A;
+   if (!hypre_ParCSRMatrixCommPkg(A)) { hypre_MatvecCommPkgCreate(A); }
+   pb->b = (HYPRE_ParVector) hypre_ParVectorCreate(pb->comm, hypre_ParCSRMatrixGlobalNumRows(A), hypre_ParCSRMatrixRowStarts(A));
+   hypre_ParVectorInitialize((hypre_ParVector *) pb->b);
+   hypre_ParVectorSetConstantValues((hypre_ParVector *) pb->b, 1.0);
+   pb->x = (HYPRE_ParVector) hypre_ParVectorCreate(pb->comm, hypre_ParCSRMatrixGlobalNumCols(A), hypre_ParCSRMatrixColStarts(A));
+   hypre_ParVectorInitialize((hypre_ParVector *) pb->x);
+   hypre_ParVectorSetConstantValues((hypre_ParVector *) pb->x, 0.0);
+   return pb;
+}
+
+/* HYPRE_IJMatrixPrint of the fine-level operator / HYPRE_IJVectorPrint-format file of the right-hand side */
+int rb_print_ij(rb_problem *pb, const char *filename)
+{
+   hypre_ParCSRMatrixPrintIJ((hypre_ParCSRMatrix *) pb->A, 0, 0, filename);
+   return (int) HYPRE_GetError();
+}
+int rb_print_vector_ij(rb_problem *pb, const double *values, const char *filename)
+{
+   hypre_ParCSRMatrix *M = (hypre_ParCSRMatrix *) pb->A;
+   hypre_ParVector *v = hypre_ParVectorCreate(pb->comm, hypre_ParCSRMatrixGlobalNumRows(M), hypre_ParCSRMatrixRowStarts(M));
+   int n = hypre_ParCSRMatrixNumRows(M), k;
+   hypre_ParVectorInitialize(v);
+   for (k = 0; k < n; k++) { hypre_VectorData(hypre_ParVectorLocalVector(v))[k] = values[k]; }
+   hypre_ParVectorPrintIJ(v, 0, filename);
+   hypre_ParVectorDestroy(v);
+   return (int) HYPRE_GetError();
+}
+
 void rb_problem_destroy(rb_problem *pb)
 {
    int l, k;
    if (!pb) { return; }
    if (pb->amg) { HYPRE_BoomerAMGDestroy(pb->amg); }
-   if (pb->A) { HYPRE_ParCSRMatrixDestroy(pb->A); }
+   if (pb->ij) { HYPRE_IJMatrixDestroy(pb->ij); }
+   else if (pb->A) { HYPRE_ParCSRMatrixDestroy(pb->A); }
    if (pb->b) { HYPRE_ParVectorDestroy(pb->b); }
    if (pb->x) { HYPRE_ParVectorDestroy(pb->x); }
    for (l = 0; l < 64; l++) for (k = 0; k < 2; k++) { free(pb->colmap64[l][k]); }

@@ -94,6 +94,9 @@ def load(mpi=None) -> C.CDLL:
         "rb_sizeof_bigint": ([], C.c_int),
         "rb_problem_create": ([C.c_int] * 7 + [C.c_double, C.c_int, C.c_int], vp),
         "rb_problem_destroy": ([vp], None),
+        "rb_problem_from_ij_file": ([C.c_char_p, C.c_int], vp),
+        "rb_print_ij": ([vp, C.c_char_p], C.c_int),
+        "rb_print_vector_ij": ([vp, vp, C.c_char_p], C.c_int),
         "rb_problem_b": ([vp], dp), "rb_problem_x": ([vp], dp),
         "rb_problem_local_rows": ([vp], C.c_int), "rb_problem_global_rows": ([vp], C.c_longlong),
         "rb_amg_setup": ([vp] + [C.c_int] * 15 + [C.c_double] * 4 + [C.c_int] * 3 + [dp], C.c_int),
@@ -150,6 +153,30 @@ class Problem:
         self.local_rows = self.lib.rb_problem_local_rows(self.h)
         self.global_rows = self.lib.rb_problem_global_rows(self.h)
         self.setup_seconds = None
+
+    @classmethod
+    def from_ij_file(cls, filename: str, matrix_market: bool = False, mpi=None) -> "Problem":
+        """ij -fromfile: the matrix the reference's own HYPRE_IJMatrixRead (/ ReadMM) assembles from the file(s)"""
+        self = cls.__new__(cls)
+        self.lib = load(mpi)
+        self.h = self.lib.rb_problem_from_ij_file(filename.encode(), 1 if matrix_market else 0)
+        if not self.h:
+            raise RuntimeError(f"the reference could not read {filename}")
+        self.kind, self.n = "file", None
+        self.local_rows = self.lib.rb_problem_local_rows(self.h)
+        self.global_rows = self.lib.rb_problem_global_rows(self.h)
+        self.setup_seconds = None
+        return self
+
+    def print_ij(self, filename: str) -> None:
+        """HYPRE_IJMatrixPrint of the fine-level operator: `<filename>.<5-digit rank>`"""
+        if self.lib.rb_print_ij(self.h, filename.encode()):
+            raise RuntimeError("reference IJ print failed")
+
+    def print_vector_ij(self, values, filename: str) -> None:
+        v = np.ascontiguousarray(values, np.float64)
+        if self.lib.rb_print_vector_ij(self.h, _p(v), filename.encode()):
+            raise RuntimeError("reference IJ vector print failed")
 
     def destroy(self):
         if getattr(self, "h", None):

@@ -93,6 +93,55 @@ def main():
                 x_ext = np.concatenate([bufs[q].numpy() for q in range(nr)]) if nr else np.zeros(0)
                 want = np.array([xg[int(c)] for c in a["col_map_offd"]])
                 assert np.array_equal(x_ext, want), (l, which)
+    # ---- IJ interface, host halves: this rank's rows of A_0 as coordinate triplets through
+    # hb200_host_ij_assemble give the reference's diag / offd blocks and col_map_offd bit for bit (A_0 comes from
+    # the generator: diagonal first, then ascending columns — the order the triplets are handed over in); the
+    # CommPkg built from the all-gathered ownership and need lists is the reference's (hypre_MatvecCommPkgCreate)
+    import ctypes as C
+    from hypre_b200._lib import lib, check
+    v = h["levels"][0]["A"]
+    a = v.arrays()
+    n = v.num_rows
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        for p in range(a["diag_i"][i], a["diag_i"][i + 1]):
+            rows.append(v.first_row + i); cols.append(v.first_col + int(a["diag_j"][p])); vals.append(a["diag_data"][p])
+        if v.num_cols_offd:
+            for p in range(a["offd_i"][i], a["offd_i"][i + 1]):
+                rows.append(v.first_row + i); cols.append(int(a["col_map_offd"][a["offd_j"][p]])); vals.append(a["offd_data"][p])
+    r = np.array(rows, np.int64); c = np.array(cols, np.int64); w = np.array(vals, np.float64)
+    head = (v.first_row, v.first_row + n - 1, v.first_col, v.first_col + v.num_cols - 1)
+    dn, on, nco = C.c_int(0), C.c_int(0), C.c_int(0)
+    args = (*head, len(r), r.ctypes.data, c.ctypes.data, w.ctypes.data, 0)
+    check(lib.hb200_host_ij_assemble(*args, C.byref(dn), C.byref(on), C.byref(nco), *([None] * 7)))
+    assert dn.value == v.diag_nnz and on.value == v.offd_nnz and nco.value == v.num_cols_offd
+    out = {"diag_i": np.zeros(n + 1, np.int32), "diag_j": np.zeros(dn.value, np.int32), "diag_data": np.zeros(dn.value),
+           "offd_i": np.zeros(n + 1, np.int32), "offd_j": np.zeros(on.value, np.int32), "offd_data": np.zeros(on.value),
+           "col_map_offd": np.zeros(nco.value, np.int64)}
+    keys = ("diag_i", "diag_j", "diag_data", "offd_i", "offd_j", "offd_data", "col_map_offd")
+    check(lib.hb200_host_ij_assemble(*args, C.byref(dn), C.byref(on), C.byref(nco), *[out[k].ctypes.data for k in keys]))
+    for k in keys:
+        if a[k] is not None:
+            assert np.array_equal(out[k], a[k]), ("ij assemble", k, rank)
+    own_all = [None] * world
+    dist.all_gather_object(own_all, (list(head) + [nco.value], out["col_map_offd"].tolist()))
+    max_offd = max(o[0][4] for o in own_all)
+    own5 = np.array([x for o in own_all for x in o[0]], np.int64)
+    need = np.full(world * max(max_offd, 1), -1, np.int64)
+    for q, o in enumerate(own_all):
+        need[q * max_offd: q * max_offd + len(o[1])] = o[1]
+    ns, nr = C.c_int(0), C.c_int(0)
+    cap = max(int(a["send_map_starts"][v.num_sends]) if v.num_sends else 0, 1) + 8
+    sp, sms, sme = np.zeros(world, np.int32), np.zeros(world + 1, np.int32), np.zeros(cap, np.int32)
+    rp, rvs = np.zeros(world, np.int32), np.zeros(world + 1, np.int32)
+    check(lib.hb200_host_ij_commpkg(world, rank, own5.ctypes.data, need.ctypes.data, max_offd, C.byref(ns), sp.ctypes.data,
+                                    sms.ctypes.data, sme.ctypes.data, cap, C.byref(nr), rp.ctypes.data, rvs.ctypes.data))
+    assert ns.value == v.num_sends and nr.value == v.num_recvs, ("ij commpkg", ns.value, v.num_sends, nr.value, v.num_recvs)
+    if v.num_sends:
+        assert np.array_equal(sp[:ns.value], a["send_procs"]) and np.array_equal(sms[:ns.value + 1], a["send_map_starts"])
+        assert np.array_equal(sme[:sms[ns.value]], a["send_map_elmts"]), ("ij commpkg send_map_elmts", rank)
+    if v.num_recvs:
+        assert np.array_equal(rp[:nr.value], a["recv_procs"]) and np.array_equal(rvs[:nr.value + 1], a["recv_vec_starts"])
     dist.barrier()
     if rank == 0:
         print("CPU MULTI-RANK OK", flush=True)

@@ -185,9 +185,9 @@ def _ij_run(binary, args, nprocs=1, env_extra=None):
 
 @pytest.mark.parametrize("args,nprocs", [("-27pt -n 18 18 18 -solver 1 -rlx 18", 1),
                                          ("-27pt -n 24 14 14 -P 2 1 1 -solver 1 -rlx 18", 2),
-                                         ("-vardifconv -n 14 14 14 -solver 9 -rlx 18", 1),     # AMG-BiCGSTAB
-                                         ("-vardifconv -n 14 14 14 -solver 61 -rlx 18", 1),    # AMG-FlexGMRES
-                                         ("-vardifconv -n 20 12 12 -P 2 1 1 -solver 16 -rlx 18", 2),   # AMG-COGMRES
+                                         ("-vardifconv -n 11 11 11 -solver 9 -rlx 18", 1),     # AMG-BiCGSTAB
+                                         ("-vardifconv -n 11 11 11 -solver 61 -rlx 18", 1),    # AMG-FlexGMRES
+                                         ("-vardifconv -n 16 9 9 -P 2 1 1 -solver 16 -rlx 18", 2),     # AMG-COGMRES
                                          ("-27pt -n 20 12 12 -P 2 1 1 -solver 10", 2)])        # DS-BiCGSTAB
 def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     """the UNMODIFIED reference driver linked in front of hypre_shim.c, the shim bound to the emulated
@@ -218,7 +218,7 @@ def test_hybrid_gs_chunks_through_the_shim_on_the_host_emulation():
     for target in ("ij", "emu_shim"):
         r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", target], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    args = "-27pt -n 9 9 9 -solver 1"
+    args = "-27pt -n 8 7 7 -solver 1"
     its3, res3, _ = _ij_run("ij_ref", args, env_extra={"OMP_NUM_THREADS": "3"})
     its5, res5, _ = _ij_run("ij_ref", args, env_extra={"OMP_NUM_THREADS": "5"})
     assert abs(res3 - res5) > 1e-6 * res3          # the thread count does change the reference's numbers

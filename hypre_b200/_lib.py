@@ -146,6 +146,7 @@ def _load() -> C.CDLL:
         "hb200_parcsr_read_ij": ([C.POINTER(vp), C.c_char_p, C.c_int], C.c_int),
         "hb200_parcsr_info": ([vp, vp], C.c_int),
         "hb200_parcsr_print_ij": ([vp, C.c_char_p], C.c_int),
+        "hb200_parcsr_print_ij_binary": ([vp, C.c_char_p], C.c_int),
         "hb200_vector_print_ij": ([vp, C.c_int64, C.c_int, C.c_char_p], C.c_int),
         "hb200_vector_read_ij": ([C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int], C.c_int),
         "hb200_host_ij_assemble": ([C.c_int64] * 5 + [vp, vp, vp, C.c_int, c_int_p, c_int_p, c_int_p] + [vp] * 7, C.c_int),

@@ -224,6 +224,74 @@ static int ij_parse_file(const char *filename, int is_mm, int rank, int64_t *ran
    return 0;
 }
 
+// hypre_IJMatrixReadBinary (src/IJ_mv/IJMatrix.c:252-470): `<name>.<5-digit rank>.bin` = 11 x uint64 header (version 1,
+// bytes per index 4 | 8, bytes per value 4 | 8, global rows, global columns, global nonzeros, local nonzeros, ilower,
+// iupper, jlower, jupper), then the row indices, the column indices, the values of the local entries
+static int ij_parse_binary(const char *filename, int rank, int64_t *range4, std::vector<int64_t> &rows,
+                           std::vector<int64_t> &cols, std::vector<double> &vals)
+{
+   char path[1024];
+   snprintf(path, sizeof(path), "%s.%05d.bin", filename, rank);
+   FILE *f = fopen(path, "rb");
+   if (!f) return set_error(HB200_ERROR_ARG, "Could not open input file %s", path);
+   uint64_t header[11];
+   if (fread(header, sizeof(uint64_t), 11, f) != 11) { fclose(f); return set_error(HB200_ERROR_GENERIC, "%s: Could not read header entries", path); }
+   if (header[0] != 1) { fclose(f); return set_error(HB200_ERROR_GENERIC, "%s: Unsupported header version: %llu", path, (unsigned long long) header[0]); }
+   if (header[6] > 0x7fffffffULL) { fclose(f); return set_error(HB200_ERROR_GENERIC, "%s: Detected integer overflow at 7th header entry", path); }
+   if ((header[1] != 4 && header[1] != 8) || (header[2] != 4 && header[2] != 8)) { fclose(f); return set_error(HB200_ERROR_GENERIC, "%s: Unsupported data type", path); }
+   const size_t nnz = (size_t) header[6];
+   range4[0] = (int64_t) header[7]; range4[1] = (int64_t) header[8]; range4[2] = (int64_t) header[9]; range4[3] = (int64_t) header[10];
+   rows.resize(nnz); cols.resize(nnz); vals.resize(nnz);
+   auto read_idx = [&](std::vector<int64_t> &dst) -> bool {
+      if (header[1] == 8) {
+         std::vector<uint64_t> b(nnz);
+         if (fread(b.data(), 8, nnz, f) != nnz) return false;
+         for (size_t k = 0; k < nnz; k++) dst[k] = (int64_t) b[k];
+      } else {
+         std::vector<uint32_t> b(nnz);
+         if (fread(b.data(), 4, nnz, f) != nnz) return false;
+         for (size_t k = 0; k < nnz; k++) dst[k] = (int64_t) b[k];
+      }
+      return true;
+   };
+   bool ok = read_idx(rows) && read_idx(cols);
+   if (ok && header[2] == 8) ok = fread(vals.data(), 8, nnz, f) == nnz;
+   else if (ok) {
+      std::vector<float> b(nnz);
+      ok = fread(b.data(), 4, nnz, f) == nnz;
+      for (size_t k = 0; ok && k < nnz; k++) vals[k] = (double) b[k];
+   }
+   fclose(f);
+   if (!ok) return set_error(HB200_ERROR_GENERIC, "%s: Could not read all entries", path);
+   return 0;
+}
+
+// this rank's entries in the order the reference prints them: diag entries, then offd entries of a row
+static int ij_download_coo(const hb200_parcsr *A, std::vector<int64_t> &rows, std::vector<int64_t> &cols, std::vector<double> &vals)
+{
+   Ctx &c = ctx();
+   const int n = A->num_rows;
+   std::vector<int> di((size_t) n + 1, 0), dj((size_t) A->diag.nnz), oi((size_t) n + 1, 0), oj((size_t) A->offd.nnz);
+   std::vector<double> da((size_t) A->diag.nnz), oa((size_t) A->offd.nnz);
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   if (n) HB_CUDA(cudaMemcpy(di.data(), A->diag.i, sizeof(int) * di.size(), cudaMemcpyDeviceToHost));
+   if (A->diag.nnz) {
+      HB_CUDA(cudaMemcpy(dj.data(), A->diag.j, sizeof(int) * dj.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(da.data(), A->diag.a, sizeof(double) * da.size(), cudaMemcpyDeviceToHost));
+   }
+   if (A->num_cols_offd > 0 && A->offd.nnz) {
+      HB_CUDA(cudaMemcpy(oi.data(), A->offd.i, sizeof(int) * oi.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(oj.data(), A->offd.j, sizeof(int) * oj.size(), cudaMemcpyDeviceToHost));
+      HB_CUDA(cudaMemcpy(oa.data(), A->offd.a, sizeof(double) * oa.size(), cudaMemcpyDeviceToHost));
+   }
+   rows.clear(); cols.clear(); vals.clear();
+   for (int i = 0; i < n; i++) {
+      for (int p = di[(size_t) i]; p < di[(size_t) i + 1]; p++) { rows.push_back(A->first_row + i); cols.push_back(A->first_col + dj[(size_t) p]); vals.push_back(da[(size_t) p]); }
+      for (int p = oi[(size_t) i]; p < oi[(size_t) i + 1]; p++) { rows.push_back(A->first_row + i); cols.push_back(A->col_map_offd[(size_t) oj[(size_t) p]]); vals.push_back(oa[(size_t) p]); }
+   }
+   return 0;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -288,12 +356,13 @@ int hb200_parcsr_read_ij(hb200_parcsr **A, const char *filename, int is_matrix_m
 {
    HB_CHECK(require_ready());
    HB_REQUIRE(A != nullptr && filename != nullptr, HB200_ERROR_ARG, "hb200_parcsr_read_ij: null argument");
-   HB_REQUIRE(!is_matrix_market || ctx().nranks == 1, HB200_ERROR_ARG, "hb200_parcsr_read_ij: a Matrix Market file is read by one rank");
+   HB_REQUIRE(is_matrix_market != 1 || ctx().nranks == 1, HB200_ERROR_ARG, "hb200_parcsr_read_ij: a Matrix Market file is read by one rank");
    int64_t range[4];
    std::vector<int64_t> rows, cols;
    std::vector<double> vals;
    // a rank that cannot read its part still takes part in the collectives below (with an empty range)
-   const int fr = ij_parse_file(filename, is_matrix_market, ctx().rank, range, rows, cols, vals);
+   const int fr = (is_matrix_market == 2) ? ij_parse_binary(filename, ctx().rank, range, rows, cols, vals)
+                                          : ij_parse_file(filename, is_matrix_market, ctx().rank, range, rows, cols, vals);
    if (fr && ctx().nranks == 1) return fr;
    if (fr) { range[0] = 0; range[1] = -1; range[2] = 0; range[3] = -1; rows.clear(); cols.clear(); vals.clear(); }
    // hypre_IJMatrixRead: rows this rank owns are set (the last value wins); a symmetric Matrix Market file may
@@ -318,33 +387,56 @@ int hb200_parcsr_print_ij(const hb200_parcsr *A, const char *filename)
 {
    HB_CHECK(require_ready());
    HB_REQUIRE(A != nullptr && filename != nullptr, HB200_ERROR_ARG, "hb200_parcsr_print_ij: null argument");
-   Ctx &c = ctx();
-   const int n = A->num_rows;
-   std::vector<int> di((size_t) n + 1, 0), dj((size_t) A->diag.nnz), oi((size_t) n + 1, 0), oj((size_t) A->offd.nnz);
-   std::vector<double> da((size_t) A->diag.nnz), oa((size_t) A->offd.nnz);
-   HB_CUDA(cudaStreamSynchronize(c.s_comp));
-   if (n) HB_CUDA(cudaMemcpy(di.data(), A->diag.i, sizeof(int) * di.size(), cudaMemcpyDeviceToHost));
-   if (A->diag.nnz) {
-      HB_CUDA(cudaMemcpy(dj.data(), A->diag.j, sizeof(int) * dj.size(), cudaMemcpyDeviceToHost));
-      HB_CUDA(cudaMemcpy(da.data(), A->diag.a, sizeof(double) * da.size(), cudaMemcpyDeviceToHost));
-   }
-   if (A->num_cols_offd > 0 && A->offd.nnz) {
-      HB_CUDA(cudaMemcpy(oi.data(), A->offd.i, sizeof(int) * oi.size(), cudaMemcpyDeviceToHost));
-      HB_CUDA(cudaMemcpy(oj.data(), A->offd.j, sizeof(int) * oj.size(), cudaMemcpyDeviceToHost));
-      HB_CUDA(cudaMemcpy(oa.data(), A->offd.a, sizeof(double) * oa.size(), cudaMemcpyDeviceToHost));
-   }
+   std::vector<int64_t> rows, cols;
+   std::vector<double> vals;
+   HB_CHECK(ij_download_coo(A, rows, cols, vals));
    char path[1024];
-   snprintf(path, sizeof(path), "%s.%05d", filename, c.rank);
+   snprintf(path, sizeof(path), "%s.%05d", filename, ctx().rank);
    FILE *f = fopen(path, "w");
    if (!f) return set_error(HB200_ERROR_GENERIC, "Error: can't open output file %s", path);
-   fprintf(f, "%lld %lld %lld %lld\n", (long long) A->first_row, (long long) (A->first_row + n - 1),
+   fprintf(f, "%lld %lld %lld %lld\n", (long long) A->first_row, (long long) (A->first_row + A->num_rows - 1),
            (long long) A->first_col, (long long) (A->first_col + A->num_cols - 1));
-   for (int i = 0; i < n; i++) {
-      const long long I = (long long) A->first_row + i;
-      for (int p = di[(size_t) i]; p < di[(size_t) i + 1]; p++) fprintf(f, "%lld %lld %.14e\n", I, (long long) A->first_col + dj[(size_t) p], da[(size_t) p]);
-      for (int p = oi[(size_t) i]; p < oi[(size_t) i + 1]; p++) fprintf(f, "%lld %lld %.14e\n", I, (long long) A->col_map_offd[(size_t) oj[(size_t) p]], oa[(size_t) p]);
-   }
+   for (size_t k = 0; k < rows.size(); k++) fprintf(f, "%lld %lld %.14e\n", (long long) rows[k], (long long) cols[k], vals[k]);
    fclose(f);
+   return 0;
+}
+
+// HYPRE_IJMatrixPrintBinary -> hypre_ParCSRMatrixPrintBinaryIJ (src/parcsr_mv/par_csr_matrix.c:1120-1400): lossless
+// (fp64 values, 64-bit indices as a HYPRE_BigInt build writes them); collective (the header holds the global count)
+int hb200_parcsr_print_ij_binary(const hb200_parcsr *A, const char *filename)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A != nullptr && filename != nullptr, HB200_ERROR_ARG, "hb200_parcsr_print_ij_binary: null argument");
+   std::vector<int64_t> rows, cols, all;
+   std::vector<double> vals;
+   HB_CHECK(ij_download_coo(A, rows, cols, vals));
+   const int64_t mine = (int64_t) rows.size();
+   HB_CHECK(allgather_i64(&mine, 1, all));
+   uint64_t gnnz = 0;
+   for (int64_t v : all) gnnz += (uint64_t) v;
+   char path[1024];
+   snprintf(path, sizeof(path), "%s.%05d.bin", filename, ctx().rank);
+   FILE *f = fopen(path, "wb");
+   if (!f) return set_error(HB200_ERROR_GENERIC, "Could not open output file %s", path);
+   // index width: 4 bytes while the global sizes fit (what a default hypre build, 32-bit HYPRE_BigInt, writes), else 8
+   const bool small = A->global_rows < 0x7fffffffLL && A->global_cols < 0x7fffffffLL;
+   const uint64_t header[11] = {1, small ? 4u : 8u, 8, (uint64_t) A->global_rows, (uint64_t) A->global_cols, gnnz, (uint64_t) mine,
+                                (uint64_t) A->first_row, (uint64_t) (A->first_row + A->num_rows - 1),
+                                (uint64_t) A->first_col, (uint64_t) (A->first_col + A->num_cols - 1)};
+   bool ok = fwrite(header, sizeof(uint64_t), 11, f) == 11;
+   if (small) {
+      std::vector<uint32_t> b(rows.size());
+      for (size_t k = 0; k < rows.size(); k++) b[k] = (uint32_t) rows[k];
+      ok = ok && fwrite(b.data(), 4, b.size(), f) == b.size();
+      for (size_t k = 0; k < cols.size(); k++) b[k] = (uint32_t) cols[k];
+      ok = ok && fwrite(b.data(), 4, b.size(), f) == b.size();
+   } else {
+      ok = ok && fwrite(rows.data(), 8, rows.size(), f) == rows.size();
+      ok = ok && fwrite(cols.data(), 8, cols.size(), f) == cols.size();
+   }
+   ok = ok && fwrite(vals.data(), 8, vals.size(), f) == vals.size();
+   fclose(f);
+   if (!ok) return set_error(HB200_ERROR_GENERIC, "Could not write %s", path);
    return 0;
 }
 

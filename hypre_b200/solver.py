@@ -150,16 +150,17 @@ class ParCSRMatrix:
         return cls._adopt(h)
 
     @classmethod
-    def read_ij(cls, filename: str, matrix_market: bool = False) -> "ParCSRMatrix":
-        """HYPRE_IJMatrixRead / HYPRE_IJMatrixReadMM: `<filename>.<5-digit rank>` per rank, or one Matrix Market file"""
+    def read_ij(cls, filename: str, matrix_market: bool = False, binary: bool = False) -> "ParCSRMatrix":
+        """HYPRE_IJMatrixRead / ReadMM / ReadBinary: `<filename>.<5-digit rank>[.bin]` per rank, or one Matrix Market file"""
         init_required()
         h = C.c_void_p()
-        check(lib.hb200_parcsr_read_ij(C.byref(h), filename.encode(), 1 if matrix_market else 0))
+        check(lib.hb200_parcsr_read_ij(C.byref(h), filename.encode(), 2 if binary else (1 if matrix_market else 0)))
         return cls._adopt(h)
 
-    def print_ij(self, filename: str) -> None:
-        """HYPRE_IJMatrixPrint: the reference's text format, one file per rank"""
-        check(lib.hb200_parcsr_print_ij(self.handle, filename.encode()))
+    def print_ij(self, filename: str, binary: bool = False) -> None:
+        """HYPRE_IJMatrixPrint / PrintBinary: the reference's formats, one file per rank"""
+        fn = lib.hb200_parcsr_print_ij_binary if binary else lib.hb200_parcsr_print_ij
+        check(fn(self.handle, filename.encode()))
 
     @classmethod
     def from_view(cls, v) -> "ParCSRMatrix":

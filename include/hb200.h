@@ -418,10 +418,12 @@ int hb200_bicgstab_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
 int hb200_parcsr_from_ij(hb200_parcsr **A, int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper,
                          int64_t num_entries, const int64_t *rows, const int64_t *cols,
                          const double *values, int add_duplicates);
-/* HYPRE_IJMatrixRead (src/IJ_mv/IJMatrix.c:110-249): every rank reads `<filename>.<5-digit rank>` (header
- * `ilower iupper jlower jupper`, then `i j value` lines); is_matrix_market: HYPRE_IJMatrixReadMM, the whole
- * file on one rank (coordinate, real / integer, general / symmetric).  Collective. */
-int hb200_parcsr_read_ij(hb200_parcsr **A, const char *filename, int is_matrix_market);
+/* HYPRE_IJMatrixRead (src/IJ_mv/IJMatrix.c:110-249): format 0 — every rank reads `<filename>.<5-digit rank>`
+ * (header `ilower iupper jlower jupper`, then `i j value` lines); format 1: HYPRE_IJMatrixReadMM, the whole
+ * Matrix Market file on one rank (coordinate, real / integer, general / symmetric); format 2:
+ * HYPRE_IJMatrixReadBinary (IJMatrix.c:252-470), `<filename>.<5-digit rank>.bin` (88-byte header, then row
+ * indices, column indices, values; 4- or 8-byte indices and values).  Collective. */
+int hb200_parcsr_read_ij(hb200_parcsr **A, const char *filename, int format);
 /* sizes of a matrix (what the caller of hb200_parcsr_create passed; needed after from_ij / read_ij): info[0..11]
  * = num_rows, num_cols, num_cols_offd, diag nonzeros, offd nonzeros, num_sends, num_recvs, send_map_starts[num_sends],
  * first_row_index, first_col_diag, global_num_rows, global_num_cols (hypre_ParCSRMatrix, par_csr_matrix.h:27-92) */
@@ -429,6 +431,9 @@ int hb200_parcsr_info(const hb200_parcsr *A, int64_t *info12);
 /* HYPRE_IJMatrixPrint -> hypre_ParCSRMatrixPrintIJ (src/parcsr_mv/par_csr_matrix.c): the same text the
  * reference writes for the same matrix (diag entries, then offd entries of a row; `%.14e`). */
 int hb200_parcsr_print_ij(const hb200_parcsr *A, const char *filename);
+/* HYPRE_IJMatrixPrintBinary -> hypre_ParCSRMatrixPrintBinaryIJ (par_csr_matrix.c:1120-1400): the lossless format
+ * (fp64 values, 64-bit indices).  Collective (the header carries the global nonzero count). */
+int hb200_parcsr_print_ij_binary(const hb200_parcsr *A, const char *filename);
 /* HYPRE_IJVectorPrint / HYPRE_IJVectorRead (hypre_ParVectorPrintIJ, src/parcsr_mv/par_vector.c): `jlower
  * jupper`, then `j value` lines, per rank file.  read with x_dev == NULL only returns the range. */
 int hb200_vector_print_ij(const double *x_dev, int64_t jlower, int num_values, const char *filename);

@@ -194,7 +194,8 @@ rb_problem *rb_problem_from_ij_file(const char *filename, int is_mm)
    pb->comm = hypre_MPI_COMM_WORLD;
    hypre_MPI_Comm_rank(pb->comm, &pb->myid);
    hypre_MPI_Comm_size(pb->comm, &pb->nprocs);
-   if (is_mm) { HYPRE_IJMatrixReadMM(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
+   if (is_mm == 2) { HYPRE_IJMatrixReadBinary(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
+   else if (is_mm) { HYPRE_IJMatrixReadMM(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
    else { HYPRE_IJMatrixRead(filename, pb->comm, HYPRE_PARCSR, &pb->ij); }
    if (HYPRE_GetError() || !pb->ij) { HYPRE_ClearAllErrors(); free(pb); return NULL; }
    HYPRE_IJMatrixGetObject(pb->ij, &obj);
@@ -214,6 +215,11 @@ rb_problem *rb_problem_from_ij_file(const char *filename, int is_mm)
 int rb_print_ij(rb_problem *pb, const char *filename)
 {
    hypre_ParCSRMatrixPrintIJ((hypre_ParCSRMatrix *) pb->A, 0, 0, filename);
+   return (int) HYPRE_GetError();
+}
+int rb_print_ij_binary(rb_problem *pb, const char *filename)
+{
+   hypre_ParCSRMatrixPrintBinaryIJ((hypre_ParCSRMatrix *) pb->A, 0, 0, filename);
    return (int) HYPRE_GetError();
 }
 int rb_print_vector_ij(rb_problem *pb, const double *values, const char *filename)

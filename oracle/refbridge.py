@@ -96,6 +96,7 @@ def load(mpi=None) -> C.CDLL:
         "rb_problem_destroy": ([vp], None),
         "rb_problem_from_ij_file": ([C.c_char_p, C.c_int], vp),
         "rb_print_ij": ([vp, C.c_char_p], C.c_int),
+        "rb_print_ij_binary": ([vp, C.c_char_p], C.c_int),
         "rb_print_vector_ij": ([vp, vp, C.c_char_p], C.c_int),
         "rb_problem_b": ([vp], dp), "rb_problem_x": ([vp], dp),
         "rb_problem_local_rows": ([vp], C.c_int), "rb_problem_global_rows": ([vp], C.c_longlong),
@@ -155,11 +156,12 @@ class Problem:
         self.setup_seconds = None
 
     @classmethod
-    def from_ij_file(cls, filename: str, matrix_market: bool = False, mpi=None) -> "Problem":
-        """ij -fromfile: the matrix the reference's own HYPRE_IJMatrixRead (/ ReadMM) assembles from the file(s)"""
+    def from_ij_file(cls, filename: str, matrix_market: bool = False, binary: bool = False, mpi=None) -> "Problem":
+        """ij -fromfile / -frombinfile: the matrix the reference's own HYPRE_IJMatrixRead (/ ReadMM / ReadBinary)
+        assembles from the file(s)"""
         self = cls.__new__(cls)
         self.lib = load(mpi)
-        self.h = self.lib.rb_problem_from_ij_file(filename.encode(), 1 if matrix_market else 0)
+        self.h = self.lib.rb_problem_from_ij_file(filename.encode(), 2 if binary else (1 if matrix_market else 0))
         if not self.h:
             raise RuntimeError(f"the reference could not read {filename}")
         self.kind, self.n = "file", None
@@ -168,9 +170,10 @@ class Problem:
         self.setup_seconds = None
         return self
 
-    def print_ij(self, filename: str) -> None:
-        """HYPRE_IJMatrixPrint of the fine-level operator: `<filename>.<5-digit rank>`"""
-        if self.lib.rb_print_ij(self.h, filename.encode()):
+    def print_ij(self, filename: str, binary: bool = False) -> None:
+        """HYPRE_IJMatrixPrint[Binary] of the fine-level operator: `<filename>.<5-digit rank>[.bin]`"""
+        fn = self.lib.rb_print_ij_binary if binary else self.lib.rb_print_ij
+        if fn(self.h, filename.encode()):
             raise RuntimeError("reference IJ print failed")
 
     def print_vector_ij(self, values, filename: str) -> None:

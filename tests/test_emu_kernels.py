@@ -34,8 +34,8 @@ def test_gpu_parity_suite_on_the_host_emulation():
         pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
     build_emu()
     # everything that runs on one device except the tests that exec the real shim binary
-    r = run_child({}, os.path.join("tests", "test_gpu_parity.py"), "-m", "gpu", "-n", "6",
-                  "-k", "not ij_dropin and not multi_gpu")
+    r = run_child({}, os.path.join("tests", "test_gpu_parity.py"), os.path.join("tests", "test_ij_formats.py"), "-m", "gpu",
+                  "-n", "6", "-k", "not ij_dropin and not multi_gpu")
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail

@@ -162,6 +162,24 @@ def test_read_ij_matvec_and_print_round_trip(rb, hb, tmp_path, kind, n):
 
 
 @pytest.mark.gpu
+def test_binary_ij_files_are_lossless_both_ways(rb, hb, tmp_path):
+    pb = rb.Problem("vardifconv", (7, 6, 5))
+    ref = pb.level_view(0, 0).arrays()
+    name = str(tmp_path / "A")
+    pb.print_ij(name, binary=True)                     # written by the reference (HYPRE_IJMatrixPrintBinary)
+    A = hb.ParCSRMatrix.read_ij(name, binary=True)
+    maps = A.download_maps()
+    assert np.array_equal(maps["diag_i"], ref["diag_i"]) and np.array_equal(maps["diag_j"], ref["diag_j"])
+    out = str(tmp_path / "B")
+    A.print_ij(out, binary=True)
+    assert open(out + ".00000.bin", "rb").read() == open(name + ".00000.bin", "rb").read()
+    pb_back = rb.Problem.from_ij_file(out, binary=True)    # ... and read back by the reference: the same bits
+    back = pb_back.level_view(0, 0).arrays()
+    for k in ("diag_i", "diag_j", "diag_data"):
+        assert np.array_equal(back[k], ref[k]), k
+
+
+@pytest.mark.gpu
 def test_from_ij_solves_like_the_reference(rb, hb, tmp_path):
     """a matrix that entered as triplets (shuffled, with duplicates to add up) drives the same diag-scaled PCG"""
     import torch

@@ -40,7 +40,7 @@ class GMRESParams(C.Structure):
         ("k_dim", C.c_int), ("min_iter", C.c_int), ("max_iter", C.c_int),
         ("rel_change", C.c_int), ("skip_real_r_check", C.c_int), ("stop_crit", C.c_int),
         ("hybrid", C.c_int), ("logging", C.c_int), ("print_level", C.c_int),
-        ("cgs", C.c_int), ("unroll", C.c_int),
+        ("cgs", C.c_int), ("unroll", C.c_int), ("aug_dim", C.c_int), ("approx_constant", C.c_int),
     ]
 
 
@@ -139,6 +139,8 @@ def _load() -> C.CDLL:
         "hb200_flexgmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_cogmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_cogmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_lgmres_solve": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
+        "hb200_lgmres_solve_host": ([vp, C.c_int, vp, C.POINTER(GMRESParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_bicgstab_default_params": ([C.POINTER(BiCGSTABParams)], None),
         "hb200_bicgstab_solve": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),
         "hb200_bicgstab_solve_host": ([vp, C.c_int, vp, C.POINTER(BiCGSTABParams), vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),

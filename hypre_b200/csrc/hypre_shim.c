@@ -9,6 +9,7 @@
  *   hypre_GMRESSolve          (src/krylov/gmres.c:294)          -> hb200_gmres_solve_host
  *   hypre_FlexGMRESSolve      (src/krylov/flexgmres.c:288)      -> hb200_flexgmres_solve_host
  *   hypre_COGMRESSolve        (src/krylov/cogmres.c:270)        -> hb200_cogmres_solve_host
+ *   hypre_LGMRESSolve         (src/krylov/lgmres.c:320)         -> hb200_lgmres_solve_host
  *   hypre_BiCGSTABSolve       (src/krylov/bicgstab.c:246)       -> hb200_bicgstab_solve_host
  *   hypre_BoomerAMGSolve      (src/parcsr_ls/par_amg_solve.c:22)-> hb200_amg_solve
  *   HYPRE_ParCSRMatrixMatvec  (src/parcsr_mv/HYPRE_parcsr_matrix.c:385) -> hb200_parcsr_matvec_host
@@ -17,7 +18,8 @@
  *
  *   hypre_BoomerAMGSetup      (src/parcsr_ls/par_amg_setup.c)   -> the reference's setup, THEN the upload
  *   hypre_PCGSetup / hypre_GMRESSetup (src/krylov/pcg.c:198, gmres.c:185) -> the reference's, THEN upload A
- *   hypre_FlexGMRESSetup / hypre_COGMRESSetup / hypre_BiCGSTABSetup (flexgmres.c:176, cogmres.c:178, bicgstab.c:150): same
+ *   hypre_FlexGMRESSetup / hypre_COGMRESSetup / hypre_LGMRESSetup / hypre_BiCGSTABSetup (flexgmres.c:176, cogmres.c:178,
+ *   lgmres.c:207, bicgstab.c:150): same
  *   HYPRE_IJMatrixAssemble    (src/IJ_mv/HYPRE_IJMatrix.c)      -> the reference's, THEN drop the stale mirror
  *
  * Everything else (IJ assembly, BoomerAMGSetup, all other solvers) stays the reference's own
@@ -734,6 +736,20 @@ HYPRE_Int hypre_COGMRESSetup(void *cogmres_vdata, void *A, void *b, void *x)
    return hypre_error_flag;
 }
 
+HYPRE_Int hypre_LGMRESSetup(void *lgmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   HYPRE_Int ierr;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_LGMRESSetup"); }
+   ierr = orig(lgmres_vdata, A, b, x);
+   if (!ierr)
+   {
+      hypre_LGMRESData *ld = (hypre_LGMRESData *) lgmres_vdata;
+      krylov_setup_upload((void *) ld->functions->Matvec, A, (void *) ld->functions->precond, ld->precond_data, NULL, 5, ld->k_dim);
+   }
+   return hypre_error_flag;
+}
+
 HYPRE_Int hypre_BiCGSTABSetup(void *bicgstab_vdata, void *A, void *b, void *x)
 {
    static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
@@ -1074,6 +1090,39 @@ HYPRE_Int hypre_COGMRESSolve(void *cogmres_vdata, void *A, void *b, void *x)
    hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
    if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
    if (g_verbose) { fprintf(stderr, "[hypre_b200] COGMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
+   return hypre_error_flag;
+}
+
+HYPRE_Int hypre_LGMRESSolve(void *lgmres_vdata, void *A, void *b, void *x)
+{
+   static HYPRE_Int (*orig)(void *, void *, void *, void *) = NULL;
+   static int noticed = 0;
+   hypre_LGMRESData *ld = (hypre_LGMRESData *) lgmres_vdata;
+   hypre_LGMRESFunctions *fn = ld->functions;
+   const char *why = NULL;
+   hb200_amg *amg = NULL;
+   hb200_parcsr *dA = NULL;
+   hb200_gmres_params P;
+   hb200_krylov_result R;
+   int kind = 0, flag, on, strict_err = 0;
+   if (!orig) { orig = (HYPRE_Int (*)(void *, void *, void *, void *)) next_sym("hypre_LGMRESSolve"); }
+   if (ld->k_dim > 100) { why = "LGMRES restart length above 100"; }
+   on = krylov_ext_on_path((void *) fn->Matvec, (void *) fn->precond, ld->precond_data, NULL, A, b, why, &noticed, &dA, &amg, &kind, &strict_err);
+   if (on < 0 || strict_err) { return hypre_error_flag; }
+   if (!on) { return orig(lgmres_vdata, A, b, x); }
+   gmres_family_params(&P, ld->tol, ld->a_tol, ld->cf_tol, ld->k_dim, ld->min_iter, ld->max_iter, 0, 0, ld->logging, ld->print_level);
+   P.aug_dim = ld->aug_dim; P.approx_constant = ld->approx_constant;
+   ld->converged = 0;
+   memset(&R, 0, sizeof(R));
+   flag = hb200_lgmres_solve_host(dA, kind, amg, &P, hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) b)),
+                                  hypre_VectorData(hypre_ParVectorLocalVector((hypre_ParVector *) x)), ld->norms, &R);
+   if (flag & ~HB200_ERROR_CONV) { hypre_error_w_msg(HYPRE_ERROR_GENERIC, hb200_last_error()); return hypre_error_flag; }
+   ld->num_iterations = R.num_iterations;
+   ld->rel_residual_norm = R.rel_residual_norm;
+   ld->converged = R.converged;
+   hypre_ParVectorAllZeros((hypre_ParVector *) x) = 0;
+   if (flag & HB200_ERROR_CONV) { hypre_error(HYPRE_ERROR_CONV); }
+   if (g_verbose) { fprintf(stderr, "[hypre_b200] LGMRES on device: %d its, %.3f ms, %lld kernel launches\n", R.num_iterations, R.solve_ms, R.kernel_launches); }
    return hypre_error_flag;
 }
 

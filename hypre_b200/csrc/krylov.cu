@@ -636,6 +636,7 @@ void hb200_gmres_default_params(hb200_gmres_params *p)
    memset(p, 0, sizeof(*p));
    p->k_dim = 5; p->tol = 1.0e-06; p->max_iter = 1000;   // gmres.c:60-75
    p->cgs = 1;                                            // cogmres.c:97
+   p->aug_dim = 2; p->approx_constant = 1;                // lgmres.c:111-112
 }
 
 static int check_precond(int kind, hb200_amg *amg, hb200_parcsr *A)
@@ -722,6 +723,7 @@ int hb200_krylov_warmup(hb200_parcsr *A, int precond_kind, hb200_amg *amg, int i
          P.k_dim = k_dim > 0 ? k_dim : 5; P.tol = 0.0; P.max_iter = P.k_dim + 1; P.skip_real_r_check = 1;
          if (is_gmres == 2) f = hb200_flexgmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
          else if (is_gmres == 3) f = hb200_cogmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
+         else if (is_gmres == 5) f = hb200_lgmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
          else f = hb200_gmres_solve(A, precond_kind, amg, &P, db, dx, nullptr, &R);
       } else {
          hb200_pcg_params P;

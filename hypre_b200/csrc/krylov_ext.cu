@@ -1,8 +1,9 @@
 // krylov_ext.cu — the other Krylov drivers of the ParCSR function table on the same device kernels
-// (SURVEY §8 row f4): BiCGSTAB, FlexGMRES and COGMRES.
+// (SURVEY §8 row f4): BiCGSTAB, FlexGMRES, COGMRES and LGMRES.
 //
 // Reference: hypre_BiCGSTABSolve (src/krylov/bicgstab.c:246-606), hypre_FlexGMRESSolve
-// (src/krylov/flexgmres.c:288-812), hypre_COGMRESSolve (src/krylov/cogmres.c:270-896) with the
+// (src/krylov/flexgmres.c:288-812), hypre_LGMRESSolve (src/krylov/lgmres.c:320-940),
+// hypre_COGMRESSolve (src/krylov/cogmres.c:270-896) with the
 // batched vector operations COGMRES is built on: hypre_ParVectorMassInnerProd / MassDotpTwo / MassAxpy
 // (src/parcsr_mv/par_vector_batched.c:17-135 over src/seq_mv/vector_batched.c:212-1208).
 //
@@ -596,6 +597,248 @@ static int arnoldi_solve_dev(int variant, hb200_parcsr *A, int pk, hb200_amg *am
    return eflag;
 }
 
+// =======================================================================================
+// LGMRES: restarted GMRES augmented with the error approximations of the previous cycles
+// =======================================================================================
+static int lgmres_solve_dev(hb200_parcsr *A, int pk, hb200_amg *amg, const hb200_gmres_params *P,
+                            const double *b, double *x, double *norms, hb200_krylov_result *res)
+{
+   Ctx &c = ctx();
+   const size_t n = (size_t) A->num_rows;
+   const size_t na = n ? n : 1;
+   cudaStream_t st = c.s_comp;
+   const int my_id = c.rank;
+   const int k_dim = P->k_dim, min_iter = P->min_iter, max_iter = P->max_iter;
+   int aug_dim = P->aug_dim < 0 ? 0 : P->aug_dim;
+   if (aug_dim > k_dim - 1) aug_dim = k_dim - 1;             // hypre_LGMRESSetAugDim (lgmres.c:975-990)
+   if (aug_dim < 0) aug_dim = 0;
+   const int approx_constant = P->approx_constant;
+   const double r_tol = P->tol, cf_tol = P->cf_tol, a_tol = P->a_tol;
+   const bool log = (P->logging > 0 || P->print_level > 0) && norms;
+   HB_REQUIRE(k_dim >= 1 && k_dim <= 100, HB200_ERROR_ARG, "k_dim out of range (1..100)");
+   int eflag = 0;
+   ProfRange pr_solve("LGMRES-Solve");
+
+   // p[0..k_dim], aug_vecs[0..aug_dim], a_aug_vecs[0..aug_dim-1] (hypre_LGMRESSetup, lgmres.c:240-275), r, w
+   double *slab = nullptr;
+   const int nvec = (k_dim + 1) + (aug_dim + 1) + aug_dim + 2;
+   HB_CHECK(ws_get(8, sizeof(double) * na * (size_t) nvec, &slab));
+   auto pv = [&](int q) { return slab + (size_t) q * na; };
+   auto augv = [&](int q) { return slab + (size_t) (k_dim + 1 + q) * na; };
+   auto aaugv = [&](int q) { return slab + (size_t) (k_dim + 1 + aug_dim + 1 + q) * na; };
+   double *r = slab + (size_t) (k_dim + 1 + aug_dim + 1 + aug_dim) * na;
+   double *w = r + na;
+   auto cleanup = [&]() { cudaStreamSynchronize(st); };
+#define LG_CHECK(expr) do { int f_ = (expr); if (f_) { cleanup(); return f_; } } while (0)
+
+   const int kd = k_dim + aug_dim;
+   std::vector<double> rs(kd + 1, 0.0), cc(kd, 0.0), ss(kd, 0.0);
+   std::vector<std::vector<double>> hh(kd + 1, std::vector<double>(kd, 0.0));
+   std::vector<int> aug_order(aug_dim > 0 ? aug_dim : 1, 0);
+   int i = 0, j, k, ii, iter = 0, break_value = 0, converged = 0;
+   int aug_ct = 0, it_arnoldi, it_total, it_aug, order, spot = 0;
+   double epsilon, gamma, t, r_norm, b_norm, den_norm, r_norm_last = 0.0, tmp_norm;
+   const double epsmac = 1.e-16;
+   double ieee_check = 0.0, cf_ave_0 = 0.0, cf_ave_1 = 0.0, weight, r_norm_0;
+
+   LG_CHECK(parcsr_matvec(A, -1.0, x, 1.0, b, pv(0)));
+   double bb, rr;
+   LG_CHECK(vec_dot2_dev(b, b, pv(0), pv(0), n, S_T0, S_T1, st));
+   LG_CHECK(scalars_allreduce(S_T0, 2, st));
+   { double v2[2]; LG_CHECK(scalars_fetch(S_T0, 2, v2, st)); bb = v2[0]; rr = v2[1]; }
+   b_norm = sqrt(bb);
+   if (b_norm != 0.0) ieee_check = b_norm / b_norm;
+   if (ieee_check != ieee_check) {
+      cleanup();
+      res->error_flag = HB200_ERROR_GENERIC;
+      return set_error(HB200_ERROR_GENERIC, "hb200_lgmres_solve: INFs and/or NaNs detected in input b");
+   }
+   r_norm = sqrt(rr);
+   r_norm_0 = r_norm;
+   if (r_norm != 0.0) ieee_check = r_norm / r_norm;
+   if (ieee_check != ieee_check) {
+      cleanup();
+      res->error_flag = HB200_ERROR_GENERIC;
+      return set_error(HB200_ERROR_GENERIC, "hb200_lgmres_solve: INFs and/or NaNs detected in A or x_0");
+   }
+   if (log) norms[0] = r_norm;
+   if (!my_id && P->print_level > 1 && (P->logging > 0 || P->print_level > 0)) {
+      printf("L2 norm of b: %e\n", b_norm);
+      if (b_norm == 0.0) printf("Rel_resid_norm actually contains the residual norm\n");
+      printf("Initial L2 norm of residual: %e\n", r_norm);
+   }
+   den_norm = b_norm > 0.0 ? b_norm : r_norm;
+   epsilon = fmax(a_tol, r_tol * den_norm);
+   if (!my_id && P->print_level > 1) print_residual_header(false, b_norm);
+
+   while (iter < max_iter) {
+      rs[0] = r_norm;
+      if (r_norm == 0.0) {
+         cleanup();
+         res->num_iterations = iter; res->converged = 0; res->error_flag = 0;
+         res->rel_residual_norm = 0.0;
+         return 0;
+      }
+      if (r_norm <= epsilon && iter >= min_iter) {
+         LG_CHECK(parcsr_matvec(A, -1.0, x, 1.0, b, r));
+         LG_CHECK(dot_global_host(r, r, n, &rr));
+         r_norm = sqrt(rr);
+         if (r_norm <= epsilon) {
+            if (!my_id && P->print_level > 1) { printf("\n\n"); printf("Final L2 norm of residual: %e\n\n", r_norm); }
+            break;
+         } else if (!my_id && P->print_level > 0) printf("false convergence 1\n");
+      }
+      t = 1.0 / r_norm;
+      r_norm_last = r_norm;
+      LG_CHECK(vec_scale(t, pv(0), n, st));
+      i = 0;
+      // the approximation space keeps its size: Krylov vectors make up for the augmentation vectors not there yet
+      it_arnoldi = approx_constant ? k_dim - aug_ct : k_dim - aug_dim;
+      it_total = it_arnoldi + aug_ct;
+      it_aug = 0;
+      while (i < it_total && iter < max_iter) {
+         i++;
+         iter++;
+         if (i <= it_arnoldi) {
+            LG_CHECK(precond_apply(pk, amg, A, pv(i - 1), r));
+            LG_CHECK(parcsr_matvec(A, 1.0, r, 0.0, pv(i), pv(i)));
+         } else {
+            it_aug++;
+            order = i - it_arnoldi - 1;
+            for (ii = 0; ii < aug_dim; ii++) { if (aug_order[ii] == order) { spot = ii; break; } }
+            LG_CHECK(vec_copy(aaugv(spot), pv(i), n, st));
+         }
+         for (j = 0; j < i; j++) {
+            LG_CHECK(dot_global(pv(j), pv(i), n, S_H0 + j));
+            FAxpyDev fa{pv(j), pv(i), c.d_scalars, S_H0 + j, -1.0};
+            HB_EW(fa, n, st);
+         }
+         LG_CHECK(dot_global(pv(i), pv(i), n, S_H0 + i));
+         { FScaleInvSqrtDev fs{pv(i), c.d_scalars, S_H0 + i}; HB_EW(fs, n, st); }
+         {
+            double hcol[kScalarSlots];
+            LG_CHECK(scalars_fetch(S_H0, i + 1, hcol, st));
+            for (j = 0; j < i; j++) hh[j][i - 1] = hcol[j];
+            hh[i][i - 1] = sqrt(hcol[i]);
+         }
+         for (j = 1; j < i; j++) {
+            t = hh[j - 1][i - 1];
+            hh[j - 1][i - 1] = ss[j - 1] * hh[j][i - 1] + cc[j - 1] * t;
+            hh[j][i - 1] = -ss[j - 1] * t + cc[j - 1] * hh[j][i - 1];
+         }
+         t = hh[i][i - 1] * hh[i][i - 1];
+         t += hh[i - 1][i - 1] * hh[i - 1][i - 1];
+         gamma = sqrt(t);
+         if (gamma == 0.0) gamma = epsmac;
+         cc[i - 1] = hh[i - 1][i - 1] / gamma;
+         ss[i - 1] = hh[i][i - 1] / gamma;
+         rs[i] = -hh[i][i - 1] * rs[i - 1];
+         rs[i] /= gamma;
+         rs[i - 1] = cc[i - 1] * rs[i - 1];
+         hh[i - 1][i - 1] = ss[i - 1] * hh[i][i - 1] + cc[i - 1] * hh[i - 1][i - 1];
+         r_norm = fabs(rs[i]);
+         if (P->print_level > 0) {
+            if (norms) norms[iter] = r_norm;
+            if (!my_id && P->print_level > 1 && norms) print_residual_row(false, iter, norms[iter], norms[iter - 1], b_norm);
+         }
+         if (cf_tol > 0.0) {
+            cf_ave_0 = cf_ave_1;
+            cf_ave_1 = pow(r_norm / r_norm_0, 1.0 / (2.0 * (double) iter));
+            weight = fabs(cf_ave_1 - cf_ave_0);
+            weight = weight / fmax(cf_ave_1, cf_ave_0);
+            weight = 1.0 - weight;
+            if (weight * cf_ave_1 > cf_tol) { break_value = 1; break; }
+         }
+         if (r_norm <= epsilon && iter >= min_iter) break;
+      }   // restart cycle
+
+      if (break_value) break;
+
+      rs[i - 1] = rs[i - 1] / hh[i - 1][i - 1];
+      for (k = i - 2; k >= 0; k--) {
+         t = 0.0;
+         for (j = k + 1; j < i; j++) t -= hh[k][j] * rs[j];
+         t += rs[k];
+         rs[k] = t / hh[k][k];
+      }
+      if (it_arnoldi > i) it_arnoldi = i;
+      if (!it_aug) {
+         LG_CHECK(vec_copy(pv(i - 1), w, n, st));
+         LG_CHECK(vec_scale(rs[i - 1], w, n, st));
+         for (j = i - 2; j >= 0; j--) LG_CHECK(vec_axpy(rs[j], pv(j), w, n, st));
+      } else {
+         // the correction holds Krylov vectors and augmentation vectors (lgmres.c:782-806)
+         LG_CHECK(vec_copy(pv(0), w, n, st));
+         LG_CHECK(vec_scale(rs[0], w, n, st));
+         for (j = 1; j < it_arnoldi; j++) LG_CHECK(vec_axpy(rs[j], pv(j), w, n, st));
+         for (ii = 0; ii < it_aug; ii++) {
+            for (j = 0; j < aug_dim; j++) { if (aug_order[j] == ii) { spot = j; break; } }
+            LG_CHECK(vec_axpy(rs[it_arnoldi + ii], augv(spot), w, n, st));
+         }
+      }
+      // w is the error approximation of this cycle: kept as the next augmentation vector
+      LG_CHECK(vec_copy(w, augv(aug_dim), n, st));
+      LG_CHECK(precond_apply(pk, amg, A, w, r));
+      LG_CHECK(vec_axpy(1.0, r, x, n, st));
+
+      if (r_norm <= epsilon && iter >= min_iter) {
+         LG_CHECK(parcsr_matvec(A, -1.0, x, 1.0, b, r));
+         LG_CHECK(dot_global_host(r, r, n, &rr));
+         r_norm = sqrt(rr);
+         if (r_norm <= epsilon) {
+            if (!my_id && P->print_level > 1) { printf("\n\n"); printf("Final L2 norm of residual: %e\n\n", r_norm); }
+            converged = 1;
+            break;
+         }
+         if (!my_id && P->print_level > 0) printf("false convergence 2\n");
+         LG_CHECK(vec_copy(r, pv(0), n, st));
+         i = 0;
+      }
+
+      // w = r_0 of this cycle (lgmres.c:844-845), then the residual vector for the restart
+      LG_CHECK(vec_copy(pv(0), w, n, st));
+      LG_CHECK(vec_scale(r_norm_last, w, n, st));
+      for (j = i; j > 0; j--) {
+         rs[j - 1] = -ss[j - 1] * rs[j];
+         rs[j] = cc[j - 1] * rs[j];
+      }
+      if (i) LG_CHECK(vec_axpy(rs[i] - 1.0, pv(i), pv(i), n, st));
+      for (j = i - 1; j > 0; j--) LG_CHECK(vec_axpy(rs[j], pv(j), pv(i), n, st));
+      if (i) {
+         LG_CHECK(vec_axpy(rs[0] - 1.0, pv(0), pv(0), n, st));
+         LG_CHECK(vec_axpy(1.0, pv(i), pv(0), n, st));
+      }
+
+      // the new augmentation vector and A times it (= (r_0 - r_m) / |z|: independent of the preconditioner)
+      if (aug_dim > 0) {
+         if (!aug_ct) { spot = 0; aug_ct++; }
+         else if (aug_ct < aug_dim) { spot = aug_ct; aug_ct++; }
+         else { for (ii = 0; ii < aug_dim; ii++) if (aug_order[ii] == aug_dim - 1) spot = ii; }
+         LG_CHECK(vec_copy(augv(aug_dim), augv(spot), n, st));
+         double zz;
+         LG_CHECK(dot_global_host(augv(spot), augv(spot), n, &zz));
+         tmp_norm = 1.0 / sqrt(zz);
+         LG_CHECK(vec_scale(tmp_norm, augv(spot), n, st));
+         for (ii = 0; ii < aug_dim; ii++) aug_order[ii]++;
+         aug_order[spot] = 0;
+         LG_CHECK(vec_copy(w, aaugv(spot), n, st));
+         LG_CHECK(vec_scale(-1.0, aaugv(spot), n, st));
+         LG_CHECK(vec_axpy(1.0, pv(0), aaugv(spot), n, st));
+         LG_CHECK(vec_scale(-tmp_norm, aaugv(spot), n, st));
+      }
+   }
+
+   if (!my_id && P->print_level > 1) printf("\n\n");
+   res->num_iterations = iter;
+   res->converged = converged;
+   res->rel_residual_norm = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   if (iter >= max_iter && r_norm > epsilon && epsilon > 0) eflag |= HB200_ERROR_CONV;
+   res->error_flag = eflag;
+   cleanup();
+#undef LG_CHECK
+   return eflag;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -679,6 +922,15 @@ int hb200_cogmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const
    return timed_solve(result, [&]() { return arnoldi_solve_dev(AV_CO, A, precond_kind, amg, params, b, x, norms, result); });
 }
 
+int hb200_lgmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const hb200_gmres_params *params,
+                       const double *b, double *x, double *norms, hb200_krylov_result *result)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(A && params && result && ((b && x) || A->num_rows == 0), HB200_ERROR_ARG, "null argument");
+   HB_CHECK(check_precond_ext(precond_kind, amg));
+   return timed_solve(result, [&]() { return lgmres_solve_dev(A, precond_kind, amg, params, b, x, norms, result); });
+}
+
 int hb200_bicgstab_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const hb200_bicgstab_params *params,
                               const double *b_host, double *x_host, double *norms, hb200_krylov_result *result)
 {
@@ -698,6 +950,13 @@ int hb200_cogmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg, 
 {
    return host_solve(A, b_host, x_host, [&](double *db, double *dx) {
       return hb200_cogmres_solve(A, precond_kind, amg, params, db, dx, norms, result); });
+}
+
+int hb200_lgmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg, const hb200_gmres_params *params,
+                            const double *b_host, double *x_host, double *norms, hb200_krylov_result *result)
+{
+   return host_solve(A, b_host, x_host, [&](double *db, double *dx) {
+      return hb200_lgmres_solve(A, precond_kind, amg, params, db, dx, norms, result); });
 }
 
 }  // extern "C"

@@ -497,6 +497,18 @@ class ParCSRCOGMRES(ParCSRFlexGMRES):
         self.params.cgs = cgs
 
 
+class ParCSRLGMRES(ParCSRFlexGMRES):
+    """HYPRE_ParCSRLGMRES: hypre_LGMRESSolve (src/krylov/lgmres.c:320): GMRES(k_dim) augmented with up to aug_dim
+    error approximations of the previous restart cycles."""
+    _dev, _host = "hb200_lgmres_solve", "hb200_lgmres_solve_host"
+
+    def __init__(self, tol: float = 1e-6, max_iter: int = 1000, k_dim: int = 20, aug_dim: int = 2, a_tol: float = 0.0,
+                 min_iter: int = 0, cf_tol: float = 0.0, logging: int = 1, print_level: int = 0):
+        ParCSRGMRES.__init__(self, tol=tol, max_iter=max_iter, k_dim=k_dim, a_tol=a_tol, min_iter=min_iter,
+                             cf_tol=cf_tol, logging=logging, print_level=print_level)
+        self.params.aug_dim = aug_dim
+
+
 class ParCSRBiCGSTAB(_Krylov):
     """HYPRE_ParCSRBiCGSTAB: hypre_BiCGSTABSolve (src/krylov/bicgstab.c:246) over the ParCSR function table."""
 
@@ -613,7 +625,7 @@ def amg_from_hierarchy(h, use_graph: bool = False, gs_chunks: int = 0):
 __all__ = [
     "init", "finalize", "comm_init", "comm_get_unique_id", "sync", "launch_count",
     "ParCSRMatrix", "BoomerAMG", "ParCSRPCG", "ParCSRGMRES", "ParCSRFlexGMRES", "ParCSRCOGMRES",
-    "ParCSRBiCGSTAB", "relax", "cheby_solve", "vector_print_ij", "vector_read_ij",
+    "ParCSRLGMRES", "ParCSRBiCGSTAB", "relax", "cheby_solve", "vector_print_ij", "vector_read_ij",
     "inner_prod", "axpy", "amg_from_hierarchy", "HB200Error", "KrylovResult",
     "PRECOND_NONE", "PRECOND_AMG", "PRECOND_DIAGSCALE",
 ]

@@ -332,7 +332,7 @@ int hb200_pcg_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
  * allocate the work vectors there): allocates the persistent Krylov workspace and runs a few
  * iterations on b = 1, x = 0 inside it so that halo plans, smoother scratch and the captured V-cycle
  * graphs of the solve exist before the application times its Solve call.  is_gmres: 0 = PCG, 1 =
- * GMRES(k_dim), 2 = FlexGMRES(k_dim), 3 = COGMRES(k_dim), 4 = BiCGSTAB.  Collective. */
+ * GMRES(k_dim), 2 = FlexGMRES(k_dim), 3 = COGMRES(k_dim), 4 = BiCGSTAB, 5 = LGMRES(k_dim).  Collective. */
 int hb200_krylov_warmup(hb200_parcsr *A, int precond_kind, hb200_amg *amg, int is_gmres, int k_dim);
 
 /* Same call with HOST b and x (what HYPRE_PCGSolve sees in a CPU-memory application):
@@ -348,6 +348,7 @@ typedef struct {
    int    k_dim, min_iter, max_iter, rel_change, skip_real_r_check, stop_crit, hybrid;
    int    logging, print_level;
    int    cgs, unroll;    /* COGMRES only (cogmres.h: cgs = 2 re-orthogonalises; the device kernels have one unrolling) */
+   int    aug_dim, approx_constant;   /* LGMRES only (lgmres.h: augmentation vectors, constant size of the space) */
 } hb200_gmres_params;
 
 void hb200_gmres_default_params(hb200_gmres_params *p);   /* hypre_GMRESCreate, gmres.c:52-110 */
@@ -384,6 +385,16 @@ int hb200_cogmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
 int hb200_cogmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
                              const hb200_gmres_params *params, const double *b_host,
                              double *x_host, double *norms, hb200_krylov_result *result);
+
+/* hypre_LGMRESSolve (src/krylov/lgmres.c:320-940), table of HYPRE_ParCSRLGMRESCreate
+ * (src/parcsr_ls/HYPRE_parcsr_lgmres.c): GMRES(k_dim) whose space holds up to params->aug_dim error
+ * approximations of the previous restart cycles. */
+int hb200_lgmres_solve(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                       const hb200_gmres_params *params, const double *b_dev, double *x_dev,
+                       double *norms, hb200_krylov_result *result);
+int hb200_lgmres_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
+                            const hb200_gmres_params *params, const double *b_host,
+                            double *x_host, double *norms, hb200_krylov_result *result);
 
 /* user-settable part of hypre_BiCGSTABData (src/krylov/bicgstab.h:70-108) */
 typedef struct {

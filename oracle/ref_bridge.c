@@ -675,7 +675,8 @@ int rb_gmres_solve(rb_problem *pb, int precond, double tol, double atol, int max
 }
 
 /* ij -solver 9 / 10 (BiCGSTAB, ij.c:8660-8690), 16 / 17 (COGMRES, ij.c:9088-9110), 61 / 60 (FlexGMRES,
- * ij.c:8226-8245) over the same ParCSR table: which = 0 BiCGSTAB, 1 FlexGMRES, 2 COGMRES; cgs only COGMRES */
+ * ij.c:8226-8245), 50 / 51 (LGMRES) over the same ParCSR table: which = 0 BiCGSTAB, 1 FlexGMRES, 2 COGMRES, 3 LGMRES;
+ * cgs: COGMRES' variant, LGMRES' aug_dim */
 int rb_krylov_ext_solve(rb_problem *pb, int which, int precond, double tol, double atol, int max_iter,
                         int k_dim, int cgs, int rel_change, const double *b_in, double *x_io,
                         int *num_iterations, double *final_res_norm, double *norms, double *solve_seconds)
@@ -728,6 +729,26 @@ int rb_krylov_ext_solve(rb_problem *pb, int which, int precond, double tol, doub
       HYPRE_FlexGMRESGetFinalRelativeResidualNorm(ks, &fr);
       nr = ((hypre_FlexGMRESData *) ks)->norms;
    }
+   else if (which == 3)
+   {
+      /* ij -solver 50 / 51 (ij.c:7990-8015); `cgs` carries aug_dim here */
+      HYPRE_ParCSRLGMRESCreate(pb->comm, &ks);
+      HYPRE_LGMRESSetKDim(ks, k_dim);
+      HYPRE_LGMRESSetAugDim(ks, cgs);
+      HYPRE_LGMRESSetMaxIter(ks, max_iter);
+      HYPRE_LGMRESSetTol(ks, tol);
+      HYPRE_LGMRESSetAbsoluteTol(ks, atol);
+      HYPRE_LGMRESSetLogging(ks, 1);
+      HYPRE_LGMRESSetPrintLevel(ks, 0);
+      if (pc) { HYPRE_LGMRESSetPrecond(ks, pc, pcs, pcd); }
+      HYPRE_LGMRESSetup(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      t0 = wall();
+      HYPRE_LGMRESSolve(ks, (HYPRE_Matrix) pb->A, (HYPRE_Vector) vb, (HYPRE_Vector) vx);
+      if (solve_seconds) { *solve_seconds = wall() - t0; }
+      HYPRE_LGMRESGetNumIterations(ks, &its);
+      HYPRE_LGMRESGetFinalRelativeResidualNorm(ks, &fr);
+      nr = ((hypre_LGMRESData *) ks)->norms;
+   }
    else
    {
       HYPRE_ParCSRCOGMRESCreate(pb->comm, &ks);
@@ -758,6 +779,7 @@ int rb_krylov_ext_solve(rb_problem *pb, int which, int precond, double tol, doub
    if (x_io) { take_vec(vx, x_io); }
    if (which == 0) { HYPRE_ParCSRBiCGSTABDestroy(ks); }
    else if (which == 1) { HYPRE_ParCSRFlexGMRESDestroy(ks); }
+   else if (which == 3) { HYPRE_ParCSRLGMRESDestroy(ks); }
    else { HYPRE_ParCSRCOGMRESDestroy(ks); }
    hypre_ParVectorDestroy(vb); hypre_ParVectorDestroy(vx);
    k = (int) HYPRE_GetError();

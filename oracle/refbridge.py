@@ -354,9 +354,12 @@ class Problem:
                 "x": x, "seconds": t.value, "error_flag": flag}
 
     def krylov_ext(self, which, precond="amg", tol=1e-8, atol=0.0, max_iter=100, k_dim=5, cgs=1, rel_change=0,
-                   b=None, x0=None) -> dict:
-        """ij -solver 9/10 (which="bicgstab"), 61/60 ("flexgmres"), 16/17 ("cogmres") with BoomerAMG / diagonal scaling"""
-        wk = {"bicgstab": 0, "flexgmres": 1, "cogmres": 2}[which]
+                   aug_dim=2, b=None, x0=None) -> dict:
+        """ij -solver 9/10 (which="bicgstab"), 61/60 ("flexgmres"), 16/17 ("cogmres"), 50/51 ("lgmres") with
+        BoomerAMG / diagonal scaling"""
+        wk = {"bicgstab": 0, "flexgmres": 1, "cogmres": 2, "lgmres": 3}[which]
+        if which == "lgmres":
+            cgs = aug_dim
         pk = {"none": 0, "amg": 1, "diagscale": 2}[precond]
         its, fr, t = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
         norms = np.zeros(max_iter + 2)

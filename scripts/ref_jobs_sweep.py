@@ -5,6 +5,9 @@ every "Iterations = N" line must be equal and every final relative residual must
 Whether the shim ran the solve on the device or handed it back to the reference is recorded per job.
 
 usage: python scripts/ref_jobs_sweep.py [emu|gpu] [file.jobs ...] [--max-seconds S] [--jobs J] [--max-rows R] [--min-rows R]
+                                        [--omp T]
+--omp T: both sides run with OMP_NUM_THREADS = T and the drop-in with HYPRE_B200_GS_CHUNKS=host: the hybrid Gauss-Seidel
+smoothers then follow the reference's T-thread semantics on the device (one launch per sweep).
 """
 import os
 import re
@@ -32,9 +35,14 @@ def read_jobs(path):
     return out
 
 
+OMP = 1
+
+
 def run(binary, nranks, args, timeout):
     cmd = [os.path.join(REF, "mpirun"), "-np", str(nranks), os.path.join(REF, binary), *args]
-    env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
+    env = dict(os.environ, OMP_NUM_THREADS=str(OMP), HYPRE_B200_VERBOSE="1")
+    if OMP > 1:
+        env["HYPRE_B200_GS_CHUNKS"] = "host"
     t0 = time.time()
     # own process group, so that a timeout takes the ranks down with their launcher
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REF, env=env, start_new_session=True)
@@ -88,6 +96,9 @@ def main():
             min_rows = int(argv.pop(0))
         elif a == "--timeout":
             timeout = float(argv.pop(0))
+        elif a == "--omp":
+            global OMP
+            OMP = int(argv.pop(0))
         else:
             files.append(a.replace(".jobs", ""))
     jobs = []

@@ -127,6 +127,8 @@ def _load() -> C.CDLL:
         "hb200_amg_set_use_graph": ([vp, C.c_int], C.c_int),
         "hb200_amg_cycle": ([vp, vp, vp, C.c_int], C.c_int),
         "hb200_amg_solve": ([vp, vp, vp, C.c_int, c_int_p, c_double_p], C.c_int),
+        "hb200_amg_solve_logged": ([vp, vp, vp, C.c_int, c_int_p, c_double_p, vp, c_double_p], C.c_int),
+        "hb200_amg_cycle_sweeps": ([vp, vp], C.c_int),
         "hb200_amg_level_vector": ([vp, C.c_int, C.c_int, C.POINTER(vp), c_int_p], C.c_int),
         "hb200_pcg_default_params": ([C.POINTER(PCGParams)], None),
         "hb200_pcg_solve": ([vp, C.c_int, vp, C.POINTER(PCGParams), vp, vp, vp, vp, C.POINTER(KrylovResult)], C.c_int),

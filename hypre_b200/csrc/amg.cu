@@ -327,19 +327,54 @@ int amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, bool u_all_zer
    return 0;
 }
 
-int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
-              int *num_iterations, double *rel_resid_norm)
+// relaxation sweeps one cycle makes on every level: the cycling state machine of cycle_body without the work
+// (the reference's "cycle complexity" adds the nonzeros of a level once per sweep, par_cycle.c:455-474)
+static void amg_cycle_sweeps(const hb200_amg *amg, int *sweeps)
 {
-   // hypre_BoomerAMGSolve (par_amg_solve.c:22-424) without the printing
+   const int nl = amg->num_levels;
+   for (int l = 0; l < nl; l++) sweeps[l] = 0;
+   std::vector<int> lev_counter(nl);
+   lev_counter[0] = 1;
+   for (int k = 1; k < nl; k++) lev_counter[k] = amg->fcycle ? 1 : amg->cycle_type;
+   int fcycle_lev = nl - 2, level = 0, cycle_param = 1;
+   bool not_finished = true;
+   while (not_finished) {
+      sweeps[level] += (nl > 1) ? amg->num_grid_sweeps[cycle_param] : amg->num_grid_sweeps[0];
+      --lev_counter[level];
+      if (lev_counter[level] >= 0 && level != nl - 1) {
+         ++level;
+         lev_counter[level] = lev_counter[level] > amg->cycle_type ? lev_counter[level] : amg->cycle_type;
+         cycle_param = (level == nl - 1) ? 3 : 1;
+      } else if (level != 0) {
+         --level;
+         cycle_param = 2;
+         if (amg->fcycle && fcycle_lev == level) {
+            lev_counter[level] = lev_counter[level] > 1 ? lev_counter[level] : 1;
+            fcycle_lev--;
+         }
+      } else {
+         not_finished = false;
+      }
+   }
+}
+
+// resid_norms != NULL: the residual norm before the first and after every cycle (max_iter + 1 values) and the
+// norm of f are handed back for the caller's per-cycle table — computed even when tol == 0, as the reference does
+// with print_level > 1 / logging > 1 (par_amg_solve.c:130, 228)
+int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
+              int *num_iterations, double *rel_resid_norm, double *resid_norms, double *rhs_norm_out)
+{
+   // hypre_BoomerAMGSolve (par_amg_solve.c:22-424); the printing is the caller's
    Ctx &c = ctx();
    (void) A;
    hb200_amg_level &L0 = amg->lev[0];
    const size_t n = (size_t) L0.n;
    const double tol = amg->tol;
+   const bool norms = tol > 0.0 || resid_norms != nullptr;
    double resid_nrm = 1.0, resid_nrm_init = 0.0, rhs_norm = 0.0, relative_resid = 1.0;
    const int S = kScalarSlots - 4;
    int flag = 0;
-   if (tol > 0.0) {
+   if (norms) {
       // Vtemp = f ; Vtemp = A u - f ; ||Vtemp||   (:170-182)
       if (u_all_zeros) { HB_CHECK(vec_set(u, 0.0, n, c.s_comp)); u_all_zeros = false; }
       HB_CHECK(parcsr_matvec(L0.A, 1.0, u, -1.0, f, L0.Vtemp));
@@ -358,12 +393,13 @@ int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool 
       } else {
          relative_resid = 1.0;
       }
+      if (resid_norms) resid_norms[0] = resid_nrm_init;
    }
    int cycle_count = 0;
    while ((relative_resid >= tol || cycle_count < amg->min_iter) && cycle_count < amg->max_iter) {
       HB_CHECK(amg_cycle(amg, f, u, u_all_zeros));
       u_all_zeros = false;
-      if (tol > 0.0) {
+      if (norms) {
          HB_CHECK(parcsr_matvec(L0.A, 1.0, u, -1.0, f, L0.Vtemp));
          HB_CHECK(vec_dot_dev(L0.Vtemp, L0.Vtemp, n, S, c.s_comp));
          HB_CHECK(scalars_allreduce(S, 1, c.s_comp));
@@ -372,9 +408,11 @@ int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool 
          resid_nrm = sqrt(v);
          if (amg->converge_type == 0) relative_resid = rhs_norm != 0.0 ? resid_nrm / rhs_norm : resid_nrm;
          else                          relative_resid = resid_nrm / resid_nrm_init;
+         if (resid_norms) resid_norms[cycle_count + 1] = resid_nrm;
       }
       ++cycle_count;
    }
+   if (rhs_norm_out) *rhs_norm_out = rhs_norm;
    if (cycle_count == amg->max_iter && tol > 0.0) flag |= HB200_ERROR_CONV;
    if (num_iterations) *num_iterations = cycle_count;
    if (rel_resid_norm) *rel_resid_norm = relative_resid;
@@ -551,7 +589,23 @@ int hb200_amg_solve(hb200_amg *amg, const double *f, double *u, int u_all_zeros,
    HB_CHECK(require_ready());
    HB_REQUIRE(amg && ((f && u) || amg->lev[0].n == 0), HB200_ERROR_ARG, "null argument");
    for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
-   return amg_solve(amg, amg->lev[0].A, f, u, u_all_zeros != 0, num_iterations, rel_resid_norm);
+   return amg_solve(amg, amg->lev[0].A, f, u, u_all_zeros != 0, num_iterations, rel_resid_norm, nullptr, nullptr);
+}
+
+int hb200_amg_solve_logged(hb200_amg *amg, const double *f, double *u, int u_all_zeros, int *num_iterations,
+                           double *rel_resid_norm, double *resid_norms, double *rhs_norm)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && resid_norms && ((f && u) || amg->lev[0].n == 0), HB200_ERROR_ARG, "null argument");
+   for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "level not set");
+   return amg_solve(amg, amg->lev[0].A, f, u, u_all_zeros != 0, num_iterations, rel_resid_norm, resid_norms, rhs_norm);
+}
+
+int hb200_amg_cycle_sweeps(const hb200_amg *amg, int *sweeps_per_level)
+{
+   HB_REQUIRE(amg && sweeps_per_level, HB200_ERROR_ARG, "null argument");
+   amg_cycle_sweeps(amg, sweeps_per_level);
+   return 0;
 }
 
 int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n)

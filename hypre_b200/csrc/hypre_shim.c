@@ -44,6 +44,7 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -793,6 +794,93 @@ HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix)
 
 /* ---- BoomerAMG solve ------------------------------------------------------------------------------- */
 
+/* print_level > 1 / logging > 1 (ij's default for the stand-alone solver): the device solve hands back the residual norm
+ * of every cycle; the tables are the reference's (par_amg_solve.c:139-143, 198-206, 273-277, 295-417), the cycle
+ * complexity from the sweeps one cycle makes on every level (par_cycle.c:455-474) */
+static int amg_solve_logged(hypre_ParAMGData *amg, hypre_ParCSRMatrix *A, hb200_amg *dev, double *df, double *du, int n,
+                            int u_zero, int *its, double *rel)
+{
+   const int print_level = hypre_ParAMGDataPrintLevel(amg), logging = hypre_ParAMGDataLogging(amg);
+   const int max_iter = hypre_ParAMGDataMaxIter(amg), converge_type = hypre_ParAMGDataConvergeType(amg);
+   const int nl = hypre_ParAMGDataNumLevels(amg);
+   const double tol = hypre_ParAMGDataTol(amg);
+   hypre_ParCSRMatrix **A_array = hypre_ParAMGDataAArray(amg);
+   double *norms = (double *) calloc((size_t) (max_iter > 0 ? max_iter : 0) + 2, sizeof(double));
+   double rhs_norm = 0.0, old_resid, conv_factor, relative;
+   int flag, k, j;
+   if (g_myid == 0 && print_level > 1) { hypre_BoomerAMGWriteSolverParams(amg); }
+   if (g_myid == 0 && print_level > 1 && tol > 0.) { hypre_printf("\n\nAMG SOLUTION INFO:\n"); }
+   flag = hb200_amg_solve_logged(dev, df, du, u_zero, its, rel, norms, &rhs_norm);
+   if (flag & ~HB200_ERROR_CONV) { free(norms); return flag; }
+   if (g_myid == 0 && print_level > 1)
+   {
+      relative = (converge_type == 0) ? (rhs_norm != 0.0 ? norms[0] / rhs_norm : norms[0]) : 1.0;
+      hypre_printf("                                            relative\n");
+      hypre_printf("               residual        factor       residual\n");
+      hypre_printf("               --------        ------       --------\n");
+      hypre_printf("    Initial    %e                 %e\n", norms[0], relative);
+      old_resid = norms[0];
+      for (k = 1; k <= *its; k++)
+      {
+         conv_factor = (old_resid != 0.0) ? norms[k] / old_resid : norms[k];
+         relative = (converge_type == 0) ? (rhs_norm != 0.0 ? norms[k] / rhs_norm : norms[k]) : norms[k] / norms[0];
+         hypre_printf("    Cycle %2d   %e    %f     %e \n", k, norms[k], conv_factor, relative);
+         old_resid = norms[k];
+      }
+   }
+   if (print_level > 1)
+   {
+      double total_coeffs = 0.0, total_variables = 0.0, cycle_op_count = 0.0, c0, v0;
+      double grid_cmplxty = 0.0, operat_cmplxty = 0.0, cycle_cmplxty = 0.0;
+      int *sweeps = (int *) calloc((size_t) nl + 1, sizeof(int));
+      conv_factor = (*its > 0 && norms[0] != 0.0) ? pow(norms[*its] / norms[0], 1.0 / (double) *its) : 1.;
+      hb200_amg_cycle_sweeps(dev, sweeps);
+      c0 = (double) hypre_ParCSRMatrixDNumNonzeros(A);
+      v0 = (double) hypre_ParCSRMatrixGlobalNumRows(A);
+      for (j = 0; j < nl; j++)
+      {
+         total_coeffs += (j == 0) ? c0 : (double) hypre_ParCSRMatrixNumNonzeros(A_array[j]);
+         total_variables += (j == 0) ? v0 : (double) hypre_ParCSRMatrixGlobalNumRows(A_array[j]);
+         cycle_op_count += (double) sweeps[j] * (double) hypre_ParCSRMatrixDNumNonzeros(j == 0 ? A : A_array[j]);
+      }
+      free(sweeps);
+      hypre_ParAMGDataCycleOpCount(amg) = cycle_op_count;
+      if (v0 != 0.0) { grid_cmplxty = total_variables / v0; }
+      if (c0 != 0.0) { operat_cmplxty = total_coeffs / c0; cycle_cmplxty = cycle_op_count / c0; }
+      if (g_myid == 0)
+      {
+         if (flag & HB200_ERROR_CONV)
+         {
+            hypre_printf("\n\n==============================================");
+            hypre_printf("\n NOTE: Convergence tolerance was not achieved\n");
+            hypre_printf("      within the allowed %d V-cycles\n", max_iter);
+            hypre_printf("==============================================");
+         }
+         hypre_printf("\n\n Average Convergence Factor = %f", conv_factor);
+         hypre_printf("\n\n     Complexity:    grid = %f\n", grid_cmplxty);
+         hypre_printf("                operator = %f\n", operat_cmplxty);
+         hypre_printf("                   cycle = %f\n\n\n\n", cycle_cmplxty);
+      }
+   }
+   if (logging > 1 && hypre_ParAMGDataResidual(amg))
+   {
+      /* the residual of the last iterate, f - A u, where hypre_BoomerAMGGetResidual looks for it */
+      hypre_ParVector *R = hypre_ParAMGDataResidual(amg);
+      hb200_parcsr *dA = mirror_matrix(A);
+      double *dr = NULL;
+      if (dA && !hb200_malloc((void **) &dr, sizeof(double) * (size_t) (n ? n : 1)))
+      {
+         if (!hb200_parcsr_matvec(dA, -1.0, du, 1.0, df, dr))
+         {
+            hb200_memcpy_d2h(hypre_VectorData(hypre_ParVectorLocalVector(R)), dr, sizeof(double) * (size_t) n);
+         }
+         hb200_free(dr);
+      }
+   }
+   free(norms);
+   return flag;
+}
+
 HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_ParVector *f, hypre_ParVector *u)
 {
    static HYPRE_Int (*orig)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *) = NULL;
@@ -802,8 +890,9 @@ HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
    hb200_amg *dev;
    double *df = NULL, *du = NULL, rel = 0.0;
    int n = hypre_ParCSRMatrixNumRows(A), its = 0, flag;
+   const int want_log = hypre_ParAMGDataPrintLevel(amg) > 1 || hypre_ParAMGDataLogging(amg) > 1;
    if (!orig) { orig = (HYPRE_Int (*)(void *, hypre_ParCSRMatrix *, hypre_ParVector *, hypre_ParVector *)) next_sym("hypre_BoomerAMGSolve"); }
-   if (!why && (hypre_ParAMGDataPrintLevel(amg) > 1 || hypre_ParAMGDataLogging(amg) > 1)) { why = "per-cycle printing / residual logging of stand-alone BoomerAMG"; }
+   if (!why && want_log && hypre_ParAMGDataGridRelaxPoints(amg)) { why = "per-cycle printing with user-set relaxation points"; }
    if (!why && hypre_ParVectorNumVectors(f) > 1) { why = "multi-vector BoomerAMG solve"; }
    if (why)
    {
@@ -831,7 +920,14 @@ HYPRE_Int hypre_BoomerAMGSolve(void *amg_vdata, hypre_ParCSRMatrix *A, hypre_Par
    }
    hb200_memcpy_h2d(df, hypre_VectorData(hypre_ParVectorLocalVector(f)), sizeof(double) * (size_t) n);
    if (!hypre_ParVectorAllZeros(u)) { hb200_memcpy_h2d(du, hypre_VectorData(hypre_ParVectorLocalVector(u)), sizeof(double) * (size_t) n); }
-   flag = hb200_amg_solve(dev, df, du, hypre_ParVectorAllZeros(u) ? 1 : 0, &its, &rel);
+   if (want_log)
+   {
+      flag = amg_solve_logged(amg, A, dev, df, du, n, hypre_ParVectorAllZeros(u) ? 1 : 0, &its, &rel);
+   }
+   else
+   {
+      flag = hb200_amg_solve(dev, df, du, hypre_ParVectorAllZeros(u) ? 1 : 0, &its, &rel);
+   }
    hb200_memcpy_d2h(hypre_VectorData(hypre_ParVectorLocalVector(u)), du, sizeof(double) * (size_t) n);
    hb200_free(df); hb200_free(du);
    hypre_ParVectorAllZeros(u) = 0;

@@ -10,7 +10,7 @@
 
 namespace hb {
 int amg_solve(hb200_amg *amg, hb200_parcsr *A, const double *f, double *u, bool u_all_zeros,
-              int *num_iterations, double *rel_resid_norm);
+              int *num_iterations, double *rel_resid_norm, double *resid_norms = nullptr, double *rhs_norm_out = nullptr);
 // fused-dot request for the next amg_solve (preconditioner use): slot >= 0 asks the cycle's last
 // level-0 sweep for <u, f>; amg_dot_fused tells whether it delivered (else the caller runs dot_kernel)
 void amg_set_dot_request(hb200_amg *amg, int slot);

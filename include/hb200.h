@@ -292,6 +292,15 @@ int hb200_amg_cycle(hb200_amg *amg, const double *f_dev, double *u_dev, int u_al
  * may be NULL. */
 int hb200_amg_solve(hb200_amg *amg, const double *f_dev, double *u_dev, int u_all_zeros,
                     int *num_iterations, double *rel_resid_norm);
+/* The same solve with what the reference prints at print_level > 1 / keeps at logging > 1 (par_amg_solve.c:130-280):
+ * resid_norms[0] = the residual norm before the first cycle, resid_norms[k] = after cycle k (max_iter + 1 values, host),
+ * *rhs_norm = the norm of f (converge_type 0).  The norms are computed after every cycle even when tol == 0, as the
+ * reference does in that mode. */
+int hb200_amg_solve_logged(hb200_amg *amg, const double *f_dev, double *u_dev, int u_all_zeros,
+                           int *num_iterations, double *rel_resid_norm, double *resid_norms, double *rhs_norm);
+/* relaxation sweeps ONE cycle makes on every level (host only): the reference's "cycle complexity" adds the nonzeros of
+ * a level once per sweep (par_cycle.c:455-474, hypre_ParAMGDataCycleOpCount) */
+int hb200_amg_cycle_sweeps(const hb200_amg *amg, int *sweeps_per_level);
 /* per-level device vectors after a cycle, for parity tests: which = 0 F_array, 1 U_array */
 int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n);
 

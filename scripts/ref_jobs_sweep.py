@@ -107,10 +107,8 @@ def main():
             if any(s in j[2] for s in SKIP_FLAGS):
                 continue
             args = list(j[2])
-            # stand-alone BoomerAMG (ij's default solver 0) prints per cycle at ij's default print level 3, which
-            # the shim leaves to the reference: ask for print level 1 (the numbers do not depend on it)
-            if "-solver" not in args and "-pout" not in args:
-                args += ["-pout", "1"]
+            # (stand-alone BoomerAMG, ij's default solver 0, prints per cycle at ij's default print level 3: the shim
+            # prints those tables itself since the end of round 2, the jobs run as they are written)
             rows = 1000
             if "-n" in args:
                 k = args.index("-n")

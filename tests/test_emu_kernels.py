@@ -208,6 +208,29 @@ def test_ij_dropin_through_the_shim_on_the_host_emulation(args, nprocs):
     assert abs(res_dev - res_ref) <= rtol * res_ref and res_dev < 1e-8, (args, res_dev, res_ref)
 
 
+def test_default_ij_invocation_prints_the_reference_tables_on_the_host_emulation():
+    """`ij` with its defaults is the stand-alone BoomerAMG solver at print level 3: parameter table, residual and
+    convergence factor of every cycle, grid / operator / cycle complexities.  The drop-in runs it on the device and
+    prints the reference's output, line for line."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs /root/reference to build the ij driver")
+    for target in ("ij", "emu_shim"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", target], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    env = dict(os.environ, OMP_NUM_THREADS="1", HYPRE_B200_VERBOSE="1")
+    outs = {}
+    for binary in ("ij_ref", "ij_b200_emu"):
+        r = subprocess.run([os.path.join(ref, binary), "-27pt", "-n", "10", "10", "10", "-rlx", "18", "-mu", "2"],
+                           capture_output=True, text=True, timeout=600, cwd=ref, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[binary] = ([l for l in r.stdout.splitlines() if l.strip() and "wall clock" not in l and "cpu clock" not in l
+                         and "seconds" not in l], r.stderr)
+    assert "BoomerAMG on device" in outs["ij_b200_emu"][1], outs["ij_b200_emu"][1][-1500:]
+    assert any(l.startswith("    Cycle  1") for l in outs["ij_ref"][0]) and any("cycle =" in l for l in outs["ij_ref"][0])
+    assert outs["ij_b200_emu"][0] == outs["ij_ref"][0]
+
+
 def test_hybrid_gs_chunks_through_the_shim_on_the_host_emulation():
     """the reference's default smoother (hybrid l1-GS 13 / 14) depends on its thread count: with
     HYPRE_B200_GS_CHUNKS=host the drop-in reproduces the 3-thread reference digit for digit (one launch per sweep);

@@ -836,6 +836,25 @@ def test_ij_dropin_matches_reference(args):
     assert res_dev < 1e-8, (args, res_dev, res_ref)
 
 
+def test_ij_dropin_default_invocation_prints_the_reference_tables():
+    """`ij` with its defaults = stand-alone BoomerAMG at print level 3: the drop-in runs it on the device and prints the
+    reference's per-cycle table and complexities"""
+    import re
+    args = "-27pt -n 20 20 20 -rlx 18"
+    its_ref, res_ref, out_ref, _ = _ij("ij_ref", args)
+    its_dev, res_dev, out_dev, err = _ij("ij_b200", args)
+    assert "BoomerAMG on device" in err, err[-1500:]
+    assert its_dev == its_ref and abs(res_dev - res_ref) <= 2e-6 * res_ref, (its_dev, its_ref, res_dev, res_ref)
+    cyc = lambda out: [(int(m.group(1)), float(m.group(2)), float(m.group(3)))
+                       for m in re.finditer(r"Cycle\s+(\d+)\s+([0-9.eE+-]+)\s+([0-9.]+)", out)]
+    c_ref, c_dev = cyc(out_ref), cyc(out_dev)
+    assert len(c_ref) == its_ref and len(c_dev) == its_ref
+    for (k1, r1, f1), (k2, r2, f2) in zip(c_ref, c_dev):
+        assert k1 == k2 and abs(r1 - r2) <= 1e-5 * r1 and abs(f1 - f2) <= 2e-6, (k1, r1, r2, f1, f2)
+    cmplx = lambda out: re.findall(r"(grid|operator|cycle) = ([0-9.]+)", out)
+    assert cmplx(out_dev) == cmplx(out_ref) and any(k == "cycle" for k, _ in cmplx(out_ref))   # (setup prints the first two as well)
+
+
 def test_ij_dropin_hybrid_gs_chunks():
     """hypre's default smoother (hybrid l1-GS 13 / 14) with the reference's OpenMP semantics on the device:
     HYPRE_B200_GS_CHUNKS=host reproduces the 4-thread reference, =5 the 5-thread one (l1 norms of that partition

@@ -71,7 +71,8 @@ def test_fused_dots_on_the_host_emulation(tmp_path):
 
 def test_kernels_under_address_sanitizer():
     """the same emulation compiled with -fsanitize=address: no kernel (or host path around it) reads or
-    writes outside its "device" buffers on the SpMV formats, the Jacobi / Chebyshev sweeps and the BLAS-1 kernels
+    writes outside its "device" buffers on the SpMV formats, the Jacobi / Chebyshev sweeps, the BLAS-1 and batched-dot kernels,
+    the chunked Gauss-Seidel sweep and the IJ assembly
     (the whole suite passes under the sanitizer as well: `make -C oracle emu_asan`, then the command below without -k)"""
     if not os.path.exists(BRIDGE):
         pytest.skip("oracle/_ref/libref_bridge.so not built (needs /root/reference)")
@@ -82,8 +83,8 @@ def test_kernels_under_address_sanitizer():
         pytest.skip("libasan.so not found")
     env = {"HB200_EMU_LIB": os.path.join(ROOT, "oracle", "_ref", "libhb200_emu_asan.so"), "LD_PRELOAD": asan,
            "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1"}
-    r = run_child(env, os.path.join("tests", "test_gpu_parity.py"), "-m", "gpu", "-n", "6",
-                  "-k", "matvec or format or pattern or blas1")
+    r = run_child(env, os.path.join("tests", "test_gpu_parity.py"), os.path.join("tests", "test_ij_formats.py"), "-m", "gpu",
+                  "-n", "6", "-k", "matvec or format or pattern or blas1 or mass_inner or (hybrid_gs_chunks and weights0-13) or binary_ij")
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0 and "AddressSanitizer" not in tail, tail
     assert " passed" in r.stdout, tail

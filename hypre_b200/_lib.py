@@ -127,6 +127,10 @@ def _load() -> C.CDLL:
         "hb200_amg_set_use_graph": ([vp, C.c_int], C.c_int),
         "hb200_amg_cycle": ([vp, vp, vp, C.c_int], C.c_int),
         "hb200_amg_solve": ([vp, vp, vp, C.c_int, c_int_p, c_double_p], C.c_int),
+        "hb200_amg_save": ([vp, C.c_char_p], C.c_int),
+        "hb200_amg_load": ([C.POINTER(vp), C.c_char_p], C.c_int),
+        "hb200_amg_level_matrix": ([vp, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "hb200_amg_num_levels": ([vp], C.c_int),
         "hb200_amg_solve_logged": ([vp, vp, vp, C.c_int, c_int_p, c_double_p, vp, c_double_p], C.c_int),
         "hb200_amg_cycle_sweeps": ([vp, vp], C.c_int),
         "hb200_amg_level_vector": ([vp, C.c_int, C.c_int, C.POINTER(vp), c_int_p], C.c_int),

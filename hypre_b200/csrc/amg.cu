@@ -17,7 +17,9 @@
 #include "hb_internal.cuh"
 #include <stdlib.h>
 #include "relax.cuh"
+#include <errno.h>
 #include <math.h>
+#include <sys/stat.h>
 
 struct hb200_amg_level {
    hb200_parcsr *A = nullptr, *P = nullptr;
@@ -47,6 +49,8 @@ struct hb200_amg {
    int min_iter = 0, max_iter = 1, converge_type = 0;
    hb::GEData ge;
    bool has_ge = false;
+   std::vector<double> ge_A_mat;      // the dense coarse matrix as it was handed over (hb200_amg_save)
+   bool owns_matrices = false;        // a loaded hierarchy (hb200_amg_load) owns its level matrices
    bool use_graph = false;
    // fused-dot request of the caller (Krylov preconditioner use): <u, f> of the cycle's result in
    // this scalar slot, produced by the last level-0 sweep when it can; dot_fused reports it
@@ -434,6 +438,14 @@ bool amg_dot_fused(const hb200_amg *amg) { return amg && amg->dot_fused; }
 
 using namespace hb;
 
+// record of a saved hierarchy (hb200_amg_save / hb200_amg_load below)
+static const unsigned long long kAmgMagic = 0x31474d4130304248ULL;   // "HB00AMG1"
+
+template <class T>
+static bool wr(FILE *f, const T *p, size_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
+template <class T>
+static bool rd(FILE *f, T *p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
+
 extern "C" {
 
 int hb200_amg_create(hb200_amg **out, int num_levels)
@@ -466,6 +478,12 @@ int hb200_amg_destroy(hb200_amg *amg)
    if (amg->ge.d_Udiag) cudaFree(amg->ge.d_Udiag);
    if (amg->ge.d_b) cudaFree(amg->ge.d_b);
    for (auto &g : amg->graphs) cudaGraphExecDestroy(g.exec);
+   if (amg->owns_matrices) {
+      for (int l = 0; l < amg->num_levels; l++) {
+         if (amg->lev[l].A) hb200_parcsr_destroy(amg->lev[l].A);
+         if (amg->lev[l].P) hb200_parcsr_destroy(amg->lev[l].P);
+      }
+   }
    delete amg;
    return 0;
 }
@@ -557,6 +575,7 @@ int hb200_amg_set_coarse_ge(hb200_amg *amg, const double *A_mat, int n, int firs
    GEData &g = amg->ge;
    g.n = n; g.first_row = first_row; g.num_local = num_local;
    const size_t nn = (size_t) n * n;
+   amg->ge_A_mat.assign(A_mat, A_mat + nn);
    HB_CUDA(cudaMalloc(&g.d_LfT, sizeof(double) * nn));
    HB_CUDA(cudaMalloc(&g.d_UT, sizeof(double) * nn));
    HB_CUDA(cudaMalloc(&g.d_Udiag, sizeof(double) * n));
@@ -606,6 +625,128 @@ int hb200_amg_cycle_sweeps(const hb200_amg *amg, int *sweeps_per_level)
    HB_REQUIRE(amg && sweeps_per_level, HB200_ERROR_ARG, "null argument");
    amg_cycle_sweeps(amg, sweeps_per_level);
    return 0;
+}
+
+// ---- a hierarchy on disk: the level matrices as binary IJ files, everything else in one record per rank ----------
+int hb200_amg_save(const hb200_amg *amg, const char *dirname)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(amg && dirname, HB200_ERROR_ARG, "hb200_amg_save: null argument");
+   Ctx &c = ctx();
+   for (int l = 0; l < amg->num_levels; l++) HB_REQUIRE(amg->lev[l].A, HB200_ERROR_ARG, "hb200_amg_save: level not set");
+   if (mkdir(dirname, 0777) != 0 && errno != EEXIST) return set_error(HB200_ERROR_GENERIC, "hb200_amg_save: cannot create %s", dirname);
+   char path[1024];
+   // level matrices (collective calls: every rank goes through the same sequence)
+   for (int l = 0; l < amg->num_levels; l++) {
+      snprintf(path, sizeof(path), "%s/A%d", dirname, l);
+      HB_CHECK(hb200_parcsr_print_ij_binary(amg->lev[l].A, path));
+      if (amg->lev[l].P) {
+         snprintf(path, sizeof(path), "%s/P%d", dirname, l);
+         HB_CHECK(hb200_parcsr_print_ij_binary(amg->lev[l].P, path));
+      }
+   }
+   snprintf(path, sizeof(path), "%s/amg.%05d.bin", dirname, c.rank);
+   FILE *f = fopen(path, "wb");
+   if (!f) return set_error(HB200_ERROR_GENERIC, "hb200_amg_save: cannot open %s", path);
+   HB_CUDA(cudaStreamSynchronize(c.s_comp));
+   const int ints[20] = {amg->num_levels, c.nranks, amg->num_grid_sweeps[0], amg->num_grid_sweeps[1], amg->num_grid_sweeps[2],
+                         amg->num_grid_sweeps[3], amg->grid_relax_type[0], amg->grid_relax_type[1], amg->grid_relax_type[2],
+                         amg->grid_relax_type[3], amg->relax_order, amg->cycle_type, amg->fcycle, amg->cheby_order, amg->cheby_scale,
+                         amg->cheby_variant, amg->user_relax_type, amg->min_iter, amg->max_iter, amg->converge_type};
+   bool ok = wr(f, &kAmgMagic, 1) && wr(f, ints, 20) && wr(f, &amg->tol, 1);
+   for (int l = 0; ok && l < amg->num_levels; l++) {
+      const hb200_amg_level &L = amg->lev[l];
+      const size_t n = (size_t) L.n;
+      const int head[6] = {L.n, L.P ? 1 : 0, L.l1 ? 1 : 0, L.cf ? 1 : 0, L.cheby_ds ? 1 : 0, (int) L.cheby_coefs.size()};
+      const int chunks = L.A->gs_chunks;
+      ok = wr(f, head, 6) && wr(f, &L.relax_weight, 1) && wr(f, &L.omega, 1) && wr(f, &L.cheby_order_set, 1) && wr(f, &chunks, 1);
+      std::vector<double> hv(n);
+      std::vector<int> hi(n);
+      if (ok && L.l1) { if (n) HB_CUDA(cudaMemcpy(hv.data(), L.l1, sizeof(double) * n, cudaMemcpyDeviceToHost)); ok = wr(f, hv.data(), n); }
+      if (ok && L.cf) { if (n) HB_CUDA(cudaMemcpy(hi.data(), L.cf, sizeof(int) * n, cudaMemcpyDeviceToHost)); ok = wr(f, hi.data(), n); }
+      if (ok && L.cheby_ds) { if (n) HB_CUDA(cudaMemcpy(hv.data(), L.cheby_ds, sizeof(double) * n, cudaMemcpyDeviceToHost)); ok = wr(f, hv.data(), n); }
+      ok = ok && wr(f, L.cheby_coefs.data(), L.cheby_coefs.size());
+   }
+   const int ge[4] = {amg->has_ge ? 1 : 0, amg->ge.n, amg->ge.first_row, amg->ge.num_local};
+   ok = ok && wr(f, ge, 4);
+   if (ok && amg->has_ge) ok = wr(f, amg->ge_A_mat.data(), amg->ge_A_mat.size());
+   fclose(f);
+   if (!ok) return set_error(HB200_ERROR_GENERIC, "hb200_amg_save: write to %s failed", path);
+   return 0;
+}
+
+int hb200_amg_load(hb200_amg **out, const char *dirname)
+{
+   HB_CHECK(require_ready());
+   HB_REQUIRE(out && dirname, HB200_ERROR_ARG, "hb200_amg_load: null argument");
+   Ctx &c = ctx();
+   char path[1024];
+   snprintf(path, sizeof(path), "%s/amg.%05d.bin", dirname, c.rank);
+   FILE *f = fopen(path, "rb");
+   if (!f) return set_error(HB200_ERROR_ARG, "hb200_amg_load: cannot open %s", path);
+   unsigned long long magic = 0;
+   int ints[20];
+   double tol = 0.0;
+   bool ok = rd(f, &magic, 1) && magic == kAmgMagic && rd(f, ints, 20) && rd(f, &tol, 1);
+   if (!ok || ints[0] < 1 || ints[0] > 100) { fclose(f); return set_error(HB200_ERROR_GENERIC, "%s is not a hierarchy record of this library", path); }
+   if (ints[1] != c.nranks) { fclose(f); return set_error(HB200_ERROR_ARG, "hb200_amg_load: the hierarchy was saved on %d ranks, this run has %d", ints[1], c.nranks); }
+   hb200_amg *amg = nullptr;
+   int fl = hb200_amg_create(&amg, ints[0]);
+   if (fl) { fclose(f); return fl; }
+   amg->owns_matrices = true;
+   auto fail = [&](int flag) { fclose(f); hb200_amg_destroy(amg); return flag; };
+   for (int l = 0; l < amg->num_levels; l++) {
+      int head[6], cheby_order_set = 0, chunks = 0;
+      double rw = 1.0, om = 1.0;
+      if (!(rd(f, head, 6) && rd(f, &rw, 1) && rd(f, &om, 1) && rd(f, &cheby_order_set, 1) && rd(f, &chunks, 1)) || head[0] < 0) {
+         return fail(set_error(HB200_ERROR_GENERIC, "hb200_amg_load: %s is truncated", path));
+      }
+      const size_t n = (size_t) head[0];
+      std::vector<double> l1(n), ds(n), coefs((size_t) (head[5] > 0 ? head[5] : 0));
+      std::vector<int> cf(n);
+      ok = (!head[2] || rd(f, l1.data(), n)) && (!head[3] || rd(f, cf.data(), n)) && (!head[4] || rd(f, ds.data(), n)) &&
+           rd(f, coefs.data(), coefs.size());
+      if (!ok) return fail(set_error(HB200_ERROR_GENERIC, "hb200_amg_load: %s is truncated", path));
+      hb200_parcsr *A = nullptr, *P = nullptr;
+      char mp[1024];
+      snprintf(mp, sizeof(mp), "%s/A%d", dirname, l);
+      fl = parcsr_read_binary_exact(&A, mp);
+      if (!fl && head[1]) { snprintf(mp, sizeof(mp), "%s/P%d", dirname, l); fl = parcsr_read_binary_exact(&P, mp); }
+      // the matrices belong to the hierarchy from here on (destroyed with it, also on the failure paths below)
+      amg->lev[l].A = A; amg->lev[l].P = P;
+      if (fl) return fail(fl);
+      if (A->num_rows != head[0]) return fail(set_error(HB200_ERROR_GENERIC, "hb200_amg_load: level %d has %d rows, the record says %d", l, A->num_rows, head[0]));
+      fl = hb200_amg_set_level(amg, l, A, P, head[2] ? l1.data() : nullptr, head[3] ? cf.data() : nullptr, rw, om);
+      if (!fl && !coefs.empty()) fl = hb200_amg_set_level_cheby(amg, l, head[4] ? ds.data() : nullptr, coefs.data(), (int) coefs.size() - 1);
+      if (!fl && chunks > 1) fl = hb200_parcsr_set_gs_chunks(A, chunks);
+      if (fl) return fail(fl);
+      amg->lev[l].cheby_order_set = cheby_order_set;
+   }
+   fl = hb200_amg_set_cycle(amg, ints + 2, ints + 6, ints[10], ints[11], ints[12], ints[13], ints[14], ints[15], ints[16]);
+   if (!fl) fl = hb200_amg_set_solve(amg, tol, ints[17], ints[18], ints[19]);
+   int ge[4];
+   if (!fl && !rd(f, ge, 4)) fl = set_error(HB200_ERROR_GENERIC, "hb200_amg_load: %s is truncated", path);
+   if (!fl && ge[0]) {
+      std::vector<double> A_mat((size_t) ge[1] * (size_t) ge[1]);
+      if (!rd(f, A_mat.data(), A_mat.size())) fl = set_error(HB200_ERROR_GENERIC, "hb200_amg_load: %s is truncated", path);
+      else fl = hb200_amg_set_coarse_ge(amg, A_mat.data(), ge[1], ge[2], ge[3]);
+   }
+   if (fl) return fail(fl);
+   fclose(f);
+   *out = amg;
+   return 0;
+}
+
+int hb200_amg_level_matrix(hb200_amg *amg, int level, int which, hb200_parcsr **M)
+{
+   HB_REQUIRE(amg && M && level >= 0 && level < amg->num_levels && (which == 0 || which == 1), HB200_ERROR_ARG, "bad arguments");
+   *M = which == 0 ? amg->lev[level].A : amg->lev[level].P;
+   return 0;
+}
+
+int hb200_amg_num_levels(const hb200_amg *amg)
+{
+   return amg ? amg->num_levels : 0;
 }
 
 int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n)

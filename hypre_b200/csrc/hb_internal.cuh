@@ -379,6 +379,7 @@ struct hb200_parcsr {
 };
 
 namespace hb {
+int parcsr_read_binary_exact(hb200_parcsr **A, const char *prefix);   // ij.cu: a matrix written by hb200_parcsr_print_ij_binary, entry order kept
 int parcsr_ensure_T(hb200_parcsr *A);
 int parcsr_diag(hb200_parcsr *A, const double **diag);   // lazily extracted diagonal of the diag block
 int parcsr_halo_begin(hb200_parcsr *A, const double *x, cudaStream_t st_comp);   // pack + exchange on s_comm

@@ -32,7 +32,8 @@ struct IjHost {
 // square block first (IJMatrix_parcsr.c:2830-2848), off-range columns compressed through the ascending
 // col_map_offd (:2954-3001)
 static int ij_assemble_host(int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper, int64_t nnz,
-                            const int64_t *rows, const int64_t *cols, const double *vals, int add, IjHost &out)
+                            const int64_t *rows, const int64_t *cols, const double *vals, int add, IjHost &out,
+                            bool move_diag = true)
 {
    const int64_t nr64 = iupper - ilower + 1, nc64 = jupper - jlower + 1;
    HB_REQUIRE(nr64 >= 0 && nc64 >= 0 && nr64 < 0x7fffffffLL && nc64 < 0x7fffffffLL, HB200_ERROR_ARG, "IJ ranges out of the 32-bit local index space");
@@ -66,7 +67,7 @@ static int ij_assemble_host(int64_t ilower, int64_t iupper, int64_t jlower, int6
          else ra[(size_t) it->second] = vals[k];
       }
       int dpos = -1;
-      for (size_t q = 0; q < rj.size(); q++) {
+      for (size_t q = 0; move_diag && q < rj.size(); q++) {
          if (rj[q] >= jlower && rj[q] <= jupper && rj[q] - jlower == (int64_t) r) { dpos = (int) q; break; }
       }
       if (dpos >= 0) { out.diag_j.push_back(r); out.diag_a.push_back(ra[(size_t) dpos]); }
@@ -290,6 +291,26 @@ static int ij_download_coo(const hb200_parcsr *A, std::vector<int64_t> &rows, st
       for (int p = oi[(size_t) i]; p < oi[(size_t) i + 1]; p++) { rows.push_back(A->first_row + i); cols.push_back(A->col_map_offd[(size_t) oj[(size_t) p]]); vals.push_back(oa[(size_t) p]); }
    }
    return 0;
+}
+
+// a matrix this library wrote itself (hb200_parcsr_print_ij_binary: diag entries, then offd entries of every row) back
+// into the same arrays: the order of the entries is kept as it is in the file (a level matrix of a saved hierarchy,
+// amg.cu; interpolation matrices are rectangular and have no diagonal to move)
+int parcsr_read_binary_exact(hb200_parcsr **A, const char *prefix)
+{
+   int64_t range[4];
+   std::vector<int64_t> rows, cols;
+   std::vector<double> vals;
+   const int fr = ij_parse_binary(prefix, ctx().rank, range, rows, cols, vals);
+   if (fr && ctx().nranks == 1) return fr;
+   if (fr) { range[0] = 0; range[1] = -1; range[2] = 0; range[3] = -1; rows.clear(); cols.clear(); vals.clear(); }
+   IjHost h;
+   const int fa = ij_assemble_host(range[0], range[1], range[2], range[3], (int64_t) rows.size(), rows.data(), cols.data(),
+                                   vals.data(), 0, h, false);
+   if (fa && ctx().nranks == 1) return fa;
+   if (fa) h = IjHost();
+   const int fc = ij_create_parcsr(h, A);
+   return fr ? fr : (fa ? fa : fc);
 }
 
 }  // namespace hb

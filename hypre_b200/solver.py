@@ -197,7 +197,8 @@ class ParCSRMatrix:
 
     def destroy(self) -> None:
         if getattr(self, "handle", None):
-            lib.hb200_parcsr_destroy(self.handle)
+            if not getattr(self, "_borrowed", False):      # (a level matrix of a loaded hierarchy belongs to it)
+                lib.hb200_parcsr_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -344,6 +345,35 @@ class BoomerAMG:
         p, n = C.c_void_p(), C.c_int(0)
         check(lib.hb200_amg_level_vector(self.handle, level, which, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def save(self, dirname: str) -> None:
+        """hb200_amg_save: the hierarchy as files (level matrices in hypre's binary IJ format + one record per rank)"""
+        check(lib.hb200_amg_save(self.handle, dirname.encode()))
+
+    @classmethod
+    def load(cls, dirname: str) -> "BoomerAMG":
+        """hb200_amg_load: the hierarchy hb200_amg_save wrote, in a process without hypre; `mats[l] = (A_l, P_l)` are
+        borrowed handles (mats[0][0] is the operator the Krylov solvers take)"""
+        init_required()
+        h = C.c_void_p()
+        check(lib.hb200_amg_load(C.byref(h), dirname.encode()))
+        self = cls.__new__(cls)
+        self.handle = h
+        self.levels = []
+        self.mats = []
+        for l in range(int(lib.hb200_amg_num_levels(h))):
+            pair = []
+            for which in (0, 1):
+                m = C.c_void_p()
+                check(lib.hb200_amg_level_matrix(h, l, which, C.byref(m)))
+                if m.value:
+                    M = ParCSRMatrix._adopt(m)
+                    M._borrowed = True
+                    pair.append(M)
+                else:
+                    pair.append(None)
+            self.mats.append(tuple(pair))
+        return self
 
     def destroy(self) -> None:
         if getattr(self, "handle", None):

@@ -301,6 +301,17 @@ int hb200_amg_solve_logged(hb200_amg *amg, const double *f_dev, double *u_dev, i
 /* relaxation sweeps ONE cycle makes on every level (host only): the reference's "cycle complexity" adds the nonzeros of
  * a level once per sweep (par_cycle.c:455-474, hypre_ParAMGDataCycleOpCount) */
 int hb200_amg_cycle_sweeps(const hb200_amg *amg, int *sweeps_per_level);
+/* A hierarchy on disk ("ship hierarchies between boxes"): hb200_amg_save writes, per rank, the level matrices
+ * A_l, P_l as binary IJ files (`<dir>/A<l>.<rank>.bin`, `<dir>/P<l>.<rank>.bin`: HYPRE_IJMatrixPrintBinary's lossless
+ * format, readable by hypre itself) and one record `<dir>/amg.<rank>.bin` with l1 norms, CF markers, weights, Chebyshev
+ * data, the dense coarse matrix and the cycle parameters.  hb200_amg_load builds the same hierarchy from it in a
+ * process that holds no hypre at all, on the same number of ranks; the loaded hierarchy owns its matrices
+ * (hb200_amg_destroy frees them; hb200_amg_level_matrix hands out borrowed handles: level 0 of `which` = 0 is the
+ * operator the Krylov solvers take).  Both are collective. */
+int hb200_amg_save(const hb200_amg *amg, const char *dirname);
+int hb200_amg_load(hb200_amg **amg, const char *dirname);
+int hb200_amg_level_matrix(hb200_amg *amg, int level, int which, hb200_parcsr **M);   /* which: 0 = A_l, 1 = P_l */
+int hb200_amg_num_levels(const hb200_amg *amg);
 /* per-level device vectors after a cycle, for parity tests: which = 0 F_array, 1 U_array */
 int hb200_amg_level_vector(hb200_amg *amg, int level, int which, double **dev, int *n);
 

@@ -228,3 +228,45 @@ def test_vector_files_and_matrix_market(rb, hb, tmp_path):
     y = torch.zeros(4, dtype=torch.float64, device="cuda")
     A.matvec(1.0, torch.from_numpy(xs).cuda(), 0.0, y)
     assert np.max(np.abs(y.cpu().numpy() - ref.matvec(1.0, xs, 0.0))) <= 1e-14
+
+
+_HIER_CASES = [("27pt", dict(relax_type=18)), ("laplacian", dict(relax_type=16)), ("vardifconv", dict(relax_type=8, relax_order=1))]
+if os.environ.get("HB200_EMU_TEST") == "1":
+    _HIER_CASES = _HIER_CASES[2:]         # (the CPU suite's emulation run takes one of them)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,smoother", _HIER_CASES)
+def test_hierarchy_saved_and_loaded_solves_identically(rb, hb, tmp_path, kind, smoother):
+    """hb200_amg_save / hb200_amg_load ("ship hierarchies between boxes"): the loaded hierarchy — level matrices from
+    hypre's binary IJ files, everything else from the record — runs the same PCG / GMRES solve, bit for bit, as the
+    hierarchy uploaded straight from the reference's setup; the level files are readable by hypre itself"""
+    import torch
+    pb = rb.Problem(kind, (11, 10, 9))
+    pb.setup_amg(**smoother)
+    mats, amg = hb.amg_from_hierarchy(pb.hierarchy())
+    d = str(tmp_path / "hier")
+    amg.save(d)
+    loaded = hb.BoomerAMG.load(d)
+    assert len(loaded.mats) == len(mats)
+    for (A, P), (A2, P2) in zip(mats, loaded.mats):
+        m1, m2 = A.download_maps(), A2.download_maps()
+        assert np.array_equal(m1["diag_i"], m2["diag_i"]) and np.array_equal(m1["diag_j"], m2["diag_j"])
+        assert (P is None) == (P2 is None)
+        if P is not None:
+            p1, p2 = P.download_maps(), P2.download_maps()
+            assert np.array_equal(p1["diag_i"], p2["diag_i"]) and np.array_equal(p1["diag_j"], p2["diag_j"])
+    b = torch.from_numpy(np.array(pb.b)).cuda()
+    xs = []
+    for M, pc in ((mats[0][0], amg), (loaded.mats[0][0], loaded)):
+        ks = hb.ParCSRGMRES(tol=1e-8, max_iter=60, k_dim=5) if kind == "vardifconv" else hb.ParCSRPCG(tol=1e-8, max_iter=60, two_norm=1)
+        ks.set_precond(pc)
+        x = torch.zeros(M.num_rows, dtype=torch.float64, device="cuda")
+        ks.solve(M, b, x)
+        xs.append((ks.num_iterations, x.cpu().numpy()))
+    assert xs[0][0] == xs[1][0] and np.array_equal(xs[0][1], xs[1][1])
+    # hypre reads the fine-level file of the saved hierarchy back to the reference's own operator
+    back = rb.Problem.from_ij_file(os.path.join(d, "A0"), binary=True)
+    ra, rr = back.level_view(0, 0).arrays(), pb.level_view(0, 0).arrays()
+    for k in ("diag_i", "diag_j", "diag_data"):
+        assert np.array_equal(ra[k], rr[k]), k

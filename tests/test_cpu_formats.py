@@ -305,3 +305,54 @@ def test_wide_variant_takes_blocks_the_one_byte_format_rejects():
     w = analyze_wide(n, n, ai, aj, aa)
     assert w["npat"] >= 400 and set(singles) <= set(w["irr"].tolist())
     assert_lossless(n, ai, aj, aa, w)
+
+
+def _same_analysis(a, b):
+    assert a["npat"] == b["npat"] and a["nirr"] == b["nirr"]
+    for k in ("code", "base", "ptr", "irr"):
+        assert np.array_equal(a[k], b[k]), k
+    ne = int(a["ptr"][-1]) if a["npat"] else 0
+    assert np.array_equal(a["off"][:ne], b["off"][:ne])
+    assert np.array_equal(a["val"][:ne].view(np.uint64), b["val"][:ne].view(np.uint64))
+
+
+def test_threaded_classification_is_the_sequential_one():
+    """blocks of >= 2^18 rows are classified by several host threads (chunks of rows, candidate lists merged in chunk
+    order): the row codes, the table and the irregular-row list are those of the one-thread pass — on a regular
+    stencil, on one with scattered one-off rows, on a rectangular block and on an irregular block (left to the
+    sequential pass)"""
+    import scipy.sparse as sp
+    n, ai, aj, aa = stencil7(64, 64, 64)
+    assert n >= 1 << 18
+    rng = np.random.default_rng(9)
+    cases = [("regular", n, n, ai, aj, aa.copy())]
+    pert = aa.copy()
+    rows = rng.choice(n, 3000, replace=False)
+    pert[ai[rows]] += rng.standard_normal(3000)            # 3000 rows with a one-off diagonal
+    cases.append(("one-off rows", n, n, ai, aj, pert))
+    # rectangular: every second column dropped from the column space (an interpolation-like block)
+    keep = (aj % 2 == 0)
+    rowsz = np.add.reduceat(keep.astype(np.int64), ai[:-1])
+    ai2 = np.concatenate([[0], np.cumsum(rowsz)]).astype(np.int32)
+    cases.append(("rectangular", n, n // 2, ai2, (aj[keep] // 2).astype(np.int32), aa[keep].copy()))
+    noisy = aa * (1.0 + 0.1 * rng.standard_normal(aa.size))   # every row its own values: not this format's business
+    cases.append(("irregular", n, n, ai, aj, noisy))
+    old = os.environ.get("HB200_ANALYSIS_THREADS")
+    try:
+        for name, nr, nc, i_, j_, a_ in cases:
+            os.environ["HB200_ANALYSIS_THREADS"] = "1"
+            seq = analyze(nr, nc, i_, j_, a_)
+            os.environ["HB200_ANALYSIS_THREADS"] = "7"
+            par = analyze(nr, nc, i_, j_, a_)
+            _same_analysis(seq, par)
+            if name == "regular":
+                assert seq["npat"] == 27 and seq["nirr"] == 0
+            if name == "one-off rows":
+                assert seq["npat"] > 0 and seq["nirr"] >= 3000
+            if name == "irregular":
+                assert seq["npat"] == 0
+    finally:
+        if old is None:
+            os.environ.pop("HB200_ANALYSIS_THREADS", None)
+        else:
+            os.environ["HB200_ANALYSIS_THREADS"] = old

@@ -33,8 +33,10 @@ struct IjHost {
 // col_map_offd (:2954-3001)
 static int ij_assemble_host(int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper, int64_t nnz,
                             const int64_t *rows, const int64_t *cols, const double *vals, int add, IjHost &out,
-                            bool move_diag = true)
+                            bool move_diag = true, int64_t add_from = -1)
 {
+   // entries k >= add_from (contributions received from other ranks) are always added, whatever `add` says
+   if (add_from < 0) add_from = nnz;
    const int64_t nr64 = iupper - ilower + 1, nc64 = jupper - jlower + 1;
    HB_REQUIRE(nr64 >= 0 && nc64 >= 0 && nr64 < 0x7fffffffLL && nc64 < 0x7fffffffLL, HB200_ERROR_ARG, "IJ ranges out of the 32-bit local index space");
    HB_REQUIRE(nnz >= 0 && nnz < 0x7fffffffLL, HB200_ERROR_ARG, "IJ triplet count out of range");
@@ -44,7 +46,7 @@ static int ij_assemble_host(int64_t ilower, int64_t iupper, int64_t jlower, int6
    // counting sort of the triplets by row, stable (insertion order inside a row)
    std::vector<int> start((size_t) nr + 1, 0);
    for (int64_t k = 0; k < nnz; k++) {
-      HB_REQUIRE(rows[k] >= ilower && rows[k] <= iupper, HB200_ERROR_ARG, "IJ triplet outside the rows this rank owns (off-processor values are not supported)");
+      HB_REQUIRE(rows[k] >= ilower && rows[k] <= iupper, HB200_ERROR_ARG, "IJ triplet outside the rows this rank owns");
       start[(size_t) (rows[k] - ilower) + 1]++;
    }
    for (int r = 0; r < nr; r++) start[(size_t) r + 1] += start[(size_t) r];
@@ -63,7 +65,7 @@ static int ij_assemble_host(int64_t ilower, int64_t iupper, int64_t jlower, int6
          const int64_t j = cols[k];
          auto it = seen.find(j);
          if (it == seen.end()) { seen.emplace(j, (int) rj.size()); rj.push_back(j); ra.push_back(vals[k]); }
-         else if (add) ra[(size_t) it->second] += vals[k];
+         else if (add || (int64_t) k >= add_from) ra[(size_t) it->second] += vals[k];
          else ra[(size_t) it->second] = vals[k];
       }
       int dpos = -1;
@@ -325,8 +327,53 @@ int hb200_parcsr_from_ij(hb200_parcsr **A, int64_t ilower, int64_t iupper, int64
 {
    HB_CHECK(require_ready());
    HB_REQUIRE(A != nullptr && (num_entries == 0 || (rows && cols && values)), HB200_ERROR_ARG, "hb200_parcsr_from_ij: null argument");
+   Ctx &c = ctx();
+   // entries for rows of other ranks (HYPRE_IJMatrixAddToValues off-processor; hypre_IJMatrixRead adds every entry of a
+   // part file that lies outside the part's row range): they travel to the owner, who ADDS them after its own entries
+   // (hypre_IJMatrixAssembleOffProcValsParCSR, src/IJ_mv/IJMatrix_parcsr.c)
+   std::vector<int64_t> own_r, own_c, far;       // far: (row, col, value bits) triples
+   std::vector<double> own_v;
+   bool any_far = false;
+   for (int64_t k = 0; k < num_entries; k++) if (rows[k] < ilower || rows[k] > iupper) { any_far = true; break; }
+   int64_t far_count = 0;
+   if (any_far) {
+      for (int64_t k = 0; k < num_entries; k++) {
+         if (rows[k] < ilower || rows[k] > iupper) {
+            int64_t bits;
+            memcpy(&bits, &values[k], 8);
+            far.push_back(rows[k]); far.push_back(cols[k]); far.push_back(bits);
+         } else { own_r.push_back(rows[k]); own_c.push_back(cols[k]); own_v.push_back(values[k]); }
+      }
+      far_count = (int64_t) far.size() / 3;
+      HB_REQUIRE(c.nranks > 1, HB200_ERROR_ARG, "hb200_parcsr_from_ij: entries outside [ilower, iupper] on one rank");
+   }
+   std::vector<int64_t> counts;
+   HB_CHECK(allgather_i64(&far_count, 1, counts));
+   int64_t max_far = 0;
+   for (int64_t v : counts) max_far = std::max(max_far, v);
+   if (max_far == 0) {
+      IjHost h;
+      HB_CHECK(ij_assemble_host(ilower, iupper, jlower, jupper, num_entries, rows, cols, values, add_duplicates, h));
+      return ij_create_parcsr(h, A);
+   }
+   if (!any_far) { own_r.assign(rows, rows + num_entries); own_c.assign(cols, cols + num_entries); own_v.assign(values, values + num_entries); }
+   const int64_t n_own = (int64_t) own_r.size();
+   std::vector<int64_t> all;
+   far.resize((size_t) max_far * 3, 0);
+   HB_CHECK(allgather_i64(far.data(), (size_t) max_far * 3, all));
+   for (int q = 0; q < c.nranks; q++) {
+      if (q == c.rank) continue;
+      const int64_t *lst = all.data() + (size_t) q * (size_t) max_far * 3;
+      for (int64_t t = 0; t < counts[(size_t) q]; t++) {
+         if (lst[3 * t] < ilower || lst[3 * t] > iupper) continue;
+         double v;
+         memcpy(&v, &lst[3 * t + 2], 8);
+         own_r.push_back(lst[3 * t]); own_c.push_back(lst[3 * t + 1]); own_v.push_back(v);
+      }
+   }
    IjHost h;
-   HB_CHECK(ij_assemble_host(ilower, iupper, jlower, jupper, num_entries, rows, cols, values, add_duplicates, h));
+   HB_CHECK(ij_assemble_host(ilower, iupper, jlower, jupper, (int64_t) own_r.size(), own_r.data(), own_c.data(), own_v.data(),
+                             add_duplicates, h, true, n_own));
    return ij_create_parcsr(h, A);
 }
 

@@ -444,8 +444,9 @@ int hb200_bicgstab_solve_host(hb200_parcsr *A, int precond_kind, hb200_amg *amg,
  * a repeated (i, j) lands on its first occurrence (add_duplicates: summed, else the last value wins), the
  * diagonal entry of a square block comes first (the relaxation sweeps rely on it, par_relax.c:274),
  * col_map_offd ascends.  On N ranks the CommPkg (hypre_MatvecCommPkgCreate, src/parcsr_mv/
- * par_csr_communication.c) is built from two NCCL all-gathers.  Values for rows of other ranks
- * (HYPRE_IJMatrixAddToValues off-processor) are not supported. */
+ * par_csr_communication.c) is built from two NCCL all-gathers.  Entries for rows of other ranks
+ * (HYPRE_IJMatrixAddToValues off-processor; what hypre_IJMatrixRead does with the entries of a part file outside its
+ * row range) travel to the owner, who adds them after its own entries (one more all-gather, only when there are any). */
 int hb200_parcsr_from_ij(hb200_parcsr **A, int64_t ilower, int64_t iupper, int64_t jlower, int64_t jupper,
                          int64_t num_entries, const int64_t *rows, const int64_t *cols,
                          const double *values, int add_duplicates);

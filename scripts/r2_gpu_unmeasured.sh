@@ -8,7 +8,7 @@ mkdir -p $OUT
 export PYTHONPATH=$PWD
 {
 echo "== parity of the new code on hardware"
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "krylov_ext or mass_inner or hybrid_gs or reference_thread_count or matvec or ij_dropin" 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "krylov_ext or mass_inner or hybrid_gs or reference_thread_count or matvec or ij_dropin" tests/test_ij_formats.py 2>&1 | tail -5
 
 echo "== spmv_box: GEO against the predicated kernel of the round-2 profiles (27-pt, one SpMV launch)"
 for n in 128 192 256 384; do
@@ -38,14 +38,21 @@ for mode in "" host auto 4736 18944; do
       oracle/_ref/ij_b200 -27pt -n 128 128 128 -solver 1 2>&1 | grep -i "on device\|Iterations\|Final Rel\|wall" | sed "s/^/chunks='$mode': /"
 done
 
-echo "== f4 drivers on config 4 (vardifconv 256^3): GMRES against COGMRES / FlexGMRES / BiCGSTAB"
-for sv in gmres cogmres flexgmres bicgstab; do
+echo "== f4 drivers on config 4 (vardifconv 256^3): GMRES against COGMRES / FlexGMRES / LGMRES / BiCGSTAB"
+for sv in gmres cogmres flexgmres lgmres bicgstab; do
    timeout 900 python bench.py --problem vardifconv --solver $sv --steps 5 --warmup 2 --no-e2e-ij > $OUT/vdc_$sv.json 2> $OUT/vdc_$sv.err
    python - <<EOF
 import json
 d = json.loads([l for l in open("$OUT/vdc_$sv.json") if l.startswith("{")][-1])
 print("$sv", "ms/solve", d["ms_per_step"], "its", d["config"]["iterations"], "parity", d["config"].get("parity_vs_reference"))
 EOF
+done
+
+echo "== upload of the 27-pt 256^3 hierarchy: single-core host passes (the round-2 trace) against the threaded ones"
+for cfg in "HB200_UPLOAD_THREADS=1 HB200_ANALYSIS_THREADS=1" "HB200_UPLOAD_THREADS=4 HB200_ANALYSIS_THREADS=8"; do
+   env $cfg HB200_TRACE=1 timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e-ij > $OUT/upload.json 2> $OUT/upload.err
+   echo "$cfg: upload_s $(python -c "import json;print(json.loads([l for l in open('$OUT/upload.json') if l.startswith('{')][-1])['config']['upload_s'])")"
+   grep "CSR copy\|row patterns" $OUT/upload.err | head -6
 done
 
 echo "== ncu: the GEO kernel (one capture), launch list of the default solve"

@@ -686,8 +686,8 @@ def main():
             ent = tab.get("spmv_box<EPI_AXPBY> on A_0")
             if ent:
                 per_level[0]["traffic_note"] = (f"no ncu capture of the GEO variant yet; the predicated variant it replaces moved "
-                                                f"{ent['bytes'] / 1e6:.0f} MB per launch ({ent['source']}) and additionally read the "
-                                                f"{per_level[0]['rows'] / 1e6:.1f} MB of row codes this one skips")
+                                                f"{ent['bytes'] / 1e6:.0f} MB per launch ({ent['source']}), "
+                                                f"{per_level[0]['rows'] / 1e6:.1f} MB of it row codes, which this one does not read")
     roofline = max(per_level, key=lambda e: e["ms_per_iteration"])
     roofline = dict(roofline, note="the level kernel with the largest share of the iteration; every level in `levels`")
     roofline["frac_of_nominal_8TBs"] = roofline["achieved"] / NOMINAL

@@ -8,6 +8,7 @@
 #include <string>
 #include <fcntl.h>
 #include <map>
+#include <signal.h>
 #include <sys/mman.h>
 #include <ucontext.h>
 #include <unistd.h>
@@ -237,6 +238,13 @@ int g_shm_seq = 0;
 struct IpcHandle { char name[48]; unsigned long long size; };
 size_t page_round(size_t n) { return (n + 4095) & ~(size_t) 4095; }
 void unlink_all() { for (auto &n : g_shm_names) shm_unlink(n.c_str()); }
+// a job stopped by `timeout` / a test harness (SIGTERM, SIGINT, SIGHUP) must not leave its arena (256 MB of tmpfs) behind
+void unlink_on_signal(int sig)
+{
+   unlink_all();
+   signal(sig, SIG_DFL);
+   raise(sig);
+}
 }  // namespace
 
 void *dev_alloc(size_t bytes)
@@ -268,7 +276,10 @@ int ipc_export(void *handle64, void *p)
    h.size = it->second;
    const int fd = shm_open(h.name, O_CREAT | O_EXCL | O_RDWR, 0600);
    if (fd < 0) return 1;
-   if (g_shm_names.empty()) atexit(unlink_all);
+   if (g_shm_names.empty()) {
+      atexit(unlink_all);
+      signal(SIGTERM, unlink_on_signal); signal(SIGINT, unlink_on_signal); signal(SIGHUP, unlink_on_signal);
+   }
    g_shm_names.push_back(h.name);
    if (ftruncate(fd, (off_t) h.size) != 0) { close(fd); return 1; }
    // keep the contents and the address: copy out, map the shared object over the block, copy back

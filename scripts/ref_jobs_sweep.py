@@ -49,8 +49,13 @@ def run(binary, nranks, args, timeout):
     try:
         out, err = p.communicate(timeout=timeout)
     except subprocess.TimeoutExpired:
-        os.killpg(p.pid, signal.SIGKILL)
-        p.communicate()
+        # SIGTERM first: the emulation unlinks its shared-memory arena on it (a SIGKILLed rank leaves 256 MB of tmpfs behind)
+        os.killpg(p.pid, signal.SIGTERM)
+        try:
+            p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            p.communicate()
         return None, None, "", time.time() - t0, "timeout"
     r = subprocess.CompletedProcess(cmd, p.returncode, out, err)
     its = [int(x) for x in re.findall(r"Iterations = (\d+)", r.stdout)]

@@ -53,7 +53,15 @@ def main():
         time.sleep(4.0)
     dist.barrier()
     dist.destroy_process_group()
-    os._exit(0)                       # the protocol state is broken on purpose: no orderly teardown
+    # the protocol state is broken on purpose: no orderly teardown — but the emulated IPC arena of this process (a POSIX
+    # shared-memory object the runtime unlinks at a normal exit) must not stay behind
+    import glob
+    for f in glob.glob("/dev/shm/hb_emu_%d_*" % os.getpid()):
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+    os._exit(0)
 
 
 if __name__ == "__main__":
